@@ -1,0 +1,265 @@
+"""Host-side mirror of the reference's aligner interface for the refinement path.
+
+The reference calls one template function per candidate:
+
+    AffineGuidedAlign(q, t, guide, scoreFn, bandSize, buffers, out, Global, false)   Blasr.cpp:863
+    GuidedAlign(q, t, guide, scoreFn, bandSize, buffers, out, Global, false)         Blasr.cpp:869
+    KBandAlign(q, t, matchMat, ins, del, k, scoreMat, pathMat, out, scoreFn, type)   Blasr.cpp:717,820
+    SWAlign(q, t, scoreMat, pathMat, out, scoreFn, type)                             SDPAlign.h:440,503,563
+    ComputeAlignmentStats(out, q, t, scoreFn, useAffine)                             Blasr.cpp:875
+
+Here the same names take a *batch* of candidates and run them on the GPU through the C ABI
+(include/blasr_gpu.h); argument meaning, defaults and returned fields follow the reference.
+This module holds no alignment arithmetic of its own.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import (AFFINE_GUIDED, FN_DISTANCE, FN_QUALITY, GLOBAL, GUIDED, KBAND, SW, BgpuError)
+
+# ScoreMatrices.h:20-26
+SMRTDistanceMatrix = np.array([[-5, 6, 6, 6, 0], [6, -5, 6, 6, 0], [6, 6, -5, 6, 0], [6, 6, 6, -5, 0],
+                               [0, 0, 0, 0, 0]], dtype=np.int32)
+
+
+@dataclass
+class DistanceMatrixScoreFunction:
+    """DistanceMatrixScoreFunction<DNASequence,FASTQSequence> (DistanceMatrixScoreFunction.h:11-105)."""
+    scoreMatrix: np.ndarray = field(default_factory=lambda: SMRTDistanceMatrix.copy())
+    ins: int = 5
+    del_: int = 5
+    affineOpen: int = 0
+    affineExtend: int = 0
+    kind: int = FN_DISTANCE
+
+    def c_struct(self) -> capi.ScoreFn:
+        s = capi.ScoreFn()
+        m = np.ascontiguousarray(self.scoreMatrix, dtype=np.int32).reshape(25)
+        for i in range(25):
+            s.M[i] = int(m[i])
+        s.ins, s.del_, s.affineOpen, s.affineExtend, s.kind = self.ins, self.del_, self.affineOpen, self.affineExtend, self.kind
+        return s
+
+
+@dataclass
+class QualityValueScoreFunction(DistanceMatrixScoreFunction):
+    """QualityValueScoreFunction<DNASequence,FASTQSequence> (QualityValueScoreFunction.h:9-85): match cost is
+    QVDistanceMatrix[q][t] * qual[q]; gap costs are the constants ins/del.  scoreMatrix is only used by the
+    stats pass, exactly as blasr rescoring always uses the distance function (Blasr.cpp:875)."""
+    kind: int = FN_QUALITY
+
+
+@dataclass
+class JobBatch:
+    """Structure-of-arrays batch (bgpu_batch)."""
+    q: np.ndarray
+    qOff: np.ndarray
+    t: np.ndarray
+    tOff: np.ndarray
+    guide: Optional[np.ndarray] = None      # (nBlocksTotal, 3) uint32 {qPos,tPos,length}
+    guideOff: Optional[np.ndarray] = None
+    qual: Optional[np.ndarray] = None
+    band: Optional[np.ndarray] = None
+
+    @property
+    def n(self) -> int:
+        return len(self.qOff) - 1
+
+    @staticmethod
+    def from_lists(qs: Sequence[bytes], ts: Sequence[bytes], guides: Optional[Sequence[np.ndarray]] = None,
+                   quals: Optional[Sequence[np.ndarray]] = None, bands: Optional[Sequence[int]] = None) -> "JobBatch":
+        def cat(seqs):
+            off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+            if len(seqs):
+                off[1:] = np.cumsum([len(s) for s in seqs])
+            data = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+            return data, off
+        q, qOff = cat(qs)
+        t, tOff = cat(ts)
+        g = gOff = None
+        if guides is not None:
+            gOff = np.zeros(len(guides) + 1, dtype=np.uint64)
+            gOff[1:] = np.cumsum([len(x) for x in guides])
+            nz = [np.asarray(x, dtype=np.uint32).reshape(-1, 3) for x in guides]
+            g = np.concatenate(nz, axis=0) if nz else np.zeros((0, 3), np.uint32)
+        ql = None
+        if quals is not None:
+            ql = np.concatenate([np.asarray(x, dtype=np.uint8) for x in quals]) if len(quals) else np.zeros(0, np.uint8)
+        bd = np.asarray(bands, dtype=np.int32) if bands is not None else None
+        return JobBatch(q, qOff, t, tOff, g, gOff, ql, bd)
+
+    def slice(self, idx: Sequence[int]) -> "JobBatch":
+        qs = [self.q[int(self.qOff[i]):int(self.qOff[i + 1])].tobytes() for i in idx]
+        ts = [self.t[int(self.tOff[i]):int(self.tOff[i + 1])].tobytes() for i in idx]
+        gs = [self.guide[int(self.guideOff[i]):int(self.guideOff[i + 1])] for i in idx] if self.guide is not None else None
+        qv = [self.qual[int(self.qOff[i]):int(self.qOff[i + 1])] for i in idx] if self.qual is not None else None
+        bd = [int(self.band[i]) for i in idx] if self.band is not None else None
+        return JobBatch.from_lists(qs, ts, gs, qv, bd)
+
+
+@dataclass
+class Alignment:
+    """The fields of the reference's Alignment the DP fills (datastructures/alignment/Alignment.h:17-41)."""
+    status: int
+    score: int
+    qPos: int
+    tPos: int
+    nCells: int
+    blocks: np.ndarray                  # (n,3) uint32
+    gaps: List[List[tuple]]             # gaps[i] = [(seq, length), ...]; seq 0 = Gap::Query, 1 = Gap::Target
+    nMatch: int = 0
+    nMismatch: int = 0
+    nIns: int = 0
+    nDel: int = 0
+    pctSimilarity: float = 0.0
+    statsScore: int = 0
+
+
+class BatchResult:
+    def __init__(self, results: np.ndarray, blocks: np.ndarray, gapCounts: np.ndarray, gaps: np.ndarray, timing=None):
+        self.results, self.blocks, self.gapCounts, self.gaps, self.timing = results, blocks, gapCounts, gaps, timing
+
+    def __len__(self):
+        return len(self.results)
+
+    def alignment(self, i: int) -> Alignment:
+        r = self.results[i]
+        b = self.blocks[int(r["blockOff"]):int(r["blockOff"]) + int(r["nBlocks"])]
+        blocks = np.stack([b["qPos"], b["tPos"], b["length"]], axis=1) if len(b) else np.zeros((0, 3), np.uint32)
+        cnt = self.gapCounts[int(r["gapListOff"]):int(r["gapListOff"]) + int(r["nGapLists"])]
+        g = self.gaps[int(r["gapOff"]):int(r["gapOff"]) + int(r["nGaps"])]
+        gaps, p = [], 0
+        for c in cnt:
+            gaps.append([(int(x["seq"]), int(x["length"])) for x in g[p:p + int(c)]])
+            p += int(c)
+        return Alignment(int(r["status"]), int(r["score"]), int(r["qPos"]), int(r["tPos"]), int(r["nCells"]), blocks, gaps,
+                         int(r["nMatch"]), int(r["nMismatch"]), int(r["nIns"]), int(r["nDel"]), float(r["pctSimilarity"]),
+                         int(r["statsScore"]))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Aligner:
+    """One GPU context (bgpu_ctx).  Raises BgpuError when no CUDA device is present: there is no CPU fallback."""
+
+    def __init__(self, device: int = 0):
+        self._lib = capi.lib()
+        self._ctx = C.c_void_p()
+        rc = self._lib.bgpu_create(C.byref(self._ctx), device)
+        if rc != 0:
+            self._ctx = None
+            raise BgpuError(f"bgpu_create(device={device}) failed with {rc}"
+                            + (" (no CUDA device: the refinement kernels cannot run)" if rc == capi.E_NO_DEVICE else ""))
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.bgpu_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def _err(self, rc: int, what: str):
+        raise BgpuError(f"{what} failed with {rc}: {self._lib.bgpu_last_error(self._ctx).decode()}")
+
+    # ---- low level: ticket API ----
+    def submit(self, batch: JobBatch, fn: DistanceMatrixScoreFunction, algo: int, alignType: int = GLOBAL, band: int = 16,
+               bndIns: int = 0, bndDel: int = 0, doStats: bool = True, statsAffine: Optional[bool] = None):
+        keep = dict(q=np.ascontiguousarray(batch.q, np.uint8), qOff=np.ascontiguousarray(batch.qOff, np.uint64),
+                    t=np.ascontiguousarray(batch.t, np.uint8), tOff=np.ascontiguousarray(batch.tOff, np.uint64))
+        n = batch.n
+        if algo in (GUIDED, AFFINE_GUIDED):
+            if batch.guide is None:
+                raise ValueError("guided aligners need batch.guide")
+            keep["guide"] = np.ascontiguousarray(batch.guide, np.uint32)
+            keep["guideOff"] = np.ascontiguousarray(batch.guideOff, np.uint64)
+        if batch.qual is not None:
+            keep["qual"] = np.ascontiguousarray(batch.qual, np.uint8)
+        if batch.band is not None:
+            keep["band"] = np.ascontiguousarray(batch.band, np.int32)
+        b = capi.Batch(n, _ptr(keep["q"]), _ptr(keep["qOff"]), _ptr(keep["t"]), _ptr(keep["tOff"]), _ptr(keep.get("qual")),
+                       _ptr(keep.get("guide")), _ptr(keep.get("guideOff")), _ptr(keep.get("band")))
+        if statsAffine is None:
+            statsAffine = algo == AFFINE_GUIDED
+        p = capi.Params(algo, alignType, band, bndIns, bndDel, int(doStats), int(statsAffine))
+        f = fn.c_struct()
+        tk = C.c_void_p()
+        rc = self._lib.bgpu_submit(self._ctx, C.byref(f), C.byref(p), C.byref(b), C.byref(tk))
+        if rc != 0:
+            self._err(rc, "bgpu_submit")
+        return tk, n
+
+    def collect(self, ticket) -> BatchResult:
+        tk, n = ticket
+        res = np.zeros(n, dtype=capi.RESULT_DTYPE)
+        arena = capi.Arena()
+        rc = self._lib.bgpu_collect(self._ctx, tk, res.ctypes.data_as(C.c_void_p), C.byref(arena))
+        if rc != 0:
+            self._err(rc, "bgpu_collect")
+
+        def view(ptr, count, dt):
+            if not count:
+                return np.zeros(0, dtype=dt)
+            buf = (C.c_char * (int(count) * dt.itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dt).copy()
+        return BatchResult(res, view(arena.blocks, arena.nBlocks, capi.BLOCK_DTYPE),
+                           view(arena.gapCounts, arena.nGapLists, np.dtype("<u4")),
+                           view(arena.gaps, arena.nGaps, capi.GAP_DTYPE), self.timing(ticket))
+
+    def rerun(self, ticket):
+        rc = self._lib.bgpu_rerun(self._ctx, ticket[0])
+        if rc != 0:
+            self._err(rc, "bgpu_rerun")
+        return self.timing(ticket)
+
+    def timing(self, ticket) -> capi.Timing:
+        tm = capi.Timing()
+        self._lib.bgpu_timing_of(self._ctx, ticket[0], C.byref(tm))
+        return tm
+
+    def release(self, ticket):
+        self._lib.bgpu_release(self._ctx, ticket[0])
+
+    def int_peak(self):
+        ops, mhz = C.c_double(), C.c_double()
+        rc = self._lib.bgpu_measure_int_peak(self._ctx, C.byref(ops), C.byref(mhz))
+        if rc != 0:
+            self._err(rc, "bgpu_measure_int_peak")
+        return ops.value, mhz.value
+
+    def _run(self, batch, fn, algo, **kw) -> BatchResult:
+        tk = self.submit(batch, fn, algo, **kw)
+        try:
+            return self.collect(tk)
+        finally:
+            self.release(tk)
+
+    # ---- the reference's names ----
+    def AffineGuidedAlign(self, batch: JobBatch, scoreFn, bandSize: int = 16, alignType: int = GLOBAL,
+                          computeStats: bool = True) -> BatchResult:
+        """AffineGuidedAlign.h:31; blasr defaults bandSize=16, ins=del=5, affineOpen=50, affineExtend=0, Global."""
+        return self._run(batch, scoreFn, AFFINE_GUIDED, alignType=alignType, band=bandSize, doStats=computeStats,
+                         statsAffine=True)
+
+    def GuidedAlign(self, batch: JobBatch, scoreFn, bandSize: int = 10, alignType: int = GLOBAL,
+                    computeStats: bool = True, statsAffine: bool = False) -> BatchResult:
+        """GuidedAlign.h:278 (computeProb=false)."""
+        return self._run(batch, scoreFn, GUIDED, alignType=alignType, band=bandSize, doStats=computeStats,
+                         statsAffine=statsAffine)
+
+    def KBandAlign(self, batch: JobBatch, scoreFn, ins: int, del_: int, k: int, alignType: int = GLOBAL,
+                   computeStats: bool = False) -> BatchResult:
+        """KBandAlign.h:75; ins/del are the boundary-cost *parameters*, the fill uses scoreFn.ins/del."""
+        return self._run(batch, scoreFn, KBAND, alignType=alignType, band=k, bndIns=ins, bndDel=del_, doStats=computeStats,
+                         statsAffine=False)
+
+    def SWAlign(self, batch: JobBatch, scoreFn, alignType: int = capi.LOCAL, computeStats: bool = False) -> BatchResult:
+        """SWAlign.h:18."""
+        return self._run(batch, scoreFn, SW, alignType=alignType, band=0, doStats=computeStats, statsAffine=False)

@@ -1,0 +1,487 @@
+// bgpu_api.cu -- host side of the C ABI declared in include/blasr_gpu.h.
+//
+// Owns device memory, pinned staging, the stream and the kernel schedule of one batch:
+//   H2D -> prep (guide rows, d-block windows) -> [host: classify by window width, order longest-first,
+//   cut into waves that fit the traceback pool] -> per wave { fill kernels, traceback kernel } ->
+//   count scan -> emit (blocks, gaps, stats) -> D2H.
+// No CPU implementation of any aligner exists here: without a CUDA device every entry point fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "bgpu_common.cuh"
+
+namespace bgpu {
+void launch_prep_guided(const BatchDev &, const ScoreParams &, int, const uint64_t *, const uint64_t *,
+                        const uint64_t *, cudaStream_t);
+void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32_t *, uint32_t, uint32_t *, int,
+                        cudaStream_t);
+void launch_trace_guided(const BatchDev &, const uint32_t *, uint32_t, uint32_t *, int, cudaStream_t);
+void launch_scan_counts(const BatchDev &, uint64_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
+void launch_emit(const BatchDev &, const ScoreParams &, bgpu_result *, bgpu_block *, uint32_t *, bgpu_gap *,
+                 const uint64_t *, const uint64_t *, const uint64_t *, int, int, cudaStream_t);
+double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz);
+}  // namespace bgpu
+
+using namespace bgpu;
+
+struct bgpu_ctx {
+  int device = 0, nSM = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::mutex mu;
+  size_t arrowPoolCap = 0;                       // max bytes of traceback pool per wave
+  std::multimap<size_t, void *> devFree, pinFree; // cached allocations by size
+  std::map<void *, size_t> devSize, pinSize;
+  bgpu_ticket lastSync = nullptr;                // ticket owned by bgpu_align
+};
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      char buf_[256];                                                                             \
+      snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = buf_;                                                                            \
+      return (e_ == cudaErrorMemoryAllocation) ? BGPU_E_OOM : BGPU_E_CUDA;                         \
+    }                                                                                             \
+  } while (0)
+
+static size_t round_up(size_t n) { const size_t g = 1u << 16; return n == 0 ? g : (n + g - 1) / g * g; }
+
+static int dev_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
+  bytes = round_up(bytes);
+  auto it = ctx->devFree.lower_bound(bytes);
+  if (it != ctx->devFree.end() && it->first <= bytes + bytes / 4 + (1u << 20)) { *p = it->second; ctx->devFree.erase(it); return BGPU_OK; }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {   // drop the cache and retry once
+    for (auto &kv : ctx->devFree) { cudaFree(kv.second); ctx->devSize.erase(kv.second); }
+    ctx->devFree.clear();
+    cudaGetLastError();
+    e = cudaMalloc(p, bytes);
+  }
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); return BGPU_E_OOM; }
+  ctx->devSize[*p] = bytes;
+  return BGPU_OK;
+}
+static void dev_free(bgpu_ctx *ctx, void *p) { if (p) ctx->devFree.emplace(ctx->devSize[p], p); }
+static int pin_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
+  bytes = round_up(bytes);
+  auto it = ctx->pinFree.lower_bound(bytes);
+  if (it != ctx->pinFree.end() && it->first <= 2 * bytes + (1u << 20)) { *p = it->second; ctx->pinFree.erase(it); return BGPU_OK; }
+  cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); return BGPU_E_OOM; }
+  ctx->pinSize[*p] = bytes;
+  return BGPU_OK;
+}
+static void pin_free(bgpu_ctx *ctx, void *p) { if (p) ctx->pinFree.emplace(ctx->pinSize[p], p); }
+
+struct Wave { uint32_t begin[4], count[4]; uint32_t traceBegin, traceCount; };  // index by class slot 0..2
+
+struct bgpu_ticket_s {
+  uint32_t nJobs = 0;
+  bgpu_params params{};
+  ScoreParams sp{};
+  BatchDev B{};
+  // device buffers (everything in `dev` is returned to the cache on release)
+  std::vector<void *> dev, pin;
+  uint64_t *d_rowOff = nullptr, *d_dblkOff = nullptr, *d_runOff = nullptr, *d_arrowOff = nullptr;
+  uint32_t *d_order = nullptr, *d_counters = nullptr;
+  uint64_t *d_blockOff = nullptr, *d_listOff = nullptr, *d_gapOff = nullptr, *d_totals = nullptr;
+  bgpu_result *d_results = nullptr;
+  bgpu_block *d_blocks = nullptr; uint32_t *d_gapCounts = nullptr; bgpu_gap *d_gaps = nullptr;
+  // pinned host
+  JobGeom *h_geom = nullptr; uint64_t *h_totals = nullptr;
+  bgpu_result *h_results = nullptr; bgpu_block *h_blocks = nullptr; uint32_t *h_gapCounts = nullptr; bgpu_gap *h_gaps = nullptr;
+  uint64_t totals[3] = {0, 0, 0};
+  std::vector<Wave> waves;
+  uint32_t nCounters = 0;
+  bool arenaReady = false, collected = false, dense = false;
+  cudaEvent_t ev[6] = {};     // start, prepEnd, fillTraceEnd(unused), scanEnd, emitEnd
+  std::vector<cudaEvent_t> waveEv;   // per wave: fillStart, fillEnd, traceEnd
+  bgpu_timing timing{};
+  void *denseState = nullptr;
+};
+
+template <typename T>
+static int talloc_dev(bgpu_ctx *ctx, bgpu_ticket t, T **p, size_t n) {
+  void *v = nullptr; int rc = dev_alloc(ctx, &v, n * sizeof(T)); if (rc) return rc;
+  t->dev.push_back(v); *p = (T *)v; return BGPU_OK;
+}
+template <typename T>
+static int talloc_pin(bgpu_ctx *ctx, bgpu_ticket t, T **p, size_t n) {
+  void *v = nullptr; int rc = pin_alloc(ctx, &v, n * sizeof(T)); if (rc) return rc;
+  t->pin.push_back(v); *p = (T *)v; return BGPU_OK;
+}
+#define RC(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+// H2D of caller memory: through pinned staging unless the caller's buffer is already pinned.
+static int upload(bgpu_ctx *ctx, bgpu_ticket t, void *dst, const void *src, size_t bytes) {
+  if (!bytes) return BGPU_OK;
+  cudaPointerAttributes at{};
+  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const void *from = src;
+  if (!pinned) {
+    void *stage = nullptr; RC(talloc_pin(ctx, t, (uint8_t **)&stage, bytes));
+    memcpy(stage, src, bytes);
+    from = stage;
+  }
+  CK(cudaMemcpyAsync(dst, from, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  t->timing.h2dBytes += bytes;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int bgpu_version(void) { return BGPU_VERSION; }
+
+extern "C" int bgpu_create(bgpu_ctx **out, int device) {
+  if (!out) return BGPU_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return BGPU_E_NO_DEVICE; }
+  if (device < 0 || device >= n) return BGPU_E_INVALID;
+  bgpu_ctx *ctx = new bgpu_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
+  cudaDeviceProp pr{};
+  cudaGetDeviceProperties(&pr, device);
+  ctx->nSM = pr.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
+  size_t freeB = 0, totalB = 0;
+  cudaMemGetInfo(&freeB, &totalB);
+  ctx->arrowPoolCap = freeB / 3;
+  const char *env = getenv("BGPU_ARROW_POOL_MB");
+  if (env) ctx->arrowPoolCap = (size_t)atoll(env) << 20;
+  *out = ctx;
+  return BGPU_OK;
+}
+
+extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->lastSync) bgpu_release(ctx, ctx->lastSync);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->devFree) cudaFree(kv.second);
+  for (auto &kv : ctx->pinFree) cudaFreeHost(kv.second);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *bgpu_last_error(const bgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+static void fill_score_params(ScoreParams &sp, const bgpu_scorefn *fn, const bgpu_params *p) {
+  memcpy(sp.M, fn->M, sizeof sp.M);
+  sp.ins = fn->ins; sp.del = fn->del; sp.open = fn->affineOpen; sp.ext = fn->affineExtend;
+  sp.kind = fn->kind; sp.alignType = p->alignType; sp.affine = (p->algo == BGPU_AFFINE_GUIDED); sp.pad = 0;
+}
+
+// ---- kernel schedule of a guided ticket (used by submit and rerun) ----
+static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
+  cudaStream_t s = ctx->stream;
+  CK(cudaEventRecord(t->ev[0], s));
+  launch_prep_guided(t->B, t->sp, t->params.band, t->d_rowOff, t->d_dblkOff, t->d_runOff, s);
+  t->timing.kernelLaunches = 1;
+  CK(cudaEventRecord(t->ev[1], s));
+  if (firstRun) {
+    // geometry back to the host: classification, ordering and wave cutting need it
+    CK(cudaMemcpyAsync(t->h_geom, t->B.geom, sizeof(JobGeom) * t->nJobs, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t n = t->nJobs;
+    std::vector<uint32_t> idx; idx.reserve(n);
+    for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) idx.push_back(i);
+    auto cls = [&](uint32_t i) { int k = t->h_geom[i].kmax; return k <= 1 ? 0 : (k == 2 ? 1 : 2); };
+    auto cost = [&](uint32_t i) { return (uint64_t)t->h_geom[i].nDB * (uint64_t)(cls(i) == 0 ? 1 : (cls(i) == 1 ? 2 : 4)); };
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { uint64_t ca = cost(a), cb = cost(b); return ca != cb ? ca > cb : a < b; });
+    // cut into waves by traceback bytes
+    std::vector<uint64_t> arrowOff(n, 0);
+    std::vector<uint32_t> order; order.reserve(idx.size() * 2);
+    size_t maxWaveBytes = 0;
+    size_t i0 = 0;
+    while (i0 < idx.size()) {
+      size_t bytes = 0, i1 = i0;
+      while (i1 < idx.size()) {
+        const uint64_t ab = t->h_geom[idx[i1]].arrowBytes;
+        if (i1 > i0 && bytes + ab > ctx->arrowPoolCap) break;
+        arrowOff[idx[i1]] = bytes; bytes += ab; i1++;
+      }
+      maxWaveBytes = std::max(maxWaveBytes, bytes);
+      Wave w{};
+      for (int c = 0; c < 3; c++) {
+        w.begin[c] = (uint32_t)order.size();
+        for (size_t i = i0; i < i1; i++) if (cls(idx[i]) == c) order.push_back(idx[i]);
+        w.count[c] = (uint32_t)order.size() - w.begin[c];
+      }
+      w.traceBegin = (uint32_t)order.size();
+      for (size_t i = i0; i < i1; i++) order.push_back(idx[i]);
+      w.traceCount = (uint32_t)(i1 - i0);
+      t->waves.push_back(w);
+      i0 = i1;
+    }
+    RC(talloc_dev(ctx, t, &t->d_order, std::max<size_t>(order.size(), 1)));
+    RC(talloc_dev(ctx, t, &t->d_arrowOff, n));
+    t->nCounters = (uint32_t)t->waves.size() * 4 + 4;
+    RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
+    uint8_t *arrows = nullptr;
+    RC(talloc_dev(ctx, t, &arrows, std::max<size_t>(maxWaveBytes, 16)));
+    t->B.arrows = arrows; t->B.arrowOff = t->d_arrowOff; t->B.order = t->d_order; t->B.counters = t->d_counters;
+    uint32_t *h_order = nullptr; uint64_t *h_aoff = nullptr;
+    RC(talloc_pin(ctx, t, &h_order, std::max<size_t>(order.size(), 1)));
+    RC(talloc_pin(ctx, t, &h_aoff, n));
+    memcpy(h_order, order.data(), order.size() * sizeof(uint32_t));
+    memcpy(h_aoff, arrowOff.data(), n * sizeof(uint64_t));
+    CK(cudaMemcpyAsync(t->d_order, h_order, order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t->d_arrowOff, h_aoff, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    t->waveEv.resize(t->waves.size() * 3);
+    for (auto &e : t->waveEv) CK(cudaEventCreate(&e));
+    uint64_t cells = 0;
+    for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) cells += (uint64_t)t->h_geom[i].nCells;
+    t->timing.cells = cells;
+    uint64_t fc = 0;
+    for (uint32_t i : idx) fc += (uint64_t)t->h_geom[i].nDB * 64ull * 32ull * (uint64_t)(cls(i) == 0 ? 1 : (cls(i) == 1 ? 2 : 4));
+    t->timing.fillCells = fc;
+  }
+  CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
+  static const int kclassOf[3] = {1, 2, 4};
+  for (size_t w = 0; w < t->waves.size(); w++) {
+    const Wave &W = t->waves[w];
+    CK(cudaEventRecord(t->waveEv[3 * w], s));
+    for (int c = 0; c < 3; c++)
+      if (W.count[c]) {
+        launch_fill_guided(t->B, t->sp, kclassOf[c], t->d_order + W.begin[c], W.count[c], t->d_counters + 4 * w + c, ctx->nSM, s);
+        t->timing.kernelLaunches++;
+      }
+    CK(cudaEventRecord(t->waveEv[3 * w + 1], s));
+    if (W.traceCount) {
+      launch_trace_guided(t->B, t->d_order + W.traceBegin, W.traceCount, t->d_counters + 4 * w + 3, ctx->nSM, s);
+      t->timing.kernelLaunches++;
+    }
+    CK(cudaEventRecord(t->waveEv[3 * w + 2], s));
+  }
+  launch_scan_counts(t->B, t->d_blockOff, t->d_listOff, t->d_gapOff, t->d_totals, s);
+  t->timing.kernelLaunches++;
+  CK(cudaEventRecord(t->ev[3], s));
+  CK(cudaGetLastError());
+  return BGPU_OK;
+}
+
+static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t) {
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(t->d_gapCounts, 0, sizeof(uint32_t) * std::max<uint64_t>(t->totals[1], 1), s));
+  launch_emit(t->B, t->sp, t->d_results, t->d_blocks, t->d_gapCounts, t->d_gaps, t->d_blockOff, t->d_listOff,
+              t->d_gapOff, t->params.doStats, t->params.statsAffine, s);
+  t->timing.kernelLaunches++;
+  CK(cudaEventRecord(t->ev[4], s));
+  CK(cudaGetLastError());
+  return BGPU_OK;
+}
+
+static void gather_timing(bgpu_ticket t) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]) == cudaSuccess) t->timing.msPrep = ms;
+  double fill = 0, trace = 0;
+  for (size_t w = 0; w < t->waves.size(); w++) {
+    if (cudaEventElapsedTime(&ms, t->waveEv[3 * w], t->waveEv[3 * w + 1]) == cudaSuccess) fill += ms;
+    if (cudaEventElapsedTime(&ms, t->waveEv[3 * w + 1], t->waveEv[3 * w + 2]) == cudaSuccess) trace += ms;
+  }
+  t->timing.msFill = fill; t->timing.msTrace = trace;
+  if (cudaEventElapsedTime(&ms, t->ev[3], t->ev[4]) == cudaSuccess) t->timing.msEmit = ms;
+  if (cudaEventElapsedTime(&ms, t->ev[0], t->ev[4]) == cudaSuccess) t->timing.msTotal = ms;
+  cudaGetLastError();
+}
+
+static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b, bgpu_ticket t) {
+  const uint32_t n = b->nJobs;
+  if (!b->qOff || !b->tOff || !b->guideOff || (n && (!b->qBases || !b->tBases))) { ctx->err = "null batch arrays"; return BGPU_E_INVALID; }
+  if (fn->kind == BGPU_FN_QUALITY && !b->qual) { ctx->err = "BGPU_FN_QUALITY needs batch.qual"; return BGPU_E_INVALID; }
+  const uint64_t totQ = b->qOff[n], totT = b->tOff[n], totG = b->guideOff[n];
+  fill_score_params(t->sp, fn, p);
+  BatchDev &B = t->B;
+  B.nJobs = n;
+  uint64_t *d_qOff, *d_tOff, *d_gOff; uint8_t *d_q, *d_t, *d_qual = nullptr; bgpu_block *d_guide; int32_t *d_band = nullptr;
+  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16));
+  RC(talloc_dev(ctx, t, &d_qOff, n + 1)); RC(talloc_dev(ctx, t, &d_tOff, n + 1)); RC(talloc_dev(ctx, t, &d_gOff, n + 1));
+  RC(talloc_dev(ctx, t, &d_guide, totG + 1));
+  if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
+  if (b->band) RC(talloc_dev(ctx, t, &d_band, n));
+  RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
+  RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));
+  RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
+  RC(upload(ctx, t, d_gOff, b->guideOff, sizeof(uint64_t) * (n + 1)));
+  RC(upload(ctx, t, d_guide, b->guide, sizeof(bgpu_block) * totG));
+  if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
+  if (b->band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
+  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tOff = d_tOff; B.qual = d_qual; B.guide = d_guide; B.guideOff = d_gOff; B.band = d_band;
+  // capacities from sequence lengths (upper bounds of the guide extents)
+  uint64_t *h_off = nullptr;
+  RC(talloc_pin(ctx, t, &h_off, 3 * (size_t)n + 3));
+  uint64_t rowTot = 0, dbTot = 0, runTot = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t ql = b->qOff[i + 1] - b->qOff[i], tl = b->tOff[i + 1] - b->tOff[i];
+    h_off[i] = rowTot; h_off[n + i] = dbTot; h_off[2 * (size_t)n + i] = runTot;
+    rowTot += ql + 1; dbTot += (ql + tl + 1) / 64 + 2; runTot += ql + tl + 2;
+  }
+  RC(talloc_dev(ctx, t, &t->d_rowOff, 3 * (size_t)n + 3));
+  t->d_dblkOff = t->d_rowOff + n; t->d_runOff = t->d_rowOff + 2 * (size_t)n;
+  CK(cudaMemcpyAsync(t->d_rowOff, h_off, sizeof(uint64_t) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+  RC(talloc_dev(ctx, t, &B.geom, n)); RC(talloc_dev(ctx, t, &B.rows, rowTot + 1)); RC(talloc_dev(ctx, t, &B.dblk, dbTot + 1));
+  RC(talloc_dev(ctx, t, &B.dmin, dbTot + 1)); RC(talloc_dev(ctx, t, &B.dmax, dbTot + 1)); RC(talloc_dev(ctx, t, &B.runs, runTot + 1));
+  RC(talloc_dev(ctx, t, &t->d_blockOff, 3 * (size_t)n + 3));
+  t->d_listOff = t->d_blockOff + n; t->d_gapOff = t->d_blockOff + 2 * (size_t)n;
+  RC(talloc_dev(ctx, t, &t->d_totals, 4)); RC(talloc_dev(ctx, t, &t->d_results, n));
+  RC(talloc_pin(ctx, t, &t->h_geom, n)); RC(talloc_pin(ctx, t, &t->h_totals, 4)); RC(talloc_pin(ctx, t, &t->h_results, n));
+  return enqueue_guided(ctx, t, true);
+}
+
+extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b, bgpu_ticket *out) {
+  if (!ctx) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!fn || !p || !b || !out) { ctx->err = "null argument"; return BGPU_E_INVALID; }
+  if (p->algo < BGPU_GUIDED || p->algo > BGPU_SW) { ctx->err = "unknown algo"; return BGPU_E_INVALID; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return BGPU_E_CUDA; }
+  bgpu_ticket t = new bgpu_ticket_s();
+  t->nJobs = b->nJobs; t->params = *p;
+  for (auto &e : t->ev) cudaEventCreate(&e);
+  int rc;
+  if (p->algo == BGPU_GUIDED || p->algo == BGPU_AFFINE_GUIDED) rc = submit_guided(ctx, fn, p, b, t);
+  else { ctx->err = "KBandAlign/SWAlign kernels are not built into this library yet"; rc = BGPU_E_INVALID; }
+  if (rc != BGPU_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    for (void *v : t->dev) dev_free(ctx, v);
+    for (void *v : t->pin) pin_free(ctx, v);
+    for (auto &e : t->ev) cudaEventDestroy(e);
+    for (auto &e : t->waveEv) cudaEventDestroy(e);
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_job *jobs,
+                                uint32_t nJobs, bgpu_ticket *out) {
+  if (!ctx || !jobs) return BGPU_E_INVALID;
+  std::vector<uint64_t> qOff(nJobs + 1, 0), tOff(nJobs + 1, 0), gOff(nJobs + 1, 0);
+  bool anyQual = false;
+  for (uint32_t i = 0; i < nJobs; i++) {
+    qOff[i + 1] = qOff[i] + jobs[i].qLen; tOff[i + 1] = tOff[i] + jobs[i].tLen; gOff[i + 1] = gOff[i] + jobs[i].nGuide;
+    anyQual |= jobs[i].qual != nullptr;
+  }
+  std::vector<uint8_t> q(qOff[nJobs] + 1), tt(tOff[nJobs] + 1), qual(anyQual ? qOff[nJobs] + 1 : 0);
+  std::vector<bgpu_block> g(gOff[nJobs] + 1);
+  std::vector<int32_t> band(nJobs + 1);
+  for (uint32_t i = 0; i < nJobs; i++) {
+    if (jobs[i].qLen) memcpy(&q[qOff[i]], jobs[i].q, jobs[i].qLen);
+    if (jobs[i].tLen) memcpy(&tt[tOff[i]], jobs[i].t, jobs[i].tLen);
+    if (anyQual && jobs[i].qual && jobs[i].qLen) memcpy(&qual[qOff[i]], jobs[i].qual, jobs[i].qLen);
+    if (jobs[i].nGuide) memcpy(&g[gOff[i]], jobs[i].guide, sizeof(bgpu_block) * jobs[i].nGuide);
+    band[i] = jobs[i].band;
+  }
+  bgpu_batch b{};
+  b.nJobs = nJobs; b.qBases = q.data(); b.qOff = qOff.data(); b.tBases = tt.data(); b.tOff = tOff.data();
+  b.qual = anyQual ? qual.data() : nullptr; b.guide = g.data(); b.guideOff = gOff.data(); b.band = band.data();
+  return bgpu_submit(ctx, fn, p, &b, out);   // inputs are staged into pinned memory before this returns
+}
+
+static int ensure_arena(bgpu_ctx *ctx, bgpu_ticket t) {
+  if (t->arenaReady) return BGPU_OK;
+  CK(cudaMemcpyAsync(t->h_totals, t->d_totals, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 3; i++) t->totals[i] = t->h_totals[i];
+  RC(talloc_dev(ctx, t, &t->d_blocks, t->totals[0] + 1)); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->totals[1] + 1));
+  RC(talloc_dev(ctx, t, &t->d_gaps, t->totals[2] + 1));
+  RC(talloc_pin(ctx, t, &t->h_blocks, t->totals[0] + 1)); RC(talloc_pin(ctx, t, &t->h_gapCounts, t->totals[1] + 1));
+  RC(talloc_pin(ctx, t, &t->h_gaps, t->totals[2] + 1));
+  t->arenaReady = true;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, bgpu_arena *arena) {
+  if (!ctx || !t) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  cudaStream_t s = ctx->stream;
+  if (!t->collected) {
+    RC(ensure_arena(ctx, t));
+    RC(enqueue_emit(ctx, t));
+    CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    t->timing.d2hBytes = sizeof(bgpu_result) * (uint64_t)t->nJobs + sizeof(bgpu_block) * t->totals[0] +
+                         sizeof(uint32_t) * t->totals[1] + sizeof(bgpu_gap) * t->totals[2];
+    gather_timing(t);
+    t->collected = true;
+  }
+  if (results && t->nJobs) memcpy(results, t->h_results, sizeof(bgpu_result) * t->nJobs);
+  if (arena) {
+    arena->blocks = t->h_blocks; arena->nBlocks = t->totals[0];
+    arena->gapCounts = t->h_gapCounts; arena->nGapLists = t->totals[1];
+    arena->gaps = t->h_gaps; arena->nGaps = t->totals[2];
+  }
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t) {
+  if (!ctx || !t) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!t->collected) { ctx->err = "bgpu_rerun needs a collected ticket"; return BGPU_E_BUSY; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  RC(enqueue_guided(ctx, t, false));
+  RC(enqueue_emit(ctx, t));
+  CK(cudaStreamSynchronize(ctx->stream));
+  gather_timing(t);
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_timing_of(bgpu_ctx *ctx, bgpu_ticket t, bgpu_timing *out) {
+  if (!ctx || !t || !out) return BGPU_E_INVALID;
+  *out = t->timing;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_release(bgpu_ctx *ctx, bgpu_ticket t) {
+  if (!ctx || !t) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (void *v : t->dev) dev_free(ctx, v);
+  for (void *v : t->pin) pin_free(ctx, v);
+  for (auto &e : t->ev) cudaEventDestroy(e);
+  for (auto &e : t->waveEv) cudaEventDestroy(e);
+  if (ctx->lastSync == t) ctx->lastSync = nullptr;
+  delete t;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b,
+                          bgpu_result *results, bgpu_arena *arena) {
+  if (!ctx) return BGPU_E_INVALID;
+  if (ctx->lastSync) bgpu_release(ctx, ctx->lastSync);
+  bgpu_ticket t = nullptr;
+  int rc = bgpu_submit(ctx, fn, p, b, &t);
+  if (rc) return rc;
+  rc = bgpu_collect(ctx, t, results, arena);
+  if (rc) { bgpu_release(ctx, t); return rc; }
+  ctx->lastSync = t;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_measure_int_peak(bgpu_ctx *ctx, double *opsPerSec, double *smClockMHz) {
+  if (!ctx || !opsPerSec) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  double mhz = 0;
+  *opsPerSec = measure_int_peak(ctx->nSM, ctx->stream, &mhz);
+  if (smClockMHz) *smClockMHz = mhz;
+  CK(cudaGetLastError());
+  return BGPU_OK;
+}

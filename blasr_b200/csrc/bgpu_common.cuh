@@ -1,0 +1,99 @@
+// bgpu_common.cuh -- device-side data layout shared by the kernels of the refinement DP.
+//
+// Coordinates used by every guided kernel (see DESIGN.md "HBM layout"):
+//   q' = q - qStart + 1  in [0, Qn]   (row 0 = the reference's boundary row, GuidedAlign.h:126-135)
+//   t' = t - tStart + 1  in [0, Tn]   (column 0 = the boundary column tStart-1)
+//   d  = q' + t'                      anti-diagonal, processed in d-blocks of 64
+//   cd = t' - q' + C0                 diagonal index (C0 even >= Qn, so cd >= 0 and cd == d mod 2)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/blasr_gpu.h"
+
+namespace bgpu {
+
+constexpr int SH = 5;                 // scores are carried as (score << SH) | tag bits
+constexpr int BIG = 1 << 30;          // "invalid neighbour" in the shifted domain (INF_INT stand-in)
+constexpr int SCORE_LIMIT = 1 << 24;  // |score| bound that keeps (score<<SH) clear of BIG
+constexpr int DBLK = 64;              // anti-diagonals per d-block
+constexpr int KMAX_BUILD = 4;         // widest fill kernel: 64*KMAX diagonals live at once
+constexpr int ROW_W_BITS = 20;
+
+// traceback byte written by the fill kernels, one per (anti-diagonal, diagonal slot)
+//   bits 0-2: 0 Diagonal, 1 Left, 2 Up, 3 AffineInsClose, 4 AffineDelClose, 7 NoArrow/out of band
+//   bit 3   : affine-ins matrix arrow is AffineInsOpen (else AffineInsUp)
+//   bit 4   : affine-del matrix arrow is AffineDelOpen (else AffineDelLeft)
+enum { TB_DIAG = 0, TB_LEFT = 1, TB_UP = 2, TB_ICLOSE = 3, TB_DCLOSE = 4, TB_NONE = 7, TB_IOPEN = 8, TB_DOPEN = 16 };
+
+struct RowInfo {          // 8 B per guide row in HBM
+  int32_t lo;             // first in-band column t' of the row (INT_MAX/2 for "no cells")
+  uint32_t packed;        // bits 0-19: hi'-lo', bits 20-22: query base code, bits 23-30: QV
+};
+
+struct DBlock {           // 16 B per d-block
+  int32_t wbase;          // even: diagonal held by slot 0 of the register window
+  int32_t k;              // active 64-diagonal groups in this block (1..KMAX)
+  uint32_t arrowUnit;     // offset of this block's arrows in 2 KB units from the job's arrowOff
+  int32_t pad;
+};
+
+struct JobGeom {          // per job, written by prep, extended by fill / trace
+  int32_t status;
+  int32_t qStart, tStart; // first guide block (absolute positions inside the job's q / t)
+  int32_t Qn, Tn;         // guide rows / target columns covered (without the boundary row/column)
+  int32_t C0;
+  int32_t nDB;            // number of d-blocks
+  int32_t kmax;           // max k over the job's d-blocks
+  int32_t band;
+  int32_t nCells;         // ComputeMatrixNElem (GuidedAlign.h:83-92)
+  int32_t hi0;            // last in-band column of row 0
+  int32_t score;          // fill result: S[qEnd-1][tEnd-1]
+  uint64_t rowOff;        // RowInfo index of row 0
+  uint64_t dblkOff;       // DBlock index of d-block 0
+  uint64_t arrowBytes;    // total arrow bytes of this job
+  uint64_t runOff;        // u32 index into the run scratch (capacity Qn+Tn+2)
+  uint32_t nRuns, nBlocks, nGaps, nGapLists;   // traceback results
+  uint32_t qPos, tPos;    // alignment.qPos/tPos after RemoveAlignmentPrefixGaps
+};
+
+struct ScoreParams {      // kernel argument (by value)
+  int32_t M[25];
+  int32_t ins, del, open, ext;
+  int32_t kind, alignType, affine, pad;
+};
+
+struct BatchDev {         // device pointers of one submitted batch
+  uint32_t nJobs;
+  uint8_t *q; const uint64_t *qOff;
+  uint8_t *t; const uint64_t *tOff;       // t is re-encoded in place to base codes by prep
+  const uint8_t *qual;
+  const bgpu_block *guide; const uint64_t *guideOff;
+  const int32_t *band;
+  JobGeom *geom;
+  RowInfo *rows;
+  DBlock *dblk;
+  int32_t *dmin, *dmax;   // per d-block live diagonal range (prep scratch)
+  uint8_t *arrows;
+  const uint64_t *arrowOff; // per job: byte offset in the arrow pool (assigned by the host per wave)
+  uint32_t *runs;
+  const uint32_t *order;  // job order for dynamic scheduling (longest first)
+  uint32_t *counters;     // [0] fill job counter, [1] trace job counter, ...
+};
+
+__device__ __forceinline__ uint8_t base_code(uint8_t c) {
+  // NucConversion.h:48-84 (ThreeBit), restated as arithmetic: ACGT/acgt and raw 0..3 -> 0..3,
+  // IUPAC ambiguity letters (and raw 4) -> 4, '$' -> 5, everything else 255.
+  if (c <= 4) return c;
+  uint8_t u = c & 0xDF;  // fold case
+  switch (u) {
+    case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+    case 'B': case 'D': case 'H': case 'K': case 'M': case 'N': case 'R': case 'S':
+    case 'U': case 'V': case 'W': case 'Y': return ((c == u) || (c == (u | 0x20))) ? 4 : 255;
+    default: break;
+  }
+  if (c == 'x') return 4;   // the table maps 'x' (but not 'X') to N
+  if (c == '$') return 5;
+  return 255;
+}
+
+}  // namespace bgpu

@@ -1,0 +1,283 @@
+// bgpu_fill.cu -- the guided banded DP fill, one warp per job.
+//
+// Reference semantics restated (not translated):
+//   GuidedAlign        common/algorithms/alignment/GuidedAlign.h:474-624   (linear gaps)
+//   AffineGuidedAlign  common/algorithms/alignment/AffineGuidedAlign.h:241-375
+//
+// B200 mapping.  The band is swept by anti-diagonals d = q'+t'.  Lane j of the warp owns the two
+// adjacent diagonals (slots) 2j and 2j+1 of a 64-diagonal register window (KMAX such windows for
+// wide bands); on an even step it computes the cell on its even slot, on an odd step the one on its
+// odd slot, so every lane has exactly one cell per step and all three DP neighbours are either its
+// own registers or one __shfl away:
+//     even step: left = lane j-1's odd slot (shfl), up = own odd slot, diag = own even slot
+//     odd  step: left = own even slot, up = lane j+1's even slot (shfl), diag = own odd slot
+// Scores live in registers as (score << 5) | tag: the five tie-ordered candidates carry their arrow
+// code in the low bits, so one VIADDMNMX chain yields both the minimum and the reference's
+// first-match-wins arrow (Diagonal > Left > Up > AffineInsClose > AffineDelClose); the affine
+// open/extend decisions land in bits 3/4 the same way.  Cells outside the guide are held at BIG,
+// which reproduces the reference's INF_INT-for-missing-neighbour rule.  Per d-block of 64 steps the
+// warp stages the band table and target codes of the rows/columns it will touch into shared memory,
+// and writes one traceback byte per cell as coalesced 128 B stores ([4 steps][32 lanes]).
+#include "bgpu_common.cuh"
+
+namespace bgpu {
+
+struct FillConsts {
+  int delT, insT;        // (del<<SH)|TB_LEFT, (ins<<SH)|TB_UP
+  int extT3, extT4;      // (ext<<SH)|TB_ICLOSE, |TB_DCLOSE
+  int ext, openI, openD; // ext<<SH, (open<<SH)|TB_IOPEN, (open<<SH)|TB_DOPEN
+  int open;              // open<<SH
+  int del0;              // row-0 step: (Global ? del : 0) << SH
+};
+
+template <bool AFFINE, bool QV, bool FIRST>
+__device__ __forceinline__ uint32_t dp_cell(int &S, int &AI, int &AD, const int leftS, const int leftAD,
+                                            const int upS, const int upAI, const int4 ri, const int tent,
+                                            const int tprime, const int *Mtab, const FillConsts &c) {
+  const bool inb = (unsigned)(tprime - ri.x) <= (unsigned)ri.y;
+  int m = *reinterpret_cast<const int *>(reinterpret_cast<const char *>(Mtab) + ri.z + tent);
+  if (QV) m *= (FIRST ? (ri.w & 0xff) : ri.w);           // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+  int cnd = S + m;                                         // Diagonal (tag 0)
+  cnd = __viaddmin_s32(leftS, c.delT, cnd);                // Left
+  cnd = __viaddmin_s32(upS, c.insT, cnd);                  // Up
+  if (AFFINE) {
+    cnd = __viaddmin_s32(upAI, c.extT3, cnd);              // AffineInsClose
+    cnd = __viaddmin_s32(leftAD, c.extT4, cnd);            // AffineDelClose
+  }
+  int s = cnd & ~31;
+  uint32_t byte = (uint32_t)cnd & 7u;
+  int ai = 0, ad = 0;
+  if (AFFINE) {
+    // strict '<' in the reference: a tie extends (AffineGuidedAlign.h:357-373) -> the open
+    // candidate carries a flag bit, so it loses ties.
+    ai = __viaddmin_s32(s, c.openI, upAI + c.ext);
+    ad = __viaddmin_s32(s, c.openD, leftAD + c.ext);
+    byte |= (uint32_t)(ai | ad) & 24u;
+    ai &= ~31; ad &= ~31;
+  }
+  if (FIRST) {
+    if (ri.w < 0) {                                        // boundary row (GuidedAlign.h:415-442)
+      s = tprime * c.del0; ai = c.open; ad = c.open;
+      byte = TB_LEFT | TB_IOPEN | TB_DOPEN;
+    }
+  }
+  if (!inb) { s = BIG; ai = BIG; ad = BIG; byte = TB_NONE; }
+  S = s;
+  if (AFFINE) { AI = ai; AD = ad; }
+  return byte;
+}
+
+__device__ __forceinline__ int rot_up(int v, int lane) { return __shfl_sync(0xffffffffu, v, (lane + 31) & 31); }
+__device__ __forceinline__ int rot_dn(int v, int lane) { return __shfl_sync(0xffffffffu, v, (lane + 1) & 31); }
+
+template <int KMAX>
+struct WarpSmem {
+  int4 rows[32 * KMAX + 32];
+  int tcol[32 * KMAX + 32];
+  int shift[64 * KMAX];
+};
+
+template <int KMAX, bool AFFINE, bool QV, bool FIRST, bool LAST>
+__device__ __forceinline__ void run_block(int (&Se)[KMAX], int (&So)[KMAX], int (&AIe)[KMAX], int (&AIo)[KMAX],
+                                          int (&ADe)[KMAX], int (&ADo)[KMAX], const WarpSmem<KMAX> &sm,
+                                          const int *Mtab, const FillConsts &c, const int k, const int lane,
+                                          const int tlo, const int eLast, uint32_t *arrowWords) {
+  // per-lane bases: row index (e>>1) + 32k-1-j-32g, column index ((e+1)>>1) + j + 32g
+  const int4 *rowBase = sm.rows + (32 * k - 1 - lane);
+  const int *colBase = sm.tcol + lane;
+  const int tl = tlo + lane;
+#pragma unroll 1
+  for (int e4 = 0; e4 < 16; e4++) {
+    if (LAST && (e4 << 2) > eLast) break;
+    uint32_t acc[KMAX];
+#pragma unroll
+    for (int g = 0; g < KMAX; g++) acc[g] = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = (e4 << 2) + u;
+      if (LAST && e > eLast) break;
+      const int rI = (e4 << 1) + (u >> 1);            // e>>1
+      const int cI = (e4 << 1) + ((u + 1) >> 1);      // (e+1)>>1
+      if ((u & 1) == 0) {
+        // even step: left from the odd slot below (ring over lanes and groups), up = own odd slot
+        int rS[KMAX], rD[KMAX];
+#pragma unroll
+        for (int g = 0; g < KMAX; g++) {
+          rS[g] = (g < k) ? rot_up(So[g], lane) : BIG;
+          if (AFFINE) rD[g] = (g < k) ? rot_up(ADo[g], lane) : BIG;
+        }
+#pragma unroll
+        for (int g = 0; g < KMAX; g++) {
+          if (g < k) {
+            int leftS = rS[g], leftAD = AFFINE ? rD[g] : 0;
+            if (KMAX > 1 && lane == 0) { leftS = rS[(g + KMAX - 1) % KMAX]; if (AFFINE) leftAD = rD[(g + KMAX - 1) % KMAX]; }
+            const int4 ri = rowBase[rI - 32 * g];
+            const int tent = colBase[cI + 32 * g];
+            const uint32_t b = dp_cell<AFFINE, QV, FIRST>(Se[g], AIe[g], ADe[g], leftS, leftAD, So[g], AIo[g], ri,
+                                                          tent, tl + cI + 32 * g, Mtab, c);
+            acc[g] |= b << (8 * u);
+          }
+        }
+      } else {
+        int rS[KMAX], rI_[KMAX];
+#pragma unroll
+        for (int g = 0; g < KMAX; g++) {
+          rS[g] = (g < k) ? rot_dn(Se[g], lane) : BIG;
+          if (AFFINE) rI_[g] = (g < k) ? rot_dn(AIe[g], lane) : BIG;
+        }
+#pragma unroll
+        for (int g = 0; g < KMAX; g++) {
+          if (g < k) {
+            int upS = rS[g], upAI = AFFINE ? rI_[g] : 0;
+            if (KMAX > 1 && lane == 31) { upS = rS[(g + 1) % KMAX]; if (AFFINE) upAI = rI_[(g + 1) % KMAX]; }
+            const int4 ri = rowBase[rI - 32 * g];
+            const int tent = colBase[cI + 32 * g];
+            const uint32_t b = dp_cell<AFFINE, QV, FIRST>(So[g], AIo[g], ADo[g], Se[g], ADe[g], upS, upAI, ri, tent,
+                                                          tl + cI + 32 * g, Mtab, c);
+            acc[g] |= b << (8 * u);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < KMAX; g++)
+      if (g < k) arrowWords[((e4 * k + g) << 5) + lane] = acc[g];
+  }
+}
+
+template <int KMAX, bool AFFINE, bool QV>
+__global__ void __launch_bounds__(128) fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order,
+                                                          uint32_t nOrder, uint32_t *counter) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ int Mtab[25];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpSmem<KMAX> &sm = reinterpret_cast<WarpSmem<KMAX> *>(smemRaw)[warp];
+  if (threadIdx.x < 25) {
+    if (QV) { const int r = threadIdx.x / 5, cc = threadIdx.x % 5; Mtab[threadIdx.x] = ((r == cc && r < 4) ? -1 : 1) << SH; }  // ScoreMatrices.h:4-10
+    else Mtab[threadIdx.x] = P.M[threadIdx.x] << SH;
+  }
+  __syncthreads();
+  FillConsts c;
+  c.delT = (P.del << SH) | TB_LEFT; c.insT = (P.ins << SH) | TB_UP;
+  c.extT3 = (P.ext << SH) | TB_ICLOSE; c.extT4 = (P.ext << SH) | TB_DCLOSE;
+  c.ext = P.ext << SH; c.open = P.open << SH;
+  c.openI = (P.open << SH) | TB_IOPEN; c.openD = (P.open << SH) | TB_DOPEN;
+  c.del0 = (P.alignType == BGPU_GLOBAL ? P.del : 0) << SH;
+
+  for (;;) {
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(counter, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= nOrder) break;
+    const uint32_t job = order[idx];
+    JobGeom &G = B.geom[job];
+    if (G.status != BGPU_JOB_OK) continue;
+    const int Qn = G.Qn, Tn = G.Tn, C0 = G.C0, nDB = G.nDB, hi0 = G.hi0, tStart = G.tStart;
+    const RowInfo *rows = B.rows + G.rowOff;
+    const DBlock *dblk = B.dblk + G.dblkOff;
+    const uint8_t *tcodes = B.t + B.tOff[job] + tStart - 1;   // tcodes[t'] for t' in [1,Tn]
+    uint32_t *arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
+    const int nD = Qn + Tn + 1;
+
+    int Se[KMAX], So[KMAX], AIe[KMAX], AIo[KMAX], ADe[KMAX], ADo[KMAX];
+#pragma unroll
+    for (int g = 0; g < KMAX; g++) { Se[g] = So[g] = AIe[g] = AIo[g] = ADe[g] = ADo[g] = BIG; }
+    int wprev = 0, kprev = 0;
+
+    for (int b = 0; b < nDB; b++) {
+      const DBlock db = dblk[b];
+      const int wbase = db.wbase, k = db.k;
+      // ---- slide the register window to this block's diagonals
+      if (b > 0 && (wbase != wprev || k != kprev)) {
+        const int delta = wbase - wprev;
+        auto slide = [&](int (&Xe)[KMAX], int (&Xo)[KMAX]) {
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < KMAX; g++) { sm.shift[64 * g + 2 * lane] = Xe[g]; sm.shift[64 * g + 2 * lane + 1] = Xo[g]; }
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < KMAX; g++) {
+            const int s = 64 * g + 2 * lane + delta;
+            const bool ok = (g < k) && s >= 0 && s < 64 * KMAX;
+            Xe[g] = ok ? sm.shift[s] : BIG;
+            Xo[g] = ok ? sm.shift[s + 1] : BIG;
+          }
+        };
+        slide(Se, So);
+        if (AFFINE) { slide(AIe, AIo); slide(ADe, ADo); }
+      }
+      wprev = wbase; kprev = k;
+      // ---- stage rows [qlo, qlo+32k+31) and columns [tlo, tlo+32k+32)
+      const int cq = (C0 - wbase) >> 1;
+      const int qlo = 32 * b + cq - 32 * k + 1, tlo = 32 * b - cq;
+      __syncwarp();
+      for (int r = lane; r < 32 * k + 31; r += 32) {
+        const int qp = qlo + r;
+        int4 v = make_int4(INT_MAX / 2, 0, 0, 0);
+        if (qp >= 0 && qp <= Qn) {
+          const RowInfo ri = rows[qp];
+          v.x = ri.lo; v.y = (int)(ri.packed & ((1u << ROW_W_BITS) - 1));
+          v.z = (int)((ri.packed >> 20) & 7u) * 20;
+          v.w = (int)((ri.packed >> 23) & 0xffu) | (qp == 0 ? (int)0x80000000 : 0);
+        }
+        sm.rows[r] = v;
+      }
+      for (int cI = lane; cI < 32 * k + 32; cI += 32) {
+        const int tp = tlo + cI;
+        sm.tcol[cI] = (tp >= 1 && tp <= Tn) ? (int)tcodes[tp] * 4 : 0;
+      }
+      __syncwarp();
+      uint32_t *aw = arrowsJob + (size_t)db.arrowUnit * 512u;
+      const bool first = (b << 6) <= hi0;               // row 0 holds cells on d <= hi0
+      const bool last = (b == nDB - 1);
+      const int eLast = (nD - 1) & 63;
+      if (first && last) run_block<KMAX, AFFINE, QV, true, true>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
+      else if (first) run_block<KMAX, AFFINE, QV, true, false>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
+      else if (last) run_block<KMAX, AFFINE, QV, false, true>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
+      else run_block<KMAX, AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
+    }
+    // ---- the end cell (Qn, Tn) sits on diagonal Tn-Qn+C0 and is the last cell written to its slot
+    {
+      const int s = Tn - Qn + C0 - wprev;
+      int v = BIG;
+#pragma unroll
+      for (int g = 0; g < KMAX; g++) if ((s >> 6) == g) v = (s & 1) ? So[g] : Se[g];
+      v = __shfl_sync(0xffffffffu, v, (s & 63) >> 1);
+      if (lane == 0) G.score = v >> SH;
+    }
+  }
+}
+
+template <int KMAX, bool AFFINE, bool QV>
+static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, uint32_t nOrder,
+                       uint32_t *counter, int nSM, cudaStream_t s) {
+  const size_t smem = sizeof(WarpSmem<KMAX>) * 4;
+  auto kern = fill_guided_kernel<KMAX, AFFINE, QV>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int perSM = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 128, smem);
+  if (perSM < 1) perSM = 1;
+  unsigned grid = (unsigned)(nSM * perSM);
+  const unsigned need = (nOrder + 3) / 4;
+  if (grid > need) grid = need;
+  if (grid) kern<<<grid, 128, smem, s>>>(B, P, order, nOrder, counter);
+}
+
+// kclass: 1 -> KMAX=1, 2 -> KMAX=2, 4 -> KMAX=4
+void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int kclass, const uint32_t *order, uint32_t nOrder,
+                        uint32_t *counter, int nSM, cudaStream_t s) {
+  const bool aff = P.affine != 0, qv = P.kind == BGPU_FN_QUALITY;
+#define BGPU_DISPATCH(K)                                                                   \
+  do {                                                                                     \
+    if (aff && qv) launch_one<K, true, true>(B, P, order, nOrder, counter, nSM, s);        \
+    else if (aff) launch_one<K, true, false>(B, P, order, nOrder, counter, nSM, s);        \
+    else if (qv) launch_one<K, false, true>(B, P, order, nOrder, counter, nSM, s);         \
+    else launch_one<K, false, false>(B, P, order, nOrder, counter, nSM, s);                \
+  } while (0)
+  if (kclass == 1) BGPU_DISPATCH(1);
+  else if (kclass == 2) BGPU_DISPATCH(2);
+  else BGPU_DISPATCH(4);
+#undef BGPU_DISPATCH
+}
+
+}  // namespace bgpu

@@ -1,0 +1,208 @@
+// bgpu_prep.cu -- guide construction on the device.
+//
+// One warp per job turns the candidate's block list into the per-row band table the fill kernels
+// stage into shared memory, exactly as AlignmentToGuide builds its GuideRow list
+// (common/algorithms/alignment/GuidedAlign.h:104-259), but without the row-to-row dependency:
+// the reference's   tPre_i = min(cap_i, t_i - (t_{i-1} - tPre_{i-1}))   is the prefix maximum
+//     L_i = max(L_{i-1}, t_i - cap_i),   L_0 = tStart - 1
+// of the left edges (cap = bandSize inside a block, 250 on gap rows, unbounded on the first row
+// of a block), so a warp scan over rows reproduces it.  The same pass measures, per block of 64
+// anti-diagonals, which diagonals hold in-band cells; that fixes the register window and the
+// traceback layout of the fill kernel.
+#include "bgpu_common.cuh"
+
+namespace bgpu {
+
+__device__ __forceinline__ int warp_incl_max(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = max(v, u); }
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_or(int v) { return __reduce_or_sync(0xffffffffu, (unsigned)v); }
+
+constexpr int MAX_BAND_SIZE = 250;  // GuidedAlign.h:29
+
+// rowOffIn / dblkOffIn / runOffIn are host-computed exclusive prefix sums of the per-job capacities.
+__global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParams P, int defaultBand,
+                                                          const uint64_t *rowOffIn, const uint64_t *dblkOffIn,
+                                                          const uint64_t *runOffIn) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (job >= B.nJobs) return;
+  JobGeom &G = B.geom[job];
+  const uint64_t g0 = B.guideOff[job];
+  const int nB = (int)(B.guideOff[job + 1] - g0);
+  const bgpu_block *blk = B.guide + g0;
+  const uint64_t qo = B.qOff[job], to = B.tOff[job];
+  const uint32_t qLen = (uint32_t)(B.qOff[job + 1] - qo), tLen = (uint32_t)(B.tOff[job + 1] - to);
+  const int band = B.band ? B.band[job] : defaultBand;
+
+  int status = BGPU_JOB_OK;
+  if (lane == 0) {
+    G.rowOff = rowOffIn[job]; G.dblkOff = dblkOffIn[job]; G.runOff = runOffIn[job];
+    G.arrowBytes = 0; G.nRuns = G.nBlocks = G.nGaps = G.nGapLists = 0;
+    G.qPos = G.tPos = 0; G.score = 0; G.nCells = 0; G.kmax = 0; G.nDB = 0; G.band = band;
+    G.Qn = G.Tn = 0; G.qStart = G.tStart = 0; G.C0 = 0; G.hi0 = 0;
+  }
+  if (nB == 0) { if (lane == 0) G.status = BGPU_JOB_EMPTY_GUIDE; return; }   // GuidedAlign.h:388-392
+  if (band < 0) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
+
+  // ---- validate the block chain: ordered, non-overlapping, non-empty, inside the sequences
+  int bad = 0;
+  for (int b = lane; b < nB; b += 32) {
+    bgpu_block c = blk[b];
+    if (c.length == 0 || c.length > 0x3fffffffu || c.qPos > 0x3fffffffu || c.tPos > 0x3fffffffu) bad = 1;
+    if (b + 1 < nB) {
+      bgpu_block n = blk[b + 1];
+      if (n.qPos < c.qPos + c.length || n.tPos < c.tPos + c.length) bad = 1;
+    }
+  }
+  const bgpu_block first = blk[0], last = blk[nB - 1];
+  const int qStart = (int)first.qPos, tStart = (int)first.tPos;
+  const long long qEndL = (long long)last.qPos + last.length, tEndL = (long long)last.tPos + last.length;
+  if (qEndL > qLen || tEndL > tLen) bad = 1;
+  if (warp_or(bad)) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
+  const int qEnd = (int)qEndL, tEnd = (int)tEndL;
+  const int Qn = qEnd - qStart, Tn = tEnd - tStart;
+  const int C0 = Qn + (Qn & 1);
+  const int nD = Qn + Tn + 1, nDB = (nD + DBLK - 1) / DBLK;
+  // score range the shifted-domain kernels can carry
+  {
+    int mx = max(max(abs(P.ins), abs(P.del)), abs(P.open) + abs(P.ext));
+    if (P.kind == BGPU_FN_QUALITY) mx = max(mx, 255);
+    else for (int i = 0; i < 25; i++) mx = max(mx, abs(P.M[i]));
+    if ((long long)mx * (Qn + Tn + 2) >= SCORE_LIMIT || mx >= (1 << 15)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }
+  }
+
+  // ---- encode + validate the target window in place (codes 0..4), and check the query bases
+  uint8_t *tb = B.t + to;
+  const uint8_t *qb = B.q + qo;
+  for (int i = tStart + lane; i < tEnd; i += 32) { uint8_t c = base_code(tb[i]); if (c > 4) bad = 1; tb[i] = c; }
+  for (int i = qStart + lane; i < qEnd; i += 32) { if (base_code(qb[i]) > 4) bad = 1; }
+  if (warp_or(bad)) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
+
+  // ---- live-diagonal range per d-block
+  int32_t *dmin = B.dmin + dblkOffIn[job], *dmax = B.dmax + dblkOffIn[job];
+  for (int b = lane; b < nDB; b += 32) { dmin[b] = INT_MAX; dmax[b] = INT_MIN; }
+  __threadfence(); __syncwarp();
+
+  RowInfo *rows = B.rows + rowOffIn[job];
+  const uint8_t *qual = B.qual ? B.qual + qo : nullptr;
+  const int drift0 = abs(tStart - qStart);                       // GuidedAlign.h:128
+  const int tPost0 = drift0 > band ? drift0 : band;              // :129-134
+  long long cells = 0;
+  int wide = 0;
+
+  auto add_row_range = [&](int i, int lo, int hi) {              // row i covers t' in [lo,hi]
+    const int bLo = (i + lo) >> 6, bHi = (i + hi) >> 6;
+    for (int b = bLo; b <= bHi; b++) {
+      int tl = max(lo, (b << 6) - i), th = min(hi, (b << 6) + 63 - i);
+      atomicMin(&dmin[b], tl - i + C0);
+      atomicMax(&dmax[b], th - i + C0);
+    }
+  };
+
+  // row 0: boundary row, t' in [0, min(tPost0, Tn)]
+  const int hi0 = min(tPost0, Tn);
+  if (lane == 0) {
+    rows[0].lo = 0; rows[0].packed = (uint32_t)hi0;   // width field only; code/QV unused
+    add_row_range(0, 0, hi0);
+    cells += (long long)tPost0 + 1;                    // tPre=0
+    if (hi0 >= (1 << ROW_W_BITS)) wide = 1;
+  }
+
+  int carryL = tStart - 1;                              // L_0
+  for (int base = 1; base <= Qn; base += 32) {
+    const int i = base + lane;
+    const bool act = i <= Qn;
+    int t = 0, cap = 0, tPost = 0, x = INT_MIN;
+    if (act) {
+      const uint32_t q = (uint32_t)(qStart + i - 1);
+      // largest b with blk[b].qPos <= q
+      int lo = 0, hi = nB - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (blk[mid].qPos <= q) lo = mid; else hi = mid - 1; }
+      const bgpu_block c = blk[lo];
+      const uint32_t off = q - c.qPos;
+      if (off < c.length) {
+        t = (int)(c.tPos + off);
+        if (off == 0) {                                 // first base of a block: :161-165
+          int drift;
+          if (lo == 0) drift = drift0;
+          else { bgpu_block p = blk[lo - 1]; drift = (int)(c.tPos - (p.tPos + p.length)) - (int)(c.qPos - (p.qPos + p.length)); }
+          cap = INT_MAX; tPost = band + abs(drift);
+        } else { cap = band; tPost = min(MAX_BAND_SIZE, band); }   // :170-174
+      } else {                                          // gap rows after block lo: :213-250
+        const bgpu_block n = blk[lo + 1];
+        const int g = (int)(off - c.length);
+        const int qGap = (int)(n.qPos - (c.qPos + c.length)), tGap = (int)(n.tPos - (c.tPos + c.length));
+        const int diag = min(qGap, tGap);
+        t = (int)(c.tPos + c.length) + min(g, diag);
+        cap = MAX_BAND_SIZE; tPost = min(MAX_BAND_SIZE, band + abs(tGap - qGap));
+      }
+      x = (cap == INT_MAX) ? INT_MIN : t - cap;
+    }
+    int L = warp_incl_max(x, lane);
+    L = max(L, carryL);
+    carryL = __shfl_sync(0xffffffffu, L, 31);
+    if (act) {
+      const int tPre = t - L;                           // >= 0 for ordered blocks
+      cells += (long long)tPre + tPost + 1;
+      const int hi = min(t + tPost, tEnd - 1);
+      const int lop = L - tStart + 1, hip = hi - tStart + 1;
+      if (tPre < 0 || hip < lop) bad = 1;
+      const int w = hip - lop;
+      if (w >= (1 << ROW_W_BITS)) wide = 1;
+      const uint32_t qc = base_code(qb[qStart + i - 1]);
+      const uint32_t qv = qual ? qual[qStart + i - 1] : 0;
+      rows[i].lo = lop;
+      rows[i].packed = ((uint32_t)w & ((1u << ROW_W_BITS) - 1)) | (qc << 20) | (qv << 23);
+      if (!bad && !wide) add_row_range(i, lop, hip);
+    }
+  }
+  cells = warp_sum_ll(cells);
+  if (warp_or(bad) || cells > INT_MAX) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
+  __threadfence(); __syncwarp();
+
+  // ---- per d-block window + arrow layout (exclusive scan of k over blocks)
+  DBlock *db = B.dblk + dblkOffIn[job];
+  uint32_t carry = 0; int kmax = 0;
+  for (int base = 0; base < nDB; base += 32) {
+    const int b = base + lane;
+    int k = 0, wbase = 0;
+    if (b < nDB) {
+      const int mn = __ldcg(&dmin[b]), mx = __ldcg(&dmax[b]);
+      // window [mn-1, mx+1] aligned down to an even diagonal (see bgpu_fill.cu: edge slots stay dead)
+      wbase = (mn - 1) & ~1;
+      k = (mx + 1 - wbase) / 64 + 1;
+      if (mx < mn) { wbase = 0; k = 1; }
+    }
+    uint32_t incl = (uint32_t)k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (b < nDB) { db[b].wbase = wbase; db[b].k = k; db[b].arrowUnit = carry + incl - (uint32_t)k; db[b].pad = 0; }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+    kmax = max(kmax, k);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  if (warp_or(wide) || kmax > KMAX_BUILD) status = BGPU_JOB_TOO_WIDE;
+  if (lane == 0) {
+    G.status = status; G.qStart = qStart; G.tStart = tStart; G.Qn = Qn; G.Tn = Tn; G.C0 = C0;
+    G.nDB = nDB; G.kmax = kmax; G.nCells = (int)cells; G.hi0 = hi0;
+    G.arrowBytes = (uint64_t)carry * 2048ull;
+  }
+}
+
+void launch_prep_guided(const BatchDev &B, const ScoreParams &P, int defaultBand, const uint64_t *rowOff,
+                        const uint64_t *dblkOff, const uint64_t *runOff, cudaStream_t s) {
+  const int warpsPerBlock = 4;
+  const unsigned grid = (B.nJobs + warpsPerBlock - 1) / warpsPerBlock;
+  if (grid) prep_guided_kernel<<<grid, warpsPerBlock * 32, 0, s>>>(B, P, defaultBand, rowOff, dblkOff, runOff);
+}
+
+}  // namespace bgpu

@@ -1,0 +1,250 @@
+// bgpu_trace.cu -- device-side traceback and alignment emission.
+//
+//   trace_guided_kernel : walks the traceback bytes of one job from (qEnd-1,tEnd-1) to the origin with the
+//                         reference's 3-matrix state machine (GuidedAlign.h:626-663,
+//                         AffineGuidedAlign.h:377-468) and records the path as run-length runs (reversed).
+//   scan_counts_kernel  : exclusive scan of per-job block / gap-list / gap counts -> arena offsets.
+//   emit_kernel         : turns the runs into Block[] / GapList[] exactly as ArrowPathToAlignment
+//                         (datastructures/alignment/Alignment.h:190-254) + RemoveAlignmentPrefixGaps
+//                         (AlignmentUtils.h:620-644) do, and evaluates ComputeAlignmentStats
+//                         (AlignmentUtils.h:535-584, :60-124) without building the three strings.
+#include "bgpu_common.cuh"
+
+namespace bgpu {
+
+enum { RUN_D = 0, RUN_U = 1, RUN_L = 2 };   // diagonal / up (insertion, Gap::Target) / left (deletion, Gap::Query)
+
+__global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder,
+                                                           uint32_t *counter) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(counter, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= nOrder) break;
+    const uint32_t job = order[idx];
+    JobGeom &G = B.geom[job];
+    if (G.status != BGPU_JOB_OK) continue;
+    const int Qn = G.Qn, Tn = G.Tn, C0 = G.C0;
+    const DBlock *dblk = B.dblk + G.dblkOff;
+    const uint8_t *arrows = B.arrows + B.arrowOff[job];
+    uint32_t *runs = B.runs + G.runOff;
+
+    int q = Qn, t = Tn, mat = 0;
+    int curB = -1, wbase = 0, k = 1; size_t blkBase = 0;
+    int runType = -1; uint32_t runLen = 0, nRuns = 0;
+    uint32_t nBlocks = 0, nGaps = 0, pendGaps = 0, pendQ = 0, pendT = 0;
+    bool seenD = false, awry = false;
+
+    auto push = [&](int type) {
+      if (type == runType) { runLen++; return; }
+      if (runType >= 0) { if (lane == 0) runs[nRuns] = ((uint32_t)runType << 30) | runLen; nRuns++; }
+      runType = type; runLen = 1;
+      if (type == RUN_D) { if (seenD) nGaps += pendGaps; pendGaps = 0; pendQ = pendT = 0; seenD = true; nBlocks++; }
+      else pendGaps++;
+    };
+
+    while (q >= 1 || t >= 1) {
+      if (q < 0 || t < 0) { awry = true; break; }
+      const int d = q + t, b = d >> 6;
+      if (b != curB) { const DBlock db = dblk[b]; wbase = db.wbase; k = db.k; blkBase = (size_t)db.arrowUnit * 2048u; curB = b; }
+      const int s = t - q + C0 - wbase;
+      if (s < 0 || s >= 64 * k) { awry = true; break; }
+      const uint32_t byte = arrows[blkBase + ((size_t)((((d & 63) >> 2) * k + (s >> 6)) * 32 + ((s & 63) >> 1)) << 2) + (d & 3)];
+      const uint32_t tag = byte & 7u;
+      if (tag == TB_NONE) { awry = true; break; }
+      if (mat == 0) {
+        if (tag == TB_DIAG) { push(RUN_D); q--; t--; }
+        else if (tag == TB_UP) { push(RUN_U); pendQ++; q--; }
+        else if (tag == TB_LEFT) { push(RUN_L); pendT++; t--; }
+        else if (tag == TB_ICLOSE) { push(RUN_U); pendQ++; mat = 1; q--; }
+        else if (tag == TB_DCLOSE) { push(RUN_L); pendT++; mat = 2; t--; }
+        else { awry = true; break; }
+      } else if (mat == 1) {
+        if (byte & TB_IOPEN) mat = 0; else { q--; push(RUN_U); pendQ++; }
+      } else {
+        if (byte & TB_DOPEN) mat = 0; else { t--; push(RUN_L); pendT++; }
+      }
+    }
+    if (runType >= 0) { if (lane == 0) runs[nRuns] = ((uint32_t)runType << 30) | runLen; nRuns++; }
+    if (lane == 0) {
+      if (awry) { G.status = BGPU_JOB_PATH_AWRY; G.nRuns = 0; G.nBlocks = G.nGaps = G.nGapLists = 0; }
+      else {
+        G.nRuns = nRuns; G.nBlocks = nBlocks; G.nGaps = nGaps; G.nGapLists = nRuns ? nBlocks + 1 : 0;
+        // leading gaps fold into qPos/tPos only when a block follows (the all-gap path is cleared first)
+        G.qPos = (uint32_t)G.qStart + (seenD ? pendQ : 0);
+        G.tPos = (uint32_t)G.tStart + (seenD ? pendT : 0);
+      }
+    }
+  }
+}
+
+// one CTA; counts -> exclusive offsets, totals in totals[0..2]
+__global__ void __launch_bounds__(1024) scan_counts_kernel(BatchDev B, uint64_t *blockOff, uint64_t *listOff,
+                                                           uint64_t *gapOff, uint64_t *totals) {
+  __shared__ unsigned long long sh[3][32];
+  __shared__ unsigned long long carry[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 3) carry[tid] = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < B.nJobs; base += 1024) {
+    const uint32_t j = base + tid;
+    unsigned long long v[3] = {0, 0, 0};
+    if (j < B.nJobs) { const JobGeom &G = B.geom[j]; v[0] = G.nBlocks; v[1] = G.nGapLists; v[2] = G.nGaps; }
+    unsigned long long inc[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      unsigned long long x = v[c];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { unsigned long long u = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += u; }
+      inc[c] = x;
+      if (lane == 31) sh[c][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        unsigned long long x = sh[c][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long u = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += u; }
+        sh[c][lane] = x;
+      }
+    }
+    __syncthreads();
+    unsigned long long off[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) off[c] = carry[c] + (warp ? sh[c][warp - 1] : 0) + inc[c] - v[c];
+    if (j < B.nJobs) { blockOff[j] = off[0]; listOff[j] = off[1]; gapOff[j] = off[2]; }
+    __syncthreads();
+    if (tid < 3) carry[tid] += sh[tid][31];
+    __syncthreads();
+  }
+  if (tid < 3) totals[tid] = carry[tid];
+}
+
+struct EmitOut {
+  bgpu_result *results;
+  bgpu_block *blocks; uint32_t *gapCounts; bgpu_gap *gaps;
+  const uint64_t *blockOff, *listOff, *gapOff;
+};
+
+__device__ __forceinline__ uint32_t warp_excl_u32(uint32_t v, int lane, uint32_t &total) {
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += u; }
+  total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
+}
+
+// warp per job.  gapCounts must be zeroed beforehand.
+__global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (job >= B.nJobs) return;
+  const JobGeom &G = B.geom[job];
+  bgpu_result R;
+  R.status = G.status; R.score = 0; R.qPos = 0; R.tPos = 0; R.nCells = 0;
+  R.nMatch = R.nMismatch = R.nIns = R.nDel = 0; R.pctSimilarity = 0.f; R.statsScore = 0;
+  R.nBlocks = 0; R.nGapLists = 0; R.nGaps = 0;
+  R.blockOff = O.blockOff[job]; R.gapListOff = O.listOff[job]; R.gapOff = O.gapOff[job];
+  if (G.status != BGPU_JOB_OK) { if (lane == 0) O.results[job] = R; return; }
+  R.score = G.score; R.qPos = G.qPos; R.tPos = G.tPos; R.nCells = G.nCells;
+  R.nBlocks = G.nBlocks; R.nGapLists = G.nGapLists; R.nGaps = G.nGaps;
+  const uint32_t nRuns = G.nRuns, nBlocks = G.nBlocks;
+  const uint32_t *runs = B.runs + G.runOff;
+  const uint8_t *qb = B.q + B.qOff[job];
+  const uint8_t *tb = B.t + B.tOff[job];             // codes inside [tStart,tEnd)
+  const uint32_t qPrefix = G.qPos - (uint32_t)G.qStart, tPrefix = G.tPos - (uint32_t)G.tStart;
+  bgpu_block *blocks = O.blocks + R.blockOff;
+  uint32_t *gapCounts = O.gapCounts + R.gapListOff;
+  bgpu_gap *gaps = O.gaps + R.gapOff;
+
+  uint32_t cq = 0, ct = 0, cD = 0, cG = 0;            // carries: q/t consumed, D runs seen, kept gap runs seen
+  int nMatch = 0, nMismatch = 0, nIns = 0, nDel = 0, score = 0; long long cols = 0;
+  for (uint32_t base = 0; base < nRuns; base += 32) {
+    const uint32_t f = base + lane;                   // forward run index
+    const bool act = f < nRuns;
+    uint32_t type = 3, len = 0;
+    if (act) { const uint32_t r = runs[nRuns - 1 - f]; type = r >> 30; len = r & 0x3fffffffu; }
+    const uint32_t dq = (type == RUN_D || type == RUN_U) ? len : 0, dt = (type == RUN_D || type == RUN_L) ? len : 0;
+    uint32_t totQ, totT, totD, totG;
+    const uint32_t pq = cq + warp_excl_u32(dq, lane, totQ), pt = ct + warp_excl_u32(dt, lane, totT);
+    const uint32_t isD = act && type == RUN_D;
+    const uint32_t dBefore = cD + warp_excl_u32(isD, lane, totD);
+    const bool kept = act && !isD && dBefore >= 1 && dBefore < nBlocks;   // between the first and last block
+    const uint32_t gBefore = cG + warp_excl_u32(kept ? 1u : 0u, lane, totG);
+    if (isD) {
+      bgpu_block bl; bl.qPos = pq - qPrefix; bl.tPos = pt - tPrefix; bl.length = len;
+      blocks[dBefore] = bl;
+      if (doStats) {
+        const uint8_t *qq = qb + G.qStart + pq, *tt = tb + G.tStart + pt;
+        for (uint32_t i = 0; i < len; i++) {
+          const int qc = base_code(qq[i]), tc = tt[i];
+          if (qc == tc) nMatch++; else nMismatch++;
+          score += P.M[qc * 5 + tc];                   // ComputeAlignmentScore :74 (row = query)
+        }
+        cols += len;
+      }
+    } else if (kept) {
+      bgpu_gap g; g.seq = (type == RUN_L) ? 0 : 1; g.length = (int32_t)len;
+      gaps[gBefore] = g;
+      atomicAdd(&gapCounts[dBefore], 1u);
+      if (doStats) {
+        if (type == RUN_L) nDel += (int)len; else nIns += (int)len;
+        cols += len;
+        if (!statsAffine) score += (int)len * (type == RUN_L ? P.del : P.ins);   // :111-116
+        else {
+          // affine: one cost per maximal run of gap columns, typed by its last column (:81-100);
+          // the lane holding the last run of the group sums the group.
+          const uint32_t nxt = runs[nRuns - 2 - f] >> 30;   // kept => a block follows eventually, f+1 < nRuns
+          if (nxt == RUN_D) {
+            long long L = len;
+            for (uint32_t b = f; b-- > 0;) {
+              const uint32_t r = runs[nRuns - 1 - b];
+              if ((r >> 30) == RUN_D) break;
+              L += r & 0x3fffffffu;
+            }
+            const int aff = (int)L * P.ext + P.open;
+            const int lin = (int)L * (type == RUN_L ? P.del : P.ins);
+            score += lin < aff ? lin : aff;
+          }
+        }
+      }
+    }
+    cq += totQ; ct += totT; cD += totD; cG += totG;
+  }
+  if (doStats) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      nMatch += __shfl_xor_sync(0xffffffffu, nMatch, o); nMismatch += __shfl_xor_sync(0xffffffffu, nMismatch, o);
+      nIns += __shfl_xor_sync(0xffffffffu, nIns, o); nDel += __shfl_xor_sync(0xffffffffu, nDel, o);
+      score += __shfl_xor_sync(0xffffffffu, score, o); cols += __shfl_xor_sync(0xffffffffu, cols, o);
+    }
+    R.nMatch = nMatch; R.nMismatch = nMismatch; R.nIns = nIns; R.nDel = nDel; R.statsScore = score;
+    R.pctSimilarity = cols > 0 ? (float)((nMatch * 2.0) / (double)(2 * cols) * 100) : 0.f;   // :566-576
+  }
+  if (lane == 0) O.results[job] = R;
+}
+
+void launch_trace_guided(const BatchDev &B, const uint32_t *order, uint32_t nOrder, uint32_t *counter, int nSM,
+                         cudaStream_t s) {
+  unsigned grid = (unsigned)nSM * 8u;
+  const unsigned need = (nOrder + 3) / 4;
+  if (grid > need) grid = need;
+  if (grid) trace_guided_kernel<<<grid, 128, 0, s>>>(B, order, nOrder, counter);
+}
+
+void launch_scan_counts(const BatchDev &B, uint64_t *blockOff, uint64_t *listOff, uint64_t *gapOff, uint64_t *totals,
+                        cudaStream_t s) {
+  scan_counts_kernel<<<1, 1024, 0, s>>>(B, blockOff, listOff, gapOff, totals);
+}
+
+void launch_emit(const BatchDev &B, const ScoreParams &P, bgpu_result *results, bgpu_block *blocks,
+                 uint32_t *gapCounts, bgpu_gap *gaps, const uint64_t *blockOff, const uint64_t *listOff,
+                 const uint64_t *gapOff, int doStats, int statsAffine, cudaStream_t s) {
+  EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff};
+  const unsigned grid = (B.nJobs + 3) / 4;
+  if (grid) emit_kernel<<<grid, 128, 0, s>>>(B, P, O, doStats, statsAffine);
+}
+
+}  // namespace bgpu

@@ -1,0 +1,116 @@
+"""Seeded synthetic workloads for the refinement path.
+
+The reference's own simulator needs HDF5 (simulator/Alchemy.cpp:15-16), so inputs are generated here:
+uniform-ACGT target windows, PacBio-like reads (error split ins 55 % / del 35 % / sub 10 %), QV tracks
+~ clamp(N(12,4),1,93), and a guide per pair.  The guide is the block list a detailed SDPAlign hands to
+RefineAlignment (Blasr.cpp:1716-1722, :850-866): every diagonal run of the read-to-window alignment,
+first block at (0,0), last block ending at the sequence ends.  Here it is derived from the simulated
+edit script instead of running SDPAlign, so the generator has no dependency on the reference or the oracle.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .align import JobBatch
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def simulate_pairs(n_jobs: int, len_lo: int, len_hi: int, err: float = 0.15, split=(0.55, 0.35, 0.10), seed: int = 1,
+                   bands: Optional[Sequence[int]] = None, with_qual: bool = False, anchor: int = 12,
+                   min_block: int = 1, n_rate: float = 0.0, chunk_bases: int = 32_000_000) -> JobBatch:
+    """n_jobs (query, window, guide) triples; window lengths ~ U[len_lo, len_hi].
+
+    min_block > 1 drops shorter interior guide blocks (anchor-only guides with real gaps between blocks).
+    """
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(len_lo, len_hi + 1, size=n_jobs, dtype=np.int64)
+    lens = np.maximum(lens, 2 * anchor + 2)
+    parts = []
+    i0 = 0
+    while i0 < n_jobs:
+        i1 = i0
+        tot = 0
+        while i1 < n_jobs and (i1 == i0 or tot + lens[i1] <= chunk_bases):
+            tot += int(lens[i1]); i1 += 1
+        parts.append(_simulate_chunk(rng, lens[i0:i1], err, split, with_qual, anchor, min_block, n_rate))
+        i0 = i1
+    q = np.concatenate([p[0] for p in parts]); t = np.concatenate([p[2] for p in parts])
+    g = np.concatenate([p[4] for p in parts], axis=0)
+
+    def cat_off(k):
+        out = [np.zeros(1, np.uint64)]
+        base = 0
+        for p in parts:
+            out.append(p[k][1:] + np.uint64(base)); base += int(p[k][-1])
+        return np.concatenate(out)
+    qOff, tOff, gOff = cat_off(1), cat_off(3), cat_off(5)
+    qual = np.concatenate([p[6] for p in parts]) if with_qual else None
+    band = None
+    if bands is not None:
+        band = np.asarray(bands, dtype=np.int32)[rng.integers(0, len(bands), size=n_jobs)]
+    return JobBatch(q, qOff, t, tOff, g, gOff, qual, band)
+
+
+def _simulate_chunk(rng, lens, err, split, with_qual, anchor, min_block, n_rate):
+    n = len(lens)
+    T = int(lens.sum())
+    tOff = np.zeros(n + 1, np.int64); tOff[1:] = np.cumsum(lens)
+    tcode = rng.integers(0, 4, size=T, dtype=np.uint8)
+    r = rng.integers(0, 65536, size=T, dtype=np.uint16).astype(np.int32)
+    p_ins, p_del, p_sub = (int(err * s * 65536) for s in split)
+    is_sub = r < p_sub
+    is_del = (r >= p_sub) & (r < p_sub + p_del)
+    is_ins = rng.integers(0, 65536, size=T, dtype=np.uint16).astype(np.int32) < p_ins   # inserted base *before* position j
+    # protect `anchor` positions at both ends of every window
+    pos = np.arange(T, dtype=np.int64) - np.repeat(tOff[:-1], lens)
+    prot = (pos < anchor) | (pos >= np.repeat(lens, lens) - anchor)
+    is_sub &= ~prot; is_del &= ~prot; is_ins &= ~prot
+    kept = ~is_del
+    sub_to = (tcode + 1 + rng.integers(0, 3, size=T, dtype=np.uint8)) % 4
+    qbase = np.where(is_sub, sub_to, tcode).astype(np.uint8)
+    # interleave insertion slots and base slots
+    vals = np.empty(2 * T, np.uint8); vals[0::2] = rng.integers(0, 4, size=T, dtype=np.uint8); vals[1::2] = qbase
+    mask = np.empty(2 * T, bool); mask[0::2] = is_ins; mask[1::2] = kept
+    qcode = vals[mask]
+    emitted = is_ins.astype(np.int64) + kept.astype(np.int64)
+    qcum = np.cumsum(emitted)                       # q bases emitted through position j (inclusive)
+    qpos_of_base = qcum - 1                         # q index of base j when kept
+    qOff = np.zeros(n + 1, np.int64); qOff[1:] = qcum[tOff[1:] - 1]
+    # guide blocks: maximal runs of kept positions with no insertion in between
+    prev_kept = np.empty(T, bool); prev_kept[0] = False; prev_kept[1:] = kept[:-1]
+    job_start = np.zeros(T, bool); job_start[tOff[:-1]] = True
+    start = kept & (job_start | ~prev_kept | is_ins)
+    sidx = np.flatnonzero(start)
+    # run length = distance to the next break (next start, next deleted position, or window end)
+    brk = start | ~kept | job_start
+    bidx = np.flatnonzero(brk)
+    nxt = np.searchsorted(bidx, sidx, side="right")
+    end = np.where(nxt < len(bidx), bidx[np.minimum(nxt, len(bidx) - 1)], T)
+    length = end - sidx
+    job_of = np.searchsorted(tOff, sidx, side="right") - 1
+    g_t = sidx - tOff[job_of]
+    g_q = qpos_of_base[sidx] - qOff[job_of]
+    if min_block > 1:
+        first = np.zeros(len(sidx), bool); last = np.zeros(len(sidx), bool)
+        chg = np.flatnonzero(np.diff(job_of)) + 1
+        first[0] = True; first[chg] = True; last[-1] = True; last[chg - 1] = True
+        keep = (length >= min_block) | first | last
+        job_of, g_t, g_q, length = job_of[keep], g_t[keep], g_q[keep], length[keep]
+    guide = np.stack([g_q, g_t, length], axis=1).astype(np.uint32)
+    gOff = np.zeros(n + 1, np.int64); gOff[1:] = np.cumsum(np.bincount(job_of, minlength=n))
+    tb = _ACGT[tcode]; qb = _ACGT[qcode]
+    if n_rate > 0:
+        tb = tb.copy(); qb = qb.copy()
+        tb[rng.random(T) < n_rate] = ord("N"); qb[rng.random(len(qb)) < n_rate] = ord("N")
+    qual = None
+    if with_qual:
+        qual = np.clip(np.rint(rng.normal(12, 4, size=len(qb))), 1, 93).astype(np.uint8)
+    return (qb, qOff.astype(np.uint64), tb, tOff.astype(np.uint64), guide, gOff.astype(np.uint64), qual)
+
+
+def batch_cells_estimate(batch: JobBatch, band: int) -> int:
+    """Rough nCells (rows x (2*band+1)), for sizing only; the exact count comes back from the library."""
+    return int((batch.qOff[-1] - batch.qOff[0])) * (2 * band + 1)

@@ -1,0 +1,166 @@
+/*
+ * blasr_gpu.h -- C ABI of the B200-native refinement DP (drop-in boundary).
+ *
+ * The reference (mchaisso/blasr) exposes no FFI; its "boundary" for this path is a set of
+ * C++ template call sites.  Each entry point below replaces the per-candidate CPU call named
+ * beside it with a batched, device-side one that returns the same score, coordinates, blocks,
+ * gaps and statistics:
+ *
+ *   AffineGuidedAlign(...)   common/algorithms/alignment/AffineGuidedAlign.h:31   called at alignment/Blasr.cpp:863
+ *   GuidedAlign(...)         common/algorithms/alignment/GuidedAlign.h:278        called at alignment/Blasr.cpp:869
+ *   KBandAlign(...)          common/algorithms/alignment/KBandAlign.h:75          called at alignment/Blasr.cpp:717,820
+ *   SWAlign(...)             common/algorithms/alignment/SWAlign.h:18             called at common/algorithms/alignment/SDPAlign.h:440,503,563
+ *   ComputeAlignmentStats    common/algorithms/alignment/AlignmentUtils.h:535     called at alignment/Blasr.cpp:740,875
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All work runs in hand-written sm_100a
+ * kernels; there is no CPU fallback -- every call fails with BGPU_E_NO_DEVICE without a GPU.
+ */
+#ifndef BLASR_GPU_H_
+#define BLASR_GPU_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGPU_VERSION 100 /* 0.1.0 */
+
+/* ---- return codes (API level) ---- */
+enum {
+  BGPU_OK = 0,
+  BGPU_E_NO_DEVICE = -1,   /* no CUDA device / driver: the product path never falls back to CPU */
+  BGPU_E_CUDA = -2,        /* a CUDA call failed; see bgpu_last_error() */
+  BGPU_E_INVALID = -3,     /* bad argument */
+  BGPU_E_OOM = -4,         /* device or pinned allocation failed */
+  BGPU_E_BUSY = -5         /* ticket not in the state the call needs */
+};
+
+/* ---- per-job status (bgpu_result.status) ---- */
+enum {
+  BGPU_JOB_OK = 0,
+  BGPU_JOB_EMPTY_GUIDE = 1,   /* guided aligners: no blocks -> score 0, empty alignment (GuidedAlign.h:388-392) */
+  BGPU_JOB_PATH_AWRY = 2,     /* traceback met NoArrow: the reference prints and exit(1)s (GuidedAlign.h:637-651) */
+  BGPU_JOB_BAD_INPUT = 3,     /* base outside ThreeBit 0..4, guide not monotone / outside the sequences, k<0 ... */
+  BGPU_JOB_REF_UNDEFINED = 4, /* the reference itself is undefined here (e.g. KBandAlign TargetFit with k > tLen) */
+  BGPU_JOB_TOO_WIDE = 5,      /* band wider than this build's widest kernel (BGPU_MAX_DIAGONALS) */
+  BGPU_JOB_RANGE = 6          /* scores could exceed the 26-bit range the kernels carry */
+};
+
+/* ---- enums mirrored from the reference ---- */
+typedef enum { BGPU_GUIDED = 0, BGPU_AFFINE_GUIDED = 1, BGPU_KBAND = 2, BGPU_SW = 3 } bgpu_algo;
+/* AlignmentType ordinals, AlignmentUtils.h:14-58 */
+typedef enum {
+  BGPU_LOCAL = 0, BGPU_GLOBAL = 1, BGPU_QUERYFIT = 2, BGPU_TARGETFIT = 3, BGPU_OVERLAP = 4,
+  BGPU_FRONTANCHORED = 5, BGPU_ENDANCHORED = 6, BGPU_FIT = 7, BGPU_TSUFFIXQPREFIX = 8, BGPU_TPREFIXQSUFFIX = 9
+} bgpu_align_type;
+typedef enum { BGPU_FN_DISTANCE = 0, /* DistanceMatrixScoreFunction.h:11 */
+               BGPU_FN_QUALITY = 1   /* QualityValueScoreFunction.h:9    */ } bgpu_fn_kind;
+
+/* ---- PODs mirroring the reference's containers ---- */
+typedef struct { uint32_t qPos, tPos, length; } bgpu_block;   /* Block, datastructures/alignment/AlignmentBlock.h:17 */
+typedef struct { int32_t seq;  /* 0 = Gap::Query (deletion), 1 = Gap::Target (insertion) */
+                 int32_t length; } bgpu_gap;                  /* Gap, datastructures/alignment/AlignmentGapList.h:9-24 */
+
+typedef struct {
+  int32_t M[25];            /* scoreMatrix[5][5], row = query code (DistanceMatrixScoreFunction.h:100-105) */
+  int32_t ins, del;         /* BaseScoreFunction.h:6-7 */
+  int32_t affineOpen, affineExtend; /* BaseScoreFunction.h:10-11 */
+  int32_t kind;             /* bgpu_fn_kind */
+} bgpu_scorefn;
+
+typedef struct {
+  int32_t algo;             /* bgpu_algo */
+  int32_t alignType;        /* bgpu_align_type */
+  int32_t band;             /* bandSize (guided) / k (KBandAlign) when batch.band == NULL */
+  int32_t bndIns, bndDel;   /* KBandAlign's int ins/del *parameters* (boundary costs, KBandAlign.h:116,121) */
+  int32_t doStats;          /* also run ComputeAlignmentStats (fills nMatch.. statsScore) */
+  int32_t statsAffine;      /* its useAffineScore argument (blasr: params.affineAlign) */
+} bgpu_params;
+
+/* A batch in structure-of-arrays form.  Sequences are ASCII exactly as DNASequence::seq holds
+ * them; job i uses qBases[qOff[i] .. qOff[i+1]) etc.  For the guided aligners the caller has
+ * already sliced q/t the way RefineAlignment does (Blasr.cpp:850-859): guide blocks are used
+ * raw, the alignment runs from guide.front() to guide.back(). */
+typedef struct {
+  uint32_t nJobs;
+  const uint8_t  *qBases; const uint64_t *qOff;     /* nJobs+1 offsets */
+  const uint8_t  *tBases; const uint64_t *tOff;     /* nJobs+1 offsets */
+  const uint8_t  *qual;                             /* QVs parallel to qBases, or NULL (needed for BGPU_FN_QUALITY) */
+  const bgpu_block *guide; const uint64_t *guideOff;/* nJobs+1 offsets; guided algos only, else NULL */
+  const int32_t  *band;                             /* per-job band / k, or NULL -> params.band */
+} bgpu_batch;
+
+/* One job in pointer form (what a per-candidate call site has in hand). */
+typedef struct {
+  const uint8_t *q; uint32_t qLen;
+  const uint8_t *t; uint32_t tLen;
+  const uint8_t *qual;                  /* nullable */
+  const bgpu_block *guide; uint32_t nGuide;
+  int32_t band;
+} bgpu_job;
+
+typedef struct {
+  int32_t  status;          /* BGPU_JOB_* */
+  int32_t  score;           /* the aligner's return value */
+  uint32_t qPos, tPos;      /* alignment.qPos / tPos */
+  int32_t  nCells;          /* alignment.nCells (0 for SWAlign, which never sets it) */
+  int32_t  nMatch, nMismatch, nIns, nDel;   /* ComputeAlignmentStats, when params.doStats */
+  float    pctSimilarity;
+  int32_t  statsScore;      /* alignment.score after ComputeAlignmentStats (what SAM AS:i / m4 / m5 print) */
+  uint32_t nBlocks;   uint64_t blockOff;    /* arena.blocks[blockOff .. +nBlocks) */
+  uint32_t nGapLists; uint64_t gapListOff;  /* arena.gapCounts[gapListOff .. +nGapLists) = alignment.gaps[i].size() */
+  uint32_t nGaps;     uint64_t gapOff;      /* arena.gaps[gapOff .. +nGaps), lists concatenated in order */
+} bgpu_result;
+
+typedef struct {
+  const bgpu_block *blocks;    uint64_t nBlocks;
+  const uint32_t   *gapCounts; uint64_t nGapLists;
+  const bgpu_gap   *gaps;      uint64_t nGaps;
+} bgpu_arena;   /* pinned host memory owned by the library until bgpu_release() */
+
+typedef struct {
+  double   msPrep, msFill, msTrace, msEmit; /* CUDA-event times of the last run of this ticket, per stage */
+  double   msTotal;                         /* first kernel start -> last kernel end */
+  uint64_t cells;                           /* sum of nCells definitions of SURVEY 8(d) over the batch */
+  uint64_t fillCells;                       /* lane-steps executed by the fill kernels (incl. idle lanes) */
+  uint32_t kernelLaunches;                  /* kernels launched by the last run */
+  uint64_t h2dBytes, d2hBytes;              /* bytes copied by submit / collect */
+} bgpu_timing;
+
+typedef struct bgpu_ctx bgpu_ctx;
+typedef struct bgpu_ticket_s *bgpu_ticket;
+
+/* ---- lifecycle ---- */
+int  bgpu_create(bgpu_ctx **ctx, int device);       /* binds to one GPU; one ctx per host thread or shared (calls are serialised) */
+void bgpu_destroy(bgpu_ctx *ctx);
+const char *bgpu_last_error(const bgpu_ctx *ctx);
+int  bgpu_version(void);
+
+/* ---- asynchronous batch API ---- */
+/* Copies the batch into pinned staging, enqueues H2D + all kernels on the ctx stream, returns at once. */
+int  bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b, bgpu_ticket *out);
+/* Pointer-form convenience: gathers jobs[] into a batch, then bgpu_submit. */
+int  bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_job *jobs,
+                      uint32_t nJobs, bgpu_ticket *out);
+/* Blocks until the ticket's kernels are done, copies results to the host. results[nJobs]. */
+int  bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, bgpu_arena *arena);
+int  bgpu_release(bgpu_ctx *ctx, bgpu_ticket t);
+/* Re-executes every kernel of an already submitted ticket on its device-resident inputs
+ * (benchmarking: inputs stay in HBM); synchronous. */
+int  bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t);
+int  bgpu_timing_of(bgpu_ctx *ctx, bgpu_ticket t, bgpu_timing *out);
+
+/* ---- synchronous one-shot: submit + collect; arena valid until the next call on ctx ---- */
+int  bgpu_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b,
+                bgpu_result *results, bgpu_arena *arena);
+
+/* ---- device introspection used by bench.py ---- */
+int  bgpu_device_count(void);
+/* Measures the int32 ALU peak of the bound device with a dependent IADD3/VIMNMX chain kernel:
+ * returns lane-ops per second (the integer roofline denominator). */
+int  bgpu_measure_int_peak(bgpu_ctx *ctx, double *opsPerSec, double *smClockMHz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,108 @@
+/*
+ * oracle/orc_align.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Flat C interface shared by the two CPU checkers of the refinement hot path:
+ *
+ *   ref_align()  (oracle/ref_harness.cpp -> oracle/_ref/libblasr_ref.so)
+ *       the UNMODIFIED reference templates, #include'd from /root/reference/common
+ *       at build time and instantiated behind this interface;
+ *   orc_align()  (oracle/orc_align.c    -> oracle/liborc.so)
+ *       a plain-C restatement of the same algorithms, each function citing the
+ *       reference file:line it follows.
+ *
+ * Nothing under oracle/ is product code: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load these libraries.
+ * The product path is include/blasr_gpu.h + blasr_b200/csrc (CUDA only, no CPU fallback).
+ */
+#ifndef ORC_ALIGN_H_
+#define ORC_ALIGN_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* algorithms (mirrors bgpu_algo in include/blasr_gpu.h) */
+enum { ORC_GUIDED = 0, ORC_AFFINE_GUIDED = 1, ORC_KBAND = 2, ORC_SW = 3 };
+/* score function kinds */
+enum { ORC_FN_DISTANCE = 0, ORC_FN_QUALITY = 1 };
+/* AlignmentType ordinals, common/algorithms/alignment/AlignmentUtils.h:14-58 */
+enum { ORC_LOCAL = 0, ORC_GLOBAL = 1, ORC_QUERYFIT = 2, ORC_TARGETFIT = 3, ORC_OVERLAP = 4,
+       ORC_FRONTANCHORED = 5, ORC_ENDANCHORED = 6, ORC_FIT = 7, ORC_TSUFFIXQPREFIX = 8,
+       ORC_TPREFIXQSUFFIX = 9 };
+/* status */
+enum { ORC_OK = 0, ORC_EMPTY_GUIDE = 1, ORC_PATH_AWRY = 2, ORC_BAD_INPUT = 3, ORC_OVERFLOW = 4 };
+
+typedef struct {
+  int32_t M[25];          /* scoreMatrix[5][5] row-major (DistanceMatrixScoreFunction.h:24) */
+  int32_t ins, del;       /* BaseScoreFunction.h:6-7 */
+  int32_t affineOpen, affineExtend; /* BaseScoreFunction.h:10-11 */
+  int32_t kind;           /* ORC_FN_* */
+} orc_scorefn;
+
+typedef struct {
+  int32_t  algo;          /* ORC_GUIDED ... */
+  int32_t  alignType;     /* AlignmentType ordinal */
+  int32_t  band;          /* bandSize (guided) or k (kband); unused for SW */
+  int32_t  bndIns, bndDel;/* KBandAlign's int ins/del parameters (KBandAlign.h:116,121) */
+  int32_t  doStats;       /* run ComputeAlignmentStats afterwards */
+  int32_t  statsAffine;   /* its useAffineScore argument */
+  const uint8_t *q; uint32_t qLen;   /* ASCII */
+  const uint8_t *t; uint32_t tLen;
+  const uint8_t *qual;    /* qLen QVs or NULL (required for ORC_FN_QUALITY) */
+  const uint32_t *guide;  /* nGuide x {qPos,tPos,length} */
+  uint32_t nGuide;
+} orc_job;
+
+typedef struct {
+  int32_t  status;
+  int32_t  score;         /* value returned by the aligner */
+  int32_t  alnScore;      /* alignment.score after the aligner (KBandAlign leaves it 0) */
+  uint32_t qPos, tPos;
+  int32_t  nCells;
+  int32_t  nMatch, nMismatch, nIns, nDel;
+  float    pctSimilarity;
+  int32_t  statsScore;    /* alignment.score after ComputeAlignmentStats */
+  uint32_t nBlocks, nGapLists, nGaps;
+} orc_result;
+
+/*
+ * blocks:    capBlocks x {qPos,tPos,length}
+ * gapCounts: one entry per GapList (alignment.gaps[i].size())
+ * gaps:      flattened {seq(0=Gap::Query,1=Gap::Target), length} pairs
+ * Returns 0, or ORC_OVERFLOW if a capacity was too small (counts are still set).
+ */
+typedef int (*orc_align_fn)(const orc_scorefn *fn, const orc_job *job, orc_result *res,
+                            uint32_t *blocks, uint32_t capBlocks,
+                            uint32_t *gapCounts, uint32_t capGapLists,
+                            int32_t *gaps, uint32_t capGaps);
+
+int orc_align(const orc_scorefn *fn, const orc_job *job, orc_result *res,
+              uint32_t *blocks, uint32_t capBlocks, uint32_t *gapCounts, uint32_t capGapLists,
+              int32_t *gaps, uint32_t capGaps);
+int ref_align(const orc_scorefn *fn, const orc_job *job, orc_result *res,
+              uint32_t *blocks, uint32_t capBlocks, uint32_t *gapCounts, uint32_t capGapLists,
+              int32_t *gaps, uint32_t capGaps);
+
+/* Guide rows exactly as AlignmentToGuide builds them (GuidedAlign.h:104-259):
+ * rows[i] = {q, t, tPre, tPost}; returns number of rows (0 for an empty guide),
+ * -1 if capRows is too small. nCells = sum(tPre+tPost+1) (GuidedAlign.h:83-92). */
+int orc_guide_rows(const uint32_t *guide, uint32_t nGuide, int band,
+                   int32_t *rows, uint32_t capRows, int64_t *nCells);
+int ref_guide_rows(const uint32_t *guide, uint32_t nGuide, int band,
+                   int32_t *rows, uint32_t capRows, int64_t *nCells);
+
+/* reference-only: SDPAlign exactly as blasr's AlignIntervals calls it (Blasr.cpp:1716-1722),
+ * returning absolute blocks (qPos/tPos folded in) usable as a guide. Returns nBlocks or -1. */
+int ref_sdp_guide(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen,
+                  const orc_scorefn *fn, int tupleSize, int sdpIns, int sdpDel, float indelRate,
+                  uint32_t *blocks, uint32_t capBlocks);
+
+/* multi-threaded replay used for the CPU baseline: runs jobs[0..n) on nThreads, returns
+ * total nCells; per-job results are discarded except score sum (anti-DCE). */
+int64_t orc_replay(const orc_scorefn *fn, const orc_job *jobs, uint32_t n, int nThreads, int64_t *scoreSum);
+int64_t ref_replay(const orc_scorefn *fn, const orc_job *jobs, uint32_t n, int nThreads, int64_t *scoreSum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,206 @@
+/*
+ * oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Instantiates the UNMODIFIED reference templates behind the flat interface of
+ * oracle/orc_align.h.  The reference headers are #include'd from where they lie
+ * (-I /root/reference/common, see oracle/Makefile); no reference source is copied
+ * into this repository.  Output: oracle/_ref/libblasr_ref.so (git-ignored).
+ *
+ * Instantiations:
+ *   GuidedAlign        common/algorithms/alignment/GuidedAlign.h:278
+ *   AffineGuidedAlign  common/algorithms/alignment/AffineGuidedAlign.h:31
+ *   KBandAlign         common/algorithms/alignment/KBandAlign.h:75
+ *   SWAlign            common/algorithms/alignment/SWAlign.h:18
+ *   ComputeAlignmentStats  common/algorithms/alignment/AlignmentUtils.h:535
+ *   SDPAlign           common/algorithms/alignment/SDPAlign.h (guide producer, test inputs only)
+ * each with DistanceMatrixScoreFunction<DNASequence,FASTQSequence> and
+ * QualityValueScoreFunction<DNASequence,FASTQSequence>.
+ */
+#define _GLIBCXX_USE_CXX11_ABI 0
+#include "algorithms/alignment.h"
+#include "algorithms/alignment/GuidedAlign.h"
+#include "algorithms/alignment/AffineGuidedAlign.h"
+#include "algorithms/alignment/SDPAlign.h"
+#include "algorithms/alignment/DistanceMatrixScoreFunction.h"
+#include "algorithms/alignment/QualityValueScoreFunction.h"
+#include "datastructures/alignment/AlignmentCandidate.h"
+#include "FASTQSequence.h"
+
+#include <thread>
+#include <atomic>
+#include <vector>
+#include "orc_align.h"
+
+typedef DistanceMatrixScoreFunction<DNASequence, FASTQSequence> DistFn;
+
+/* GuidedAlign references NormalizedMatch/Insertion/Deletion even with computeProb=false
+ * (GuidedAlign.h:577-583); QualityValueScoreFunction lacks them, so add a no-op shim.
+ * The integer path never evaluates them. */
+class QVFn : public QualityValueScoreFunction<DNASequence, FASTQSequence> {
+ public:
+  float NormalizedMatch(DNASequence &, DNALength, FASTQSequence &, DNALength) { return 0; }
+  float NormalizedInsertion(DNASequence &, DNALength, FASTQSequence &, DNALength) { return 0; }
+  float NormalizedDeletion(DNASequence &, DNALength, FASTQSequence &, DNALength) { return 0; }
+};
+
+static void FillDist(const orc_scorefn *fn, DistFn &f) {
+  int m[5][5];
+  for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) m[i][j] = fn->M[i * 5 + j];
+  f.InitializeScoreMatrix(m);
+  f.ins = fn->ins; f.del = fn->del;
+  f.affineOpen = fn->affineOpen; f.affineExtend = fn->affineExtend;
+}
+static void FillQV(const orc_scorefn *fn, QVFn &f) {
+  f.ins = fn->ins; f.del = fn->del;
+  f.affineOpen = fn->affineOpen; f.affineExtend = fn->affineExtend;
+}
+
+struct Scratch {
+  vector<int> scoreMat; vector<Arrow> pathMat; vector<double> probMat, optPathProbMat;
+  vector<float> a, b, c, d;
+};
+
+template <typename T_Fn>
+static int RunAligner(const orc_job *job, T_Fn &f, const orc_scorefn *fn, FASTQSequence &q, DNASequence &t,
+                      Alignment &aln, Scratch &s) {
+  int m[5][5];
+  for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) m[i][j] = fn->M[i * 5 + j];
+  AlignmentType at = (AlignmentType)job->alignType;
+  switch (job->algo) {
+    case ORC_GUIDED:
+    case ORC_AFFINE_GUIDED: {
+      Alignment guide;
+      guide.blocks.resize(job->nGuide);
+      for (uint32_t i = 0; i < job->nGuide; i++) {
+        guide.blocks[i].qPos = job->guide[3 * i];
+        guide.blocks[i].tPos = job->guide[3 * i + 1];
+        guide.blocks[i].length = job->guide[3 * i + 2];
+      }
+      if (job->algo == ORC_GUIDED)
+        return GuidedAlign(q, t, guide, f, job->band, aln, s.scoreMat, s.pathMat, s.probMat, s.optPathProbMat,
+                           s.a, s.b, s.c, s.d, at, false);
+      return AffineGuidedAlign(q, t, guide, f, job->band, aln, s.scoreMat, s.pathMat, s.probMat,
+                               s.optPathProbMat, s.a, s.b, s.c, s.d, at, false);
+    }
+    case ORC_KBAND:
+      return KBandAlign(q, t, m, job->bndIns, job->bndDel, (int)job->band, s.scoreMat, s.pathMat, aln, at, f,
+                        false);
+    case ORC_SW:
+      return SWAlign(q, t, s.scoreMat, s.pathMat, aln, f, at);
+  }
+  return 0;
+}
+
+static int RunOne(const orc_scorefn *fn, const orc_job *job, orc_result *res, Scratch &s, Alignment &aln) {
+  memset(res, 0, sizeof(*res));
+  FASTQSequence q; DNASequence t;
+  q.seq = (Nucleotide *)job->q; q.length = job->qLen;
+  t.seq = (Nucleotide *)job->t; t.length = job->tLen;
+  if (job->qual) q.qual.data = (QualityValue *)job->qual;
+  DistFn df; FillDist(fn, df);
+  int score;
+  if (fn->kind == ORC_FN_QUALITY) {
+    if (!job->qual) { q.qual.data = NULL; res->status = ORC_BAD_INPUT; return 0; }
+    QVFn qf; FillQV(fn, qf);
+    score = RunAligner(job, qf, fn, q, t, aln, s);
+  } else {
+    score = RunAligner(job, df, fn, q, t, aln, s);
+  }
+  res->score = score;
+  res->alnScore = aln.score;
+  res->qPos = aln.qPos; res->tPos = aln.tPos; res->nCells = aln.nCells;
+  if ((job->algo == ORC_GUIDED || job->algo == ORC_AFFINE_GUIDED) && job->nGuide == 0)
+    res->status = ORC_EMPTY_GUIDE;
+  if (job->doStats) {
+    /* blasr always rescoring with the distance-matrix function (Blasr.cpp:875-878) */
+    ComputeAlignmentStats(aln, q.seq, t.seq, df, job->statsAffine != 0);
+    res->nMatch = aln.nMatch; res->nMismatch = aln.nMismatch; res->nIns = aln.nIns; res->nDel = aln.nDel;
+    res->pctSimilarity = aln.pctSimilarity; res->statsScore = aln.score;
+  }
+  q.qual.data = NULL; /* borrowed */
+  return 0;
+}
+
+extern "C" int ref_align(const orc_scorefn *fn, const orc_job *job, orc_result *res, uint32_t *blocks,
+                         uint32_t capBlocks, uint32_t *gapCounts, uint32_t capGapLists, int32_t *gaps,
+                         uint32_t capGaps) {
+  Scratch s; Alignment aln;
+  RunOne(fn, job, res, s, aln);
+  res->nBlocks = aln.blocks.size();
+  res->nGapLists = aln.gaps.size();
+  uint32_t ng = 0;
+  for (size_t i = 0; i < aln.gaps.size(); i++) ng += aln.gaps[i].size();
+  res->nGaps = ng;
+  if (res->nBlocks > capBlocks || res->nGapLists > capGapLists || ng > capGaps) return ORC_OVERFLOW;
+  for (size_t i = 0; i < aln.blocks.size(); i++) {
+    blocks[3 * i] = aln.blocks[i].qPos; blocks[3 * i + 1] = aln.blocks[i].tPos;
+    blocks[3 * i + 2] = aln.blocks[i].length;
+  }
+  uint32_t g = 0;
+  for (size_t i = 0; i < aln.gaps.size(); i++) {
+    gapCounts[i] = aln.gaps[i].size();
+    for (size_t j = 0; j < aln.gaps[i].size(); j++) {
+      gaps[2 * g] = (int)aln.gaps[i][j].seq; gaps[2 * g + 1] = aln.gaps[i][j].length; g++;
+    }
+  }
+  return 0;
+}
+
+extern "C" int ref_guide_rows(const uint32_t *guide, uint32_t nGuide, int band, int32_t *rows, uint32_t capRows,
+                              int64_t *nCells) {
+  Alignment a; a.blocks.resize(nGuide);
+  for (uint32_t i = 0; i < nGuide; i++) {
+    a.blocks[i].qPos = guide[3 * i]; a.blocks[i].tPos = guide[3 * i + 1]; a.blocks[i].length = guide[3 * i + 2];
+  }
+  Guide g;
+  AlignmentToGuide(a, g, band);
+  if (nCells) *nCells = ComputeMatrixNElem(g);
+  if (g.size() > capRows) return -1;
+  for (size_t i = 0; i < g.size(); i++) {
+    rows[4 * i] = g[i].q; rows[4 * i + 1] = g[i].t; rows[4 * i + 2] = g[i].tPre; rows[4 * i + 3] = g[i].tPost;
+  }
+  return (int)g.size();
+}
+
+extern "C" int ref_sdp_guide(const uint8_t *qs, uint32_t qLen, const uint8_t *ts, uint32_t tLen,
+                             const orc_scorefn *fn, int tupleSize, int sdpIns, int sdpDel, float indelRate,
+                             uint32_t *blocks, uint32_t capBlocks) {
+  FASTQSequence q; DNASequence t;
+  q.seq = (Nucleotide *)qs; q.length = qLen; t.seq = (Nucleotide *)ts; t.length = tLen;
+  DistFn df; FillDist(fn, df);
+  Alignment sdp;
+  /* argument pattern of Blasr.cpp:1716-1722 with MappingParameters defaults
+   * (detailedSDPAlignment=true, extendFrontAlignment=false, sdpPrefix=50, recurse=2, recurseOver=1000) */
+  SDPAlign(q, t, df, tupleSize, sdpIns, sdpDel, indelRate, sdp, Local, true, false, 50, 2, 1000);
+  if (sdp.blocks.size() > capBlocks) return -1;
+  for (size_t i = 0; i < sdp.blocks.size(); i++) {
+    blocks[3 * i] = sdp.blocks[i].qPos + sdp.qPos;
+    blocks[3 * i + 1] = sdp.blocks[i].tPos + sdp.tPos;
+    blocks[3 * i + 2] = sdp.blocks[i].length;
+  }
+  return (int)sdp.blocks.size();
+}
+
+extern "C" int64_t ref_replay(const orc_scorefn *fn, const orc_job *jobs, uint32_t n, int nThreads,
+                              int64_t *scoreSum) {
+  std::atomic<uint32_t> next(0);
+  std::atomic<long long> cells(0), ssum(0);
+  if (nThreads < 1) nThreads = 1;
+  auto worker = [&]() {
+    Scratch s;
+    long long myCells = 0, mySum = 0;
+    for (;;) {
+      uint32_t i = next.fetch_add(1);
+      if (i >= n) break;
+      Alignment aln; orc_result r;
+      RunOne(fn, &jobs[i], &r, s, aln);
+      myCells += r.nCells; mySum += r.score + (long long)aln.blocks.size();
+    }
+    cells += myCells; ssum += mySum;
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < nThreads; i++) th.emplace_back(worker);
+  for (auto &x : th) x.join();
+  if (scoreSum) *scoreSum = ssum;
+  return cells;
+}

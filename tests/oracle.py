@@ -1,0 +1,147 @@
+"""ctypes bindings of the two CPU checkers under oracle/ (TEST INFRASTRUCTURE ONLY).
+
+  orc  -> oracle/liborc.so              plain-C restatement (oracle/orc_align.c)
+  ref  -> oracle/_ref/libblasr_ref.so   the unmodified reference templates (oracle/ref_harness.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_PATH = os.path.join(ROOT, "oracle", "liborc.so")
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libblasr_ref.so")
+
+
+class OrcScoreFn(C.Structure):
+    _fields_ = [("M", C.c_int32 * 25), ("ins", C.c_int32), ("del_", C.c_int32), ("affineOpen", C.c_int32),
+                ("affineExtend", C.c_int32), ("kind", C.c_int32)]
+
+
+class OrcJob(C.Structure):
+    _fields_ = [("algo", C.c_int32), ("alignType", C.c_int32), ("band", C.c_int32), ("bndIns", C.c_int32),
+                ("bndDel", C.c_int32), ("doStats", C.c_int32), ("statsAffine", C.c_int32),
+                ("q", C.c_void_p), ("qLen", C.c_uint32), ("t", C.c_void_p), ("tLen", C.c_uint32),
+                ("qual", C.c_void_p), ("guide", C.c_void_p), ("nGuide", C.c_uint32)]
+
+
+class OrcResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("score", C.c_int32), ("alnScore", C.c_int32), ("qPos", C.c_uint32),
+                ("tPos", C.c_uint32), ("nCells", C.c_int32), ("nMatch", C.c_int32), ("nMismatch", C.c_int32),
+                ("nIns", C.c_int32), ("nDel", C.c_int32), ("pctSimilarity", C.c_float), ("statsScore", C.c_int32),
+                ("nBlocks", C.c_uint32), ("nGapLists", C.c_uint32), ("nGaps", C.c_uint32)]
+
+
+def build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "all"], stdout=subprocess.DEVNULL)
+
+
+_libs = {}
+
+
+def _load(which: str):
+    if which in _libs:
+        return _libs[which]
+    path = ORC_PATH if which == "orc" else REF_PATH
+    if not os.path.exists(path):
+        build()
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    fn = getattr(L, f"{which}_align")
+    fn.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.POINTER(OrcResult), C.c_void_p, C.c_uint32, C.c_void_p,
+                   C.c_uint32, C.c_void_p, C.c_uint32]
+    gr = getattr(L, f"{which}_guide_rows")
+    gr.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_int64)]
+    rp = getattr(L, f"{which}_replay")
+    rp.argtypes = [C.POINTER(OrcScoreFn), C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_int64)]
+    rp.restype = C.c_int64
+    if which == "ref":
+        L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
+                                    C.c_int, C.c_float, C.c_void_p, C.c_uint32]
+    _libs[which] = L
+    return L
+
+
+def have_ref() -> bool:
+    return _load("ref") is not None
+
+
+def score_fn(M, ins, del_, affineOpen=0, affineExtend=0, kind=0) -> OrcScoreFn:
+    f = OrcScoreFn()
+    m = np.asarray(M, dtype=np.int32).reshape(25)
+    for i in range(25):
+        f.M[i] = int(m[i])
+    f.ins, f.del_, f.affineOpen, f.affineExtend, f.kind = ins, del_, affineOpen, affineExtend, kind
+    return f
+
+
+def make_job(algo, alignType, band, q: np.ndarray, t: np.ndarray, guide=None, qual=None, bndIns=0, bndDel=0, doStats=1,
+             statsAffine=0):
+    """Returns (OrcJob, keepalive)."""
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    keep = [q, t]
+    j = OrcJob()
+    j.algo, j.alignType, j.band, j.bndIns, j.bndDel, j.doStats, j.statsAffine = algo, alignType, band, bndIns, bndDel, doStats, statsAffine
+    j.q, j.qLen, j.t, j.tLen = q.ctypes.data, len(q), t.ctypes.data, len(t)
+    if qual is not None:
+        qual = np.ascontiguousarray(qual, np.uint8); keep.append(qual); j.qual = qual.ctypes.data
+    if guide is not None and len(guide):
+        guide = np.ascontiguousarray(guide, np.uint32).reshape(-1, 3); keep.append(guide)
+        j.guide, j.nGuide = guide.ctypes.data, len(guide)
+    return j, keep
+
+
+def align(which: str, fn: OrcScoreFn, job: OrcJob):
+    """Run one job; returns dict with the result fields, blocks (n,3), gaps (list of lists of (seq,len))."""
+    L = _load(which)
+    if L is None:
+        raise RuntimeError(f"oracle library '{which}' unavailable")
+    cap = int(job.qLen) + int(job.tLen) + 8
+    blocks = np.zeros((cap, 3), np.uint32); cnt = np.zeros(cap + 1, np.uint32); gaps = np.zeros((2 * cap, 2), np.int32)
+    r = OrcResult()
+    rc = getattr(L, f"{which}_align")(C.byref(fn), C.byref(job), C.byref(r), blocks.ctypes.data, cap, cnt.ctypes.data,
+                                      cap + 1, gaps.ctypes.data, 2 * cap)
+    if rc != 0:
+        raise RuntimeError(f"{which}_align overflow rc={rc}")
+    out = {k: getattr(r, k) for k, _ in OrcResult._fields_}
+    out["blocks"] = blocks[:r.nBlocks].copy()
+    gl, p = [], 0
+    for i in range(r.nGapLists):
+        gl.append([(int(a), int(b)) for a, b in gaps[p:p + int(cnt[i])]]); p += int(cnt[i])
+    out["gaps"] = gl
+    return out
+
+
+def guide_rows(which: str, guide: np.ndarray, band: int):
+    L = _load(which)
+    guide = np.ascontiguousarray(guide, np.uint32).reshape(-1, 3)
+    cap = int(guide[-1, 0] + guide[-1, 2]) + 8 if len(guide) else 8
+    rows = np.zeros((cap, 4), np.int32); nc = C.c_int64(0)
+    n = getattr(L, f"{which}_guide_rows")(guide.ctypes.data, len(guide), band, rows.ctypes.data, cap, C.byref(nc))
+    return rows[:max(n, 0)].copy(), nc.value
+
+
+def sdp_guide(q: np.ndarray, t: np.ndarray, fn: OrcScoreFn, tupleSize=11, sdpIns=5, sdpDel=10, indelRate=0.9):
+    """Reference SDPAlign blocks (absolute), the guide blasr hands to RefineAlignment."""
+    L = _load("ref")
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    cap = len(q) + len(t) + 8
+    blocks = np.zeros((cap, 3), np.uint32)
+    n = L.ref_sdp_guide(q.ctypes.data, len(q), t.ctypes.data, len(t), C.byref(fn), tupleSize, sdpIns, sdpDel,
+                        C.c_float(indelRate), blocks.ctypes.data, cap)
+    return blocks[:max(n, 0)].copy()
+
+
+def replay(which: str, fn: OrcScoreFn, jobs, nThreads: int):
+    """jobs: list of OrcJob. Returns (total nCells, checksum)."""
+    L = _load(which)
+    arr = (OrcJob * len(jobs))(*jobs)
+    s = C.c_int64(0)
+    cells = getattr(L, f"{which}_replay")(C.byref(fn), arr, len(jobs), nThreads, C.byref(s))
+    return int(cells), int(s.value)
