@@ -232,6 +232,9 @@ class Aligner:
         rc = self._lib.bgpu_measure_int_peak(self._ctx, C.byref(ops), C.byref(mhz))
         if rc != 0:
             self._err(rc, "bgpu_measure_int_peak")
+        modes = (C.c_double * 4)()
+        self._lib.bgpu_int_peak_modes(C.byref(modes))
+        self.int_peak_modes = dict(zip(("add", "min", "mad", "add+mad"), [float(x) for x in modes]))
         return ops.value, mhz.value
 
     def _run(self, batch, fn, algo, **kw) -> BatchResult:

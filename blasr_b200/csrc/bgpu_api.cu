@@ -24,6 +24,7 @@ void launch_scan_counts(const BatchDev &, uint64_t *, uint64_t *, uint64_t *, ui
 void launch_emit(const BatchDev &, const ScoreParams &, bgpu_result *, bgpu_block *, uint32_t *, bgpu_gap *,
                  const uint64_t *, const uint64_t *, const uint64_t *, int, int, cudaStream_t);
 double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz);
+extern double g_peakByMode[4];
 }  // namespace bgpu
 
 using namespace bgpu;
@@ -79,7 +80,7 @@ static int pin_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
 }
 static void pin_free(bgpu_ctx *ctx, void *p) { if (p) ctx->pinFree.emplace(ctx->pinSize[p], p); }
 
-struct Wave { uint32_t begin[4], count[4]; uint32_t traceBegin, traceCount; };  // index by class slot 0..2
+struct Wave { uint32_t begin[4], count[4]; uint32_t traceBegin, traceCount; };  // index by width class 0..3
 
 struct bgpu_ticket_s {
   uint32_t nJobs = 0;
@@ -197,7 +198,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     const uint32_t n = t->nJobs;
     std::vector<uint32_t> idx; idx.reserve(n);
     for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) idx.push_back(i);
-    auto cls = [&](uint32_t i) { int k = t->h_geom[i].kmax; return k <= 1 ? 0 : (k == 2 ? 1 : 2); };
+    auto cls = [&](uint32_t i) { int k = t->h_geom[i].kmax; return k <= 1 ? 0 : (k == 2 ? 1 : (k <= 4 ? 2 : 3)); };
     auto cost = [&](uint32_t i) { return (uint64_t)t->h_geom[i].nDB * (uint64_t)(cls(i) == 0 ? 1 : (cls(i) == 1 ? 2 : 4)); };
     std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { uint64_t ca = cost(a), cb = cost(b); return ca != cb ? ca > cb : a < b; });
     // cut into waves by traceback bytes
@@ -214,7 +215,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
       }
       maxWaveBytes = std::max(maxWaveBytes, bytes);
       Wave w{};
-      for (int c = 0; c < 3; c++) {
+      for (int c = 0; c < 4; c++) {
         w.begin[c] = (uint32_t)order.size();
         for (size_t i = i0; i < i1; i++) if (cls(idx[i]) == c) order.push_back(idx[i]);
         w.count[c] = (uint32_t)order.size() - w.begin[c];
@@ -227,7 +228,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     }
     RC(talloc_dev(ctx, t, &t->d_order, std::max<size_t>(order.size(), 1)));
     RC(talloc_dev(ctx, t, &t->d_arrowOff, n));
-    t->nCounters = (uint32_t)t->waves.size() * 4 + 4;
+    t->nCounters = (uint32_t)t->waves.size() * 8 + 8;
     RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
     uint8_t *arrows = nullptr;
     RC(talloc_dev(ctx, t, &arrows, std::max<size_t>(maxWaveBytes, 16)));
@@ -249,18 +250,18 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     t->timing.fillCells = fc;
   }
   CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
-  static const int kclassOf[3] = {1, 2, 4};
+  static const int kclassOf[4] = {1, 2, 4, 1 << 20};
   for (size_t w = 0; w < t->waves.size(); w++) {
     const Wave &W = t->waves[w];
     CK(cudaEventRecord(t->waveEv[3 * w], s));
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < 4; c++)
       if (W.count[c]) {
-        launch_fill_guided(t->B, t->sp, kclassOf[c], t->d_order + W.begin[c], W.count[c], t->d_counters + 4 * w + c, ctx->nSM, s);
+        launch_fill_guided(t->B, t->sp, kclassOf[c], t->d_order + W.begin[c], W.count[c], t->d_counters + 8 * w + c, ctx->nSM, s);
         t->timing.kernelLaunches++;
       }
     CK(cudaEventRecord(t->waveEv[3 * w + 1], s));
     if (W.traceCount) {
-      launch_trace_guided(t->B, t->d_order + W.traceBegin, W.traceCount, t->d_counters + 4 * w + 3, ctx->nSM, s);
+      launch_trace_guided(t->B, t->d_order + W.traceBegin, W.traceCount, t->d_counters + 8 * w + 4, ctx->nSM, s);
       t->timing.kernelLaunches++;
     }
     CK(cudaEventRecord(t->waveEv[3 * w + 2], s));
@@ -483,5 +484,11 @@ extern "C" int bgpu_measure_int_peak(bgpu_ctx *ctx, double *opsPerSec, double *s
   *opsPerSec = measure_int_peak(ctx->nSM, ctx->stream, &mhz);
   if (smClockMHz) *smClockMHz = mhz;
   CK(cudaGetLastError());
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_int_peak_modes(double out[4]) {
+  if (!out) return BGPU_E_INVALID;
+  for (int i = 0; i < 4; i++) out[i] = bgpu::g_peakByMode[i];
   return BGPU_OK;
 }

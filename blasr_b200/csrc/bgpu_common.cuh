@@ -16,7 +16,7 @@ constexpr int SH = 5;                 // scores are carried as (score << SH) | t
 constexpr int BIG = 1 << 30;          // "invalid neighbour" in the shifted domain (INF_INT stand-in)
 constexpr int SCORE_LIMIT = 1 << 24;  // |score| bound that keeps (score<<SH) clear of BIG
 constexpr int DBLK = 64;              // anti-diagonals per d-block
-constexpr int KMAX_BUILD = 4;         // widest fill kernel: 64*KMAX diagonals live at once
+constexpr int KMAX_BUILD = 128;       // widest fill kernel: 64*KMAX diagonals live at once (8192)
 constexpr int ROW_W_BITS = 20;
 
 // traceback byte written by the fill kernels, one per (anti-diagonal, diagonal slot)

@@ -82,6 +82,10 @@ __device__ __forceinline__ void run_block(int (&Se)[KMAX], int (&So)[KMAX], int 
                                           int (&ADe)[KMAX], int (&ADo)[KMAX], const WarpSmem<KMAX> &sm,
                                           const int *Mtab, const FillConsts &c, const int k, const int lane,
                                           const int tlo, const int eLast, uint32_t *arrowWords) {
+  // KMAX <= 4: groups are unrolled and live in registers; the wide kernel loops over the k active
+  // groups with its state in (L1-resident) local memory.
+  constexpr int UG = KMAX <= 4 ? KMAX : 1;
+  const int gEnd = KMAX <= 4 ? KMAX : k;
   // per-lane bases: row index (e>>1) + 32k-1-j-32g, column index ((e+1)>>1) + j + 32g
   const int4 *rowBase = sm.rows + (32 * k - 1 - lane);
   const int *colBase = sm.tcol + lane;
@@ -90,27 +94,29 @@ __device__ __forceinline__ void run_block(int (&Se)[KMAX], int (&So)[KMAX], int 
   for (int e4 = 0; e4 < 16; e4++) {
     if (LAST && (e4 << 2) > eLast) break;
     uint32_t acc[KMAX];
-#pragma unroll
-    for (int g = 0; g < KMAX; g++) acc[g] = 0;
+#pragma unroll(UG)
+    for (int g = 0; g < gEnd; g++) acc[g] = 0;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int e = (e4 << 2) + u;
       if (LAST && e > eLast) break;
       const int rI = (e4 << 1) + (u >> 1);            // e>>1
       const int cI = (e4 << 1) + ((u + 1) >> 1);      // (e+1)>>1
+      int rS[KMAX], rA[KMAX];
       if ((u & 1) == 0) {
-        // even step: left from the odd slot below (ring over lanes and groups), up = own odd slot
-        int rS[KMAX], rD[KMAX];
-#pragma unroll
-        for (int g = 0; g < KMAX; g++) {
-          rS[g] = (g < k) ? rot_up(So[g], lane) : BIG;
-          if (AFFINE) rD[g] = (g < k) ? rot_up(ADo[g], lane) : BIG;
-        }
-#pragma unroll
-        for (int g = 0; g < KMAX; g++) {
+        // even step: left = odd slot of the lane below (ring over lanes and groups), up = own odd slot
+#pragma unroll(UG)
+        for (int g = 0; g < gEnd; g++)
+          if (g < k) { rS[g] = rot_up(So[g], lane); if (AFFINE) rA[g] = rot_up(ADo[g], lane); }
+#pragma unroll(UG)
+        for (int g = 0; g < gEnd; g++) {
           if (g < k) {
-            int leftS = rS[g], leftAD = AFFINE ? rD[g] : 0;
-            if (KMAX > 1 && lane == 0) { leftS = rS[(g + KMAX - 1) % KMAX]; if (AFFINE) leftAD = rD[(g + KMAX - 1) % KMAX]; }
+            int leftS = rS[g], leftAD = AFFINE ? rA[g] : 0;
+            if (KMAX > 1 && lane == 0) {
+              const int pg = g > 0 ? g - 1 : KMAX - 1;     // the slot below slot 64g is the top slot of group g-1
+              leftS = pg < k ? rS[pg] : BIG;
+              if (AFFINE) leftAD = pg < k ? rA[pg] : BIG;
+            }
             const int4 ri = rowBase[rI - 32 * g];
             const int tent = colBase[cI + 32 * g];
             const uint32_t b = dp_cell<AFFINE, QV, FIRST>(Se[g], AIe[g], ADe[g], leftS, leftAD, So[g], AIo[g], ri,
@@ -119,17 +125,18 @@ __device__ __forceinline__ void run_block(int (&Se)[KMAX], int (&So)[KMAX], int 
           }
         }
       } else {
-        int rS[KMAX], rI_[KMAX];
-#pragma unroll
-        for (int g = 0; g < KMAX; g++) {
-          rS[g] = (g < k) ? rot_dn(Se[g], lane) : BIG;
-          if (AFFINE) rI_[g] = (g < k) ? rot_dn(AIe[g], lane) : BIG;
-        }
-#pragma unroll
-        for (int g = 0; g < KMAX; g++) {
+#pragma unroll(UG)
+        for (int g = 0; g < gEnd; g++)
+          if (g < k) { rS[g] = rot_dn(Se[g], lane); if (AFFINE) rA[g] = rot_dn(AIe[g], lane); }
+#pragma unroll(UG)
+        for (int g = 0; g < gEnd; g++) {
           if (g < k) {
-            int upS = rS[g], upAI = AFFINE ? rI_[g] : 0;
-            if (KMAX > 1 && lane == 31) { upS = rS[(g + 1) % KMAX]; if (AFFINE) upAI = rI_[(g + 1) % KMAX]; }
+            int upS = rS[g], upAI = AFFINE ? rA[g] : 0;
+            if (KMAX > 1 && lane == 31) {
+              const int ng = g + 1 < KMAX ? g + 1 : 0;
+              upS = ng < k ? rS[ng] : BIG;
+              if (AFFINE) upAI = ng < k ? rA[ng] : BIG;
+            }
             const int4 ri = rowBase[rI - 32 * g];
             const int tent = colBase[cI + 32 * g];
             const uint32_t b = dp_cell<AFFINE, QV, FIRST>(So[g], AIo[g], ADo[g], Se[g], ADe[g], upS, upAI, ri, tent,
@@ -139,14 +146,14 @@ __device__ __forceinline__ void run_block(int (&Se)[KMAX], int (&So)[KMAX], int 
         }
       }
     }
-#pragma unroll
-    for (int g = 0; g < KMAX; g++)
+#pragma unroll(UG)
+    for (int g = 0; g < gEnd; g++)
       if (g < k) arrowWords[((e4 * k + g) << 5) + lane] = acc[g];
   }
 }
 
 template <int KMAX, bool AFFINE, bool QV>
-__global__ void __launch_bounds__(128) fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order,
+__global__ void __launch_bounds__(KMAX <= 4 ? 128 : 32) fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order,
                                                           uint32_t nOrder, uint32_t *counter) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ int Mtab[25];
@@ -179,8 +186,9 @@ __global__ void __launch_bounds__(128) fill_guided_kernel(BatchDev B, ScoreParam
     uint32_t *arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
     const int nD = Qn + Tn + 1;
 
+    constexpr int UG = KMAX <= 4 ? KMAX : 1;
     int Se[KMAX], So[KMAX], AIe[KMAX], AIo[KMAX], ADe[KMAX], ADo[KMAX];
-#pragma unroll
+#pragma unroll(UG)
     for (int g = 0; g < KMAX; g++) { Se[g] = So[g] = AIe[g] = AIo[g] = ADe[g] = ADo[g] = BIG; }
     int wprev = 0, kprev = 0;
 
@@ -190,15 +198,17 @@ __global__ void __launch_bounds__(128) fill_guided_kernel(BatchDev B, ScoreParam
       // ---- slide the register window to this block's diagonals
       if (b > 0 && (wbase != wprev || k != kprev)) {
         const int delta = wbase - wprev;
+        // invariant: groups >= kprev hold BIG.  Old slot s' = s + delta feeds new slot s.
+        const int gW = KMAX <= 4 ? KMAX : kprev, gR = KMAX <= 4 ? KMAX : max(k, kprev);
         auto slide = [&](int (&Xe)[KMAX], int (&Xo)[KMAX]) {
           __syncwarp();
-#pragma unroll
-          for (int g = 0; g < KMAX; g++) { sm.shift[64 * g + 2 * lane] = Xe[g]; sm.shift[64 * g + 2 * lane + 1] = Xo[g]; }
+#pragma unroll(UG)
+          for (int g = 0; g < gW; g++) { sm.shift[64 * g + 2 * lane] = Xe[g]; sm.shift[64 * g + 2 * lane + 1] = Xo[g]; }
           __syncwarp();
-#pragma unroll
-          for (int g = 0; g < KMAX; g++) {
+#pragma unroll(UG)
+          for (int g = 0; g < gR; g++) {
             const int s = 64 * g + 2 * lane + delta;
-            const bool ok = (g < k) && s >= 0 && s < 64 * KMAX;
+            const bool ok = (g < k) && s >= 0 && s < 64 * (KMAX <= 4 ? KMAX : kprev);
             Xe[g] = ok ? sm.shift[s] : BIG;
             Xo[g] = ok ? sm.shift[s + 1] : BIG;
           }
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(128) fill_guided_kernel(BatchDev B, ScoreParam
     {
       const int s = Tn - Qn + C0 - wprev;
       int v = BIG;
-#pragma unroll
+#pragma unroll(UG)
       for (int g = 0; g < KMAX; g++) if ((s >> 6) == g) v = (s & 1) ? So[g] : Se[g];
       v = __shfl_sync(0xffffffffu, v, (s & 63) >> 1);
       if (lane == 0) G.score = v >> SH;
@@ -251,19 +261,20 @@ __global__ void __launch_bounds__(128) fill_guided_kernel(BatchDev B, ScoreParam
 template <int KMAX, bool AFFINE, bool QV>
 static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, uint32_t nOrder,
                        uint32_t *counter, int nSM, cudaStream_t s) {
-  const size_t smem = sizeof(WarpSmem<KMAX>) * 4;
+  constexpr int WPC = KMAX <= 4 ? 4 : 1;           // warps per CTA
+  const size_t smem = sizeof(WarpSmem<KMAX>) * WPC;
   auto kern = fill_guided_kernel<KMAX, AFFINE, QV>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int perSM = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 128, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, WPC * 32, smem);
   if (perSM < 1) perSM = 1;
   unsigned grid = (unsigned)(nSM * perSM);
-  const unsigned need = (nOrder + 3) / 4;
+  const unsigned need = (nOrder + WPC - 1) / WPC;
   if (grid > need) grid = need;
-  if (grid) kern<<<grid, 128, smem, s>>>(B, P, order, nOrder, counter);
+  if (grid) kern<<<grid, WPC * 32, smem, s>>>(B, P, order, nOrder, counter);
 }
 
-// kclass: 1 -> KMAX=1, 2 -> KMAX=2, 4 -> KMAX=4
+// kclass: 1 -> KMAX=1, 2 -> KMAX=2, 4 -> KMAX=4, anything larger -> the wide kernel (KMAX_BUILD groups)
 void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int kclass, const uint32_t *order, uint32_t nOrder,
                         uint32_t *counter, int nSM, cudaStream_t s) {
   const bool aff = P.affine != 0, qv = P.kind == BGPU_FN_QUALITY;
@@ -276,7 +287,8 @@ void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int kclass, con
   } while (0)
   if (kclass == 1) BGPU_DISPATCH(1);
   else if (kclass == 2) BGPU_DISPATCH(2);
-  else BGPU_DISPATCH(4);
+  else if (kclass == 4) BGPU_DISPATCH(4);
+  else BGPU_DISPATCH(KMAX_BUILD);
 #undef BGPU_DISPATCH
 }
 

@@ -5,18 +5,25 @@
 
 namespace bgpu {
 
-template <int MODE>   // 0: add.s32 only, 1: min.s32 only, 2: alternating add / min on separate chains
-__global__ void __launch_bounds__(256) int_peak_kernel(int *out, int iters, int a, int b) {
+// Every chain reads its neighbour chain, so ptxas cannot fold the sequence into fewer instructions.
+//   MODE 0: x[i] += x[i+1]            (IADD3, alu pipe)
+//   MODE 1: x[i] = min(x[i], x[i+1])  (VIMNMX, alu pipe)
+//   MODE 2: x[i] = x[i+1] * m + x[i]  (IMAD, fma pipe)
+//   MODE 3: even chains IADD3, odd chains IMAD (both pipes busy)
+template <int MODE>
+__global__ void __launch_bounds__(256) int_peak_kernel(int *out, int iters, int a, int m) {
   int x[16];
 #pragma unroll
-  for (int i = 0; i < 16; i++) x[i] = threadIdx.x + i * a;
+  for (int i = 0; i < 16; i++) x[i] = threadIdx.x * a + i + out[i & 1];
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int r = 0; r < 4; r++) {
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        if (MODE == 0 || (MODE == 2 && (i & 1) == 0)) asm volatile("add.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
-        else asm volatile("min.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(b - i - r));
+        const int y = x[(i + 1) & 15];
+        if (MODE == 0 || (MODE == 3 && (i & 1) == 0)) asm volatile("add.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(y));
+        else if (MODE == 1) asm volatile("min.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(y));
+        else asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(y), "r"(m));
       }
     }
   }
@@ -26,6 +33,8 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int *out, int iters, int 
   if (s == 0x7fffffff) out[0] = s;
 }
 
+double g_peakByMode[4] = {0, 0, 0, 0};
+
 double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz) {
   int *d = nullptr;
   if (cudaMalloc(&d, 64) != cudaSuccess) return 0;
@@ -33,17 +42,19 @@ double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   double best = 0;
-  for (int mode = 0; mode < 3; mode++) {
+  cudaMemsetAsync(d, 0, 64, s);
+  for (int mode = 0; mode < 4; mode++) {
     for (int rep = 0; rep < 4; rep++) {
       cudaEventRecord(e0, s);
-      if (mode == 0) int_peak_kernel<0><<<grid, block, 0, s>>>(d, iters, 3, 1 << 30);
-      else if (mode == 1) int_peak_kernel<1><<<grid, block, 0, s>>>(d, iters, 3, 1 << 30);
-      else int_peak_kernel<2><<<grid, block, 0, s>>>(d, iters, 3, 1 << 30);
+      if (mode == 0) int_peak_kernel<0><<<grid, block, 0, s>>>(d, iters, 3, 5);
+      else if (mode == 1) int_peak_kernel<1><<<grid, block, 0, s>>>(d, iters, 3, 5);
+      else if (mode == 2) int_peak_kernel<2><<<grid, block, 0, s>>>(d, iters, 3, 5);
+      else int_peak_kernel<3><<<grid, block, 0, s>>>(d, iters, 3, 5);
       cudaEventRecord(e1, s);
       cudaEventSynchronize(e1);
       float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
       const double ops = (double)grid * block * (double)iters * 64.0;
-      if (rep > 0 && ms > 0) best = best > ops / (ms * 1e-3) ? best : ops / (ms * 1e-3);
+      if (rep > 0 && ms > 0) { const double r = ops / (ms * 1e-3); g_peakByMode[mode] = g_peakByMode[mode] > r ? g_peakByMode[mode] : r; best = best > r ? best : r; }
     }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -9,6 +9,7 @@ edit script instead of running SDPAlign, so the generator has no dependency on t
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -18,25 +19,37 @@ from .align import JobBatch
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
+def _chunk_worker(args):
+    seed, ci, lens, err, split, with_qual, anchor, min_block, n_rate = args
+    return _simulate_chunk(np.random.default_rng([seed, ci]), lens, err, split, with_qual, anchor, min_block, n_rate)
+
+
 def simulate_pairs(n_jobs: int, len_lo: int, len_hi: int, err: float = 0.15, split=(0.55, 0.35, 0.10), seed: int = 1,
                    bands: Optional[Sequence[int]] = None, with_qual: bool = False, anchor: int = 12,
-                   min_block: int = 1, n_rate: float = 0.0, chunk_bases: int = 32_000_000) -> JobBatch:
+                   min_block: int = 1, n_rate: float = 0.0, chunk_jobs: int = 512, workers: int = 0) -> JobBatch:
     """n_jobs (query, window, guide) triples; window lengths ~ U[len_lo, len_hi].
 
     min_block > 1 drops shorter interior guide blocks (anchor-only guides with real gaps between blocks).
+    Chunks of chunk_jobs jobs are seeded by (seed, chunk index), so the result does not depend on `workers`
+    (0 = all host cores for large requests, in-process for small ones).
     """
     rng = np.random.default_rng(seed)
     lens = rng.integers(len_lo, len_hi + 1, size=n_jobs, dtype=np.int64)
     lens = np.maximum(lens, 2 * anchor + 2)
-    parts = []
-    i0 = 0
-    while i0 < n_jobs:
-        i1 = i0
-        tot = 0
-        while i1 < n_jobs and (i1 == i0 or tot + lens[i1] <= chunk_bases):
-            tot += int(lens[i1]); i1 += 1
-        parts.append(_simulate_chunk(rng, lens[i0:i1], err, split, with_qual, anchor, min_block, n_rate))
-        i0 = i1
+    tasks = [(seed, ci, lens[i0:i0 + chunk_jobs], err, split, with_qual, anchor, min_block, n_rate)
+             for ci, i0 in enumerate(range(0, n_jobs, chunk_jobs))]
+    if workers == 0:
+        workers = min(len(tasks), os.cpu_count() or 1) if int(lens.sum()) > 20_000_000 else 1
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_chunk_worker, tasks, chunksize=1)
+    else:
+        parts = [_chunk_worker(t) for t in tasks]
+    if not parts:
+        z = np.zeros(1, np.uint64)
+        return JobBatch(np.zeros(0, np.uint8), z, np.zeros(0, np.uint8), z.copy(), np.zeros((0, 3), np.uint32), z.copy(),
+                        np.zeros(0, np.uint8) if with_qual else None, None)
     q = np.concatenate([p[0] for p in parts]); t = np.concatenate([p[2] for p in parts])
     g = np.concatenate([p[4] for p in parts], axis=0)
 

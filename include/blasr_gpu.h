@@ -159,6 +159,10 @@ int  bgpu_device_count(void);
 /* Measures the int32 ALU peak of the bound device with a dependent IADD3/VIMNMX chain kernel:
  * returns lane-ops per second (the integer roofline denominator). */
 int  bgpu_measure_int_peak(bgpu_ctx *ctx, double *opsPerSec, double *smClockMHz);
+/* Per-instruction-mix rates of the last bgpu_measure_int_peak call, lane-ops/s:
+ * [0] add (ptxas splits it over IADD3/alu and IMAD.IADD/fma), [1] min (VIMNMX, alu only),
+ * [2] mad (IMAD, fma only), [3] add+mad interleaved. */
+int  bgpu_int_peak_modes(double out[4]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,110 @@
+"""GPU parity: GuidedAlign / AffineGuidedAlign through the C ABI vs the oracle, bit-exact on every field
+(score, qPos, tPos, nCells, blocks, gap lists, stats)."""
+import numpy as np
+import pytest
+
+from blasr_b200 import DistanceMatrixScoreFunction, QualityValueScoreFunction, SMRTDistanceMatrix
+from blasr_b200 import capi
+from . import cases, oracle as O
+
+pytestmark = pytest.mark.gpu
+WHICH = "ref" if O.have_ref() else "orc"
+
+
+def _run(aligner, b, algo, fn, band, at=1):
+    if algo:
+        res = aligner.AffineGuidedAlign(b, fn, band, alignType=at)
+    else:
+        res = aligner.GuidedAlign(b, fn, band, alignType=at)
+    ofn = O.score_fn(fn.scoreMatrix, fn.ins, fn.del_, fn.affineOpen, fn.affineExtend, fn.kind)
+    bd = b.band if b.band is not None else band
+    want = cases.oracle_batch(WHICH, b, ofn, algo, at, bd, statsAffine=algo)
+    nbad = 0
+    for i in range(b.n):
+        got = cases.gpu_to_dict(res, i)
+        if got["status"] == capi.JOB_TOO_WIDE:
+            continue
+        bad = cases.compare(got, want[i], cases.GPU_FIELDS)
+        assert not bad, f"job {i}: {bad}"
+    return res, want
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("band", [4, 10, 16, 32, 64])
+def test_natural_guides(aligner, algo, band):
+    b = cases.guided_batch(seed=200 + band, n=40, lo=100, hi=4000, n_rate=0.01, lower=True)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    res, want = _run(aligner, b, algo, fn, band)
+    assert (res.results["status"] == 0).all()
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("at", [0, 1])
+def test_adversarial_and_params(aligner, algo, at):
+    rng = np.random.default_rng(7 + algo + 2 * at)
+    ok = 0
+    for rep in range(10):
+        b = cases.guided_batch(seed=300 + rep, n=12, lo=60, hi=2500, err=float(rng.choice([0.02, 0.15, 0.3])),
+                               adversarial=float(rng.choice([0.0, 0.2, 0.6])), run=int(rng.choice([1, 5, 40])), n_rate=0.01)
+        M = SMRTDistanceMatrix.copy()
+        if rep % 3 == 0:
+            M = rng.integers(-6, 8, size=(5, 5)).astype(np.int32)
+        fn = DistanceMatrixScoreFunction(M, int(rng.integers(1, 9)), int(rng.integers(1, 9)), int(rng.choice([0, 3, 7, 11, 50])),
+                                         int(rng.choice([0, 1, 2])))
+        res, _ = _run(aligner, b, algo, fn, int(rng.choice([4, 10, 16, 32])), at)
+        ok += int((res.results["status"] == 0).sum())
+    assert ok >= 115   # wide post-gap rows go through the looped-group kernel, nothing may be skipped
+
+
+def test_per_job_bands_and_lengths(aligner):
+    b = cases.guided_batch(seed=41, n=64, lo=50, hi=6000)
+    b.band = np.random.default_rng(1).choice([8, 16, 32, 64], size=b.n).astype(np.int32)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    _run(aligner, b, 1, fn, 16)
+    _run(aligner, b, 0, fn, 16)
+
+
+def test_quality_value_score_function(aligner):
+    b = cases.guided_batch(seed=52, n=24, lo=100, hi=2000, with_qual=True, n_rate=0.01)
+    fn = QualityValueScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    _run(aligner, b, 0, fn, 16)
+    _run(aligner, b, 1, fn, 16)
+
+
+def test_edge_cases(aligner):
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    from blasr_b200 import JobBatch
+    # empty guide -> EMPTY_GUIDE, score 0, empty alignment (GuidedAlign.h:388-392); tiny single-block jobs
+    qs = [b"ACGTACGT", b"A", b"ACGTTTGA", b"ACGT"]
+    ts = [b"ACGTACGT", b"A", b"ACGAATGA", b"ACXT"]
+    gs = [np.zeros((0, 3), np.uint32), np.array([[0, 0, 1]], np.uint32), np.array([[0, 0, 3], [5, 5, 3]], np.uint32),
+          np.array([[0, 0, 4]], np.uint32)]
+    b = JobBatch.from_lists(qs, ts, gs)
+    res = aligner.AffineGuidedAlign(b, fn, 16)
+    assert res.results["status"][0] == capi.JOB_EMPTY_GUIDE and res.results["score"][0] == 0 and res.results["nBlocks"][0] == 0
+    assert res.results["status"][3] == capi.JOB_BAD_INPUT          # 'X' is outside ThreeBit 0..4
+    ofn = O.score_fn(fn.scoreMatrix, 5, 5, 50, 0)
+    for i in (1, 2):
+        j, keep = O.make_job(1, 1, 16, b.q[int(b.qOff[i]):int(b.qOff[i + 1])], b.t[int(b.tOff[i]):int(b.tOff[i + 1])], gs[i], None, 0, 0, 1, 1)
+        want = O.align(WHICH, ofn, j)
+        assert not cases.compare(cases.gpu_to_dict(res, i), want, cases.GPU_FIELDS)
+    # empty batch
+    e = JobBatch.from_lists([], [], [])
+    assert len(aligner.AffineGuidedAlign(e, fn, 16)) == 0
+
+
+def test_long_reads_properties(aligner):
+    """BASELINE-size jobs (10-30 kb): exact vs oracle on a few, plus size-independent properties on all:
+    blocks tile the path monotonically, rescoring the returned alignment reproduces the DP score for linear gaps."""
+    b = cases.guided_batch(seed=61, n=12, lo=10000, hi=30000)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    res, want = _run(aligner, b, 1, fn, 16)
+    res0, want0 = _run(aligner, b, 0, fn, 16)
+    for i in range(b.n):
+        al = res0.alignment(i)
+        blk = al.blocks.astype(np.int64)
+        assert (np.diff(blk[:, 0]) >= blk[:-1, 2]).all() and (np.diff(blk[:, 1]) >= blk[:-1, 2]).all()
+        # GuidedAlign (linear gaps): stats score over the whole returned alignment == DP score when the path has no
+        # leading/trailing gaps (first guide block at (0,0), last at the ends)
+        if al.qPos == 0 and al.tPos == 0 and blk[-1, 0] + blk[-1, 2] == b.qOff[i + 1] - b.qOff[i]:
+            assert al.statsScore == al.score
