@@ -174,9 +174,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- e2e: submit (H2D + kernels) + collect (D2H) through the C ABI, host buffers in, host results out
+    e2e_host = {}
+
     def e2e_step():
+        h0 = time.perf_counter()
         tk = al.submit(batch, fn, algo, band=16, doStats=True)
+        h1 = time.perf_counter()
         res = al.collect(tk)
+        h2 = time.perf_counter()
+        e2e_host.update(py_submit_ms=(h1 - h0) * 1e3, py_collect_ms=(h2 - h1) * 1e3, c_submit_ms=res.timing.msHostSubmit,
+                        c_collect_ms=res.timing.msHostCollect)
         return tk, res
     e2e_warm = max(1, min(args.warmup, 2))
     for _ in range(e2e_warm):
@@ -239,7 +246,7 @@ def run_ours(args):
         "dtype": "int32", "data": "synthetic", "config": config_dict(args, args.jobs),
         "aligned_pairs_per_s": jobs_all * args.steps / (dev_ms_max * 1e-3),
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "pairs_per_s": jobs_all / e2e_sec_max, "ms_per_step": e2e_sec_max * 1e3},
+                "pairs_per_s": jobs_all / e2e_sec_max, "ms_per_step": e2e_sec_max * 1e3, "host_breakdown_ms": e2e_host},
         "gpu_launches": launches,
         "stage_ms": {"prep": float(np.mean(ms_prep)), "fill": float(np.mean(ms_fill)), "trace": float(np.mean(ms_trace)),
                      "emit": float(np.mean(ms_emit)), "wall_per_step": wall / args.steps * 1e3},

@@ -196,7 +196,9 @@ class Aligner:
             self._err(rc, "bgpu_submit")
         return tk, n
 
-    def collect(self, ticket) -> BatchResult:
+    def collect(self, ticket, copy: bool = False) -> BatchResult:
+        """Blocks until the ticket is done.  With copy=False the block / gap arrays are zero-copy views of the
+        library's pinned result arena and stay valid until release(ticket)."""
         tk, n = ticket
         res = np.zeros(n, dtype=capi.RESULT_DTYPE)
         arena = capi.Arena()
@@ -207,8 +209,9 @@ class Aligner:
         def view(ptr, count, dt):
             if not count:
                 return np.zeros(0, dtype=dt)
-            buf = (C.c_char * (int(count) * dt.itemsize)).from_address(ptr)
-            return np.frombuffer(buf, dtype=dt).copy()
+            buf = (C.c_ubyte * (int(count) * dt.itemsize)).from_address(ptr)
+            a = np.frombuffer(buf, dtype=dt)
+            return a.copy() if copy else a
         return BatchResult(res, view(arena.blocks, arena.nBlocks, capi.BLOCK_DTYPE),
                            view(arena.gapCounts, arena.nGapLists, np.dtype("<u4")),
                            view(arena.gaps, arena.nGaps, capi.GAP_DTYPE), self.timing(ticket))
@@ -240,7 +243,7 @@ class Aligner:
     def _run(self, batch, fn, algo, **kw) -> BatchResult:
         tk = self.submit(batch, fn, algo, **kw)
         try:
-            return self.collect(tk)
+            return self.collect(tk, copy=True)
         finally:
             self.release(tk)
 

@@ -6,6 +6,7 @@
 //   count scan -> emit (blocks, gaps, stats) -> D2H.
 // No CPU implementation of any aligner exists here: without a CUDA device every entry point fails.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -347,6 +348,7 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
   if (!fn || !p || !b || !out) { ctx->err = "null argument"; return BGPU_E_INVALID; }
   if (p->algo < BGPU_GUIDED || p->algo > BGPU_SW) { ctx->err = "unknown algo"; return BGPU_E_INVALID; }
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return BGPU_E_CUDA; }
+  const auto h0 = std::chrono::steady_clock::now();
   bgpu_ticket t = new bgpu_ticket_s();
   t->nJobs = b->nJobs; t->params = *p;
   for (auto &e : t->ev) cudaEventCreate(&e);
@@ -362,6 +364,7 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
     delete t;
     return rc;
   }
+  t->timing.msHostSubmit = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
   *out = t;
   return BGPU_OK;
 }
@@ -409,6 +412,7 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
   cudaStream_t s = ctx->stream;
+  const auto h0 = std::chrono::steady_clock::now();
   if (!t->collected) {
     RC(ensure_arena(ctx, t));
     RC(enqueue_emit(ctx, t));
@@ -423,6 +427,7 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
     t->collected = true;
   }
   if (results && t->nJobs) memcpy(results, t->h_results, sizeof(bgpu_result) * t->nJobs);
+  t->timing.msHostCollect = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
   if (arena) {
     arena->blocks = t->h_blocks; arena->nBlocks = t->totals[0];
     arena->gapCounts = t->h_gapCounts; arena->nGapLists = t->totals[1];

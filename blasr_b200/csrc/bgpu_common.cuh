@@ -25,7 +25,7 @@ constexpr int ROW_W_BITS = 20;
 //   bit 4   : affine-del matrix arrow is AffineDelOpen (else AffineDelLeft)
 enum { TB_DIAG = 0, TB_LEFT = 1, TB_UP = 2, TB_ICLOSE = 3, TB_DCLOSE = 4, TB_NONE = 7, TB_IOPEN = 8, TB_DOPEN = 16 };
 
-struct RowInfo {          // 8 B per guide row in HBM
+struct alignas(8) RowInfo {  // 8 B per guide row in HBM
   int32_t lo;             // first in-band column t' of the row (INT_MAX/2 for "no cells")
   uint32_t packed;        // bits 0-19: hi'-lo', bits 20-22: query base code, bits 23-30: QV
 };

@@ -33,9 +33,10 @@ struct FillConsts {
 template <bool AFFINE, bool QV, bool FIRST>
 __device__ __forceinline__ uint32_t dp_cell(int &S, int &AI, int &AD, const int leftS, const int leftAD,
                                             const int upS, const int upAI, const int4 ri, const int tent,
-                                            const int tprime, const int *Mtab, const FillConsts &c) {
+                                            const int tprime, const uint32_t mtabAddr, const FillConsts &c) {
   const bool inb = (unsigned)(tprime - ri.x) <= (unsigned)ri.y;
-  int m = *reinterpret_cast<const int *>(reinterpret_cast<const char *>(Mtab) + ri.z + tent);
+  int m;
+  asm("ld.shared.s32 %0, [%1];" : "=r"(m) : "r"(mtabAddr + (uint32_t)(ri.z + tent)));
   if (QV) m *= (FIRST ? (ri.w & 0xff) : ri.w);           // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
   int cnd = S + m;                                         // Diagonal (tag 0)
   cnd = __viaddmin_s32(leftS, c.delT, cnd);                // Left
@@ -44,27 +45,25 @@ __device__ __forceinline__ uint32_t dp_cell(int &S, int &AI, int &AD, const int 
     cnd = __viaddmin_s32(upAI, c.extT3, cnd);              // AffineInsClose
     cnd = __viaddmin_s32(leftAD, c.extT4, cnd);            // AffineDelClose
   }
-  int s = cnd & ~31;
-  uint32_t byte = (uint32_t)cnd & 7u;
   int ai = 0, ad = 0;
   if (AFFINE) {
     // strict '<' in the reference: a tie extends (AffineGuidedAlign.h:357-373) -> the open
     // candidate carries a flag bit, so it loses ties.
-    ai = __viaddmin_s32(s, c.openI, upAI + c.ext);
-    ad = __viaddmin_s32(s, c.openD, leftAD + c.ext);
-    byte |= (uint32_t)(ai | ad) & 24u;
-    ai &= ~31; ad &= ~31;
+    const int s0 = cnd & ~31;
+    ai = __viaddmin_s32(s0, c.openI, upAI + c.ext);
+    ad = __viaddmin_s32(s0, c.openD, leftAD + c.ext);
+    cnd |= (ai | ad) & 24;                                  // tag | affine flags, still below bit 5
   }
   if (FIRST) {
     if (ri.w < 0) {                                        // boundary row (GuidedAlign.h:415-442)
-      s = tprime * c.del0; ai = c.open; ad = c.open;
-      byte = TB_LEFT | TB_IOPEN | TB_DOPEN;
+      cnd = (tprime * c.del0) | (TB_LEFT | TB_IOPEN | TB_DOPEN); ai = c.open; ad = c.open;
     }
   }
-  if (!inb) { s = BIG; ai = BIG; ad = BIG; byte = TB_NONE; }
-  S = s;
-  if (AFFINE) { AI = ai; AD = ad; }
-  return byte;
+  // cells outside the guide: BIG everywhere, arrow NoArrow
+  cnd = inb ? cnd : (BIG | TB_NONE);
+  S = cnd & ~31;
+  if (AFFINE) { AI = inb ? (ai & ~31) : BIG; AD = inb ? (ad & ~31) : BIG; }
+  return (uint32_t)cnd & 31u;
 }
 
 __device__ __forceinline__ int rot_up(int v, int lane) { return __shfl_sync(0xffffffffu, v, (lane + 31) & 31); }
@@ -77,79 +76,83 @@ struct WarpSmem {
   int shift[64 * KMAX];
 };
 
-template <int KMAX, bool AFFINE, bool QV, bool FIRST, bool LAST>
+// KACT > 0: exactly KACT groups are active (compile time, registers, no per-group branches);
+// KACT == 0: the active count k is a run-time value (first/last blocks and the wide kernel).
+template <int KMAX, int KACT, bool AFFINE, bool QV, bool FIRST, bool LAST>
 __device__ __forceinline__ void run_block(int (&Se)[KMAX], int (&So)[KMAX], int (&AIe)[KMAX], int (&AIo)[KMAX],
                                           int (&ADe)[KMAX], int (&ADo)[KMAX], const WarpSmem<KMAX> &sm,
-                                          const int *Mtab, const FillConsts &c, const int k, const int lane,
+                                          const uint32_t mtabAddr, const FillConsts &c, const int k, const int lane,
                                           const int tlo, const int eLast, uint32_t *arrowWords) {
-  // KMAX <= 4: groups are unrolled and live in registers; the wide kernel loops over the k active
-  // groups with its state in (L1-resident) local memory.
   constexpr int UG = KMAX <= 4 ? KMAX : 1;
-  const int gEnd = KMAX <= 4 ? KMAX : k;
+  const int gEnd = KACT > 0 ? KACT : (KMAX <= 4 ? KMAX : k);
+  const int kk = KACT > 0 ? KACT : k;
+#define BGPU_ACTIVE(g) (KACT > 0 || (g) < k)
   // per-lane bases: row index (e>>1) + 32k-1-j-32g, column index ((e+1)>>1) + j + 32g
-  const int4 *rowBase = sm.rows + (32 * k - 1 - lane);
-  const int *colBase = sm.tcol + lane;
-  const int tl = tlo + lane;
+  const int4 *rp = sm.rows + (32 * kk - 1 - lane);
+  const int *cp = sm.tcol + lane;
+  int tcur = tlo + lane;
+  uint32_t *aw = arrowWords + lane;
 #pragma unroll 1
-  for (int e4 = 0; e4 < 16; e4++) {
+  for (int e4 = 0; e4 < 16; e4++, rp += 2, cp += 2, tcur += 2, aw += 32 * kk) {
     if (LAST && (e4 << 2) > eLast) break;
     uint32_t acc[KMAX];
 #pragma unroll(UG)
     for (int g = 0; g < gEnd; g++) acc[g] = 0;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int e = (e4 << 2) + u;
-      if (LAST && e > eLast) break;
-      const int rI = (e4 << 1) + (u >> 1);            // e>>1
-      const int cI = (e4 << 1) + ((u + 1) >> 1);      // (e+1)>>1
+      if (LAST && (e4 << 2) + u > eLast) break;
+      constexpr int dummy = 0; (void)dummy;
+      const int rI = u >> 1;            // (e>>1) - 2*e4
+      const int cI = (u + 1) >> 1;      // ((e+1)>>1) - 2*e4
       int rS[KMAX], rA[KMAX];
       if ((u & 1) == 0) {
         // even step: left = odd slot of the lane below (ring over lanes and groups), up = own odd slot
 #pragma unroll(UG)
         for (int g = 0; g < gEnd; g++)
-          if (g < k) { rS[g] = rot_up(So[g], lane); if (AFFINE) rA[g] = rot_up(ADo[g], lane); }
+          if (BGPU_ACTIVE(g)) { rS[g] = rot_up(So[g], lane); if (AFFINE) rA[g] = rot_up(ADo[g], lane); }
 #pragma unroll(UG)
         for (int g = 0; g < gEnd; g++) {
-          if (g < k) {
+          if (BGPU_ACTIVE(g)) {
             int leftS = rS[g], leftAD = AFFINE ? rA[g] : 0;
             if (KMAX > 1 && lane == 0) {
               const int pg = g > 0 ? g - 1 : KMAX - 1;     // the slot below slot 64g is the top slot of group g-1
-              leftS = pg < k ? rS[pg] : BIG;
-              if (AFFINE) leftAD = pg < k ? rA[pg] : BIG;
+              leftS = pg < kk ? rS[pg] : BIG;
+              if (AFFINE) leftAD = pg < kk ? rA[pg] : BIG;
             }
-            const int4 ri = rowBase[rI - 32 * g];
-            const int tent = colBase[cI + 32 * g];
+            const int4 ri = rp[rI - 32 * g];
+            const int tent = cp[cI + 32 * g];
             const uint32_t b = dp_cell<AFFINE, QV, FIRST>(Se[g], AIe[g], ADe[g], leftS, leftAD, So[g], AIo[g], ri,
-                                                          tent, tl + cI + 32 * g, Mtab, c);
-            acc[g] |= b << (8 * u);
+                                                          tent, tcur + cI + 32 * g, mtabAddr, c);
+            acc[g] += b << (8 * u);
           }
         }
       } else {
 #pragma unroll(UG)
         for (int g = 0; g < gEnd; g++)
-          if (g < k) { rS[g] = rot_dn(Se[g], lane); if (AFFINE) rA[g] = rot_dn(AIe[g], lane); }
+          if (BGPU_ACTIVE(g)) { rS[g] = rot_dn(Se[g], lane); if (AFFINE) rA[g] = rot_dn(AIe[g], lane); }
 #pragma unroll(UG)
         for (int g = 0; g < gEnd; g++) {
-          if (g < k) {
+          if (BGPU_ACTIVE(g)) {
             int upS = rS[g], upAI = AFFINE ? rA[g] : 0;
             if (KMAX > 1 && lane == 31) {
               const int ng = g + 1 < KMAX ? g + 1 : 0;
-              upS = ng < k ? rS[ng] : BIG;
-              if (AFFINE) upAI = ng < k ? rA[ng] : BIG;
+              upS = ng < kk ? rS[ng] : BIG;
+              if (AFFINE) upAI = ng < kk ? rA[ng] : BIG;
             }
-            const int4 ri = rowBase[rI - 32 * g];
-            const int tent = colBase[cI + 32 * g];
+            const int4 ri = rp[rI - 32 * g];
+            const int tent = cp[cI + 32 * g];
             const uint32_t b = dp_cell<AFFINE, QV, FIRST>(So[g], AIo[g], ADo[g], Se[g], ADe[g], upS, upAI, ri, tent,
-                                                          tl + cI + 32 * g, Mtab, c);
-            acc[g] |= b << (8 * u);
+                                                          tcur + cI + 32 * g, mtabAddr, c);
+            acc[g] += b << (8 * u);
           }
         }
       }
     }
 #pragma unroll(UG)
     for (int g = 0; g < gEnd; g++)
-      if (g < k) arrowWords[((e4 * k + g) << 5) + lane] = acc[g];
+      if (BGPU_ACTIVE(g)) aw[g << 5] = acc[g];
   }
+#undef BGPU_ACTIVE
 }
 
 template <int KMAX, bool AFFINE, bool QV>
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(KMAX <= 4 ? 128 : 32) fill_guided_kernel(Batch
     else Mtab[threadIdx.x] = P.M[threadIdx.x] << SH;
   }
   __syncthreads();
+  const uint32_t mtabAddr = (uint32_t)__cvta_generic_to_shared(Mtab);
   FillConsts c;
   c.delT = (P.del << SH) | TB_LEFT; c.insT = (P.ins << SH) | TB_UP;
   c.extT3 = (P.ext << SH) | TB_ICLOSE; c.extT4 = (P.ext << SH) | TB_DCLOSE;
@@ -241,10 +245,14 @@ __global__ void __launch_bounds__(KMAX <= 4 ? 128 : 32) fill_guided_kernel(Batch
       const bool first = (b << 6) <= hi0;               // row 0 holds cells on d <= hi0
       const bool last = (b == nDB - 1);
       const int eLast = (nD - 1) & 63;
-      if (first && last) run_block<KMAX, AFFINE, QV, true, true>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
-      else if (first) run_block<KMAX, AFFINE, QV, true, false>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
-      else if (last) run_block<KMAX, AFFINE, QV, false, true>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
-      else run_block<KMAX, AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, Mtab, c, k, lane, tlo, eLast, aw);
+      if (first && last) run_block<KMAX, 0, AFFINE, QV, true, true>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
+      else if (first) run_block<KMAX, 0, AFFINE, QV, true, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
+      else if (last) run_block<KMAX, 0, AFFINE, QV, false, true>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
+      else if (KMAX > 4) run_block<KMAX, 0, AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
+      else if (k == 1) run_block<KMAX, 1, AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
+      else if (KMAX >= 2 && k == 2) run_block<KMAX, (KMAX >= 2 ? 2 : 1), AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
+      else if (KMAX >= 4 && k == 3) run_block<KMAX, (KMAX >= 4 ? 3 : 1), AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
+      else run_block<KMAX, (KMAX >= 4 ? 4 : 1), AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
     }
     // ---- the end cell (Qn, Tn) sits on diagonal Tn-Qn+C0 and is the last cell written to its slot
     {

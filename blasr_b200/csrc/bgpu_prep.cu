@@ -31,6 +31,9 @@ constexpr int MAX_BAND_SIZE = 250;  // GuidedAlign.h:29
 __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParams P, int defaultBand,
                                                           const uint64_t *rowOffIn, const uint64_t *dblkOffIn,
                                                           const uint64_t *runOffIn) {
+  __shared__ uint8_t lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = base_code((uint8_t)i);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (job >= B.nJobs) return;
@@ -82,14 +85,14 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   // ---- encode + validate the target window in place (codes 0..4), and check the query bases
   uint8_t *tb = B.t + to;
   const uint8_t *qb = B.q + qo;
-  for (int i = tStart + lane; i < tEnd; i += 32) { uint8_t c = base_code(tb[i]); if (c > 4) bad = 1; tb[i] = c; }
-  for (int i = qStart + lane; i < qEnd; i += 32) { if (base_code(qb[i]) > 4) bad = 1; }
+  for (int i = tStart + lane; i < tEnd; i += 32) { uint8_t c = lut[tb[i]]; if (c > 4) bad = 1; tb[i] = c; }
   if (warp_or(bad)) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
 
-  // ---- live-diagonal range per d-block
+  // ---- live-diagonal range per d-block.  The warp owns these arrays: contributions are reduced across the
+  //      lanes with REDUX and lane 0 does a plain read-modify-write, no atomics.
   int32_t *dmin = B.dmin + dblkOffIn[job], *dmax = B.dmax + dblkOffIn[job];
   for (int b = lane; b < nDB; b += 32) { dmin[b] = INT_MAX; dmax[b] = INT_MIN; }
-  __threadfence(); __syncwarp();
+  __syncwarp();
 
   RowInfo *rows = B.rows + rowOffIn[job];
   const uint8_t *qual = B.qual ? B.qual + qo : nullptr;
@@ -98,12 +101,19 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   long long cells = 0;
   int wide = 0;
 
-  auto add_row_range = [&](int i, int lo, int hi) {              // row i covers t' in [lo,hi]
-    const int bLo = (i + lo) >> 6, bHi = (i + hi) >> 6;
-    for (int b = bLo; b <= bHi; b++) {
-      int tl = max(lo, (b << 6) - i), th = min(hi, (b << 6) + 63 - i);
-      atomicMin(&dmin[b], tl - i + C0);
-      atomicMax(&dmax[b], th - i + C0);
+  // every lane passes its row (or an empty range lo > hi); row i covers t' in [lo,hi]
+  auto add_rows = [&](int i, int lo, int hi) {
+    const bool has = lo <= hi;
+    const int bLo = has ? (i + lo) >> 6 : INT_MAX, bHi = has ? (i + hi) >> 6 : INT_MIN;
+    const int w0 = __reduce_min_sync(0xffffffffu, bLo), w1 = __reduce_max_sync(0xffffffffu, bHi);
+    for (int b = w0; b <= w1; b++) {
+      int mn = INT_MAX, mx = INT_MIN;
+      if (has && b >= bLo && b <= bHi) {
+        const int tl = max(lo, (b << 6) - i), th = min(hi, (b << 6) + 63 - i);
+        mn = tl - i + C0; mx = th - i + C0;
+      }
+      mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+      if (lane == 0) { dmin[b] = min(dmin[b], mn); dmax[b] = max(dmax[b], mx); }
     }
   };
 
@@ -111,21 +121,25 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   const int hi0 = min(tPost0, Tn);
   if (lane == 0) {
     rows[0].lo = 0; rows[0].packed = (uint32_t)hi0;   // width field only; code/QV unused
-    add_row_range(0, 0, hi0);
     cells += (long long)tPost0 + 1;                    // tPre=0
     if (hi0 >= (1 << ROW_W_BITS)) wide = 1;
   }
+  add_rows(0, lane == 0 ? 0 : 1, lane == 0 ? hi0 : 0);
 
   int carryL = tStart - 1;                              // L_0
+  int bcur = 0;                                         // guide block of the chunk's first row
   for (int base = 1; base <= Qn; base += 32) {
     const int i = base + lane;
     const bool act = i <= Qn;
-    int t = 0, cap = 0, tPost = 0, x = INT_MIN;
+    int t = 0, cap = 0, tPost = 0, x = INT_MIN, myB = bcur;
+    uint8_t qch = 0;
     if (act) {
       const uint32_t q = (uint32_t)(qStart + i - 1);
-      // largest b with blk[b].qPos <= q
-      int lo = 0, hi = nB - 1;
+      qch = qb[q];
+      // largest b with blk[b].qPos <= q; every block holds >= 1 row, so it lies within 32 of the previous chunk's last
+      int lo = bcur, hi = min(bcur + 32, nB - 1);
       while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (blk[mid].qPos <= q) lo = mid; else hi = mid - 1; }
+      myB = lo;
       const bgpu_block c = blk[lo];
       const uint32_t off = q - c.qPos;
       if (off < c.length) {
@@ -146,23 +160,27 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
       }
       x = (cap == INT_MAX) ? INT_MIN : t - cap;
     }
+    bcur = __shfl_sync(0xffffffffu, myB, 31);
     int L = warp_incl_max(x, lane);
     L = max(L, carryL);
     carryL = __shfl_sync(0xffffffffu, L, 31);
+    int lop = 1, hip = 0;
     if (act) {
       const int tPre = t - L;                           // >= 0 for ordered blocks
       cells += (long long)tPre + tPost + 1;
       const int hi = min(t + tPost, tEnd - 1);
-      const int lop = L - tStart + 1, hip = hi - tStart + 1;
+      lop = L - tStart + 1; hip = hi - tStart + 1;
       if (tPre < 0 || hip < lop) bad = 1;
       const int w = hip - lop;
       if (w >= (1 << ROW_W_BITS)) wide = 1;
-      const uint32_t qc = base_code(qb[qStart + i - 1]);
+      const uint32_t qc = lut[qch];
+      if (qc > 4) bad = 1;
       const uint32_t qv = qual ? qual[qStart + i - 1] : 0;
-      rows[i].lo = lop;
-      rows[i].packed = ((uint32_t)w & ((1u << ROW_W_BITS) - 1)) | (qc << 20) | (qv << 23);
-      if (!bad && !wide) add_row_range(i, lop, hip);
+      RowInfo r; r.lo = lop; r.packed = ((uint32_t)w & ((1u << ROW_W_BITS) - 1)) | ((qc & 7u) << 20) | (qv << 23);
+      rows[i] = r;
+      if (bad || wide) { lop = 1; hip = 0; }
     }
+    add_rows(i, lop, hip);
   }
   cells = warp_sum_ll(cells);
   if (warp_or(bad) || cells > INT_MAX) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }

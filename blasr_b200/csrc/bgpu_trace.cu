@@ -1,6 +1,6 @@
 // bgpu_trace.cu -- device-side traceback and alignment emission.
 //
-//   trace_guided_kernel : walks the traceback bytes of one job from (qEnd-1,tEnd-1) to the origin with the
+//   trace_guided_kernel : (one thread per job) walks the traceback bytes of one job from (qEnd-1,tEnd-1) to the origin with the
 //                         reference's 3-matrix state machine (GuidedAlign.h:626-663,
 //                         AffineGuidedAlign.h:377-468) and records the path as run-length runs (reversed).
 //   scan_counts_kernel  : exclusive scan of per-job block / gap-list / gap counts -> arena offsets.
@@ -14,68 +14,78 @@ namespace bgpu {
 
 enum { RUN_D = 0, RUN_U = 1, RUN_L = 2 };   // diagonal / up (insertion, Gap::Target) / left (deletion, Gap::Query)
 
-__global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder,
-                                                           uint32_t *counter) {
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(counter, 1u);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
-    if (idx >= nOrder) break;
-    const uint32_t job = order[idx];
-    JobGeom &G = B.geom[job];
-    if (G.status != BGPU_JOB_OK) continue;
-    const int Qn = G.Qn, Tn = G.Tn, C0 = G.C0;
-    const DBlock *dblk = B.dblk + G.dblkOff;
-    const uint8_t *arrows = B.arrows + B.arrowOff[job];
-    uint32_t *runs = B.runs + G.runOff;
+// One THREAD per job: a traceback is a serial pointer chase, so a warp walks 32 independent paths at
+// once (jobs are ordered longest-first, neighbouring threads have similar path lengths).  The walk only
+// ever moves to lower anti-diagonals and at most one diagonal sideways per step, so the 128 B line that
+// holds the next rows of the same slot is prefetched two rows (8 anti-diagonals) ahead.
+__global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nOrder) return;
+  const uint32_t job = order[idx];
+  JobGeom &G = B.geom[job];
+  if (G.status != BGPU_JOB_OK) return;
+  const int Qn = G.Qn, Tn = G.Tn, C0 = G.C0;
+  const DBlock *dblk = B.dblk + G.dblkOff;
+  const uint8_t *arrows = B.arrows + B.arrowOff[job];
+  uint32_t *runs = B.runs + G.runOff;
 
-    int q = Qn, t = Tn, mat = 0;
-    int curB = -1, wbase = 0, k = 1; size_t blkBase = 0;
-    int runType = -1; uint32_t runLen = 0, nRuns = 0;
-    uint32_t nBlocks = 0, nGaps = 0, pendGaps = 0, pendQ = 0, pendT = 0;
-    bool seenD = false, awry = false;
+  int q = Qn, t = Tn, mat = 0;
+  int curB = -1, wbase = 0, k = 1; size_t blkBase = 0;
+  int pW = 0, pK = 1; size_t pBase = 0;               // previous d-block (next one the walk enters)
+  int runType = -1; uint32_t runLen = 0, nRuns = 0;
+  uint32_t nBlocks = 0, nGaps = 0, pendGaps = 0, pendQ = 0, pendT = 0;
+  bool seenD = false, awry = false;
 
-    auto push = [&](int type) {
-      if (type == runType) { runLen++; return; }
-      if (runType >= 0) { if (lane == 0) runs[nRuns] = ((uint32_t)runType << 30) | runLen; nRuns++; }
-      runType = type; runLen = 1;
-      if (type == RUN_D) { if (seenD) nGaps += pendGaps; pendGaps = 0; pendQ = pendT = 0; seenD = true; nBlocks++; }
-      else pendGaps++;
-    };
+  auto push = [&](int type) {
+    if (type == runType) { runLen++; return; }
+    if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
+    runType = type; runLen = 1;
+    if (type == RUN_D) { if (seenD) nGaps += pendGaps; pendGaps = 0; pendQ = pendT = 0; seenD = true; nBlocks++; }
+    else pendGaps++;
+  };
 
-    while (q >= 1 || t >= 1) {
-      if (q < 0 || t < 0) { awry = true; break; }
-      const int d = q + t, b = d >> 6;
-      if (b != curB) { const DBlock db = dblk[b]; wbase = db.wbase; k = db.k; blkBase = (size_t)db.arrowUnit * 2048u; curB = b; }
-      const int s = t - q + C0 - wbase;
-      if (s < 0 || s >= 64 * k) { awry = true; break; }
-      const uint32_t byte = arrows[blkBase + ((size_t)((((d & 63) >> 2) * k + (s >> 6)) * 32 + ((s & 63) >> 1)) << 2) + (d & 3)];
-      const uint32_t tag = byte & 7u;
-      if (tag == TB_NONE) { awry = true; break; }
-      if (mat == 0) {
-        if (tag == TB_DIAG) { push(RUN_D); q--; t--; }
-        else if (tag == TB_UP) { push(RUN_U); pendQ++; q--; }
-        else if (tag == TB_LEFT) { push(RUN_L); pendT++; t--; }
-        else if (tag == TB_ICLOSE) { push(RUN_U); pendQ++; mat = 1; q--; }
-        else if (tag == TB_DCLOSE) { push(RUN_L); pendT++; mat = 2; t--; }
-        else { awry = true; break; }
-      } else if (mat == 1) {
-        if (byte & TB_IOPEN) mat = 0; else { q--; push(RUN_U); pendQ++; }
-      } else {
-        if (byte & TB_DOPEN) mat = 0; else { t--; push(RUN_L); pendT++; }
+  while (q >= 1 || t >= 1) {
+    if (q < 0 || t < 0) { awry = true; break; }
+    const int d = q + t, b = d >> 6;
+    if (b != curB) {
+      const DBlock db = dblk[b]; wbase = db.wbase; k = db.k; blkBase = (size_t)db.arrowUnit * 2048u; curB = b;
+      if (b > 0) { const DBlock pb = dblk[b - 1]; pW = pb.wbase; pK = pb.k; pBase = (size_t)pb.arrowUnit * 2048u; }
+    }
+    const int cd = t - q + C0;
+    const int s = cd - wbase;
+    if (s < 0 || s >= 64 * k) { awry = true; break; }
+    if ((d & 3) == 3 || (d & 3) == 2) {                 // entering a new 4-step row: prefetch 2 rows down
+      const int dp = d - 8;
+      if (dp >= (b << 6)) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(arrows + blkBase + ((size_t)((((dp & 63) >> 2) * k + (s >> 6)) * 32 + ((s & 63) >> 1)) << 2)));
+      } else if (b > 0) {
+        int sp = cd - pW; sp = sp < 0 ? 0 : (sp >= 64 * pK ? 64 * pK - 1 : sp);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(arrows + pBase + ((size_t)((((dp & 63) >> 2) * pK + (sp >> 6)) * 32 + ((sp & 63) >> 1)) << 2)));
       }
     }
-    if (runType >= 0) { if (lane == 0) runs[nRuns] = ((uint32_t)runType << 30) | runLen; nRuns++; }
-    if (lane == 0) {
-      if (awry) { G.status = BGPU_JOB_PATH_AWRY; G.nRuns = 0; G.nBlocks = G.nGaps = G.nGapLists = 0; }
-      else {
-        G.nRuns = nRuns; G.nBlocks = nBlocks; G.nGaps = nGaps; G.nGapLists = nRuns ? nBlocks + 1 : 0;
-        // leading gaps fold into qPos/tPos only when a block follows (the all-gap path is cleared first)
-        G.qPos = (uint32_t)G.qStart + (seenD ? pendQ : 0);
-        G.tPos = (uint32_t)G.tStart + (seenD ? pendT : 0);
-      }
+    const uint32_t byte = arrows[blkBase + ((size_t)((((d & 63) >> 2) * k + (s >> 6)) * 32 + ((s & 63) >> 1)) << 2) + (d & 3)];
+    const uint32_t tag = byte & 7u;
+    if (tag == TB_NONE) { awry = true; break; }
+    if (mat == 0) {
+      if (tag == TB_DIAG) { push(RUN_D); q--; t--; }
+      else if (tag == TB_UP) { push(RUN_U); pendQ++; q--; }
+      else if (tag == TB_LEFT) { push(RUN_L); pendT++; t--; }
+      else if (tag == TB_ICLOSE) { push(RUN_U); pendQ++; mat = 1; q--; }
+      else if (tag == TB_DCLOSE) { push(RUN_L); pendT++; mat = 2; t--; }
+      else { awry = true; break; }
+    } else if (mat == 1) {
+      if (byte & TB_IOPEN) mat = 0; else { q--; push(RUN_U); pendQ++; }
+    } else {
+      if (byte & TB_DOPEN) mat = 0; else { t--; push(RUN_L); pendT++; }
     }
+  }
+  if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
+  if (awry) { G.status = BGPU_JOB_PATH_AWRY; G.nRuns = 0; G.nBlocks = G.nGaps = G.nGapLists = 0; }
+  else {
+    G.nRuns = nRuns; G.nBlocks = nBlocks; G.nGaps = nGaps; G.nGapLists = nRuns ? nBlocks + 1 : 0;
+    // leading gaps fold into qPos/tPos only when a block follows (the all-gap path is cleared first)
+    G.qPos = (uint32_t)G.qStart + (seenD ? pendQ : 0);
+    G.tPos = (uint32_t)G.tStart + (seenD ? pendT : 0);
   }
 }
 
@@ -228,10 +238,10 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
 
 void launch_trace_guided(const BatchDev &B, const uint32_t *order, uint32_t nOrder, uint32_t *counter, int nSM,
                          cudaStream_t s) {
-  unsigned grid = (unsigned)nSM * 8u;
-  const unsigned need = (nOrder + 3) / 4;
-  if (grid > need) grid = need;
-  if (grid) trace_guided_kernel<<<grid, 128, 0, s>>>(B, order, nOrder, counter);
+  (void)counter; (void)nSM;
+  const unsigned block = 32;   // one warp per CTA spreads the (few, long) walks over all SMs
+  const unsigned grid = (nOrder + block - 1) / block;
+  if (grid) trace_guided_kernel<<<grid, block, 0, s>>>(B, order, nOrder);
 }
 
 void launch_scan_counts(const BatchDev &B, uint64_t *blockOff, uint64_t *listOff, uint64_t *gapOff, uint64_t *totals,

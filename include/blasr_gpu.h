@@ -125,6 +125,7 @@ typedef struct {
   uint64_t fillCells;                       /* lane-steps executed by the fill kernels (incl. idle lanes) */
   uint32_t kernelLaunches;                  /* kernels launched by the last run */
   uint64_t h2dBytes, d2hBytes;              /* bytes copied by submit / collect */
+  double   msHostSubmit, msHostCollect;     /* wall time spent inside bgpu_submit / bgpu_collect */
 } bgpu_timing;
 
 typedef struct bgpu_ctx bgpu_ctx;
