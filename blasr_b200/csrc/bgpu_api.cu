@@ -23,7 +23,11 @@ void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32
 void launch_trace_guided(const BatchDev &, const uint32_t *, uint32_t, uint32_t *, int, cudaStream_t);
 void launch_scan_counts(const BatchDev &, uint64_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
 void launch_emit(const BatchDev &, const ScoreParams &, bgpu_result *, bgpu_block *, uint32_t *, bgpu_gap *,
-                 const uint64_t *, const uint64_t *, const uint64_t *, int, int, cudaStream_t);
+                 const uint64_t *, const uint64_t *, const uint64_t *, int, int, int, cudaStream_t);
+void launch_dense_prep(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint64_t *, const uint64_t *, cudaStream_t);
+void launch_dense_fill(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, uint32_t *, int,
+                       cudaStream_t);
+void launch_dense_trace(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, cudaStream_t);
 double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz);
 extern double g_peakByMode[4];
 }  // namespace bgpu
@@ -105,7 +109,9 @@ struct bgpu_ticket_s {
   cudaEvent_t ev[6] = {};     // start, prepEnd, fillTraceEnd(unused), scanEnd, emitEnd
   std::vector<cudaEvent_t> waveEv;   // per wave: fillStart, fillEnd, traceEnd
   bgpu_timing timing{};
-  void *denseState = nullptr;
+  DenseArgs dargs{};
+  std::vector<uint64_t> h_arrowBytes;   // dense: host-computed traceback bytes per job
+  std::vector<uint64_t> h_cellsMetric;  // dense: SURVEY 8(d) cell count per job
 };
 
 template <typename T>
@@ -278,7 +284,7 @@ static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t) {
   cudaStream_t s = ctx->stream;
   CK(cudaMemsetAsync(t->d_gapCounts, 0, sizeof(uint32_t) * std::max<uint64_t>(t->totals[1], 1), s));
   launch_emit(t->B, t->sp, t->d_results, t->d_blocks, t->d_gapCounts, t->d_gaps, t->d_blockOff, t->d_listOff,
-              t->d_gapOff, t->params.doStats, t->params.statsAffine, s);
+              t->d_gapOff, t->params.doStats, t->params.statsAffine, t->dense ? 1 : 0, s);
   t->timing.kernelLaunches++;
   CK(cudaEventRecord(t->ev[4], s));
   CK(cudaGetLastError());
@@ -342,6 +348,127 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   return enqueue_guided(ctx, t, true);
 }
 
+
+// ---- kernel schedule of a KBandAlign / SWAlign ticket ----
+static int enqueue_dense(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
+  cudaStream_t s = ctx->stream;
+  CK(cudaEventRecord(t->ev[0], s));
+  launch_dense_prep(t->B, t->sp, t->dargs, t->d_dblkOff /* row-buffer offsets */, t->d_runOff, s);
+  t->timing.kernelLaunches = 1;
+  CK(cudaEventRecord(t->ev[1], s));
+  if (firstRun) {
+    CK(cudaMemcpyAsync(t->h_geom, t->B.geom, sizeof(JobGeom) * t->nJobs, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t n = t->nJobs;
+    std::vector<uint32_t> idx; idx.reserve(n);
+    for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) idx.push_back(i);
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { uint64_t ca = t->h_arrowBytes[a], cb = t->h_arrowBytes[b]; return ca != cb ? ca > cb : a < b; });
+    std::vector<uint64_t> arrowOff(n, 0);
+    std::vector<uint32_t> order; order.reserve(idx.size());
+    size_t maxWaveBytes = 0, i0 = 0;
+    while (i0 < idx.size()) {
+      size_t bytes = 0, i1 = i0;
+      while (i1 < idx.size()) {
+        const uint64_t ab = (t->h_arrowBytes[idx[i1]] + 15) & ~15ull;
+        if (i1 > i0 && bytes + ab > ctx->arrowPoolCap) break;
+        arrowOff[idx[i1]] = bytes; bytes += ab; i1++;
+      }
+      maxWaveBytes = std::max(maxWaveBytes, bytes);
+      Wave w{};
+      w.begin[0] = (uint32_t)order.size();
+      for (size_t i = i0; i < i1; i++) order.push_back(idx[i]);
+      w.count[0] = (uint32_t)(i1 - i0); w.traceBegin = w.begin[0]; w.traceCount = w.count[0];
+      t->waves.push_back(w);
+      i0 = i1;
+    }
+    RC(talloc_dev(ctx, t, &t->d_order, std::max<size_t>(order.size(), 1)));
+    RC(talloc_dev(ctx, t, &t->d_arrowOff, std::max<uint32_t>(n, 1)));
+    t->nCounters = (uint32_t)t->waves.size() * 8 + 8;
+    RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
+    uint8_t *arrows = nullptr;
+    RC(talloc_dev(ctx, t, &arrows, std::max<size_t>(maxWaveBytes, 16)));
+    t->B.arrows = arrows; t->B.arrowOff = t->d_arrowOff; t->dargs.arrowOff = t->d_arrowOff;
+    uint32_t *h_order = nullptr; uint64_t *h_aoff = nullptr;
+    RC(talloc_pin(ctx, t, &h_order, std::max<size_t>(order.size(), 1)));
+    RC(talloc_pin(ctx, t, &h_aoff, std::max<uint32_t>(n, 1)));
+    memcpy(h_order, order.data(), order.size() * sizeof(uint32_t));
+    memcpy(h_aoff, arrowOff.data(), n * sizeof(uint64_t));
+    CK(cudaMemcpyAsync(t->d_order, h_order, order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t->d_arrowOff, h_aoff, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    t->waveEv.resize(t->waves.size() * 3);
+    for (auto &e : t->waveEv) CK(cudaEventCreate(&e));
+    uint64_t cells = 0;
+    for (uint32_t i : idx) cells += t->h_cellsMetric[i];
+    t->timing.cells = cells; t->timing.fillCells = cells;
+  }
+  CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
+  for (size_t w = 0; w < t->waves.size(); w++) {
+    const Wave &W = t->waves[w];
+    CK(cudaEventRecord(t->waveEv[3 * w], s));
+    if (W.count[0]) { launch_dense_fill(t->B, t->sp, t->dargs, t->d_order + W.begin[0], W.count[0], t->d_counters + 8 * w, ctx->nSM, s); t->timing.kernelLaunches++; }
+    CK(cudaEventRecord(t->waveEv[3 * w + 1], s));
+    if (W.traceCount) { launch_dense_trace(t->B, t->sp, t->dargs, t->d_order + W.traceBegin, W.traceCount, s); t->timing.kernelLaunches++; }
+    CK(cudaEventRecord(t->waveEv[3 * w + 2], s));
+  }
+  launch_scan_counts(t->B, t->d_blockOff, t->d_listOff, t->d_gapOff, t->d_totals, s);
+  t->timing.kernelLaunches++;
+  CK(cudaEventRecord(t->ev[3], s));
+  CK(cudaGetLastError());
+  return BGPU_OK;
+}
+
+namespace bgpu { void kbounded_host(uint32_t, uint32_t, uint32_t, uint32_t &, uint32_t &); }
+
+static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b, bgpu_ticket t) {
+  const uint32_t n = b->nJobs;
+  if (!b->qOff || !b->tOff || (n && (!b->qBases || !b->tBases))) { ctx->err = "null batch arrays"; return BGPU_E_INVALID; }
+  if (fn->kind == BGPU_FN_QUALITY && !b->qual) { ctx->err = "BGPU_FN_QUALITY needs batch.qual"; return BGPU_E_INVALID; }
+  const uint64_t totQ = b->qOff[n], totT = b->tOff[n];
+  fill_score_params(t->sp, fn, p);
+  t->dense = true;
+  t->dargs.algo = p->algo; t->dargs.defaultBand = p->band; t->dargs.bndIns = p->bndIns; t->dargs.bndDel = p->bndDel;
+  BatchDev &B = t->B;
+  B.nJobs = n;
+  uint64_t *d_qOff, *d_tOff; uint8_t *d_q, *d_t, *d_qual = nullptr; int32_t *d_band = nullptr;
+  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16));
+  RC(talloc_dev(ctx, t, &d_qOff, n + 1)); RC(talloc_dev(ctx, t, &d_tOff, n + 1));
+  if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
+  if (b->band && p->algo == BGPU_KBAND) RC(talloc_dev(ctx, t, &d_band, std::max<uint32_t>(n, 1)));
+  RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
+  RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));
+  RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
+  if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
+  if (d_band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
+  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tOff = d_tOff; B.qual = d_qual; B.guide = nullptr; B.guideOff = nullptr; B.band = d_band;
+  uint64_t *h_off = nullptr;
+  RC(talloc_pin(ctx, t, &h_off, 2 * (size_t)n + 2));
+  t->h_arrowBytes.assign(n, 0); t->h_cellsMetric.assign(n, 0);
+  uint64_t rbTot = 0, runTot = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t ql = b->qOff[i + 1] - b->qOff[i], tl = b->tOff[i + 1] - b->tOff[i];
+    uint32_t qb = (uint32_t)ql, tb = (uint32_t)tl;
+    uint64_t bytes, cells;
+    if (p->algo == BGPU_KBAND) {
+      const int k = d_band ? b->band[i] : p->band;
+      if (k >= 0) kbounded_host((uint32_t)tl, (uint32_t)ql, (uint32_t)k, tb, qb);
+      bytes = k >= 0 ? ((uint64_t)qb + 1) * (2ull * (uint64_t)k + 1) : 16; cells = bytes;
+    } else { bytes = (ql + 1) * (tl + 1); cells = bytes; }
+    if (bytes > (1ull << 31)) bytes = 16;          // rejected by the prep kernel (matrix size is an int in the reference)
+    t->h_arrowBytes[i] = bytes; t->h_cellsMetric[i] = cells;
+    h_off[i] = rbTot; h_off[n + i] = runTot;
+    rbTot += 2 * ((uint64_t)tb + 2); runTot += ql + tl + 2;
+  }
+  RC(talloc_dev(ctx, t, &t->d_dblkOff, 2 * (size_t)n + 2));
+  t->d_runOff = t->d_dblkOff + n;
+  CK(cudaMemcpyAsync(t->d_dblkOff, h_off, sizeof(uint64_t) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+  RC(talloc_dev(ctx, t, &B.geom, std::max<uint32_t>(n, 1))); RC(talloc_dev(ctx, t, &B.rowBuf, rbTot + 4)); RC(talloc_dev(ctx, t, &B.runs, runTot + 1));
+  RC(talloc_dev(ctx, t, &t->d_blockOff, 3 * (size_t)n + 3));
+  t->d_listOff = t->d_blockOff + n; t->d_gapOff = t->d_blockOff + 2 * (size_t)n;
+  RC(talloc_dev(ctx, t, &t->d_totals, 4)); RC(talloc_dev(ctx, t, &t->d_results, std::max<uint32_t>(n, 1)));
+  RC(talloc_pin(ctx, t, &t->h_geom, std::max<uint32_t>(n, 1))); RC(talloc_pin(ctx, t, &t->h_totals, 4)); RC(talloc_pin(ctx, t, &t->h_results, std::max<uint32_t>(n, 1)));
+  return enqueue_dense(ctx, t, true);
+}
+
 extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b, bgpu_ticket *out) {
   if (!ctx) return BGPU_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -354,7 +481,7 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
   for (auto &e : t->ev) cudaEventCreate(&e);
   int rc;
   if (p->algo == BGPU_GUIDED || p->algo == BGPU_AFFINE_GUIDED) rc = submit_guided(ctx, fn, p, b, t);
-  else { ctx->err = "KBandAlign/SWAlign kernels are not built into this library yet"; rc = BGPU_E_INVALID; }
+  else rc = submit_dense(ctx, fn, p, b, t);
   if (rc != BGPU_OK) {
     cudaStreamSynchronize(ctx->stream);
     for (void *v : t->dev) dev_free(ctx, v);
@@ -441,7 +568,7 @@ extern "C" int bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!t->collected) { ctx->err = "bgpu_rerun needs a collected ticket"; return BGPU_E_BUSY; }
   if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
-  RC(enqueue_guided(ctx, t, false));
+  if (t->dense) RC(enqueue_dense(ctx, t, false)); else RC(enqueue_guided(ctx, t, false));
   RC(enqueue_emit(ctx, t));
   CK(cudaStreamSynchronize(ctx->stream));
   gather_timing(t);

@@ -54,6 +54,8 @@ struct JobGeom {          // per job, written by prep, extended by fill / trace
   uint64_t runOff;        // u32 index into the run scratch (capacity Qn+Tn+2)
   uint32_t nRuns, nBlocks, nGaps, nGapLists;   // traceback results
   uint32_t qPos, tPos;    // alignment.qPos/tPos after RemoveAlignmentPrefixGaps
+  int32_t startR, startC; // dense aligners (KBandAlign/SWAlign): traceback start cell chosen by the fill
+  uint64_t rowBufOff;     // dense aligners: int index of the job's two score rows
 };
 
 struct ScoreParams {      // kernel argument (by value)
@@ -76,8 +78,15 @@ struct BatchDev {         // device pointers of one submitted batch
   uint8_t *arrows;
   const uint64_t *arrowOff; // per job: byte offset in the arrow pool (assigned by the host per wave)
   uint32_t *runs;
+  int32_t *rowBuf;        // dense aligners: ping-pong score rows
   const uint32_t *order;  // job order for dynamic scheduling (longest first)
   uint32_t *counters;     // [0] fill job counter, [1] trace job counter, ...
+};
+
+struct DenseArgs {
+  int algo;            // BGPU_KBAND / BGPU_SW
+  int defaultBand, bndIns, bndDel;
+  const uint64_t *arrowOff;   // per job byte offset into B.arrows
 };
 
 __device__ __forceinline__ uint8_t base_code(uint8_t c) {

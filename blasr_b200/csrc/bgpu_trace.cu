@@ -147,7 +147,8 @@ __device__ __forceinline__ uint32_t warp_excl_u32(uint32_t v, int lane, uint32_t
 }
 
 // warp per job.  gapCounts must be zeroed beforehand.
-__global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine) {
+__global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine,
+                                                   int keepLeading) {
   const int lane = threadIdx.x & 31;
   const uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (job >= B.nJobs) return;
@@ -164,6 +165,8 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
   const uint32_t *runs = B.runs + G.runOff;
   const uint8_t *qb = B.q + B.qOff[job];
   const uint8_t *tb = B.t + B.tOff[job];             // codes inside [tStart,tEnd)
+  const long long qLenJ = (long long)(B.qOff[job + 1] - B.qOff[job]), tLenJ = (long long)(B.tOff[job + 1] - B.tOff[job]);
+  int oob = 0;
   const uint32_t qPrefix = G.qPos - (uint32_t)G.qStart, tPrefix = G.tPos - (uint32_t)G.tStart;
   bgpu_block *blocks = O.blocks + R.blockOff;
   uint32_t *gapCounts = O.gapCounts + R.gapListOff;
@@ -181,14 +184,20 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
     const uint32_t pq = cq + warp_excl_u32(dq, lane, totQ), pt = ct + warp_excl_u32(dt, lane, totT);
     const uint32_t isD = act && type == RUN_D;
     const uint32_t dBefore = cD + warp_excl_u32(isD, lane, totD);
-    const bool kept = act && !isD && dBefore >= 1 && dBefore < nBlocks;   // between the first and last block
+    // gap runs after the last block are dropped; the ones before the first block are folded into qPos/tPos by the
+    // guided aligners (RemoveAlignmentPrefixGaps) and kept as gaps[0] by KBandAlign / SWAlign
+    const bool kept = act && !isD && (keepLeading || dBefore >= 1) && dBefore < nBlocks;
     const uint32_t gBefore = cG + warp_excl_u32(kept ? 1u : 0u, lane, totG);
     if (isD) {
       bgpu_block bl; bl.qPos = pq - qPrefix; bl.tPos = pt - tPrefix; bl.length = len;
       blocks[dBefore] = bl;
       if (doStats) {
-        const uint8_t *qq = qb + G.qStart + pq, *tt = tb + G.tStart + pt;
-        for (uint32_t i = 0; i < len; i++) {
+        const long long q0 = (long long)G.qStart + pq, t0 = (long long)G.tStart + pt;
+        const uint8_t *qq = qb + q0, *tt = tb + t0;
+        // KBandAlign can leave qPos/tPos pointing outside the sequences (KBandAlign.h:394-399); the reference then reads
+        // out of bounds, here the job is flagged instead
+        if (q0 < 0 || t0 < 0 || q0 + len > qLenJ || t0 + len > tLenJ) oob = 1;
+        else for (uint32_t i = 0; i < len; i++) {
           const int qc = base_code(qq[i]), tc = tt[i];
           if (qc == tc) nMatch++; else nMismatch++;
           score += P.M[qc * 5 + tc];                   // ComputeAlignmentScore :74 (row = query)
@@ -230,6 +239,8 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
       nIns += __shfl_xor_sync(0xffffffffu, nIns, o); nDel += __shfl_xor_sync(0xffffffffu, nDel, o);
       score += __shfl_xor_sync(0xffffffffu, score, o); cols += __shfl_xor_sync(0xffffffffu, cols, o);
     }
+    oob = __reduce_or_sync(0xffffffffu, (unsigned)oob);
+    if (oob) { nMatch = nMismatch = nIns = nDel = score = 0; cols = 0; R.status = BGPU_JOB_REF_UNDEFINED; }
     R.nMatch = nMatch; R.nMismatch = nMismatch; R.nIns = nIns; R.nDel = nDel; R.statsScore = score;
     R.pctSimilarity = cols > 0 ? (float)((nMatch * 2.0) / (double)(2 * cols) * 100) : 0.f;   // :566-576
   }
@@ -251,10 +262,10 @@ void launch_scan_counts(const BatchDev &B, uint64_t *blockOff, uint64_t *listOff
 
 void launch_emit(const BatchDev &B, const ScoreParams &P, bgpu_result *results, bgpu_block *blocks,
                  uint32_t *gapCounts, bgpu_gap *gaps, const uint64_t *blockOff, const uint64_t *listOff,
-                 const uint64_t *gapOff, int doStats, int statsAffine, cudaStream_t s) {
+                 const uint64_t *gapOff, int doStats, int statsAffine, int keepLeading, cudaStream_t s) {
   EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff};
   const unsigned grid = (B.nJobs + 3) / 4;
-  if (grid) emit_kernel<<<grid, 128, 0, s>>>(B, P, O, doStats, statsAffine);
+  if (grid) emit_kernel<<<grid, 128, 0, s>>>(B, P, O, doStats, statsAffine, keepLeading);
 }
 
 }  // namespace bgpu
