@@ -4,6 +4,7 @@ Only the hot path lives here: csrc/ (sm_100a kernels + the C ABI), capi.py (ctyp
 align.py (host-side mirror of the reference's aligner interface) and synth.py (seeded workloads).
 """
 from . import capi  # noqa: F401
+from .capi import BgpuError  # noqa: F401
 from .align import (Aligner, Alignment, BatchResult, DistanceMatrixScoreFunction, JobBatch,  # noqa: F401
                     QualityValueScoreFunction, SMRTDistanceMatrix)
 
