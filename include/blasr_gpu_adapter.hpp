@@ -1,0 +1,126 @@
+// blasr_gpu_adapter.hpp -- header-only C++ glue between blasr's own containers and the C ABI (blasr_gpu.h).
+//
+// This is the binding a blasr maintainer adds next to alignment/Blasr.cpp.  It is written
+// against *duck-typed* template parameters, so it compiles both against the reference's real types
+//   T_AlignmentCandidate   common/datastructures/alignment/AlignmentCandidate.h:306
+//   DNASequence            common/DNASequence.h            (seq, length)
+//   Block / Gap / GapList  common/datastructures/alignment/AlignmentBlock.h:9-41, AlignmentGapList.h:9-24
+//   DistanceMatrixScoreFunction  common/algorithms/alignment/DistanceMatrixScoreFunction.h:11
+// and against the small stand-ins of tests/cpp/adapter_check.cpp; it contains no alignment arithmetic.
+//
+// Replaces, per batch of candidates instead of per candidate:
+//   AffineGuidedAlign / GuidedAlign + ComputeAlignmentStats      alignment/Blasr.cpp:863-878
+#ifndef BLASR_GPU_ADAPTER_HPP_
+#define BLASR_GPU_ADAPTER_HPP_
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "blasr_gpu.h"
+
+namespace blasr_gpu {
+
+struct Error : std::runtime_error { int code; Error(int c, const std::string &m) : std::runtime_error(m), code(c) {} };
+
+// One GPU context; the blasr thread driver (MapReads, Blasr.cpp:3193) creates one per device and shares it between
+// its pthreads (calls are serialised inside the library).
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    int rc = bgpu_create(&ctx_, device);
+    if (rc != BGPU_OK) throw Error(rc, rc == BGPU_E_NO_DEVICE ? "blasr_gpu: no CUDA device (there is no CPU fallback)" : "blasr_gpu: bgpu_create failed");
+  }
+  ~Context() { if (ctx_) bgpu_destroy(ctx_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  bgpu_ctx *get() const { return ctx_; }
+ private:
+  bgpu_ctx *ctx_ = nullptr;
+};
+
+template <typename T_ScoreFn>
+inline bgpu_scorefn MakeScoreFn(const T_ScoreFn &fn, int kind = BGPU_FN_DISTANCE) {
+  bgpu_scorefn s;
+  for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) s.M[i * 5 + j] = fn.scoreMatrix[i][j];
+  s.ins = fn.ins; s.del = fn.del; s.affineOpen = fn.affineOpen; s.affineExtend = fn.affineExtend; s.kind = kind;
+  return s;
+}
+
+// Collects the per-candidate slices RefineAlignment builds (Blasr.cpp:850-859) and runs them as one batch.
+class RefineBatch {
+ public:
+  // q/t: the slices handed to (Affine)GuidedAlign; blocks: candidate.blocks (used raw as the guide).
+  template <typename T_BlockVector>
+  void Add(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, const T_BlockVector &blocks,
+           const uint8_t *qual = nullptr) {
+    const size_t g0 = guide_.size();
+    guide_.resize(g0 + blocks.size());
+    for (size_t i = 0; i < blocks.size(); i++) { guide_[g0 + i].qPos = blocks[i].qPos; guide_[g0 + i].tPos = blocks[i].tPos; guide_[g0 + i].length = blocks[i].length; }
+    q_.insert(q_.end(), q, q + qLen); t_.insert(t_.end(), t, t + tLen);
+    if (qual) { qual_.resize(q_.size() - qLen, 0); qual_.insert(qual_.end(), qual, qual + qLen); }
+    qOff_.push_back(q_.size()); tOff_.push_back(t_.size()); gOff_.push_back(guide_.size());
+  }
+  uint32_t size() const { return (uint32_t)qOff_.size() - 1; }
+
+  // Runs AffineGuidedAlign (affine=true: what blasr does, MappingParameters.h:539) or GuidedAlign on every job and
+  // ComputeAlignmentStats afterwards.  Results stay valid until the next Run()/destruction.
+  template <typename T_ScoreFn>
+  void Run(Context &ctx, const T_ScoreFn &fn, int bandSize, bool affine, int alignType = BGPU_GLOBAL) {
+    bgpu_scorefn s = MakeScoreFn(fn);
+    bgpu_params p;
+    p.algo = affine ? BGPU_AFFINE_GUIDED : BGPU_GUIDED; p.alignType = alignType; p.band = bandSize;
+    p.bndIns = p.bndDel = 0; p.doStats = 1; p.statsAffine = affine ? 1 : 0;
+    if (!qual_.empty()) qual_.resize(q_.size(), 0);
+    bgpu_batch b;
+    b.nJobs = size(); b.qBases = q_.data(); b.qOff = qOff_.data(); b.tBases = t_.data(); b.tOff = tOff_.data();
+    b.qual = qual_.empty() ? nullptr : qual_.data(); b.guide = guide_.data(); b.guideOff = gOff_.data(); b.band = nullptr;
+    results_.resize(b.nJobs);
+    int rc = bgpu_align(ctx.get(), &s, &p, &b, results_.data(), &arena_);
+    if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
+  }
+
+  const bgpu_result &Result(uint32_t i) const { return results_[i]; }
+
+  // Writes job i into a reference-style alignment exactly as Blasr.cpp:888-914 copies refinedAlignment back.
+  // T_Alignment needs: blocks (vector of {qPos,tPos,length}), gaps (vector<vector<T_Gap>>), score, nCells, qPos, tPos,
+  // nMatch, nMismatch, nIns, nDel, pctSimilarity.  T_Gap needs {seq, length} with seq convertible from int
+  // (Gap::Query = 0, Gap::Target = 1, AlignmentGapList.h:11-14).
+  template <typename T_Alignment>
+  void Store(uint32_t i, T_Alignment &out) const {
+    const bgpu_result &r = results_[i];
+    if (r.status == BGPU_JOB_PATH_AWRY)   // GuidedAlign.h:637-651 prints and exit(1)s here
+      throw Error(r.status, "ERROR, this path has gone awry");
+    if (r.status != BGPU_JOB_OK && r.status != BGPU_JOB_EMPTY_GUIDE) throw Error(r.status, "blasr_gpu: job rejected");
+    out.blocks.resize(r.nBlocks);
+    for (uint32_t k = 0; k < r.nBlocks; k++) {
+      const bgpu_block &bk = arena_.blocks[r.blockOff + k];
+      out.blocks[k].qPos = bk.qPos; out.blocks[k].tPos = bk.tPos; out.blocks[k].length = bk.length;
+    }
+    out.gaps.clear(); out.gaps.resize(r.nGapLists);
+    uint64_t g = r.gapOff;
+    for (uint32_t k = 0; k < r.nGapLists; k++) {
+      const uint32_t c = arena_.gapCounts[r.gapListOff + k];
+      out.gaps[k].resize(c);
+      for (uint32_t x = 0; x < c; x++, g++) {
+        typedef decltype(out.gaps[k][x].seq) seq_t;
+        out.gaps[k][x].seq = (seq_t)arena_.gaps[g].seq; out.gaps[k][x].length = arena_.gaps[g].length;
+      }
+    }
+    out.qPos = r.qPos; out.tPos = r.tPos; out.nCells = r.nCells;
+    out.nMatch = r.nMatch; out.nMismatch = r.nMismatch; out.nIns = r.nIns; out.nDel = r.nDel;
+    out.pctSimilarity = r.pctSimilarity; out.score = r.statsScore;   // ComputeAlignmentStats overwrites score, AlignmentUtils.h:578
+  }
+
+  void Clear() { q_.clear(); t_.clear(); qual_.clear(); guide_.clear(); qOff_.assign(1, 0); tOff_.assign(1, 0); gOff_.assign(1, 0); results_.clear(); }
+
+ private:
+  std::vector<uint8_t> q_, t_, qual_;
+  std::vector<bgpu_block> guide_;
+  std::vector<uint64_t> qOff_{0}, tOff_{0}, gOff_{0};
+  std::vector<bgpu_result> results_;
+  bgpu_arena arena_{};
+};
+
+}  // namespace blasr_gpu
+#endif

@@ -1,0 +1,120 @@
+/*
+ * oracle/adapter_check.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * The drop-in proof at the reference's own call site: builds candidates with the reference's SDPAlign the way
+ * AlignIntervals does (alignment/Blasr.cpp:1716-1722), then refines every candidate twice --
+ *   (1) with the reference's own AffineGuidedAlign/GuidedAlign + ComputeAlignmentStats (alignment/Blasr.cpp:863-878),
+ *   (2) with blasr_gpu::RefineBatch (include/blasr_gpu_adapter.hpp) on the GPU, storing into the reference's real
+ *       T_AlignmentCandidate --
+ * and compares blocks, gaps, qPos, tPos, nCells, score and the stats fields.  Exit code 0 = identical.
+ *
+ * Built by oracle/Makefile into oracle/_ref/adapter_check (it contains compiled reference templates, so it lives
+ * beside libblasr_ref.so, git-ignored, and travels to the GPU box); run by tests/test_gpu_adapter.py.
+ */
+#define _GLIBCXX_USE_CXX11_ABI 0
+#include "algorithms/alignment.h"
+#include "algorithms/alignment/GuidedAlign.h"
+#include "algorithms/alignment/AffineGuidedAlign.h"
+#include "algorithms/alignment/SDPAlign.h"
+#include "algorithms/alignment/DistanceMatrixScoreFunction.h"
+#include "datastructures/alignment/AlignmentCandidate.h"
+#include "FASTQSequence.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <string>
+#include <vector>
+#include "blasr_gpu_adapter.hpp"
+
+typedef DistanceMatrixScoreFunction<DNASequence, FASTQSequence> DistFn;
+
+struct Pair { std::string q, t; };
+
+static Pair MakePair(std::mt19937 &rng, int len, double err) {
+  static const char B[] = "ACGT";
+  Pair p;
+  std::uniform_real_distribution<double> U(0, 1);
+  for (int i = 0; i < len; i++) p.t.push_back(B[rng() & 3]);
+  for (int i = 0; i < len; i++) {
+    const bool prot = i < 20 || i >= len - 20;
+    const double r = prot ? 1.0 : U(rng);
+    if (r < err * 0.55) { p.q.push_back(B[rng() & 3]); p.q.push_back(p.t[i]); }
+    else if (r < err * 0.90) { /* deletion */ }
+    else if (r < err) p.q.push_back(B[(std::string(B).find(p.t[i]) + 1 + rng() % 3) & 3]);
+    else p.q.push_back(p.t[i]);
+  }
+  return p;
+}
+
+template <typename A, typename B>
+static int Diff(const A &a, const B &b, int job, const char *what) {
+  int bad = 0;
+#define CHK(f) if (a.f != b.f) { printf("job %d %s: %s differs (%ld vs %ld)\n", job, what, #f, (long)a.f, (long)b.f); bad++; }
+  CHK(qPos) CHK(tPos) CHK(nCells) CHK(score) CHK(nMatch) CHK(nMismatch) CHK(nIns) CHK(nDel)
+#undef CHK
+  if (a.pctSimilarity != b.pctSimilarity) { printf("job %d %s: pctSimilarity differs\n", job, what); bad++; }
+  if (a.blocks.size() != b.blocks.size()) { printf("job %d %s: %zu vs %zu blocks\n", job, what, a.blocks.size(), b.blocks.size()); return bad + 1; }
+  for (size_t i = 0; i < a.blocks.size(); i++)
+    if (a.blocks[i].qPos != b.blocks[i].qPos || a.blocks[i].tPos != b.blocks[i].tPos || a.blocks[i].length != b.blocks[i].length) { printf("job %d %s: block %zu differs\n", job, what, i); return bad + 1; }
+  if (a.gaps.size() != b.gaps.size()) { printf("job %d %s: %zu vs %zu gap lists\n", job, what, a.gaps.size(), b.gaps.size()); return bad + 1; }
+  for (size_t i = 0; i < a.gaps.size(); i++) {
+    if (a.gaps[i].size() != b.gaps[i].size()) { printf("job %d %s: gap list %zu size differs\n", job, what, i); return bad + 1; }
+    for (size_t j = 0; j < a.gaps[i].size(); j++)
+      if (a.gaps[i][j].seq != b.gaps[i][j].seq || a.gaps[i][j].length != b.gaps[i][j].length) { printf("job %d %s: gap %zu/%zu differs\n", job, what, i, j); return bad + 1; }
+  }
+  return bad;
+}
+
+int main(int argc, char **argv) {
+  const int nJobs = argc > 1 ? atoi(argv[1]) : 48;
+  const int maxLen = argc > 2 ? atoi(argv[2]) : 6000;
+  std::mt19937 rng(20261017);
+  DistFn fn;
+  fn.InitializeScoreMatrix(SMRTDistanceMatrix);
+  fn.ins = 5; fn.del = 5; fn.affineOpen = 50; fn.affineExtend = 0;          /* MappingParameters.h:339-342 */
+
+  std::vector<Pair> pairs;
+  std::vector<T_AlignmentCandidate> cands(nJobs);
+  for (int i = 0; i < nJobs; i++) {
+    pairs.push_back(MakePair(rng, 300 + (int)(rng() % (maxLen - 300)), 0.15));
+    FASTQSequence q; DNASequence t;
+    q.seq = (Nucleotide *)pairs[i].q.data(); q.length = pairs[i].q.size();
+    t.seq = (Nucleotide *)pairs[i].t.data(); t.length = pairs[i].t.size();
+    /* the candidate AlignIntervals hands to RefineAlignment: SDPAlign(Local, detailed), Blasr.cpp:1716-1722 */
+    SDPAlign(q, t, fn, 11, 5, 10, 0.30f, cands[i], Local, true, false, 50, 2, 1000);
+  }
+
+  int bad = 0;
+  for (int affine = 1; affine >= 0; affine--) {
+    const int band = affine ? 16 : 10;                                       /* bandSize / guidedAlignBandSize */
+    blasr_gpu::Context ctx(0);
+    blasr_gpu::RefineBatch batch;
+    std::vector<FASTQSequence> qs(nJobs); std::vector<DNASequence> ts(nJobs);
+    std::vector<int> jobOf;
+    for (int i = 0; i < nJobs; i++) {
+      T_AlignmentCandidate &c = cands[i];
+      if (c.blocks.size() == 0) continue;
+      const int last = c.blocks.size() - 1;
+      /* the slices of Blasr.cpp:850-859 */
+      ts[i].seq = (Nucleotide *)pairs[i].t.data() + c.tPos; ts[i].length = c.blocks[last].tPos + c.blocks[last].length;
+      qs[i].seq = (Nucleotide *)pairs[i].q.data() + c.qPos; qs[i].length = c.blocks[last].qPos + c.blocks[last].length;
+      batch.Add(qs[i].seq, qs[i].length, ts[i].seq, ts[i].length, c.blocks);
+      jobOf.push_back(i);
+    }
+    batch.Run(ctx, fn, band, affine != 0);
+    for (size_t j = 0; j < jobOf.size(); j++) {
+      const int i = jobOf[j];
+      T_AlignmentCandidate refRefined, gpuRefined;
+      vector<int> scoreMat; vector<Arrow> pathMat; vector<double> pm, opm; vector<float> a, b, c, d;
+      if (affine) AffineGuidedAlign(qs[i], ts[i], cands[i], fn, band, refRefined, scoreMat, pathMat, pm, opm, a, b, c, d, Global, false);
+      else GuidedAlign(qs[i], ts[i], cands[i], fn, band, refRefined, scoreMat, pathMat, pm, opm, a, b, c, d, Global, false);
+      ComputeAlignmentStats(refRefined, qs[i].seq, ts[i].seq, fn, affine != 0);
+      batch.Store(j, gpuRefined);
+      bad += Diff(refRefined, gpuRefined, i, affine ? "AffineGuidedAlign" : "GuidedAlign");
+    }
+    printf("adapter_check: %s x%zu candidates through blasr_gpu::RefineBatch: %s\n", affine ? "AffineGuidedAlign" : "GuidedAlign",
+           jobOf.size(), bad ? "MISMATCH" : "identical to the reference call site");
+  }
+  return bad ? 1 : 0;
+}

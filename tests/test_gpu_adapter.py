@@ -1,0 +1,30 @@
+"""The drop-in check at the reference's own call site (oracle/adapter_check.cpp): reference SDPAlign candidates refined by
+the reference's (Affine)GuidedAlign + ComputeAlignmentStats and by include/blasr_gpu_adapter.hpp into the reference's real
+T_AlignmentCandidate.  The binary is prebuilt by oracle/Makefile (it needs /root/reference at build time only)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "adapter_check")
+
+needs_bin = pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/adapter_check not built (needs /root/reference)")
+
+
+@needs_bin
+@pytest.mark.gpu
+def test_adapter_matches_reference_call_site():
+    r = subprocess.run([BIN, "64", "8000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("identical to the reference call site") == 2, r.stdout
+
+
+@needs_bin
+def test_adapter_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([BIN, "2", "400"], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stdout + r.stderr)
