@@ -20,7 +20,7 @@ void launch_prep_guided(const BatchDev &, const ScoreParams &, int, const uint64
                         const uint64_t *, cudaStream_t);
 void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32_t *, uint32_t, uint32_t *, int,
                         cudaStream_t);
-void launch_trace_guided(const BatchDev &, const uint32_t *, uint32_t, uint32_t *, int, cudaStream_t);
+void launch_trace_guided(const BatchDev &, bool, const uint32_t *, uint32_t, cudaStream_t);
 void launch_scan_counts(const BatchDev &, uint64_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
 void launch_emit(const BatchDev &, const ScoreParams &, bgpu_result *, bgpu_block *, uint32_t *, bgpu_gap *,
                  const uint64_t *, const uint64_t *, const uint64_t *, int, int, int, cudaStream_t);
@@ -199,42 +199,86 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   t->timing.kernelLaunches = 1;
   CK(cudaEventRecord(t->ev[1], s));
   if (firstRun) {
-    // geometry back to the host: classification, ordering and wave cutting need it
+    // geometry back to the host: class lists, warp groups and wave cutting need it
     CK(cudaMemcpyAsync(t->h_geom, t->B.geom, sizeof(JobGeom) * t->nJobs, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const uint32_t n = t->nJobs;
-    std::vector<uint32_t> idx; idx.reserve(n);
-    for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) idx.push_back(i);
-    auto cls = [&](uint32_t i) { int k = t->h_geom[i].kmax; return k <= 1 ? 0 : (k == 2 ? 1 : (k <= 4 ? 2 : 3)); };
-    auto cost = [&](uint32_t i) { return (uint64_t)t->h_geom[i].nDB * (uint64_t)(cls(i) == 0 ? 1 : (cls(i) == 1 ? 2 : 4)); };
-    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { uint64_t ca = cost(a), cb = cost(b); return ca != cb ? ca > cb : a < b; });
-    // cut into waves by traceback bytes
+    const bool affine = t->sp.affine != 0;
+    const uint64_t rowsPerBlock = affine ? 16 : 4;             // 64 anti-diagonals / steps per traceback word
+    std::vector<uint32_t> byCls[N_CLS];
+    for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) byCls[t->h_geom[i].cls].push_back(i);
+    // a warp sweeps 32/LPJ jobs in lockstep with k = the widest member's need: put jobs of similar typical width and
+    // length side by side (typical width first, longest first inside it)
+    struct Group { uint32_t first, count; uint64_t bytes, cost; int cls; };
+    std::vector<Group> groups;
+    std::vector<uint32_t> sorted;                                // job indices, class-major
+    std::vector<uint64_t> bound(n, 0);                           // traceback bytes reserved per job
+    uint64_t laneSteps = 0;
+    for (int c = 0; c < N_CLS; c++) {
+      auto &v = byCls[c];
+      auto kt = [&](uint32_t i) { const JobGeom &g = t->h_geom[i]; return (g.ksum + g.nDB / 2) / std::max(g.nDB, 1); };
+      std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) {
+        const int ka = kt(a), kb = kt(b);
+        if (ka != kb) return ka > kb;
+        const int da = t->h_geom[a].nDB, db = t->h_geom[b].nDB;
+        return da != db ? da > db : a < b;
+      });
+      const uint32_t lpj = (uint32_t)cls_lpj(c), nj = 32 / lpj;
+      for (size_t i0 = 0; i0 < v.size(); i0 += nj) {
+        const size_t i1 = std::min(v.size(), i0 + nj);
+        int kmaxG = 1, nDBmax = 0; uint64_t ksumMax = 0;
+        for (size_t i = i0; i < i1; i++) {
+          kmaxG = std::max(kmaxG, t->h_geom[v[i]].kmax); nDBmax = std::max(nDBmax, t->h_geom[v[i]].nDB);
+          ksumMax = std::max<uint64_t>(ksumMax, (uint64_t)t->h_geom[v[i]].ksum);
+        }
+        Group g{(uint32_t)sorted.size(), (uint32_t)(i1 - i0), 0, (uint64_t)nDBmax * (uint64_t)kmaxG, c};
+        for (size_t i = i0; i < i1; i++) {
+          const uint64_t bb = (uint64_t)t->h_geom[v[i]].nDB * (uint64_t)kmaxG * rowsPerBlock * lpj * 4ull;
+          bound[v[i]] = (bb + 255) & ~255ull; g.bytes += bound[v[i]];
+          sorted.push_back(v[i]);
+        }
+        laneSteps += ksumMax * 64ull * 32ull;                    // lower bound of the cell slots the warp executes
+        groups.push_back(g);
+      }
+    }
+    // cut into waves by reserved traceback bytes (groups stay whole)
     std::vector<uint64_t> arrowOff(n, 0);
-    std::vector<uint32_t> order; order.reserve(idx.size() * 2);
-    size_t maxWaveBytes = 0;
-    size_t i0 = 0;
-    while (i0 < idx.size()) {
-      size_t bytes = 0, i1 = i0;
-      while (i1 < idx.size()) {
-        const uint64_t ab = t->h_geom[idx[i1]].arrowBytes;
-        if (i1 > i0 && bytes + ab > ctx->arrowPoolCap) break;
-        arrowOff[idx[i1]] = bytes; bytes += ab; i1++;
+    std::vector<uint32_t> order;
+    size_t maxWaveBytes = 0, g0 = 0;
+    while (g0 < groups.size()) {
+      size_t bytes = 0, g1 = g0;
+      while (g1 < groups.size()) {
+        if (g1 > g0 && bytes + groups[g1].bytes > ctx->arrowPoolCap) break;
+        bytes += groups[g1].bytes; g1++;
       }
-      maxWaveBytes = std::max(maxWaveBytes, bytes);
       Wave w{};
-      for (int c = 0; c < 4; c++) {
-        w.begin[c] = (uint32_t)order.size();
-        for (size_t i = i0; i < i1; i++) if (cls(idx[i]) == c) order.push_back(idx[i]);
-        w.count[c] = (uint32_t)order.size() - w.begin[c];
+      size_t off = 0;
+      for (int c = 0; c < N_CLS; c++) {
+        const uint32_t nj = 32 / (uint32_t)cls_lpj(c);
+        w.begin[c] = (uint32_t)order.size(); w.count[c] = 0;
+        for (size_t gi = g0; gi < g1; gi++) {
+          const Group &g = groups[gi];
+          if (g.cls != c) continue;
+          for (uint32_t j = 0; j < nj; j++) {
+            if (j < g.count) { const uint32_t job = sorted[g.first + j]; arrowOff[job] = off; off += bound[job]; order.push_back(job); }
+            else order.push_back(0xffffffffu);
+          }
+          w.count[c]++;
+        }
       }
+      // traceback list: longest jobs first
       w.traceBegin = (uint32_t)order.size();
-      for (size_t i = i0; i < i1; i++) order.push_back(idx[i]);
-      w.traceCount = (uint32_t)(i1 - i0);
+      std::vector<uint32_t> tl;
+      for (size_t gi = g0; gi < g1; gi++) for (uint32_t j = 0; j < groups[gi].count; j++) tl.push_back(sorted[groups[gi].first + j]);
+      std::sort(tl.begin(), tl.end(), [&](uint32_t a, uint32_t b) { const int da = t->h_geom[a].nDB, db = t->h_geom[b].nDB; return da != db ? da > db : a < b; });
+      order.insert(order.end(), tl.begin(), tl.end());
+      w.traceCount = (uint32_t)tl.size();
+      maxWaveBytes = std::max(maxWaveBytes, off);
       t->waves.push_back(w);
-      i0 = i1;
+      g0 = g1;
     }
     RC(talloc_dev(ctx, t, &t->d_order, std::max<size_t>(order.size(), 1)));
-    RC(talloc_dev(ctx, t, &t->d_arrowOff, n));
+    RC(talloc_dev(ctx, t, &t->d_arrowOff, std::max<uint32_t>(n, 1)));
     t->nCounters = (uint32_t)t->waves.size() * 8 + 8;
     RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
     uint8_t *arrows = nullptr;
@@ -242,7 +286,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     t->B.arrows = arrows; t->B.arrowOff = t->d_arrowOff; t->B.order = t->d_order; t->B.counters = t->d_counters;
     uint32_t *h_order = nullptr; uint64_t *h_aoff = nullptr;
     RC(talloc_pin(ctx, t, &h_order, std::max<size_t>(order.size(), 1)));
-    RC(talloc_pin(ctx, t, &h_aoff, n));
+    RC(talloc_pin(ctx, t, &h_aoff, std::max<uint32_t>(n, 1)));
     memcpy(h_order, order.data(), order.size() * sizeof(uint32_t));
     memcpy(h_aoff, arrowOff.data(), n * sizeof(uint64_t));
     CK(cudaMemcpyAsync(t->d_order, h_order, order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
@@ -252,23 +296,20 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     uint64_t cells = 0;
     for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) cells += (uint64_t)t->h_geom[i].nCells;
     t->timing.cells = cells;
-    uint64_t fc = 0;
-    for (uint32_t i : idx) fc += (uint64_t)t->h_geom[i].nDB * 64ull * 32ull * (uint64_t)(cls(i) == 0 ? 1 : (cls(i) == 1 ? 2 : 4));
-    t->timing.fillCells = fc;
+    t->timing.fillCells = laneSteps;
   }
   CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
-  static const int kclassOf[4] = {1, 2, 4, 1 << 20};
   for (size_t w = 0; w < t->waves.size(); w++) {
     const Wave &W = t->waves[w];
     CK(cudaEventRecord(t->waveEv[3 * w], s));
-    for (int c = 0; c < 4; c++)
+    for (int c = 0; c < N_CLS; c++)
       if (W.count[c]) {
-        launch_fill_guided(t->B, t->sp, kclassOf[c], t->d_order + W.begin[c], W.count[c], t->d_counters + 8 * w + c, ctx->nSM, s);
+        launch_fill_guided(t->B, t->sp, c, t->d_order + W.begin[c], W.count[c], t->d_counters + 8 * w + c, ctx->nSM, s);
         t->timing.kernelLaunches++;
       }
     CK(cudaEventRecord(t->waveEv[3 * w + 1], s));
     if (W.traceCount) {
-      launch_trace_guided(t->B, t->d_order + W.traceBegin, W.traceCount, t->d_counters + 8 * w + 4, ctx->nSM, s);
+      launch_trace_guided(t->B, t->sp.affine != 0, t->d_order + W.traceBegin, W.traceCount, s);
       t->timing.kernelLaunches++;
     }
     CK(cudaEventRecord(t->waveEv[3 * w + 2], s));

@@ -12,18 +12,30 @@
 
 namespace bgpu {
 
-constexpr int SH = 5;                 // scores are carried as (score << SH) | tag bits
-constexpr int BIG = 1 << 30;          // "invalid neighbour" in the shifted domain (INF_INT stand-in)
-constexpr int SCORE_LIMIT = 1 << 24;  // |score| bound that keeps (score<<SH) clear of BIG
-constexpr int DBLK = 64;              // anti-diagonals per d-block
-constexpr int KMAX_BUILD = 128;       // widest fill kernel: 64*KMAX diagonals live at once (8192)
+constexpr int SH_LIN = 2;              // linear kernels carry (score << 2) | arrow
+constexpr int SH_AFF = 5;              // affine kernels carry (score << 5) | arrow | open flags
+constexpr int BIG = 1 << 30;           // "invalid neighbour" in the shifted domain (INF_INT stand-in)
+constexpr int SCORE_LIMIT_AFF = 1 << 24;  // |score| bounds that keep (score << SH) clear of BIG
+constexpr int SCORE_LIMIT_LIN = 1 << 27;
+constexpr int DBLK = 64;               // anti-diagonals per d-block
+constexpr int KRING = 8;               // most diagonal groups per lane in the register-ring kernels
+constexpr int KWIDE = 128;             // groups per lane of the wide fallback kernel (32 lanes x 2 x 128 = 8192 diagonals)
 constexpr int ROW_W_BITS = 20;
 
-// traceback byte written by the fill kernels, one per (anti-diagonal, diagonal slot)
-//   bits 0-2: 0 Diagonal, 1 Left, 2 Up, 3 AffineInsClose, 4 AffineDelClose, 7 NoArrow/out of band
-//   bit 3   : affine-ins matrix arrow is AffineInsOpen (else AffineInsUp)
-//   bit 4   : affine-del matrix arrow is AffineDelOpen (else AffineDelLeft)
+// Job classes: how many lanes of a warp sweep one job.  A lane owns 2k consecutive diagonals ("lane-major"
+// slots), k = groups active in the current d-block, so a class covers windows of up to 2 * LPJ * KRING diagonals.
+enum { CLS_L8 = 0, CLS_L16 = 1, CLS_L32 = 2, CLS_WIDE = 3, N_CLS = 4 };
+__host__ __device__ inline int cls_lpj(int cls) { return cls == CLS_L8 ? 8 : (cls == CLS_L16 ? 16 : 32); }
+
+// traceback codes written by the fill kernels
+//   linear (2 bits / step, 16 steps per 32-bit word): 0 Diagonal, 1 Left, 2 Up, 3 NoArrow / out of band
+//   affine (8 bits / step, 4 steps per word):
+//     bits 0-2: 0 Diagonal, 1 Left, 2 Up, 3 AffineInsClose, 4 AffineDelClose, 7 NoArrow
+//     bit 3   : affine-ins matrix arrow is AffineInsOpen (else AffineInsUp)
+//     bit 4   : affine-del matrix arrow is AffineDelOpen (else AffineDelLeft)
+// word layout per job: [d-block][row = (d & 63) / stepsPerWord][sigma = slot / 2], a row holding k * LPJ words.
 enum { TB_DIAG = 0, TB_LEFT = 1, TB_UP = 2, TB_ICLOSE = 3, TB_DCLOSE = 4, TB_NONE = 7, TB_IOPEN = 8, TB_DOPEN = 16 };
+enum { TL_DIAG = 0, TL_LEFT = 1, TL_UP = 2, TL_NONE = 3 };
 
 struct alignas(8) RowInfo {  // 8 B per guide row in HBM
   int32_t lo;             // first in-band column t' of the row (INT_MAX/2 for "no cells")
@@ -31,9 +43,9 @@ struct alignas(8) RowInfo {  // 8 B per guide row in HBM
 };
 
 struct DBlock {           // 16 B per d-block
-  int32_t wbase;          // even: diagonal held by slot 0 of the register window
-  int32_t k;              // active 64-diagonal groups in this block (1..KMAX)
-  uint32_t arrowUnit;     // offset of this block's arrows in 2 KB units from the job's arrowOff
+  int32_t wbase;          // even: diagonal held by slot 0 of the job's window in this block
+  int32_t k;              // prep: groups this job needs; fill: groups its warp actually used (>= needed)
+  uint32_t arrowUnit;     // fill: offset of this block's arrows, in units of (64 / stepsPerWord) * LPJ words
   int32_t pad;
 };
 
@@ -43,14 +55,16 @@ struct JobGeom {          // per job, written by prep, extended by fill / trace
   int32_t Qn, Tn;         // guide rows / target columns covered (without the boundary row/column)
   int32_t C0;
   int32_t nDB;            // number of d-blocks
-  int32_t kmax;           // max k over the job's d-blocks
+  int32_t kmax;           // max k over the job's d-blocks (for its class)
   int32_t band;
   int32_t nCells;         // ComputeMatrixNElem (GuidedAlign.h:83-92)
   int32_t hi0;            // last in-band column of row 0
   int32_t score;          // fill result: S[qEnd-1][tEnd-1]
+  int32_t cls;            // CLS_*
+  int32_t ksum;           // sum of k over the d-blocks
   uint64_t rowOff;        // RowInfo index of row 0
   uint64_t dblkOff;       // DBlock index of d-block 0
-  uint64_t arrowBytes;    // total arrow bytes of this job
+  uint64_t arrowBytes;    // unused by the guided path (the host bounds it per warp group)
   uint64_t runOff;        // u32 index into the run scratch (capacity Qn+Tn+2)
   uint32_t nRuns, nBlocks, nGaps, nGapLists;   // traceback results
   uint32_t qPos, tPos;    // alignment.qPos/tPos after RemoveAlignmentPrefixGaps

@@ -1,303 +1,434 @@
-// bgpu_fill.cu -- the guided banded DP fill, one warp per job.
+// bgpu_fill.cu -- the guided banded DP fill.
 //
 // Reference semantics restated (not translated):
 //   GuidedAlign        common/algorithms/alignment/GuidedAlign.h:474-624   (linear gaps)
 //   AffineGuidedAlign  common/algorithms/alignment/AffineGuidedAlign.h:241-375
 //
-// B200 mapping.  The band is swept by anti-diagonals d = q'+t'.  Lane j of the warp owns the two
-// adjacent diagonals (slots) 2j and 2j+1 of a 64-diagonal register window (KMAX such windows for
-// wide bands); on an even step it computes the cell on its even slot, on an odd step the one on its
-// odd slot, so every lane has exactly one cell per step and all three DP neighbours are either its
-// own registers or one __shfl away:
-//     even step: left = lane j-1's odd slot (shfl), up = own odd slot, diag = own even slot
-//     odd  step: left = own even slot, up = lane j+1's even slot (shfl), diag = own odd slot
-// Scores live in registers as (score << 5) | tag: the five tie-ordered candidates carry their arrow
-// code in the low bits, so one VIADDMNMX chain yields both the minimum and the reference's
-// first-match-wins arrow (Diagonal > Left > Up > AffineInsClose > AffineDelClose); the affine
-// open/extend decisions land in bits 3/4 the same way.  Cells outside the guide are held at BIG,
-// which reproduces the reference's INF_INT-for-missing-neighbour rule.  Per d-block of 64 steps the
-// warp stages the band table and target codes of the rows/columns it will touch into shared memory,
-// and writes one traceback byte per cell as coalesced 128 B stores ([4 steps][32 lanes]).
+// B200 mapping.  The band is swept by anti-diagonals d = q'+t' in blocks of 64.  A job is swept by LPJ lanes
+// (8, 16 or 32: narrow bands put 4 or 2 jobs in one warp so the lanes stay busy); lane `sl` of the job owns the
+// 2k consecutive diagonals [2k*sl, 2k*sl + 2k) of the job's window ("slots", k = groups active in this block).
+// On an even step every lane computes the cells on its k even slots, on an odd step the k odd ones, so
+//     even step, group g: left = own odd slot g-1 (g = 0: lane sl-1's top odd slot, one __shfl), up = own odd slot g
+//     odd  step, group g: left = own even slot g, up = own even slot g+1 (g = k-1: lane sl+1's first even slot)
+// i.e. ONE shuffle per lane-step however wide the band is.  Scores live in registers as (score << SH) | tag: the
+// tie-ordered candidates carry their arrow code in the low bits, so one VIADDMNMX chain (DPX) yields both the
+// minimum and the reference's first-match-wins arrow (Diagonal > Left > Up > AffineInsClose > AffineDelClose);
+// the affine open/extend decisions land in two more tag bits the same way.  Cells outside the guide are held at
+// BIG, which reproduces the reference's INF_INT-for-missing-neighbour rule.
+//
+// Inner loop (run_block_ring): the k rows and k columns a lane touches slide by one per two steps, so they are kept
+// in register rings (the loop is unrolled by k, every ring index is static) and refilled with one shared-memory
+// load per row / column; per cell that leaves one LDS (the substitution score), two VIADDMNMX, the in-band test,
+// the tag split and one funnel shift that appends the 2-bit arrow to the lane's traceback word.  Words are stored
+// [d-block][16-step row][slot pair], 2 bits per cell for the linear aligner (8 for the affine one).
+// Blocks that touch the boundary row, a job's last block, the QV score function and very wide windows take the
+// generic path (run_block_gen), which reads its rows and columns from shared memory per cell.
 #include "bgpu_common.cuh"
 
 namespace bgpu {
 
+constexpr uint32_t NOJOB = 0xffffffffu;
+
 struct FillConsts {
-  int delT, insT;        // (del<<SH)|TB_LEFT, (ins<<SH)|TB_UP
+  int delT, insT;        // (del<<SH)|LEFT, (ins<<SH)|UP
   int extT3, extT4;      // (ext<<SH)|TB_ICLOSE, |TB_DCLOSE
   int ext, openI, openD; // ext<<SH, (open<<SH)|TB_IOPEN, (open<<SH)|TB_DOPEN
   int open;              // open<<SH
   int del0;              // row-0 step: (Global ? del : 0) << SH
 };
 
-template <bool AFFINE, bool QV, bool FIRST>
-__device__ __forceinline__ uint32_t dp_cell(int &S, int &AI, int &AD, const int leftS, const int leftAD,
-                                            const int upS, const int upAI, const int4 ri, const int tent,
-                                            const int tprime, const uint32_t mtabAddr, const FillConsts &c) {
-  const bool inb = (unsigned)(tprime - ri.x) <= (unsigned)ri.y;
-  int m;
-  asm("ld.shared.s32 %0, [%1];" : "=r"(m) : "r"(mtabAddr + (uint32_t)(ri.z + tent)));
-  if (QV) m *= (FIRST ? (ri.w & 0xff) : ri.w);           // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+template <int LPJ, int KM>
+struct SubSmem {          // staging of one job's current d-block
+  int2 rows[KM * LPJ + 32];   // {dloRel << 8, (width << 8) | qcode * 20}
+  int rowq[KM * LPJ + 32];    // QV | (boundary row ? 1 << 31 : 0)          (generic path only)
+  int cols[KM * LPJ + 36];    // target code * 4
+  int shift[2 * KM * LPJ];    // window re-mapping scratch
+};
+
+template <bool AFFINE> struct Fmt {
+  static constexpr int SHv = AFFINE ? SH_AFF : SH_LIN;
+  static constexpr int BITS = AFFINE ? 8 : 2;
+  static constexpr int SPW = 32 / BITS;                    // steps per traceback word
+  static constexpr int TAGMASK = (1 << SHv) - 1;
+  static constexpr int NONE = AFFINE ? (int)TB_NONE : (int)TL_NONE;
+};
+
+__device__ __forceinline__ int lds32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// One DP cell.  x8 = (slot - first in-band slot of the row) << 8, y = (row width << 8) | junk < 256.
+template <bool AFFINE>
+__device__ __forceinline__ int dp_core(const int S, const int leftS, const int leftAD, const int upS, const int upAI,
+                                       const int m, const FillConsts &c, int &ai, int &ad) {
   int cnd = S + m;                                         // Diagonal (tag 0)
   cnd = __viaddmin_s32(leftS, c.delT, cnd);                // Left
   cnd = __viaddmin_s32(upS, c.insT, cnd);                  // Up
   if (AFFINE) {
     cnd = __viaddmin_s32(upAI, c.extT3, cnd);              // AffineInsClose
     cnd = __viaddmin_s32(leftAD, c.extT4, cnd);            // AffineDelClose
-  }
-  int ai = 0, ad = 0;
-  if (AFFINE) {
-    // strict '<' in the reference: a tie extends (AffineGuidedAlign.h:357-373) -> the open
-    // candidate carries a flag bit, so it loses ties.
+    // strict '<' in the reference: a tie extends (AffineGuidedAlign.h:357-373) -> the open candidate carries a
+    // flag bit, so it loses ties.
     const int s0 = cnd & ~31;
     ai = __viaddmin_s32(s0, c.openI, upAI + c.ext);
     ad = __viaddmin_s32(s0, c.openD, leftAD + c.ext);
     cnd |= (ai | ad) & 24;                                  // tag | affine flags, still below bit 5
   }
-  if (FIRST) {
-    if (ri.w < 0) {                                        // boundary row (GuidedAlign.h:415-442)
-      cnd = (tprime * c.del0) | (TB_LEFT | TB_IOPEN | TB_DOPEN); ai = c.open; ad = c.open;
-    }
-  }
-  // cells outside the guide: BIG everywhere, arrow NoArrow
-  cnd = inb ? cnd : (BIG | TB_NONE);
-  S = cnd & ~31;
-  if (AFFINE) { AI = inb ? (ai & ~31) : BIG; AD = inb ? (ad & ~31) : BIG; }
-  return (uint32_t)cnd & 31u;
+  return cnd;
 }
 
-__device__ __forceinline__ int rot_up(int v, int lane) { return __shfl_sync(0xffffffffu, v, (lane + 31) & 31); }
-__device__ __forceinline__ int rot_dn(int v, int lane) { return __shfl_sync(0xffffffffu, v, (lane + 1) & 31); }
+template <int LPJ>
+__device__ __forceinline__ int sub_up(int v) { return __shfl_up_sync(0xffffffffu, v, 1, LPJ); }
+template <int LPJ>
+__device__ __forceinline__ int sub_dn(int v) { return __shfl_down_sync(0xffffffffu, v, 1, LPJ); }
 
-template <int KMAX>
-struct WarpSmem {
-  int4 rows[32 * KMAX + 32];
-  int tcol[32 * KMAX + 32];
-  int shift[64 * KMAX];
-};
-
-// KACT > 0: exactly KACT groups are active (compile time, registers, no per-group branches);
-// KACT == 0: the active count k is a run-time value (first/last blocks and the wide kernel).
-template <int KMAX, int KACT, bool AFFINE, bool QV, bool FIRST, bool LAST>
-__device__ __forceinline__ void run_block(int (&Se)[KMAX], int (&So)[KMAX], int (&AIe)[KMAX], int (&AIo)[KMAX],
-                                          int (&ADe)[KMAX], int (&ADo)[KMAX], const WarpSmem<KMAX> &sm,
-                                          const uint32_t mtabAddr, const FillConsts &c, const int k, const int lane,
-                                          const int tlo, const int eLast, uint32_t *arrowWords) {
-  constexpr int UG = KMAX <= 4 ? KMAX : 1;
-  const int gEnd = KACT > 0 ? KACT : (KMAX <= 4 ? KMAX : k);
-  const int kk = KACT > 0 ? KACT : k;
-#define BGPU_ACTIVE(g) (KACT > 0 || (g) < k)
-  // per-lane bases: row index (e>>1) + 32k-1-j-32g, column index ((e+1)>>1) + j + 32g
-  const int4 *rp = sm.rows + (32 * kk - 1 - lane);
-  const int *cp = sm.tcol + lane;
-  int tcur = tlo + lane;
-  uint32_t *aw = arrowWords + lane;
-#pragma unroll 1
-  for (int e4 = 0; e4 < 16; e4++, rp += 2, cp += 2, tcur += 2, aw += 32 * kk) {
-    if (LAST && (e4 << 2) > eLast) break;
-    uint32_t acc[KMAX];
-#pragma unroll(UG)
-    for (int g = 0; g < gEnd; g++) acc[g] = 0;
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path: KA groups per lane (compile time), rows / columns in register rings, no boundary row, full 64 steps.
+template <int LPJ, int KM, int KA, bool AFFINE>
+__device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
+                                               int (&ADe)[KM], int (&ADo)[KM], const SubSmem<LPJ, KM> &sm,
+                                               const uint32_t mtabAddr, const FillConsts &c, const int sl,
+                                               uint32_t *aw, const bool live) {
+  typedef Fmt<AFFINE> F;
+  const int kL = KA * sl;
+  const int2 *rp = sm.rows + KA * (LPJ - 1 - sl);           // rp[i + m]: row of group KA-1-m at step pair i
+  const int *cp = sm.cols + kL;                              // cp[i + g]: column of group g on the even step of pair i
+  const int s08 = (2 * kL) << 8;
+  int rX[KA], rY[KA], rQ[KA], cT[KA];
+  uint32_t acc[KA];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (LAST && (e4 << 2) + u > eLast) break;
-      constexpr int dummy = 0; (void)dummy;
-      const int rI = u >> 1;            // (e>>1) - 2*e4
-      const int cI = (u + 1) >> 1;      // ((e+1)>>1) - 2*e4
-      int rS[KMAX], rA[KMAX];
-      if ((u & 1) == 0) {
-        // even step: left = odd slot of the lane below (ring over lanes and groups), up = own odd slot
-#pragma unroll(UG)
-        for (int g = 0; g < gEnd; g++)
-          if (BGPU_ACTIVE(g)) { rS[g] = rot_up(So[g], lane); if (AFFINE) rA[g] = rot_up(ADo[g], lane); }
-#pragma unroll(UG)
-        for (int g = 0; g < gEnd; g++) {
-          if (BGPU_ACTIVE(g)) {
-            int leftS = rS[g], leftAD = AFFINE ? rA[g] : 0;
-            if (KMAX > 1 && lane == 0) {
-              const int pg = g > 0 ? g - 1 : KMAX - 1;     // the slot below slot 64g is the top slot of group g-1
-              leftS = pg < kk ? rS[pg] : BIG;
-              if (AFFINE) leftAD = pg < kk ? rA[pg] : BIG;
-            }
-            const int4 ri = rp[rI - 32 * g];
-            const int tent = cp[cI + 32 * g];
-            const uint32_t b = dp_cell<AFFINE, QV, FIRST>(Se[g], AIe[g], ADe[g], leftS, leftAD, So[g], AIo[g], ri,
-                                                          tent, tcur + cI + 32 * g, mtabAddr, c);
-            acc[g] += b << (8 * u);
-          }
+  for (int m = 0; m < KA; m++) {
+    const int2 v = rp[m];
+    rX[m] = s08 - v.x; rY[m] = v.y; rQ[m] = (int)mtabAddr + (v.y & 0xff);
+    cT[m] = cp[m];
+    acc[m] = 0;
+  }
+  aw += kL;
+#pragma unroll 1
+  for (int i0 = 0; i0 < 32; i0 += KA) {
+#pragma unroll
+    for (int j = 0; j < KA; j++) {
+      if ((32 % KA) != 0 && i0 + j >= 32) break;
+      // ---- even step: cells on slots 2g
+      {
+        const int left0 = sub_up<LPJ>(So[KA - 1]);
+        const int leftA0 = AFFINE ? sub_up<LPJ>(ADo[KA - 1]) : 0;
+#pragma unroll
+        for (int g = 0; g < KA; g++) {
+          const int p = (j + KA - 1 - g) % KA, cs = (j + g) % KA;
+          const int leftS = g == 0 ? left0 : So[g - 1];
+          const int leftAD = AFFINE ? (g == 0 ? leftA0 : ADo[g - 1]) : 0;
+          const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
+          int ai = 0, ad = 0;
+          int cnd = dp_core<AFFINE>(Se[g], leftS, leftAD, So[g], AFFINE ? AIo[g] : 0, m, c, ai, ad);
+          const bool inb = (unsigned)(rX[p] + ((2 * g) << 8)) <= (unsigned)rY[p];
+          cnd = inb ? cnd : (BIG | F::NONE);
+          Se[g] = cnd & ~F::TAGMASK;
+          if (AFFINE) { AIe[g] = inb ? (ai & ~31) : BIG; ADe[g] = inb ? (ad & ~31) : BIG; }
+          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);
         }
-      } else {
+      }
+      cT[j] = cp[i0 + j + KA];                               // column kL + i + KA replaces kL + i
+      // ---- odd step: cells on slots 2g+1
+      {
+        const int up0 = sub_dn<LPJ>(Se[0]);
+        const int upA0 = AFFINE ? sub_dn<LPJ>(AIe[0]) : 0;
+#pragma unroll
+        for (int g = 0; g < KA; g++) {
+          const int p = (j + KA - 1 - g) % KA, cs = (j + 1 + g) % KA;
+          const int upS = g == KA - 1 ? up0 : Se[g + 1];
+          const int upAI = AFFINE ? (g == KA - 1 ? upA0 : AIe[g + 1]) : 0;
+          const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
+          int ai = 0, ad = 0;
+          int cnd = dp_core<AFFINE>(So[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, m, c, ai, ad);
+          const bool inb = (unsigned)(rX[p] + ((2 * g + 1) << 8)) <= (unsigned)rY[p];
+          cnd = inb ? cnd : (BIG | F::NONE);
+          So[g] = cnd & ~F::TAGMASK;
+          if (AFFINE) { AIo[g] = inb ? (ai & ~31) : BIG; ADo[g] = inb ? (ad & ~31) : BIG; }
+          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);
+        }
+      }
+      {                                                       // row baseR + i + KA replaces row baseR + i
+        const int2 v = rp[i0 + j + KA];
+        rX[j] = s08 - v.x; rY[j] = v.y; rQ[j] = (int)mtabAddr + (v.y & 0xff);
+      }
+      if (((i0 + j) & (F::SPW / 2 - 1)) == F::SPW / 2 - 1) {  // a traceback word is complete
+        if (live) {
+#pragma unroll
+          for (int g = 0; g < KA; g++) aw[g] = acc[g];
+        }
+        aw += KA * LPJ;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generic path: run-time k, rows / columns read from shared memory per cell, boundary row (first) and the early
+// stop of a job's last block (eLast) handled per cell.
+template <int LPJ, int KM, bool AFFINE, bool QV>
+__device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
+                                              int (&ADe)[KM], int (&ADo)[KM], const SubSmem<LPJ, KM> &sm,
+                                              const uint32_t mtabAddr, const FillConsts &c, const int k, const int sl,
+                                              const int tlo, const bool first, const int eLast, uint32_t *aw,
+                                              const bool live) {
+  typedef Fmt<AFFINE> F;
+  constexpr int UG = KM <= KRING ? KM : 1;
+  const int kL = k * sl, baseR = k * (LPJ - 1 - sl);
+  uint32_t acc[KM];
 #pragma unroll(UG)
-        for (int g = 0; g < gEnd; g++)
-          if (BGPU_ACTIVE(g)) { rS[g] = rot_dn(Se[g], lane); if (AFFINE) rA[g] = rot_dn(AIe[g], lane); }
+  for (int g = 0; g < KM; g++) acc[g] = 0;
+  aw += kL;
+  auto cell = [&](int &S, int &AI, int &AD, const int leftS, const int leftAD, const int upS, const int upAI,
+                  const int ridx, const int cidx, const int slot, const int e, uint32_t &a) {
+    const int2 rv = sm.rows[ridx];
+    const int rq = sm.rowq[ridx];
+    const int tent = sm.cols[cidx];
+    int m = lds32(mtabAddr + (uint32_t)((rv.y & 0xff) + tent));
+    if (QV) m *= (rq & 0xff);                               // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+    int ai = 0, ad = 0;
+    int cnd = dp_core<AFFINE>(S, leftS, leftAD, upS, upAI, m, c, ai, ad);
+    if (first && rq < 0) {                                  // boundary row (GuidedAlign.h:415-442)
+      cnd = ((tlo + cidx) * c.del0) | (AFFINE ? (TB_LEFT | TB_IOPEN | TB_DOPEN) : TL_LEFT);
+      ai = c.open; ad = c.open;
+    }
+    const bool inb = (unsigned)((slot << 8) - rv.x) <= (unsigned)rv.y;
+    cnd = inb ? cnd : (BIG | F::NONE);
+    if (e <= eLast) {
+      S = cnd & ~F::TAGMASK;
+      if (AFFINE) { AI = inb ? (ai & ~31) : BIG; AD = inb ? (ad & ~31) : BIG; }
+    } else cnd = F::NONE;
+    a = __funnelshift_r(a, (uint32_t)cnd, F::BITS);
+  };
+  auto pick = [&](int (&X)[KM], const int idx) {
+    int v = BIG;
+    if (KM <= KRING) {
+#pragma unroll
+      for (int g = 0; g < KM; g++) if (g == idx) v = X[g];
+    } else v = X[idx];
+    return v;
+  };
+#pragma unroll 1
+  for (int i = 0; i < 32; i++) {
+    {
+      const int left0 = sub_up<LPJ>(pick(So, k - 1));
+      const int leftA0 = AFFINE ? sub_up<LPJ>(pick(ADo, k - 1)) : 0;
+      int prevS = left0, prevA = leftA0;
 #pragma unroll(UG)
-        for (int g = 0; g < gEnd; g++) {
-          if (BGPU_ACTIVE(g)) {
-            int upS = rS[g], upAI = AFFINE ? rA[g] : 0;
-            if (KMAX > 1 && lane == 31) {
-              const int ng = g + 1 < KMAX ? g + 1 : 0;
-              upS = ng < kk ? rS[ng] : BIG;
-              if (AFFINE) upAI = ng < kk ? rA[ng] : BIG;
-            }
-            const int4 ri = rp[rI - 32 * g];
-            const int tent = cp[cI + 32 * g];
-            const uint32_t b = dp_cell<AFFINE, QV, FIRST>(So[g], AIo[g], ADo[g], Se[g], ADe[g], upS, upAI, ri, tent,
-                                                          tcur + cI + 32 * g, mtabAddr, c);
-            acc[g] += b << (8 * u);
-          }
+      for (int g = 0; g < KM; g++) {
+        if (g < k) {
+          const int so = So[g], ado = AFFINE ? ADo[g] : 0;
+          cell(Se[g], AIe[g], ADe[g], prevS, prevA, so, AFFINE ? AIo[g] : 0, baseR + i + (k - 1 - g), kL + g + i,
+               2 * (kL + g), 2 * i, acc[g]);
+          prevS = so; prevA = ado;
         }
       }
     }
+    {
+      const int up0 = sub_dn<LPJ>(Se[0]);
+      const int upA0 = AFFINE ? sub_dn<LPJ>(AIe[0]) : 0;
 #pragma unroll(UG)
-    for (int g = 0; g < gEnd; g++)
-      if (BGPU_ACTIVE(g)) aw[g << 5] = acc[g];
+      for (int g = 0; g < KM; g++) {
+        if (g < k) {
+          int upS = up0, upAI = upA0;
+          if (g + 1 < k) { upS = Se[(g + 1) % KM]; if (AFFINE) upAI = AIe[(g + 1) % KM]; }
+          cell(So[g], AIo[g], ADo[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, baseR + i + (k - 1 - g), kL + g + i + 1,
+               2 * (kL + g) + 1, 2 * i + 1, acc[g]);
+        }
+      }
+    }
+    if ((i & (F::SPW / 2 - 1)) == F::SPW / 2 - 1) {
+      if (live) {
+#pragma unroll(UG)
+        for (int g = 0; g < KM; g++) if (g < k) aw[g] = acc[g];
+      }
+      aw += k * LPJ;
+    }
   }
-#undef BGPU_ACTIVE
 }
 
-template <int KMAX, bool AFFINE, bool QV>
-__global__ void __launch_bounds__(KMAX <= 4 ? 128 : 32) fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order,
-                                                          uint32_t nOrder, uint32_t *counter) {
+template <int LPJ, int KM, bool AFFINE, int KA>
+struct RingDispatch {
+  static __device__ __forceinline__ void run(const int k, int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
+                                             int (&ADe)[KM], int (&ADo)[KM], const SubSmem<LPJ, KM> &sm,
+                                             const uint32_t mtabAddr, const FillConsts &c, const int sl, uint32_t *aw,
+                                             const bool live) {
+    if (k == KA) run_block_ring<LPJ, KM, KA, AFFINE>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, sl, aw, live);
+    else RingDispatch<LPJ, KM, AFFINE, KA + 1>::run(k, Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, sl, aw, live);
+  }
+};
+template <int LPJ, int KM, bool AFFINE>
+struct RingDispatch<LPJ, KM, AFFINE, KRING + 1> {
+  static __device__ __forceinline__ void run(const int, int (&)[KM], int (&)[KM], int (&)[KM], int (&)[KM], int (&)[KM],
+                                             int (&)[KM], const SubSmem<LPJ, KM> &, const uint32_t, const FillConsts &,
+                                             const int, uint32_t *, const bool) {}
+};
+
+// order[] holds warp groups: 32 / LPJ job indices each (NOJOB pads the last group); a warp sweeps its jobs in
+// lockstep from d-block 0, with k = the widest member's need per block.
+template <int LPJ, int KM, bool AFFINE, bool QV>
+__global__ void __launch_bounds__(KM <= KRING ? 128 : 32)
+fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nGroups, uint32_t *counter) {
+  typedef Fmt<AFFINE> F;
+  constexpr int NJ = 32 / LPJ;
+  constexpr bool RING = KM <= KRING && !QV;
+  constexpr int UG = KM <= KRING ? KM : 1;
+  constexpr int UNITW = (64 / F::SPW) * LPJ;                // words per arrow unit
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ int Mtab[25];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpSmem<KMAX> &sm = reinterpret_cast<WarpSmem<KMAX> *>(smemRaw)[warp];
+  const int sub = lane / LPJ, sl = lane % LPJ;
+  SubSmem<LPJ, KM> &sm = reinterpret_cast<SubSmem<LPJ, KM> *>(smemRaw)[warp * NJ + sub];
   if (threadIdx.x < 25) {
-    if (QV) { const int r = threadIdx.x / 5, cc = threadIdx.x % 5; Mtab[threadIdx.x] = ((r == cc && r < 4) ? -1 : 1) << SH; }  // ScoreMatrices.h:4-10
-    else Mtab[threadIdx.x] = P.M[threadIdx.x] << SH;
+    if (QV) { const int r = threadIdx.x / 5, cc = threadIdx.x % 5; Mtab[threadIdx.x] = ((r == cc && r < 4) ? -1 : 1) << F::SHv; }  // ScoreMatrices.h:4-10
+    else Mtab[threadIdx.x] = P.M[threadIdx.x] << F::SHv;
   }
   __syncthreads();
   const uint32_t mtabAddr = (uint32_t)__cvta_generic_to_shared(Mtab);
   FillConsts c;
-  c.delT = (P.del << SH) | TB_LEFT; c.insT = (P.ins << SH) | TB_UP;
-  c.extT3 = (P.ext << SH) | TB_ICLOSE; c.extT4 = (P.ext << SH) | TB_DCLOSE;
-  c.ext = P.ext << SH; c.open = P.open << SH;
-  c.openI = (P.open << SH) | TB_IOPEN; c.openD = (P.open << SH) | TB_DOPEN;
-  c.del0 = (P.alignType == BGPU_GLOBAL ? P.del : 0) << SH;
+  c.delT = (P.del << F::SHv) | TB_LEFT; c.insT = (P.ins << F::SHv) | TB_UP;
+  c.extT3 = (P.ext << F::SHv) | TB_ICLOSE; c.extT4 = (P.ext << F::SHv) | TB_DCLOSE;
+  c.ext = P.ext << F::SHv; c.open = P.open << F::SHv;
+  c.openI = (P.open << F::SHv) | TB_IOPEN; c.openD = (P.open << F::SHv) | TB_DOPEN;
+  c.del0 = (P.alignType == BGPU_GLOBAL ? P.del : 0) << F::SHv;
 
   for (;;) {
-    uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(counter, 1u);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
-    if (idx >= nOrder) break;
-    const uint32_t job = order[idx];
-    JobGeom &G = B.geom[job];
-    if (G.status != BGPU_JOB_OK) continue;
-    const int Qn = G.Qn, Tn = G.Tn, C0 = G.C0, nDB = G.nDB, hi0 = G.hi0, tStart = G.tStart;
-    const RowInfo *rows = B.rows + G.rowOff;
-    const DBlock *dblk = B.dblk + G.dblkOff;
-    const uint8_t *tcodes = B.t + B.tOff[job] + tStart - 1;   // tcodes[t'] for t' in [1,Tn]
-    uint32_t *arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
+    uint32_t grp = 0;
+    if (lane == 0) grp = atomicAdd(counter, 1u);
+    grp = __shfl_sync(0xffffffffu, grp, 0);
+    if (grp >= nGroups) break;
+    const uint32_t job = order[(size_t)grp * NJ + sub];
+    bool have = job != NOJOB;
+    JobGeom *G = have ? &B.geom[job] : nullptr;
+    if (have && G->status != BGPU_JOB_OK) have = false;
+    int Qn = 0, Tn = 0, C0 = 0, nDB = 0, hi0 = 0;
+    const RowInfo *rows = nullptr; DBlock *dblk = nullptr; const uint8_t *tcodes = nullptr; uint32_t *arrowsJob = nullptr;
+    if (have) {
+      Qn = G->Qn; Tn = G->Tn; C0 = G->C0; nDB = G->nDB; hi0 = G->hi0;
+      rows = B.rows + G->rowOff; dblk = B.dblk + G->dblkOff;
+      tcodes = B.t + B.tOff[job] + G->tStart - 1;            // tcodes[t'] for t' in [1,Tn]
+      arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
+    }
+    const int nDBw = __reduce_max_sync(0xffffffffu, nDB);
     const int nD = Qn + Tn + 1;
 
-    constexpr int UG = KMAX <= 4 ? KMAX : 1;
-    int Se[KMAX], So[KMAX], AIe[KMAX], AIo[KMAX], ADe[KMAX], ADo[KMAX];
+    int Se[KM], So[KM], AIe[KM], AIo[KM], ADe[KM], ADo[KM];
 #pragma unroll(UG)
-    for (int g = 0; g < KMAX; g++) { Se[g] = So[g] = AIe[g] = AIo[g] = ADe[g] = ADo[g] = BIG; }
+    for (int g = 0; g < KM; g++) { Se[g] = So[g] = AIe[g] = AIo[g] = ADe[g] = ADo[g] = BIG; }
     int wprev = 0, kprev = 0;
+    uint32_t unit = 0;
 
-    for (int b = 0; b < nDB; b++) {
-      const DBlock db = dblk[b];
-      const int wbase = db.wbase, k = db.k;
-      // ---- slide the register window to this block's diagonals
-      if (b > 0 && (wbase != wprev || k != kprev)) {
+    for (int b = 0; b < nDBw; b++) {
+      const bool live = have && b < nDB;
+      int wbase = wprev, kown = 1;
+      if (live) { const DBlock db = dblk[b]; wbase = db.wbase; kown = db.k; }
+      const int k = __reduce_max_sync(0xffffffffu, kown);
+      // ---- re-map the register window (old: kprev groups from diagonal wprev; new: k groups from wbase)
+      if (b > 0 && __any_sync(0xffffffffu, wbase != wprev || k != kprev)) {
         const int delta = wbase - wprev;
-        // invariant: groups >= kprev hold BIG.  Old slot s' = s + delta feeds new slot s.
-        const int gW = KMAX <= 4 ? KMAX : kprev, gR = KMAX <= 4 ? KMAX : max(k, kprev);
-        auto slide = [&](int (&Xe)[KMAX], int (&Xo)[KMAX]) {
+        auto remap = [&](int (&Xe)[KM], int (&Xo)[KM]) {
           __syncwarp();
 #pragma unroll(UG)
-          for (int g = 0; g < gW; g++) { sm.shift[64 * g + 2 * lane] = Xe[g]; sm.shift[64 * g + 2 * lane + 1] = Xo[g]; }
+          for (int g = 0; g < KM; g++)
+            if (g < kprev) { sm.shift[2 * (kprev * sl + g)] = Xe[g]; sm.shift[2 * (kprev * sl + g) + 1] = Xo[g]; }
           __syncwarp();
 #pragma unroll(UG)
-          for (int g = 0; g < gR; g++) {
-            const int s = 64 * g + 2 * lane + delta;
-            const bool ok = (g < k) && s >= 0 && s < 64 * (KMAX <= 4 ? KMAX : kprev);
-            Xe[g] = ok ? sm.shift[s] : BIG;
-            Xo[g] = ok ? sm.shift[s + 1] : BIG;
+          for (int g = 0; g < KM; g++) {
+            if (g < k) {
+              const int s = 2 * (k * sl + g) + delta;
+              const bool ok = s >= 0 && s < 2 * kprev * LPJ;
+              Xe[g] = ok ? sm.shift[s] : BIG;
+              Xo[g] = ok ? sm.shift[s + 1] : BIG;
+            }
           }
         };
-        slide(Se, So);
-        if (AFFINE) { slide(AIe, AIo); slide(ADe, ADo); }
+        remap(Se, So);
+        if (AFFINE) { remap(AIe, AIo); remap(ADe, ADo); }
       }
       wprev = wbase; kprev = k;
-      // ---- stage rows [qlo, qlo+32k+31) and columns [tlo, tlo+32k+32)
+      // ---- stage rows [qlo, qlo + k*LPJ + 32) and columns [tlo, tlo + k*LPJ + 33)
       const int cq = (C0 - wbase) >> 1;
-      const int qlo = 32 * b + cq - 32 * k + 1, tlo = 32 * b - cq;
+      const int qlo = 32 * b + cq - (k * LPJ - 1), tlo = 32 * b - cq;
       __syncwarp();
-      for (int r = lane; r < 32 * k + 31; r += 32) {
+      for (int r = sl; r < k * LPJ + 32; r += LPJ) {
         const int qp = qlo + r;
-        int4 v = make_int4(INT_MAX / 2, 0, 0, 0);
-        if (qp >= 0 && qp <= Qn) {
+        int2 v = make_int2(1 << 28, 0);
+        int rq = 0;
+        if (live && qp >= 0 && qp <= Qn) {
           const RowInfo ri = rows[qp];
-          v.x = ri.lo; v.y = (int)(ri.packed & ((1u << ROW_W_BITS) - 1));
-          v.z = (int)((ri.packed >> 20) & 7u) * 20;
-          v.w = (int)((ri.packed >> 23) & 0xffu) | (qp == 0 ? (int)0x80000000 : 0);
+          const int w = (int)(ri.packed & ((1u << ROW_W_BITS) - 1));
+          v.x = (ri.lo - qp + C0 - wbase) << 8;
+          v.y = (w << 8) | ((int)((ri.packed >> 20) & 7u) * 20);
+          rq = (int)((ri.packed >> 23) & 0xffu) | (qp == 0 ? (int)0x80000000 : 0);
         }
-        sm.rows[r] = v;
+        sm.rows[r] = v; sm.rowq[r] = rq;
       }
-      for (int cI = lane; cI < 32 * k + 32; cI += 32) {
+      for (int cI = sl; cI < k * LPJ + 33; cI += LPJ) {
         const int tp = tlo + cI;
-        sm.tcol[cI] = (tp >= 1 && tp <= Tn) ? (int)tcodes[tp] * 4 : 0;
+        sm.cols[cI] = (live && tp >= 1 && tp <= Tn) ? (int)tcodes[tp] * 4 : 0;
       }
       __syncwarp();
-      uint32_t *aw = arrowsJob + (size_t)db.arrowUnit * 512u;
-      const bool first = (b << 6) <= hi0;               // row 0 holds cells on d <= hi0
-      const bool last = (b == nDB - 1);
-      const int eLast = (nD - 1) & 63;
-      if (first && last) run_block<KMAX, 0, AFFINE, QV, true, true>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-      else if (first) run_block<KMAX, 0, AFFINE, QV, true, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-      else if (last) run_block<KMAX, 0, AFFINE, QV, false, true>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-      else if (KMAX > 4) run_block<KMAX, 0, AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-      else if (k == 1) run_block<KMAX, 1, AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-      else if (KMAX >= 2 && k == 2) run_block<KMAX, (KMAX >= 2 ? 2 : 1), AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-      else if (KMAX >= 4 && k == 3) run_block<KMAX, (KMAX >= 4 ? 3 : 1), AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-      else run_block<KMAX, (KMAX >= 4 ? 4 : 1), AFFINE, QV, false, false>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, lane, tlo, eLast, aw);
-    }
-    // ---- the end cell (Qn, Tn) sits on diagonal Tn-Qn+C0 and is the last cell written to its slot
-    {
-      const int s = Tn - Qn + C0 - wprev;
-      int v = BIG;
-#pragma unroll(UG)
-      for (int g = 0; g < KMAX; g++) if ((s >> 6) == g) v = (s & 1) ? So[g] : Se[g];
-      v = __shfl_sync(0xffffffffu, v, (s & 63) >> 1);
-      if (lane == 0) G.score = v >> SH;
+      uint32_t *aw = arrowsJob + (size_t)unit * UNITW;
+      const bool first = live && (b << 6) <= hi0;          // row 0 holds cells on d <= hi0
+      const bool last = live && (b == nDB - 1);
+      const int eLast = last ? ((nD - 1) & 63) : 63;
+      if (RING && k <= KRING && !__any_sync(0xffffffffu, first || last))
+        RingDispatch<LPJ, KM, AFFINE, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, sl, aw, live);
+      else
+        run_block_gen<LPJ, KM, AFFINE, QV>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, sl, tlo, first, eLast, aw, live);
+      if (live && sl == 0) { dblk[b].k = k; dblk[b].arrowUnit = unit; }
+      unit += (uint32_t)k;
+      // ---- the end cell (Qn, Tn) sits on diagonal Tn-Qn+C0 and is the last cell written to its slot
+      if (__any_sync(0xffffffffu, last)) {
+        const int s = Tn - Qn + C0 - wbase;
+        const int sg = s >> 1, owner = last ? sg / k : 0, g = last ? sg % k : 0;
+        int v = BIG;
+        if (KM <= KRING) {
+#pragma unroll
+          for (int gg = 0; gg < KM; gg++) if (gg == g) v = (s & 1) ? So[gg] : Se[gg];
+        } else v = (s & 1) ? So[g] : Se[g];
+        v = __shfl_sync(0xffffffffu, v, owner, LPJ);
+        if (last && sl == 0) G->score = v >> F::SHv;
+      }
     }
   }
 }
 
-template <int KMAX, bool AFFINE, bool QV>
-static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, uint32_t nOrder,
+template <int LPJ, int KM, bool AFFINE, bool QV>
+static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, uint32_t nGroups,
                        uint32_t *counter, int nSM, cudaStream_t s) {
-  constexpr int WPC = KMAX <= 4 ? 4 : 1;           // warps per CTA
-  const size_t smem = sizeof(WarpSmem<KMAX>) * WPC;
-  auto kern = fill_guided_kernel<KMAX, AFFINE, QV>;
+  constexpr int WPC = KM <= KRING ? 4 : 1;          // warps per CTA
+  const size_t smem = sizeof(SubSmem<LPJ, KM>) * (32 / LPJ) * WPC;
+  auto kern = fill_guided_kernel<LPJ, KM, AFFINE, QV>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int perSM = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, WPC * 32, smem);
   if (perSM < 1) perSM = 1;
   unsigned grid = (unsigned)(nSM * perSM);
-  const unsigned need = (nOrder + WPC - 1) / WPC;
+  const unsigned need = (nGroups + WPC - 1) / WPC;
   if (grid > need) grid = need;
-  if (grid) kern<<<grid, WPC * 32, smem, s>>>(B, P, order, nOrder, counter);
+  if (grid) kern<<<grid, WPC * 32, smem, s>>>(B, P, order, nGroups, counter);
 }
 
-// kclass: 1 -> KMAX=1, 2 -> KMAX=2, 4 -> KMAX=4, anything larger -> the wide kernel (KMAX_BUILD groups)
-void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int kclass, const uint32_t *order, uint32_t nOrder,
+template <bool AFFINE, bool QV>
+static void launch_cls(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, uint32_t nGroups,
+                       uint32_t *counter, int nSM, cudaStream_t s) {
+  if (cls == CLS_L8) launch_one<8, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
+  else if (cls == CLS_L16) launch_one<16, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
+  else if (cls == CLS_L32) launch_one<32, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
+  else launch_one<32, KWIDE, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
+}
+
+// cls: CLS_*; order: nGroups groups of 32 / cls_lpj(cls) job indices
+void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, uint32_t nGroups,
                         uint32_t *counter, int nSM, cudaStream_t s) {
   const bool aff = P.affine != 0, qv = P.kind == BGPU_FN_QUALITY;
-#define BGPU_DISPATCH(K)                                                                   \
-  do {                                                                                     \
-    if (aff && qv) launch_one<K, true, true>(B, P, order, nOrder, counter, nSM, s);        \
-    else if (aff) launch_one<K, true, false>(B, P, order, nOrder, counter, nSM, s);        \
-    else if (qv) launch_one<K, false, true>(B, P, order, nOrder, counter, nSM, s);         \
-    else launch_one<K, false, false>(B, P, order, nOrder, counter, nSM, s);                \
-  } while (0)
-  if (kclass == 1) BGPU_DISPATCH(1);
-  else if (kclass == 2) BGPU_DISPATCH(2);
-  else if (kclass == 4) BGPU_DISPATCH(4);
-  else BGPU_DISPATCH(KMAX_BUILD);
-#undef BGPU_DISPATCH
+  if (aff && qv) launch_cls<true, true>(B, P, cls, order, nGroups, counter, nSM, s);
+  else if (aff) launch_cls<true, false>(B, P, cls, order, nGroups, counter, nSM, s);
+  else if (qv) launch_cls<false, true>(B, P, cls, order, nGroups, counter, nSM, s);
+  else launch_cls<false, false>(B, P, cls, order, nGroups, counter, nSM, s);
 }
 
 }  // namespace bgpu

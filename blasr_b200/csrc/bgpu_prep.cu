@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
     G.rowOff = rowOffIn[job]; G.dblkOff = dblkOffIn[job]; G.runOff = runOffIn[job];
     G.arrowBytes = 0; G.nRuns = G.nBlocks = G.nGaps = G.nGapLists = 0;
     G.qPos = G.tPos = 0; G.score = 0; G.nCells = 0; G.kmax = 0; G.nDB = 0; G.band = band;
-    G.Qn = G.Tn = 0; G.qStart = G.tStart = 0; G.C0 = 0; G.hi0 = 0;
+    G.Qn = G.Tn = 0; G.qStart = G.tStart = 0; G.C0 = 0; G.hi0 = 0; G.cls = 0; G.ksum = 0;
   }
   if (nB == 0) { if (lane == 0) G.status = BGPU_JOB_EMPTY_GUIDE; return; }   // GuidedAlign.h:388-392
   if (band < 0) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
     int mx = max(max(abs(P.ins), abs(P.del)), abs(P.open) + abs(P.ext));
     if (P.kind == BGPU_FN_QUALITY) mx = max(mx, 255);
     else for (int i = 0; i < 25; i++) mx = max(mx, abs(P.M[i]));
-    if ((long long)mx * (Qn + Tn + 2) >= SCORE_LIMIT || mx >= (1 << 15)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }
+    if ((long long)mx * (Qn + Tn + 2) >= (P.affine ? SCORE_LIMIT_AFF : SCORE_LIMIT_LIN) || mx >= (1 << 15)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }
   }
 
   // ---- encode + validate the target window in place (codes 0..4), and check the query bases
@@ -186,33 +186,38 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   if (warp_or(bad) || cells > INT_MAX) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
   __threadfence(); __syncwarp();
 
-  // ---- per d-block window + arrow layout (exclusive scan of k over blocks)
+  // ---- per d-block window [mn-1, mx+1] aligned down to an even diagonal (the edge slots stay dead, see
+  //      bgpu_fill.cu); the widest window picks the job's class, i.e. how many lanes sweep it
   DBlock *db = B.dblk + dblkOffIn[job];
-  uint32_t carry = 0; int kmax = 0;
-  for (int base = 0; base < nDB; base += 32) {
-    const int b = base + lane;
-    int k = 0, wbase = 0;
-    if (b < nDB) {
-      const int mn = __ldcg(&dmin[b]), mx = __ldcg(&dmax[b]);
-      // window [mn-1, mx+1] aligned down to an even diagonal (see bgpu_fill.cu: edge slots stay dead)
-      wbase = (mn - 1) & ~1;
-      k = (mx + 1 - wbase) / 64 + 1;
-      if (mx < mn) { wbase = 0; k = 1; }
-    }
-    uint32_t incl = (uint32_t)k;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-    if (b < nDB) { db[b].wbase = wbase; db[b].k = k; db[b].arrowUnit = carry + incl - (uint32_t)k; db[b].pad = 0; }
-    carry += __shfl_sync(0xffffffffu, incl, 31);
-    kmax = max(kmax, k);
+  int maxSpan = 0;
+  for (int b = lane; b < nDB; b += 32) {
+    const int mn = __ldcg(&dmin[b]), mx = __ldcg(&dmax[b]);
+    int wbase = (mn - 1) & ~1, span = mx + 1 - wbase;
+    if (mx < mn) { wbase = 0; span = 0; }
+    db[b].wbase = wbase;
+    maxSpan = max(maxSpan, span);
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-  if (warp_or(wide) || kmax > KMAX_BUILD) status = BGPU_JOB_TOO_WIDE;
+  maxSpan = __reduce_max_sync(0xffffffffu, maxSpan);
+  int cls = CLS_L8;
+  if (maxSpan >= 2 * 8 * KRING) cls = CLS_L16;
+  if (maxSpan >= 2 * 16 * KRING) cls = CLS_L32;
+  if (maxSpan >= 2 * 32 * KRING) cls = CLS_WIDE;
+  if (warp_or(wide) || maxSpan >= 2 * 32 * KWIDE) status = BGPU_JOB_TOO_WIDE;
+  const int gw = 2 * cls_lpj(cls);
+  int kmax = 0, ksum = 0;
+  for (int b = lane; b < nDB; b += 32) {
+    const int mn = __ldcg(&dmin[b]), mx = __ldcg(&dmax[b]);
+    const int span = mx < mn ? 0 : mx + 1 - db[b].wbase;
+    const int k = span / gw + 1;
+    db[b].k = k; db[b].arrowUnit = 0; db[b].pad = 0;
+    kmax = max(kmax, k); ksum += k;
+  }
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  ksum = __reduce_add_sync(0xffffffffu, ksum);
   if (lane == 0) {
     G.status = status; G.qStart = qStart; G.tStart = tStart; G.Qn = Qn; G.Tn = Tn; G.C0 = C0;
-    G.nDB = nDB; G.kmax = kmax; G.nCells = (int)cells; G.hi0 = hi0;
-    G.arrowBytes = (uint64_t)carry * 2048ull;
+    G.nDB = nDB; G.kmax = kmax; G.nCells = (int)cells; G.hi0 = hi0; G.cls = cls; G.ksum = ksum;
+    G.arrowBytes = 0;
   }
 }
 

@@ -14,69 +14,95 @@ namespace bgpu {
 
 enum { RUN_D = 0, RUN_U = 1, RUN_L = 2 };   // diagonal / up (insertion, Gap::Target) / left (deletion, Gap::Query)
 
-// One THREAD per job: a traceback is a serial pointer chase, so a warp walks 32 independent paths at
-// once (jobs are ordered longest-first, neighbouring threads have similar path lengths).  The walk only
-// ever moves to lower anti-diagonals and at most one diagonal sideways per step, so the 128 B line that
-// holds the next rows of the same slot is prefetched two rows (8 anti-diagonals) ahead.
+// One THREAD per job: a traceback is a serial pointer chase, so a warp walks 32 independent paths at once (jobs are
+// ordered longest-first, neighbouring threads have similar path lengths).  The fill kernels store the arrows
+// [d-block][row of 16 (linear) / 4 (affine) anti-diagonals][slot pair], so the walk, which only ever moves to lower
+// anti-diagonals and at most one diagonal sideways per step, stays inside one 32 B sector for many steps; the
+// sector two rows further down is prefetched.  Linear words hold 16 two-bit arrows of one slot pair: a run of
+// Diagonal arrows (every other field, the slot does not change) is consumed with one CLZ instead of one step each.
+template <bool AFFINE>
 __global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder) {
+  constexpr int BITS = AFFINE ? 8 : 2, SPW = 32 / BITS, ROWS = 64 / SPW;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nOrder) return;
   const uint32_t job = order[idx];
+  if (job == 0xffffffffu) return;
   JobGeom &G = B.geom[job];
   if (G.status != BGPU_JOB_OK) return;
   const int Qn = G.Qn, Tn = G.Tn, C0 = G.C0;
+  const int lpj = cls_lpj(G.cls);
+  const size_t unitBytes = (size_t)ROWS * lpj * 4;
   const DBlock *dblk = B.dblk + G.dblkOff;
   const uint8_t *arrows = B.arrows + B.arrowOff[job];
   uint32_t *runs = B.runs + G.runOff;
 
   int q = Qn, t = Tn, mat = 0;
-  int curB = -1, wbase = 0, k = 1; size_t blkBase = 0;
-  int pW = 0, pK = 1; size_t pBase = 0;               // previous d-block (next one the walk enters)
+  int curB = -1, wbase = 0; size_t blkBase = 0, rowBytes = 0;
+  int pW = 0; size_t pBase = 0, pRowBytes = 0;          // previous d-block (next one the walk enters)
+  const uint8_t *curAddr = nullptr; uint32_t word = 0;
   int runType = -1; uint32_t runLen = 0, nRuns = 0;
   uint32_t nBlocks = 0, nGaps = 0, pendGaps = 0, pendQ = 0, pendT = 0;
   bool seenD = false, awry = false;
 
-  auto push = [&](int type) {
-    if (type == runType) { runLen++; return; }
+  auto push = [&](int type, uint32_t n) {
+    if (type == runType) { runLen += n; return; }
     if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
-    runType = type; runLen = 1;
+    runType = type; runLen = n;
     if (type == RUN_D) { if (seenD) nGaps += pendGaps; pendGaps = 0; pendQ = pendT = 0; seenD = true; nBlocks++; }
     else pendGaps++;
   };
 
   while (q >= 1 || t >= 1) {
     if (q < 0 || t < 0) { awry = true; break; }
-    const int d = q + t, b = d >> 6;
+    const int d = q + t, b = d >> 6, e = d & 63;
     if (b != curB) {
-      const DBlock db = dblk[b]; wbase = db.wbase; k = db.k; blkBase = (size_t)db.arrowUnit * 2048u; curB = b;
-      if (b > 0) { const DBlock pb = dblk[b - 1]; pW = pb.wbase; pK = pb.k; pBase = (size_t)pb.arrowUnit * 2048u; }
+      const DBlock db = dblk[b]; wbase = db.wbase; rowBytes = (size_t)db.k * lpj * 4; blkBase = (size_t)db.arrowUnit * unitBytes; curB = b;
+      if (b > 0) { const DBlock pb = dblk[b - 1]; pW = pb.wbase; pRowBytes = (size_t)pb.k * lpj * 4; pBase = (size_t)pb.arrowUnit * unitBytes; }
     }
     const int cd = t - q + C0;
     const int s = cd - wbase;
-    if (s < 0 || s >= 64 * k) { awry = true; break; }
-    if ((d & 3) == 3 || (d & 3) == 2) {                 // entering a new 4-step row: prefetch 2 rows down
-      const int dp = d - 8;
-      if (dp >= (b << 6)) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(arrows + blkBase + ((size_t)((((dp & 63) >> 2) * k + (s >> 6)) * 32 + ((s & 63) >> 1)) << 2)));
-      } else if (b > 0) {
-        int sp = cd - pW; sp = sp < 0 ? 0 : (sp >= 64 * pK ? 64 * pK - 1 : sp);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(arrows + pBase + ((size_t)((((dp & 63) >> 2) * pK + (sp >> 6)) * 32 + ((sp & 63) >> 1)) << 2)));
+    if (s < 0 || (size_t)(s >> 1) * 4 >= rowBytes) { awry = true; break; }
+    const int row = e / SPW;
+    const uint8_t *addr = arrows + blkBase + (size_t)row * rowBytes + (size_t)(s >> 1) * 4;
+    if (addr != curAddr) {
+      word = __ldg(reinterpret_cast<const uint32_t *>(addr)); curAddr = addr;
+      if (row >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(addr - 2 * rowBytes));
+      else if (b > 0) {
+        long sp = (cd - pW) >> 1; const long lim = (long)(pRowBytes >> 2) - 1;
+        sp = sp < 0 ? 0 : (sp > lim ? lim : sp);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(arrows + pBase + (size_t)(ROWS + row - 2) * pRowBytes + (size_t)sp * 4));
       }
     }
-    const uint32_t byte = arrows[blkBase + ((size_t)((((d & 63) >> 2) * k + (s >> 6)) * 32 + ((s & 63) >> 1)) << 2) + (d & 3)];
-    const uint32_t tag = byte & 7u;
-    if (tag == TB_NONE) { awry = true; break; }
-    if (mat == 0) {
-      if (tag == TB_DIAG) { push(RUN_D); q--; t--; }
-      else if (tag == TB_UP) { push(RUN_U); pendQ++; q--; }
-      else if (tag == TB_LEFT) { push(RUN_L); pendT++; t--; }
-      else if (tag == TB_ICLOSE) { push(RUN_U); pendQ++; mat = 1; q--; }
-      else if (tag == TB_DCLOSE) { push(RUN_L); pendT++; mat = 2; t--; }
+    const int pos = e % SPW;
+    const uint32_t f = (word >> (BITS * pos)) & ((1u << BITS) - 1u);
+    if (!AFFINE) {
+      if (f == TL_DIAG) {
+        // Diagonal arrows of this slot sit in fields pos, pos-2, ...: take the whole run inside the word at once
+        uint32_t x = word & (0x33333333u << (2 * (pos & 1)));
+        x &= 0xffffffffu >> (30 - 2 * pos);
+        int n = x == 0 ? (pos >> 1) + 1 : (pos - ((31 - __clz((int)x)) >> 1)) >> 1;
+        n = min(n, min(q, t));
+        if (n <= 0) { awry = true; break; }
+        push(RUN_D, (uint32_t)n); q -= n; t -= n;
+      }
+      else if (f == TL_UP) { push(RUN_U, 1); pendQ++; q--; }
+      else if (f == TL_LEFT) { push(RUN_L, 1); pendT++; t--; }
       else { awry = true; break; }
-    } else if (mat == 1) {
-      if (byte & TB_IOPEN) mat = 0; else { q--; push(RUN_U); pendQ++; }
     } else {
-      if (byte & TB_DOPEN) mat = 0; else { t--; push(RUN_L); pendT++; }
+      const uint32_t tag = f & 7u;
+      if (tag == TB_NONE) { awry = true; break; }
+      if (mat == 0) {
+        if (tag == TB_DIAG) { push(RUN_D, 1); q--; t--; }
+        else if (tag == TB_UP) { push(RUN_U, 1); pendQ++; q--; }
+        else if (tag == TB_LEFT) { push(RUN_L, 1); pendT++; t--; }
+        else if (tag == TB_ICLOSE) { push(RUN_U, 1); pendQ++; mat = 1; q--; }
+        else if (tag == TB_DCLOSE) { push(RUN_L, 1); pendT++; mat = 2; t--; }
+        else { awry = true; break; }
+      } else if (mat == 1) {
+        if (f & TB_IOPEN) mat = 0; else { q--; push(RUN_U, 1); pendQ++; }
+      } else {
+        if (f & TB_DOPEN) mat = 0; else { t--; push(RUN_L, 1); pendT++; }
+      }
     }
   }
   if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
@@ -247,12 +273,12 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
   if (lane == 0) O.results[job] = R;
 }
 
-void launch_trace_guided(const BatchDev &B, const uint32_t *order, uint32_t nOrder, uint32_t *counter, int nSM,
-                         cudaStream_t s) {
-  (void)counter; (void)nSM;
+void launch_trace_guided(const BatchDev &B, bool affine, const uint32_t *order, uint32_t nOrder, cudaStream_t s) {
   const unsigned block = 32;   // one warp per CTA spreads the (few, long) walks over all SMs
   const unsigned grid = (nOrder + block - 1) / block;
-  if (grid) trace_guided_kernel<<<grid, block, 0, s>>>(B, order, nOrder);
+  if (!grid) return;
+  if (affine) trace_guided_kernel<true><<<grid, block, 0, s>>>(B, order, nOrder);
+  else trace_guided_kernel<false><<<grid, block, 0, s>>>(B, order, nOrder);
 }
 
 void launch_scan_counts(const BatchDev &B, uint64_t *blockOff, uint64_t *listOff, uint64_t *gapOff, uint64_t *totals,
