@@ -37,6 +37,8 @@ using namespace bgpu;
 struct bgpu_ctx {
   int device = 0, nSM = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[N_CLS] = {};                  // one per job class: the class kernels of a wave run concurrently
+  cudaEvent_t evFork = nullptr, evJoin[N_CLS] = {};
   std::string err;
   std::mutex mu;
   size_t arrowPoolCap = 0;                       // max bytes of traceback pool per wave
@@ -85,7 +87,7 @@ static int pin_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
 }
 static void pin_free(bgpu_ctx *ctx, void *p) { if (p) ctx->pinFree.emplace(ctx->pinSize[p], p); }
 
-struct Wave { uint32_t begin[4], count[4]; uint32_t traceBegin, traceCount; };  // index by width class 0..3
+struct Wave { uint32_t begin[N_CLS], count[N_CLS]; uint32_t traceBegin, traceCount; };  // index by job class
 
 struct bgpu_ticket_s {
   uint32_t nJobs = 0;
@@ -163,6 +165,11 @@ extern "C" int bgpu_create(bgpu_ctx **out, int device) {
   cudaGetDeviceProperties(&pr, device);
   ctx->nSM = pr.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
+  for (int c = 0; c < N_CLS; c++) {
+    if (cudaStreamCreateWithFlags(&ctx->aux[c], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evJoin[c], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
+  }
+  if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
   size_t freeB = 0, totalB = 0;
   cudaMemGetInfo(&freeB, &totalB);
   ctx->arrowPoolCap = freeB / 3;
@@ -179,6 +186,8 @@ extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->devFree) cudaFree(kv.second);
   for (auto &kv : ctx->pinFree) cudaFreeHost(kv.second);
+  for (int c = 0; c < N_CLS; c++) { cudaStreamDestroy(ctx->aux[c]); cudaEventDestroy(ctx->evJoin[c]); }
+  cudaEventDestroy(ctx->evFork);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -231,7 +240,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
           kmaxG = std::max(kmaxG, t->h_geom[v[i]].kmax); nDBmax = std::max(nDBmax, t->h_geom[v[i]].nDB);
           ksumMax = std::max<uint64_t>(ksumMax, (uint64_t)t->h_geom[v[i]].ksum);
         }
-        Group g{(uint32_t)sorted.size(), (uint32_t)(i1 - i0), 0, (uint64_t)nDBmax * (uint64_t)kmaxG, c};
+        Group g{(uint32_t)sorted.size(), (uint32_t)(i1 - i0), 0, std::max<uint64_t>(ksumMax, (uint64_t)nDBmax), c};
         for (size_t i = i0; i < i1; i++) {
           const uint64_t bb = (uint64_t)t->h_geom[v[i]].nDB * (uint64_t)kmaxG * rowsPerBlock * lpj * 4ull;
           bound[v[i]] = (bb + 255) & ~255ull; g.bytes += bound[v[i]];
@@ -241,6 +250,8 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
         groups.push_back(g);
       }
     }
+    // dispatch order inside a class: most expensive warp group first (the queue's tail is then made of short jobs)
+    std::stable_sort(groups.begin(), groups.end(), [](const Group &a, const Group &b) { return a.cls != b.cls ? a.cls < b.cls : a.cost > b.cost; });
     // cut into waves by reserved traceback bytes (groups stay whole)
     std::vector<uint64_t> arrowOff(n, 0);
     std::vector<uint32_t> order;
@@ -299,12 +310,19 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     t->timing.fillCells = laneSteps;
   }
   CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
+  CK(cudaMemsetAsync(t->d_totals + 3, 0, sizeof(uint64_t), s));
+  t->B.cellSlots = reinterpret_cast<unsigned long long *>(t->d_totals + 3);
   for (size_t w = 0; w < t->waves.size(); w++) {
     const Wave &W = t->waves[w];
     CK(cudaEventRecord(t->waveEv[3 * w], s));
-    for (int c = 0; c < N_CLS; c++)
+    // the class kernels are independent: fork them onto their own streams (heaviest classes first), join on s
+    CK(cudaEventRecord(ctx->evFork, s));
+    for (int c = N_CLS - 1; c >= 0; c--)
       if (W.count[c]) {
-        launch_fill_guided(t->B, t->sp, c, t->d_order + W.begin[c], W.count[c], t->d_counters + 8 * w + c, ctx->nSM, s);
+        CK(cudaStreamWaitEvent(ctx->aux[c], ctx->evFork, 0));
+        launch_fill_guided(t->B, t->sp, c, t->d_order + W.begin[c], W.count[c], t->d_counters + 8 * w + c, ctx->nSM, ctx->aux[c]);
+        CK(cudaEventRecord(ctx->evJoin[c], ctx->aux[c]));
+        CK(cudaStreamWaitEvent(s, ctx->evJoin[c], 0));
         t->timing.kernelLaunches++;
       }
     CK(cudaEventRecord(t->waveEv[3 * w + 1], s));
@@ -564,9 +582,10 @@ extern "C" int bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgp
 
 static int ensure_arena(bgpu_ctx *ctx, bgpu_ticket t) {
   if (t->arenaReady) return BGPU_OK;
-  CK(cudaMemcpyAsync(t->h_totals, t->d_totals, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(t->h_totals, t->d_totals, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 3; i++) t->totals[i] = t->h_totals[i];
+  if (!t->dense) t->timing.fillCells = t->h_totals[3];
   RC(talloc_dev(ctx, t, &t->d_blocks, t->totals[0] + 1)); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->totals[1] + 1));
   RC(talloc_dev(ctx, t, &t->d_gaps, t->totals[2] + 1));
   RC(talloc_pin(ctx, t, &t->h_blocks, t->totals[0] + 1)); RC(talloc_pin(ctx, t, &t->h_gapCounts, t->totals[1] + 1));

@@ -24,8 +24,9 @@ constexpr int ROW_W_BITS = 20;
 
 // Job classes: how many lanes of a warp sweep one job.  A lane owns 2k consecutive diagonals ("lane-major"
 // slots), k = groups active in the current d-block, so a class covers windows of up to 2 * LPJ * KRING diagonals.
-enum { CLS_L8 = 0, CLS_L16 = 1, CLS_L32 = 2, CLS_WIDE = 3, N_CLS = 4 };
-__host__ __device__ inline int cls_lpj(int cls) { return cls == CLS_L8 ? 8 : (cls == CLS_L16 ? 16 : 32); }
+// CLS_L8N is CLS_L8 restricted to k <= 4 (its kernel needs half the registers).
+enum { CLS_L8N = 0, CLS_L8 = 1, CLS_L16 = 2, CLS_L32 = 3, CLS_WIDE = 4, N_CLS = 5 };
+__host__ __device__ inline int cls_lpj(int cls) { return cls <= CLS_L8 ? 8 : (cls == CLS_L16 ? 16 : 32); }
 
 // traceback codes written by the fill kernels
 //   linear (2 bits / step, 16 steps per 32-bit word): 0 Diagonal, 1 Left, 2 Up, 3 NoArrow / out of band
@@ -37,9 +38,9 @@ __host__ __device__ inline int cls_lpj(int cls) { return cls == CLS_L8 ? 8 : (cl
 enum { TB_DIAG = 0, TB_LEFT = 1, TB_UP = 2, TB_ICLOSE = 3, TB_DCLOSE = 4, TB_NONE = 7, TB_IOPEN = 8, TB_DOPEN = 16 };
 enum { TL_DIAG = 0, TL_LEFT = 1, TL_UP = 2, TL_NONE = 3 };
 
-struct alignas(8) RowInfo {  // 8 B per guide row in HBM
-  int32_t lo;             // first in-band column t' of the row (INT_MAX/2 for "no cells")
-  uint32_t packed;        // bits 0-19: hi'-lo', bits 20-22: query base code, bits 23-30: QV
+struct alignas(8) RowInfo {  // 8 B per guide row in HBM, consumed as is by the fill kernels
+  int32_t cd8;            // (diagonal of the row's first in-band cell) << 8, diagonal = t' - q' + C0
+  uint32_t packed;        // bits 8-27: hi'-lo' (cells in the row - 1), bits 0-7: query base code * 20
 };
 
 struct DBlock {           // 16 B per d-block
@@ -95,6 +96,7 @@ struct BatchDev {         // device pointers of one submitted batch
   int32_t *rowBuf;        // dense aligners: ping-pong score rows
   const uint32_t *order;  // job order for dynamic scheduling (longest first)
   uint32_t *counters;     // [0] fill job counter, [1] trace job counter, ...
+  unsigned long long *cellSlots;  // cell slots executed by the guided fill kernels (lane-steps x groups), or NULL
 };
 
 struct DenseArgs {

@@ -16,11 +16,15 @@
 // the affine open/extend decisions land in two more tag bits the same way.  Cells outside the guide are held at
 // BIG, which reproduces the reference's INF_INT-for-missing-neighbour rule.
 //
+// Staging.  The band table rows (RowInfo, 8 B, written by prep in the form the inner loop consumes) and the target
+// codes of block b+1 are copied global -> shared with cp.async while block b is computed (double buffer), so the
+// DP loop never waits on HBM.
+//
 // Inner loop (run_block_ring): the k rows and k columns a lane touches slide by one per two steps, so they are kept
 // in register rings (the loop is unrolled by k, every ring index is static) and refilled with one shared-memory
-// load per row / column; per cell that leaves one LDS (the substitution score), two VIADDMNMX, the in-band test,
-// the tag split and one funnel shift that appends the 2-bit arrow to the lane's traceback word.  Words are stored
-// [d-block][16-step row][slot pair], 2 bits per cell for the linear aligner (8 for the affine one).
+// load per row / column; per cell that leaves one LDS (the substitution score), two VIADDMNMX, the in-band test
+// and the tag split; one funnel shift appends the arrow to the lane's traceback word.  Words are
+// stored [d-block][16-step row][slot pair], 2 bits per cell for the linear aligner (8 for the affine one).
 // Blocks that touch the boundary row, a job's last block, the QV score function and very wide windows take the
 // generic path (run_block_gen), which reads its rows and columns from shared memory per cell.
 #include "bgpu_common.cuh"
@@ -28,6 +32,7 @@
 namespace bgpu {
 
 constexpr uint32_t NOJOB = 0xffffffffu;
+constexpr int DEAD_CD8 = 1 << 30;   // a row no slot can be inside of
 
 struct FillConsts {
   int delT, insT;        // (del<<SH)|LEFT, (ins<<SH)|UP
@@ -35,14 +40,16 @@ struct FillConsts {
   int ext, openI, openD; // ext<<SH, (open<<SH)|TB_IOPEN, (open<<SH)|TB_DOPEN
   int open;              // open<<SH
   int del0;              // row-0 step: (Global ? del : 0) << SH
+  int k256, kacc;        // 256 and 1 << BITS held in registers the compiler cannot fold: keeps these
+                         // multiply-adds on the FMA pipe (IMAD) instead of the busier ALU pipe
 };
 
-template <int LPJ, int KM>
-struct SubSmem {          // staging of one job's current d-block
-  int2 rows[KM * LPJ + 32];   // {dloRel << 8, (width << 8) | qcode * 20}
-  int rowq[KM * LPJ + 32];    // QV | (boundary row ? 1 << 31 : 0)          (generic path only)
-  int cols[KM * LPJ + 36];    // target code * 4
-  int shift[2 * KM * LPJ];    // window re-mapping scratch
+template <int LPJ, int KM, bool QV>
+struct SubSmem {          // staging of one job: two d-blocks (current, next)
+  int2 rows[2][KM * LPJ + 32];           // RowInfo as prep wrote it: {cd8, (width << 8) | qcode * 20}
+  uint32_t colw[2][(KM * LPJ + 44) / 4]; // target codes (bytes), 4-byte chunks from an aligned-down address
+  int shift[2 * KM * LPJ];               // window re-mapping scratch
+  int rowq[QV ? KM * LPJ + 32 : 2];      // QV of the current block's rows (QualityValueScoreFunction only)
 };
 
 template <bool AFFINE> struct Fmt {
@@ -58,8 +65,16 @@ __device__ __forceinline__ int lds32(uint32_t addr) {
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One DP cell.  x8 = (slot - first in-band slot of the row) << 8, y = (row width << 8) | junk < 256.
+// The min chain of one DP cell.
 template <bool AFFINE>
 __device__ __forceinline__ int dp_core(const int S, const int leftS, const int leftAD, const int upS, const int upAI,
                                        const int m, const FillConsts &c, int &ai, int &ad) {
@@ -84,25 +99,33 @@ __device__ __forceinline__ int sub_up(int v) { return __shfl_up_sync(0xffffffffu
 template <int LPJ>
 __device__ __forceinline__ int sub_dn(int v) { return __shfl_down_sync(0xffffffffu, v, 1, LPJ); }
 
+// Per-block view of the staged data.  Row index r <-> q' = qlo + r, column index c <-> t' = tlo + c.
+struct BlockView {
+  const int2 *rows;       // staged RowInfo
+  const uint8_t *cols;    // staged target codes, cols[c]
+  int wbase8;             // window base diagonal << 8
+  int qlo, tlo;
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Fast path: KA groups per lane (compile time), rows / columns in register rings, no boundary row, full 64 steps.
 template <int LPJ, int KM, int KA, bool AFFINE>
 __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
-                                               int (&ADe)[KM], int (&ADo)[KM], const SubSmem<LPJ, KM> &sm,
-                                               const uint32_t mtabAddr, const FillConsts &c, const int sl,
+                                               int (&ADe)[KM], int (&ADo)[KM], const BlockView &bv,
+                                               const int mtabAddr, const FillConsts &c, const int sl,
                                                uint32_t *aw, const bool live) {
   typedef Fmt<AFFINE> F;
   const int kL = KA * sl;
-  const int2 *rp = sm.rows + KA * (LPJ - 1 - sl);           // rp[i + m]: row of group KA-1-m at step pair i
-  const int *cp = sm.cols + kL;                              // cp[i + g]: column of group g on the even step of pair i
-  const int s08 = (2 * kL) << 8;
+  const int2 *rp = bv.rows + KA * (LPJ - 1 - sl);           // rp[i + m]: row of group KA-1-m at step pair i
+  const uint8_t *cp = bv.cols + kL;                          // cp[i + g]: column of group g on the even step of pair i
+  const int s08 = bv.wbase8 + ((2 * kL) << 8);
   int rX[KA], rY[KA], rQ[KA], cT[KA];
   uint32_t acc[KA];
 #pragma unroll
   for (int m = 0; m < KA; m++) {
     const int2 v = rp[m];
-    rX[m] = s08 - v.x; rY[m] = v.y; rQ[m] = (int)mtabAddr + (v.y & 0xff);
-    cT[m] = cp[m];
+    rX[m] = s08 - v.x; rY[m] = v.y; rQ[m] = v.y & 0xff;
+    cT[m] = (int)cp[m] * 4 + mtabAddr;
     acc[m] = 0;
   }
   aw += kL;
@@ -123,14 +146,14 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
           const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
           int ai = 0, ad = 0;
           int cnd = dp_core<AFFINE>(Se[g], leftS, leftAD, So[g], AFFINE ? AIo[g] : 0, m, c, ai, ad);
-          const bool inb = (unsigned)(rX[p] + ((2 * g) << 8)) <= (unsigned)rY[p];
+          const bool inb = (unsigned)(c.k256 * (2 * g) + rX[p]) <= (unsigned)rY[p];
           cnd = inb ? cnd : (BIG | F::NONE);
           Se[g] = cnd & ~F::TAGMASK;
           if (AFFINE) { AIe[g] = inb ? (ai & ~31) : BIG; ADe[g] = inb ? (ad & ~31) : BIG; }
-          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);
+          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);   // first step of a word ends up in its lowest field
         }
       }
-      cT[j] = cp[i0 + j + KA];                               // column kL + i + KA replaces kL + i
+      cT[j] = (int)cp[i0 + j + KA] * 4 + mtabAddr;          // column kL + i + KA replaces kL + i
       // ---- odd step: cells on slots 2g+1
       {
         const int up0 = sub_dn<LPJ>(Se[0]);
@@ -143,16 +166,16 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
           const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
           int ai = 0, ad = 0;
           int cnd = dp_core<AFFINE>(So[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, m, c, ai, ad);
-          const bool inb = (unsigned)(rX[p] + ((2 * g + 1) << 8)) <= (unsigned)rY[p];
+          const bool inb = (unsigned)(c.k256 * (2 * g + 1) + rX[p]) <= (unsigned)rY[p];
           cnd = inb ? cnd : (BIG | F::NONE);
           So[g] = cnd & ~F::TAGMASK;
           if (AFFINE) { AIo[g] = inb ? (ai & ~31) : BIG; ADo[g] = inb ? (ad & ~31) : BIG; }
-          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);
+          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);   // first step of a word ends up in its lowest field
         }
       }
       {                                                       // row baseR + i + KA replaces row baseR + i
         const int2 v = rp[i0 + j + KA];
-        rX[j] = s08 - v.x; rY[j] = v.y; rQ[j] = (int)mtabAddr + (v.y & 0xff);
+        rX[j] = s08 - v.x; rY[j] = v.y; rQ[j] = v.y & 0xff;
       }
       if (((i0 + j) & (F::SPW / 2 - 1)) == F::SPW / 2 - 1) {  // a traceback word is complete
         if (live) {
@@ -170,10 +193,9 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
 // stop of a job's last block (eLast) handled per cell.
 template <int LPJ, int KM, bool AFFINE, bool QV>
 __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
-                                              int (&ADe)[KM], int (&ADo)[KM], const SubSmem<LPJ, KM> &sm,
-                                              const uint32_t mtabAddr, const FillConsts &c, const int k, const int sl,
-                                              const int tlo, const bool first, const int eLast, uint32_t *aw,
-                                              const bool live) {
+                                              int (&ADe)[KM], int (&ADo)[KM], const BlockView &bv, const int *rowq,
+                                              const int mtabAddr, const FillConsts &c, const int k, const int sl,
+                                              const bool first, const int eLast, uint32_t *aw, const bool live) {
   typedef Fmt<AFFINE> F;
   constexpr int UG = KM <= KRING ? KM : 1;
   const int kL = k * sl, baseR = k * (LPJ - 1 - sl);
@@ -183,18 +205,16 @@ __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int 
   aw += kL;
   auto cell = [&](int &S, int &AI, int &AD, const int leftS, const int leftAD, const int upS, const int upAI,
                   const int ridx, const int cidx, const int slot, const int e, uint32_t &a) {
-    const int2 rv = sm.rows[ridx];
-    const int rq = sm.rowq[ridx];
-    const int tent = sm.cols[cidx];
-    int m = lds32(mtabAddr + (uint32_t)((rv.y & 0xff) + tent));
-    if (QV) m *= (rq & 0xff);                               // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+    const int2 rv = bv.rows[ridx];
+    int m = lds32((uint32_t)(mtabAddr + (rv.y & 0xff) + (int)bv.cols[cidx] * 4));
+    if (QV) m *= rowq[ridx];                                // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
     int ai = 0, ad = 0;
     int cnd = dp_core<AFFINE>(S, leftS, leftAD, upS, upAI, m, c, ai, ad);
-    if (first && rq < 0) {                                  // boundary row (GuidedAlign.h:415-442)
-      cnd = ((tlo + cidx) * c.del0) | (AFFINE ? (TB_LEFT | TB_IOPEN | TB_DOPEN) : TL_LEFT);
+    if (first && bv.qlo + ridx == 0) {                      // boundary row (GuidedAlign.h:415-442)
+      cnd = ((bv.tlo + cidx) * c.del0) | (AFFINE ? (TB_LEFT | TB_IOPEN | TB_DOPEN) : TL_LEFT);
       ai = c.open; ad = c.open;
     }
-    const bool inb = (unsigned)((slot << 8) - rv.x) <= (unsigned)rv.y;
+    const bool inb = (unsigned)(bv.wbase8 + (slot << 8) - rv.x) <= (unsigned)rv.y;
     cnd = inb ? cnd : (BIG | F::NONE);
     if (e <= eLast) {
       S = cnd & ~F::TAGMASK;
@@ -252,26 +272,26 @@ __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int 
 template <int LPJ, int KM, bool AFFINE, int KA>
 struct RingDispatch {
   static __device__ __forceinline__ void run(const int k, int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
-                                             int (&ADe)[KM], int (&ADo)[KM], const SubSmem<LPJ, KM> &sm,
-                                             const uint32_t mtabAddr, const FillConsts &c, const int sl, uint32_t *aw,
-                                             const bool live) {
-    if (k == KA) run_block_ring<LPJ, KM, KA, AFFINE>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, sl, aw, live);
-    else RingDispatch<LPJ, KM, AFFINE, KA + 1>::run(k, Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, sl, aw, live);
+                                             int (&ADe)[KM], int (&ADo)[KM], const BlockView &bv, const int mtabAddr,
+                                             const FillConsts &c, const int sl, uint32_t *aw, const bool live) {
+    if (k == KA) run_block_ring<LPJ, KM, KA, AFFINE>(Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
+    else RingDispatch<LPJ, KM, AFFINE, KA + 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
   }
 };
 template <int LPJ, int KM, bool AFFINE>
-struct RingDispatch<LPJ, KM, AFFINE, KRING + 1> {
+struct RingDispatch<LPJ, KM, AFFINE, KM + 1> {
   static __device__ __forceinline__ void run(const int, int (&)[KM], int (&)[KM], int (&)[KM], int (&)[KM], int (&)[KM],
-                                             int (&)[KM], const SubSmem<LPJ, KM> &, const uint32_t, const FillConsts &,
-                                             const int, uint32_t *, const bool) {}
+                                             int (&)[KM], const BlockView &, const int, const FillConsts &, const int,
+                                             uint32_t *, const bool) {}
 };
 
 // order[] holds warp groups: 32 / LPJ job indices each (NOJOB pads the last group); a warp sweeps its jobs in
 // lockstep from d-block 0, with k = the widest member's need per block.
 template <int LPJ, int KM, bool AFFINE, bool QV>
-__global__ void __launch_bounds__(KM <= KRING ? 128 : 32)
+__global__ void __launch_bounds__(KM <= KRING ? 128 : 32, KM <= 4 ? (AFFINE ? 4 : 5) : (KM <= KRING ? (AFFINE ? 3 : 4) : 1))
 fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nGroups, uint32_t *counter) {
   typedef Fmt<AFFINE> F;
+  typedef SubSmem<LPJ, KM, QV> Smem;
   constexpr int NJ = 32 / LPJ;
   constexpr bool RING = KM <= KRING && !QV;
   constexpr int UG = KM <= KRING ? KM : 1;
@@ -280,19 +300,20 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
   __shared__ int Mtab[25];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPJ, sl = lane % LPJ;
-  SubSmem<LPJ, KM> &sm = reinterpret_cast<SubSmem<LPJ, KM> *>(smemRaw)[warp * NJ + sub];
+  Smem &sm = reinterpret_cast<Smem *>(smemRaw)[warp * NJ + sub];
   if (threadIdx.x < 25) {
     if (QV) { const int r = threadIdx.x / 5, cc = threadIdx.x % 5; Mtab[threadIdx.x] = ((r == cc && r < 4) ? -1 : 1) << F::SHv; }  // ScoreMatrices.h:4-10
     else Mtab[threadIdx.x] = P.M[threadIdx.x] << F::SHv;
   }
   __syncthreads();
-  const uint32_t mtabAddr = (uint32_t)__cvta_generic_to_shared(Mtab);
+  const int mtabAddr = (int)__cvta_generic_to_shared(Mtab);
   FillConsts c;
   c.delT = (P.del << F::SHv) | TB_LEFT; c.insT = (P.ins << F::SHv) | TB_UP;
   c.extT3 = (P.ext << F::SHv) | TB_ICLOSE; c.extT4 = (P.ext << F::SHv) | TB_DCLOSE;
   c.ext = P.ext << F::SHv; c.open = P.open << F::SHv;
   c.openI = (P.open << F::SHv) | TB_IOPEN; c.openD = (P.open << F::SHv) | TB_DOPEN;
   c.del0 = (P.alignType == BGPU_GLOBAL ? P.del : 0) << F::SHv;
+  c.k256 = 256 + P.pad; c.kacc = (1 << F::BITS) + P.pad;    // P.pad is always 0
 
   for (;;) {
     uint32_t grp = 0;
@@ -304,15 +325,47 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
     JobGeom *G = have ? &B.geom[job] : nullptr;
     if (have && G->status != BGPU_JOB_OK) have = false;
     int Qn = 0, Tn = 0, C0 = 0, nDB = 0, hi0 = 0;
-    const RowInfo *rows = nullptr; DBlock *dblk = nullptr; const uint8_t *tcodes = nullptr; uint32_t *arrowsJob = nullptr;
+    const RowInfo *rows = nullptr; DBlock *dblk = nullptr; const uint8_t *tcodes = nullptr, *tJobLo = nullptr, *tJobHi = nullptr;
+    const uint8_t *qualRow = nullptr;
+    uint32_t *arrowsJob = nullptr;
     if (have) {
       Qn = G->Qn; Tn = G->Tn; C0 = G->C0; nDB = G->nDB; hi0 = G->hi0;
       rows = B.rows + G->rowOff; dblk = B.dblk + G->dblkOff;
-      tcodes = B.t + B.tOff[job] + G->tStart - 1;            // tcodes[t'] for t' in [1,Tn]
+      tJobLo = B.t + B.tOff[job]; tJobHi = B.t + B.tOff[job + 1];
+      tcodes = tJobLo + G->tStart - 1;                       // tcodes[t'] for t' in [1,Tn]
+      if (QV) qualRow = B.qual + B.qOff[job] + G->qStart - 1; // qualRow[q'] for q' in [1,Qn]
       arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
     }
     const int nDBw = __reduce_max_sync(0xffffffffu, nDB);
     const int nD = Qn + Tn + 1;
+
+    // issue the cp.async copies of one block's rows and columns into buffer `buf`
+    auto stage = [&](const int buf, const int b, const int wbase, const int k, const bool liveB, int &colShift) {
+      const int cq = (C0 - wbase) >> 1;
+      const int qlo = 32 * b + cq - (k * LPJ - 1), tlo = 32 * b - cq;
+      for (int r = sl; r < k * LPJ + 32; r += LPJ) {
+        const int qp = qlo + r;
+        if (liveB && qp >= 0 && qp <= Qn) cp_async8(&sm.rows[buf][r], rows + qp);
+        else sm.rows[buf][r] = make_int2(DEAD_CD8, 0);
+      }
+      // columns: bytes [tcodes + tlo, + k*LPJ + 33), copied as aligned 4-byte chunks clamped to the job's own bytes
+      const uint8_t *p0 = tcodes + tlo;
+      const int a = liveB ? (int)((uintptr_t)p0 & 3u) : 0;
+      colShift = a;
+      if (liveB) {
+        const uint8_t *lo4 = (const uint8_t *)((uintptr_t)tJobLo & ~(uintptr_t)3);
+        const uint8_t *hi4 = (const uint8_t *)(((uintptr_t)tJobHi + 3) & ~(uintptr_t)3);
+        const int nch = (k * LPJ + 33 + a + 3) >> 2;
+        for (int ch = sl; ch < nch; ch += LPJ) {
+          const uint8_t *src = p0 - a + 4 * ch;
+          if (src >= lo4 && src < hi4) cp_async4(&sm.colw[buf][ch], src);
+          else sm.colw[buf][ch] = 0;
+        }
+      } else {
+        for (int ch = sl; ch < (k * LPJ + 36) >> 2; ch += LPJ) sm.colw[buf][ch] = 0;
+      }
+      cp_async_commit();
+    };
 
     int Se[KM], So[KM], AIe[KM], AIo[KM], ADe[KM], ADo[KM];
 #pragma unroll(UG)
@@ -320,11 +373,28 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
     int wprev = 0, kprev = 0;
     uint32_t unit = 0;
 
+    // block 0 is staged up front; the DBlock of block b+1 is always in registers one block ahead
+    int wbase = 0, kown = 1;
+    if (have && nDB > 0) { const DBlock db = dblk[0]; wbase = db.wbase; kown = db.k; }
+    int k = __reduce_max_sync(0xffffffffu, kown);
+    int colShift0 = 0, colShift1 = 0;
+    __syncwarp();
+    stage(0, 0, wbase, k, have && nDB > 0, colShift0);
+    int wnext = wbase, knextOwn = 1;
+    if (have && 1 < nDB) { const DBlock db = dblk[1]; wnext = db.wbase; knextOwn = db.k; }
+
     for (int b = 0; b < nDBw; b++) {
       const bool live = have && b < nDB;
-      int wbase = wprev, kown = 1;
-      if (live) { const DBlock db = dblk[b]; wbase = db.wbase; kown = db.k; }
-      const int k = __reduce_max_sync(0xffffffffu, kown);
+      const int buf = b & 1;
+      // ---- next block: its window is known, start its copies, fetch the DBlock after it
+      const int knext = __reduce_max_sync(0xffffffffu, knextOwn);
+      const bool liveN = have && b + 1 < nDB;
+      if (b + 1 < nDBw) { if (buf) stage(0, b + 1, wnext, knext, liveN, colShift0); else stage(1, b + 1, wnext, knext, liveN, colShift1); }
+      int wnext2 = wnext, knext2 = 1;
+      if (have && b + 2 < nDB) { const DBlock db = dblk[b + 2]; wnext2 = db.wbase; knext2 = db.k; }
+      // ---- this block's data has landed
+      if (b + 1 < nDBw) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
       // ---- re-map the register window (old: kprev groups from diagonal wprev; new: k groups from wbase)
       if (b > 0 && __any_sync(0xffffffffu, wbase != wprev || k != kprev)) {
         const int delta = wbase - wprev;
@@ -348,36 +418,27 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
         if (AFFINE) { remap(AIe, AIo); remap(ADe, ADo); }
       }
       wprev = wbase; kprev = k;
-      // ---- stage rows [qlo, qlo + k*LPJ + 32) and columns [tlo, tlo + k*LPJ + 33)
       const int cq = (C0 - wbase) >> 1;
-      const int qlo = 32 * b + cq - (k * LPJ - 1), tlo = 32 * b - cq;
-      __syncwarp();
-      for (int r = sl; r < k * LPJ + 32; r += LPJ) {
-        const int qp = qlo + r;
-        int2 v = make_int2(1 << 28, 0);
-        int rq = 0;
-        if (live && qp >= 0 && qp <= Qn) {
-          const RowInfo ri = rows[qp];
-          const int w = (int)(ri.packed & ((1u << ROW_W_BITS) - 1));
-          v.x = (ri.lo - qp + C0 - wbase) << 8;
-          v.y = (w << 8) | ((int)((ri.packed >> 20) & 7u) * 20);
-          rq = (int)((ri.packed >> 23) & 0xffu) | (qp == 0 ? (int)0x80000000 : 0);
+      BlockView bv;
+      bv.rows = sm.rows[buf];
+      bv.cols = reinterpret_cast<const uint8_t *>(sm.colw[buf]) + (buf ? colShift1 : colShift0);
+      bv.wbase8 = wbase << 8;
+      bv.qlo = 32 * b + cq - (k * LPJ - 1); bv.tlo = 32 * b - cq;
+      if (QV) {
+        for (int r = sl; r < k * LPJ + 32; r += LPJ) {
+          const int qp = bv.qlo + r;
+          sm.rowq[r] = (live && qp >= 1 && qp <= Qn) ? (int)qualRow[qp] : 0;
         }
-        sm.rows[r] = v; sm.rowq[r] = rq;
+        __syncwarp();
       }
-      for (int cI = sl; cI < k * LPJ + 33; cI += LPJ) {
-        const int tp = tlo + cI;
-        sm.cols[cI] = (live && tp >= 1 && tp <= Tn) ? (int)tcodes[tp] * 4 : 0;
-      }
-      __syncwarp();
       uint32_t *aw = arrowsJob + (size_t)unit * UNITW;
       const bool first = live && (b << 6) <= hi0;          // row 0 holds cells on d <= hi0
       const bool last = live && (b == nDB - 1);
       const int eLast = last ? ((nD - 1) & 63) : 63;
-      if (RING && k <= KRING && !__any_sync(0xffffffffu, first || last))
-        RingDispatch<LPJ, KM, AFFINE, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, sl, aw, live);
+      if (RING && !__any_sync(0xffffffffu, first || last))
+        RingDispatch<LPJ, KM, AFFINE, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
       else
-        run_block_gen<LPJ, KM, AFFINE, QV>(Se, So, AIe, AIo, ADe, ADo, sm, mtabAddr, c, k, sl, tlo, first, eLast, aw, live);
+        run_block_gen<LPJ, KM, AFFINE, QV>(Se, So, AIe, AIo, ADe, ADo, bv, sm.rowq, mtabAddr, c, k, sl, first, eLast, aw, live);
       if (live && sl == 0) { dblk[b].k = k; dblk[b].arrowUnit = unit; }
       unit += (uint32_t)k;
       // ---- the end cell (Qn, Tn) sits on diagonal Tn-Qn+C0 and is the last cell written to its slot
@@ -392,7 +453,10 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
         v = __shfl_sync(0xffffffffu, v, owner, LPJ);
         if (last && sl == 0) G->score = v >> F::SHv;
       }
+      __syncwarp();                                         // everyone is done with buffer `buf` before it is refilled
+      wbase = wnext; k = knext; wnext = wnext2; knextOwn = knext2;
     }
+    if (lane == 0 && B.cellSlots) atomicAdd(B.cellSlots, (unsigned long long)unit * 2048ull);   // 64 steps x 32 lanes x k cells
   }
 }
 
@@ -400,7 +464,7 @@ template <int LPJ, int KM, bool AFFINE, bool QV>
 static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, uint32_t nGroups,
                        uint32_t *counter, int nSM, cudaStream_t s) {
   constexpr int WPC = KM <= KRING ? 4 : 1;          // warps per CTA
-  const size_t smem = sizeof(SubSmem<LPJ, KM>) * (32 / LPJ) * WPC;
+  const size_t smem = sizeof(SubSmem<LPJ, KM, QV>) * (32 / LPJ) * WPC;
   auto kern = fill_guided_kernel<LPJ, KM, AFFINE, QV>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int perSM = 0;
@@ -415,7 +479,8 @@ static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *
 template <bool AFFINE, bool QV>
 static void launch_cls(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, uint32_t nGroups,
                        uint32_t *counter, int nSM, cudaStream_t s) {
-  if (cls == CLS_L8) launch_one<8, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
+  if (cls == CLS_L8N) launch_one<8, 4, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
+  else if (cls == CLS_L8) launch_one<8, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
   else if (cls == CLS_L16) launch_one<16, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
   else if (cls == CLS_L32) launch_one<32, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
   else launch_one<32, KWIDE, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);

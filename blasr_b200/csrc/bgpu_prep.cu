@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   const int Qn = qEnd - qStart, Tn = tEnd - tStart;
   const int C0 = Qn + (Qn & 1);
   const int nD = Qn + Tn + 1, nDB = (nD + DBLK - 1) / DBLK;
+  if (nD >= (1 << 21)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }   // diagonals are carried << 8
   // score range the shifted-domain kernels can carry
   {
     int mx = max(max(abs(P.ins), abs(P.del)), abs(P.open) + abs(P.ext));
@@ -95,7 +96,6 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   __syncwarp();
 
   RowInfo *rows = B.rows + rowOffIn[job];
-  const uint8_t *qual = B.qual ? B.qual + qo : nullptr;
   const int drift0 = abs(tStart - qStart);                       // GuidedAlign.h:128
   const int tPost0 = drift0 > band ? drift0 : band;              // :129-134
   long long cells = 0;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   // row 0: boundary row, t' in [0, min(tPost0, Tn)]
   const int hi0 = min(tPost0, Tn);
   if (lane == 0) {
-    rows[0].lo = 0; rows[0].packed = (uint32_t)hi0;   // width field only; code/QV unused
+    rows[0].cd8 = C0 << 8; rows[0].packed = (uint32_t)hi0 << 8;   // boundary row: columns [0, hi0], no base
     cells += (long long)tPost0 + 1;                    // tPre=0
     if (hi0 >= (1 << ROW_W_BITS)) wide = 1;
   }
@@ -175,8 +175,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
       if (w >= (1 << ROW_W_BITS)) wide = 1;
       const uint32_t qc = lut[qch];
       if (qc > 4) bad = 1;
-      const uint32_t qv = qual ? qual[qStart + i - 1] : 0;
-      RowInfo r; r.lo = lop; r.packed = ((uint32_t)w & ((1u << ROW_W_BITS) - 1)) | ((qc & 7u) << 20) | (qv << 23);
+      RowInfo r; r.cd8 = (lop - i + C0) << 8; r.packed = (((uint32_t)w & ((1u << ROW_W_BITS) - 1)) << 8) | ((qc & 7u) * 20u);
       rows[i] = r;
       if (bad || wide) { lop = 1; hip = 0; }
     }
@@ -198,7 +197,8 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
     maxSpan = max(maxSpan, span);
   }
   maxSpan = __reduce_max_sync(0xffffffffu, maxSpan);
-  int cls = CLS_L8;
+  int cls = CLS_L8N;
+  if (maxSpan >= 2 * 8 * 4) cls = CLS_L8;
   if (maxSpan >= 2 * 8 * KRING) cls = CLS_L16;
   if (maxSpan >= 2 * 16 * KRING) cls = CLS_L32;
   if (maxSpan >= 2 * 32 * KRING) cls = CLS_WIDE;

@@ -73,11 +73,12 @@ __global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uin
         asm volatile("prefetch.global.L2 [%0];" ::"l"(arrows + pBase + (size_t)(ROWS + row - 2) * pRowBytes + (size_t)sp * 4));
       }
     }
-    const int pos = e % SPW;
+    const int pos = e % SPW;                                   // the first step of a word sits in its lowest field
     const uint32_t f = (word >> (BITS * pos)) & ((1u << BITS) - 1u);
     if (!AFFINE) {
       if (f == TL_DIAG) {
-        // Diagonal arrows of this slot sit in fields pos, pos-2, ...: take the whole run inside the word at once
+        // earlier anti-diagonals of this slot sit in fields pos-2, pos-4, ...: take the whole run of Diagonal
+        // arrows inside the word at once
         uint32_t x = word & (0x33333333u << (2 * (pos & 1)));
         x &= 0xffffffffu >> (30 - 2 * pos);
         int n = x == 0 ? (pos >> 1) + 1 : (pos - ((31 - __clz((int)x)) >> 1)) >> 1;
