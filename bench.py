@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--algo", default="guided", choices=["guided", "affine"])
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--e2e-threads", type=int, default=3, help="host threads (one context each) of the e2e measurement")
+    ap.add_argument("--e2e-chunks", type=int, default=12, help="sub-batches the shard is cut into for the e2e measurement")
     return ap.parse_args()
 
 
@@ -147,6 +149,16 @@ def pinned_copy(a):
     return v, t
 
 
+def range_view(batch, a, b):
+    """Jobs [a, b) of a JobBatch as views into the same (pinned) arrays, offsets rebased."""
+    from blasr_b200 import JobBatch
+    q0, q1 = int(batch.qOff[a]), int(batch.qOff[b]); t0, t1 = int(batch.tOff[a]), int(batch.tOff[b])
+    g0, g1 = int(batch.guideOff[a]), int(batch.guideOff[b])
+    return JobBatch(batch.q[q0:q1], batch.qOff[a:b + 1] - batch.qOff[a], batch.t[t0:t1], batch.tOff[a:b + 1] - batch.tOff[a],
+                    batch.guide[g0:g1], batch.guideOff[a:b + 1] - batch.guideOff[a],
+                    batch.qual[q0:q1] if batch.qual is not None else None, batch.band[a:b] if batch.band is not None else None)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -173,34 +185,70 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- e2e: submit (H2D + kernels) + collect (D2H) through the C ABI, host buffers in, host results out
+    # ---- e2e: submit (H2D + kernels) + collect (D2H) through the C ABI, host buffers in, host results out.
+    # The way a multi-threaded host (blasr's MapReads pthreads) drives the library: a few host threads, each with its
+    # own context, push sub-batches of the shard; copies of one sub-batch overlap the kernels of another.
     e2e_host = {}
+    n_chunks = max(1, min(args.e2e_chunks, batch.n))
+    bounds = np.linspace(0, batch.n, n_chunks + 1).astype(np.int64)
+    chunks = [range_view(batch, int(bounds[i]), int(bounds[i + 1])) for i in range(n_chunks)]
+    workers = [Aligner(local) for _ in range(max(1, min(args.e2e_threads, n_chunks)))]
 
-    def e2e_step():
-        h0 = time.perf_counter()
-        tk = al.submit(batch, fn, algo, band=16, doStats=True)
-        h1 = time.perf_counter()
-        res = al.collect(tk)
-        h2 = time.perf_counter()
-        e2e_host.update(py_submit_ms=(h1 - h0) * 1e3, py_collect_ms=(h2 - h1) * 1e3, c_submit_ms=res.timing.msHostSubmit,
-                        c_collect_ms=res.timing.msHostCollect)
-        return tk, res
+    def e2e_pass():
+        nxt = iter(range(n_chunks)); lock = threading.Lock()
+        tot = {"cells": 0, "ok": 0, "h2d": 0, "d2h": 0}
+        errs = []
+
+        def work(a):
+            try:
+                while True:
+                    with lock:
+                        i = next(nxt, None)
+                    if i is None:
+                        return
+                    tk = a.submit(chunks[i], fn, algo, band=16, doStats=True)
+                    res = a.collect(tk)
+                    with lock:
+                        tot["cells"] += int(res.timing.cells); tot["ok"] += int((res.results["status"] == 0).sum())
+                        tot["h2d"] += int(res.timing.h2dBytes); tot["d2h"] += int(res.timing.d2hBytes)
+                    a.release(tk)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(a,)) for a in workers]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errs:
+            raise errs[0]
+        return tot
     e2e_warm = max(1, min(args.warmup, 2))
     for _ in range(e2e_warm):
-        tk, res = e2e_step(); al.release(tk)
+        e2e_pass()
     barrier()
     e2e_steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        tk, res = e2e_step()
-        if i + 1 < e2e_steps:
-            al.release(tk)
+        tot = e2e_pass()
     barrier()
     e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    for a in workers:
+        a.close()
+    e2e_cells, h2d, d2h = tot["cells"], tot["h2d"], tot["d2h"]
+    e2e_host.update(threads=len(workers), sub_batches=n_chunks)
+
+    # one ticket for the whole shard: the device-resident measurement below re-runs it; its own submit -> collect time
+    # is reported as e2e.single_ticket (no copy/compute overlap)
+    h0 = time.perf_counter()
+    tk = al.submit(batch, fn, algo, band=16, doStats=True)
+    h1 = time.perf_counter()
+    res = al.collect(tk)
+    h2 = time.perf_counter()
+    e2e_host.update(single_submit_ms=(h1 - h0) * 1e3, single_collect_ms=(h2 - h1) * 1e3)
     tm = res.timing
     cells = int(tm.cells)
+    assert cells == e2e_cells, (cells, e2e_cells)
     ok = int((res.results["status"] == 0).sum())
-    h2d, d2h = int(tm.h2dBytes), int(tm.d2hBytes)
 
     # ---- device-resident: re-run every kernel of the ticket on inputs already in HBM
     for _ in range(args.warmup):
@@ -246,7 +294,11 @@ def run_ours(args):
         "dtype": "int32", "data": "synthetic", "config": config_dict(args, args.jobs),
         "aligned_pairs_per_s": jobs_all * args.steps / (dev_ms_max * 1e-3),
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "pairs_per_s": jobs_all / e2e_sec_max, "ms_per_step": e2e_sec_max * 1e3, "host_breakdown_ms": e2e_host},
+                "pairs_per_s": jobs_all / e2e_sec_max, "ms_per_step": e2e_sec_max * 1e3,
+                "how": f"{e2e_host['threads']} host threads x own context, {e2e_host['sub_batches']} sub-batches of the shard, pinned host buffers "
+                       "in, pinned result arena out, H2D + D2H inside the timed region",
+                "single_ticket": {"value": cells / ((e2e_host["single_submit_ms"] + e2e_host["single_collect_ms"]) * 1e-3) / 1e9,
+                                  "submit_ms": e2e_host["single_submit_ms"], "collect_ms": e2e_host["single_collect_ms"]}},
         "gpu_launches": launches,
         "stage_ms": {"prep": float(np.mean(ms_prep)), "fill": float(np.mean(ms_fill)), "trace": float(np.mean(ms_trace)),
                      "emit": float(np.mean(ms_emit)), "wall_per_step": wall / args.steps * 1e3},

@@ -59,7 +59,8 @@ class Timing(C.Structure):
     _fields_ = [("msPrep", C.c_double), ("msFill", C.c_double), ("msTrace", C.c_double), ("msEmit", C.c_double),
                 ("msTotal", C.c_double), ("cells", C.c_uint64), ("fillCells", C.c_uint64),
                 ("kernelLaunches", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
-                ("msHostSubmit", C.c_double), ("msHostCollect", C.c_double)]
+                ("msHostSubmit", C.c_double), ("msHostCollect", C.c_double), ("devAllocs", C.c_uint32),
+                ("pinAllocs", C.c_uint32)]
 
 
 # numpy view of bgpu_result (natural C alignment)

@@ -45,6 +45,7 @@ struct bgpu_ctx {
   std::multimap<size_t, void *> devFree, pinFree; // cached allocations by size
   std::map<void *, size_t> devSize, pinSize;
   bgpu_ticket lastSync = nullptr;                // ticket owned by bgpu_align
+  uint32_t nDevAlloc = 0, nPinAlloc = 0;         // cudaMalloc / cudaHostAlloc calls so far (cache misses)
 };
 
 #define CK(call)                                                                                  \
@@ -64,6 +65,7 @@ static int dev_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
   bytes = round_up(bytes);
   auto it = ctx->devFree.lower_bound(bytes);
   if (it != ctx->devFree.end() && it->first <= bytes + bytes / 4 + (1u << 20)) { *p = it->second; ctx->devFree.erase(it); return BGPU_OK; }
+  ctx->nDevAlloc++;
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) {   // drop the cache and retry once
     for (auto &kv : ctx->devFree) { cudaFree(kv.second); ctx->devSize.erase(kv.second); }
@@ -80,6 +82,7 @@ static int pin_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
   bytes = round_up(bytes);
   auto it = ctx->pinFree.lower_bound(bytes);
   if (it != ctx->pinFree.end() && it->first <= 2 * bytes + (1u << 20)) { *p = it->second; ctx->pinFree.erase(it); return BGPU_OK; }
+  ctx->nPinAlloc++;
   cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
   if (e != cudaSuccess) { ctx->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); return BGPU_E_OOM; }
   ctx->pinSize[*p] = bytes;
@@ -638,6 +641,7 @@ extern "C" int bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t) {
 extern "C" int bgpu_timing_of(bgpu_ctx *ctx, bgpu_ticket t, bgpu_timing *out) {
   if (!ctx || !t || !out) return BGPU_E_INVALID;
   *out = t->timing;
+  out->devAllocs = ctx->nDevAlloc; out->pinAllocs = ctx->nPinAlloc;
   return BGPU_OK;
 }
 

@@ -126,6 +126,7 @@ typedef struct {
   uint32_t kernelLaunches;                  /* kernels launched by the last run */
   uint64_t h2dBytes, d2hBytes;              /* bytes copied by submit / collect */
   double   msHostSubmit, msHostCollect;     /* wall time spent inside bgpu_submit / bgpu_collect */
+  uint32_t devAllocs, pinAllocs;            /* cudaMalloc / cudaHostAlloc calls made by the context so far (allocation-cache misses) */
 } bgpu_timing;
 
 typedef struct bgpu_ctx bgpu_ctx;
