@@ -5,7 +5,7 @@ align.py (host-side mirror of the reference's aligner interface) and synth.py (s
 """
 from . import capi  # noqa: F401
 from .capi import BgpuError  # noqa: F401
-from .align import (Aligner, Alignment, BatchResult, DistanceMatrixScoreFunction, JobBatch,  # noqa: F401
-                    QualityValueScoreFunction, SMRTDistanceMatrix)
+from .align import (Aligner, Alignment, BatchResult, DistanceMatrixScoreFunction, IDSScoreFunction,  # noqa: F401
+                    JobBatch, QualityValueScoreFunction, SMRTDistanceMatrix)
 
 __version__ = "0.1.0"

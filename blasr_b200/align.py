@@ -21,7 +21,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import capi
-from .capi import (AFFINE_GUIDED, FN_DISTANCE, FN_QUALITY, GLOBAL, GUIDED, KBAND, SW, BgpuError)
+from .capi import (AFFINE_GUIDED, FN_DISTANCE, FN_IDS, FN_QUALITY, GLOBAL, GUIDED, KBAND, SW, BgpuError)
 
 # ScoreMatrices.h:20-26
 SMRTDistanceMatrix = np.array([[-5, 6, 6, 6, 0], [6, -5, 6, 6, 0], [6, 6, -5, 6, 0], [6, 6, 6, -5, 0],
@@ -37,6 +37,8 @@ class DistanceMatrixScoreFunction:
     affineOpen: int = 0
     affineExtend: int = 0
     kind: int = FN_DISTANCE
+    substitutionPrior: int = 0      # BaseScoreFunction.h:8-9 (only IDSScoreFunction reads them)
+    globalDeletionPrior: int = 0
 
     def c_struct(self) -> capi.ScoreFn:
         s = capi.ScoreFn()
@@ -44,6 +46,7 @@ class DistanceMatrixScoreFunction:
         for i in range(25):
             s.M[i] = int(m[i])
         s.ins, s.del_, s.affineOpen, s.affineExtend, s.kind = self.ins, self.del_, self.affineOpen, self.affineExtend, self.kind
+        s.substitutionPrior, s.globalDeletionPrior = self.substitutionPrior, self.globalDeletionPrior
         return s
 
 
@@ -53,6 +56,19 @@ class QualityValueScoreFunction(DistanceMatrixScoreFunction):
     QVDistanceMatrix[q][t] * qual[q]; gap costs are the constants ins/del.  scoreMatrix is only used by the
     stats pass, exactly as blasr rescoring always uses the distance function (Blasr.cpp:875)."""
     kind: int = FN_QUALITY
+
+
+@dataclass
+class IDSScoreFunction(DistanceMatrixScoreFunction):
+    """IDSScoreFunction<DNASequence,FASTQSequence> (IDSScoreFunction.h:21-139): Match is 0 on equal raw bytes, else
+    substitutionQV[q] when substitutionTag[q] is the target base, else substitutionPrior; Insertion is insertionQV[q];
+    Deletion is deletionQV[q] when deletionTag[q] is the target base, else globalDeletionPrior (the constant del
+    without deletion tracks).  Needs batch.insQV / subQV / subTag (delQV + delTag optional).  scoreMatrix, ins, del
+    are used by the boundary rows and by the stats pass, which always rescores with the distance function
+    (Blasr.cpp:875)."""
+    kind: int = FN_IDS
+    substitutionPrior: int = 20     # IDSScoreFunction.h:30-31
+    globalDeletionPrior: int = 13
 
 
 @dataclass
@@ -66,6 +82,14 @@ class JobBatch:
     guideOff: Optional[np.ndarray] = None
     qual: Optional[np.ndarray] = None
     band: Optional[np.ndarray] = None
+    # rich QV tracks of FASTQSequence (FASTQSequence.h:19-26), parallel to q; read by IDSScoreFunction only
+    insQV: Optional[np.ndarray] = None
+    delQV: Optional[np.ndarray] = None
+    subQV: Optional[np.ndarray] = None
+    delTag: Optional[np.ndarray] = None
+    subTag: Optional[np.ndarray] = None
+
+    TRACKS = ("insQV", "delQV", "subQV", "delTag", "subTag")
 
     @property
     def n(self) -> int:
@@ -100,7 +124,13 @@ class JobBatch:
         gs = [self.guide[int(self.guideOff[i]):int(self.guideOff[i + 1])] for i in idx] if self.guide is not None else None
         qv = [self.qual[int(self.qOff[i]):int(self.qOff[i + 1])] for i in idx] if self.qual is not None else None
         bd = [int(self.band[i]) for i in idx] if self.band is not None else None
-        return JobBatch.from_lists(qs, ts, gs, qv, bd)
+        out = JobBatch.from_lists(qs, ts, gs, qv, bd)
+        for name in JobBatch.TRACKS:
+            a = getattr(self, name)
+            if a is not None:
+                parts = [a[int(self.qOff[i]):int(self.qOff[i + 1])] for i in idx]
+                setattr(out, name, np.concatenate(parts) if parts else np.zeros(0, np.uint8))
+        return out
 
 
 @dataclass
@@ -184,8 +214,12 @@ class Aligner:
             keep["qual"] = np.ascontiguousarray(batch.qual, np.uint8)
         if batch.band is not None:
             keep["band"] = np.ascontiguousarray(batch.band, np.int32)
+        for name in JobBatch.TRACKS:
+            if getattr(batch, name, None) is not None:
+                keep[name] = np.ascontiguousarray(getattr(batch, name), np.uint8)
         b = capi.Batch(n, _ptr(keep["q"]), _ptr(keep["qOff"]), _ptr(keep["t"]), _ptr(keep["tOff"]), _ptr(keep.get("qual")),
-                       _ptr(keep.get("guide")), _ptr(keep.get("guideOff")), _ptr(keep.get("band")))
+                       _ptr(keep.get("guide")), _ptr(keep.get("guideOff")), _ptr(keep.get("band")),
+                       *[_ptr(keep.get(name)) for name in JobBatch.TRACKS])
         if statsAffine is None:
             statsAffine = algo == AFFINE_GUIDED
         p = capi.Params(algo, alignType, band, bndIns, bndDel, int(doStats), int(statsAffine))

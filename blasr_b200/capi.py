@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # --- enums (mirror include/blasr_gpu.h) ---
 GUIDED, AFFINE_GUIDED, KBAND, SW = 0, 1, 2, 3
 LOCAL, GLOBAL, QUERYFIT, TARGETFIT, OVERLAP, FRONTANCHORED, ENDANCHORED, FIT, TSUFFIXQPREFIX, TPREFIXQSUFFIX = range(10)
-FN_DISTANCE, FN_QUALITY = 0, 1
+FN_DISTANCE, FN_QUALITY, FN_IDS = 0, 1, 2
 JOB_OK, JOB_EMPTY_GUIDE, JOB_PATH_AWRY, JOB_BAD_INPUT, JOB_REF_UNDEFINED, JOB_TOO_WIDE, JOB_RANGE = range(7)
 E_NO_DEVICE, E_CUDA, E_INVALID, E_OOM, E_BUSY = -1, -2, -3, -4, -5
 
@@ -31,7 +31,8 @@ EXPORTS = [
 
 class ScoreFn(C.Structure):
     _fields_ = [("M", C.c_int32 * 25), ("ins", C.c_int32), ("del_", C.c_int32), ("affineOpen", C.c_int32),
-                ("affineExtend", C.c_int32), ("kind", C.c_int32)]
+                ("affineExtend", C.c_int32), ("kind", C.c_int32), ("substitutionPrior", C.c_int32),
+                ("globalDeletionPrior", C.c_int32)]
 
 
 class Params(C.Structure):
@@ -42,12 +43,15 @@ class Params(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("nJobs", C.c_uint32), ("qBases", C.c_void_p), ("qOff", C.c_void_p), ("tBases", C.c_void_p),
                 ("tOff", C.c_void_p), ("qual", C.c_void_p), ("guide", C.c_void_p), ("guideOff", C.c_void_p),
-                ("band", C.c_void_p)]
+                ("band", C.c_void_p), ("insQV", C.c_void_p), ("delQV", C.c_void_p), ("subQV", C.c_void_p),
+                ("delTag", C.c_void_p), ("subTag", C.c_void_p)]
 
 
 class Job(C.Structure):
     _fields_ = [("q", C.c_void_p), ("qLen", C.c_uint32), ("t", C.c_void_p), ("tLen", C.c_uint32),
-                ("qual", C.c_void_p), ("guide", C.c_void_p), ("nGuide", C.c_uint32), ("band", C.c_int32)]
+                ("qual", C.c_void_p), ("guide", C.c_void_p), ("nGuide", C.c_uint32), ("band", C.c_int32),
+                ("insQV", C.c_void_p), ("delQV", C.c_void_p), ("subQV", C.c_void_p), ("delTag", C.c_void_p),
+                ("subTag", C.c_void_p)]
 
 
 class Arena(C.Structure):

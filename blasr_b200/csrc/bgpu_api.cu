@@ -201,6 +201,33 @@ static void fill_score_params(ScoreParams &sp, const bgpu_scorefn *fn, const bgp
   memcpy(sp.M, fn->M, sizeof sp.M);
   sp.ins = fn->ins; sp.del = fn->del; sp.open = fn->affineOpen; sp.ext = fn->affineExtend;
   sp.kind = fn->kind; sp.alignType = p->alignType; sp.affine = (p->algo == BGPU_AFFINE_GUIDED); sp.pad = 0;
+  sp.subPrior = fn->substitutionPrior; sp.delPrior = fn->globalDeletionPrior;
+}
+
+// IDSScoreFunction (IDSScoreFunction.h:80-139) reads insertionQV / substitutionQV / substitutionTag unconditionally and
+// deletionQV / deletionTag when both are present; SWAlign hands it transposed positions (SWAlign.h:166-167) and the
+// reference then reads past the ends of the tracks, so that combination is refused.
+static int check_ids_tracks(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b) {
+  if (fn->kind != BGPU_FN_IDS) return BGPU_OK;
+  if (p->algo == BGPU_SW) { ctx->err = "SWAlign x BGPU_FN_IDS is undefined in the reference (out-of-bounds track reads)"; return BGPU_E_INVALID; }
+  if (b->nJobs && (!b->insQV || !b->subQV || !b->subTag)) { ctx->err = "BGPU_FN_IDS needs batch.insQV, subQV and subTag"; return BGPU_E_INVALID; }
+  if ((b->delQV == nullptr) != (b->delTag == nullptr)) { ctx->err = "BGPU_FN_IDS: delQV and delTag come as a pair"; return BGPU_E_INVALID; }
+  return BGPU_OK;
+}
+static int upload_ids_tracks(bgpu_ctx *ctx, bgpu_ticket t, const bgpu_scorefn *fn, const bgpu_batch *b, uint64_t totQ) {
+  BatchDev &B = t->B;
+  B.insQV = B.delQV = B.subQV = B.delTag = B.subTag = nullptr;
+  if (fn->kind != BGPU_FN_IDS) return BGPU_OK;
+  const uint8_t *src[5] = {b->insQV, b->delQV, b->subQV, b->delTag, b->subTag};
+  const uint8_t **dst[5] = {&B.insQV, &B.delQV, &B.subQV, &B.delTag, &B.subTag};
+  for (int i = 0; i < 5; i++) {
+    if (!src[i]) continue;
+    uint8_t *d = nullptr;
+    RC(talloc_dev(ctx, t, &d, totQ + 16));
+    RC(upload(ctx, t, d, src[i], totQ));
+    *dst[i] = d;
+  }
+  return BGPU_OK;
 }
 
 // ---- kernel schedule of a guided ticket (used by submit and rerun) ----
@@ -371,6 +398,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   const uint32_t n = b->nJobs;
   if (!b->qOff || !b->tOff || !b->guideOff || (n && (!b->qBases || !b->tBases))) { ctx->err = "null batch arrays"; return BGPU_E_INVALID; }
   if (fn->kind == BGPU_FN_QUALITY && !b->qual) { ctx->err = "BGPU_FN_QUALITY needs batch.qual"; return BGPU_E_INVALID; }
+  RC(check_ids_tracks(ctx, fn, p, b));
   const uint64_t totQ = b->qOff[n], totT = b->tOff[n], totG = b->guideOff[n];
   fill_score_params(t->sp, fn, p);
   BatchDev &B = t->B;
@@ -389,6 +417,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
   if (b->band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
   B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tOff = d_tOff; B.qual = d_qual; B.guide = d_guide; B.guideOff = d_gOff; B.band = d_band;
+  RC(upload_ids_tracks(ctx, t, fn, b, totQ));
   // capacities from sequence lengths (upper bounds of the guide extents)
   uint64_t *h_off = nullptr;
   RC(talloc_pin(ctx, t, &h_off, 3 * (size_t)n + 3));
@@ -485,6 +514,7 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
   const uint32_t n = b->nJobs;
   if (!b->qOff || !b->tOff || (n && (!b->qBases || !b->tBases))) { ctx->err = "null batch arrays"; return BGPU_E_INVALID; }
   if (fn->kind == BGPU_FN_QUALITY && !b->qual) { ctx->err = "BGPU_FN_QUALITY needs batch.qual"; return BGPU_E_INVALID; }
+  RC(check_ids_tracks(ctx, fn, p, b));
   const uint64_t totQ = b->qOff[n], totT = b->tOff[n];
   fill_score_params(t->sp, fn, p);
   t->dense = true;
@@ -502,6 +532,7 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
   if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
   if (d_band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
   B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tOff = d_tOff; B.qual = d_qual; B.guide = nullptr; B.guideOff = nullptr; B.band = d_band;
+  RC(upload_ids_tracks(ctx, t, fn, b, totQ));
   uint64_t *h_off = nullptr;
   RC(talloc_pin(ctx, t, &h_off, 2 * (size_t)n + 2));
   t->h_arrowBytes.assign(n, 0); t->h_cellsMetric.assign(n, 0);
@@ -536,6 +567,7 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!fn || !p || !b || !out) { ctx->err = "null argument"; return BGPU_E_INVALID; }
   if (p->algo < BGPU_GUIDED || p->algo > BGPU_SW) { ctx->err = "unknown algo"; return BGPU_E_INVALID; }
+  if (fn->kind < BGPU_FN_DISTANCE || fn->kind > BGPU_FN_IDS) { ctx->err = "unknown score function kind"; return BGPU_E_INVALID; }
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return BGPU_E_CUDA; }
   const auto h0 = std::chrono::steady_clock::now();
   bgpu_ticket t = new bgpu_ticket_s();
@@ -562,11 +594,15 @@ extern "C" int bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgp
                                 uint32_t nJobs, bgpu_ticket *out) {
   if (!ctx || !jobs) return BGPU_E_INVALID;
   std::vector<uint64_t> qOff(nJobs + 1, 0), tOff(nJobs + 1, 0), gOff(nJobs + 1, 0);
-  bool anyQual = false;
+  bool anyQual = false, anyTrack[5] = {false, false, false, false, false};
+  auto track = [](const bgpu_job &j, int k) { return k == 0 ? j.insQV : k == 1 ? j.delQV : k == 2 ? j.subQV : k == 3 ? j.delTag : j.subTag; };
   for (uint32_t i = 0; i < nJobs; i++) {
     qOff[i + 1] = qOff[i] + jobs[i].qLen; tOff[i + 1] = tOff[i] + jobs[i].tLen; gOff[i + 1] = gOff[i] + jobs[i].nGuide;
     anyQual |= jobs[i].qual != nullptr;
+    for (int k = 0; k < 5; k++) anyTrack[k] |= track(jobs[i], k) != nullptr;
   }
+  std::vector<uint8_t> tracks[5];
+  for (int k = 0; k < 5; k++) if (anyTrack[k]) tracks[k].assign(qOff[nJobs] + 1, 0);
   std::vector<uint8_t> q(qOff[nJobs] + 1), tt(tOff[nJobs] + 1), qual(anyQual ? qOff[nJobs] + 1 : 0);
   std::vector<bgpu_block> g(gOff[nJobs] + 1);
   std::vector<int32_t> band(nJobs + 1);
@@ -576,10 +612,14 @@ extern "C" int bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgp
     if (anyQual && jobs[i].qual && jobs[i].qLen) memcpy(&qual[qOff[i]], jobs[i].qual, jobs[i].qLen);
     if (jobs[i].nGuide) memcpy(&g[gOff[i]], jobs[i].guide, sizeof(bgpu_block) * jobs[i].nGuide);
     band[i] = jobs[i].band;
+    for (int k = 0; k < 5; k++) if (anyTrack[k] && track(jobs[i], k) && jobs[i].qLen) memcpy(&tracks[k][qOff[i]], track(jobs[i], k), jobs[i].qLen);
   }
   bgpu_batch b{};
   b.nJobs = nJobs; b.qBases = q.data(); b.qOff = qOff.data(); b.tBases = tt.data(); b.tOff = tOff.data();
   b.qual = anyQual ? qual.data() : nullptr; b.guide = g.data(); b.guideOff = gOff.data(); b.band = band.data();
+  b.insQV = anyTrack[0] ? tracks[0].data() : nullptr; b.delQV = anyTrack[1] ? tracks[1].data() : nullptr;
+  b.subQV = anyTrack[2] ? tracks[2].data() : nullptr; b.delTag = anyTrack[3] ? tracks[3].data() : nullptr;
+  b.subTag = anyTrack[4] ? tracks[4].data() : nullptr;
   return bgpu_submit(ctx, fn, p, &b, out);   // inputs are staged into pinned memory before this returns
 }
 

@@ -77,13 +77,15 @@ struct ScoreParams {      // kernel argument (by value)
   int32_t M[25];
   int32_t ins, del, open, ext;
   int32_t kind, alignType, affine, pad;
+  int32_t subPrior, delPrior;   // IDSScoreFunction: substitutionPrior, globalDeletionPrior (BaseScoreFunction.h:8-9)
 };
 
 struct BatchDev {         // device pointers of one submitted batch
   uint32_t nJobs;
   uint8_t *q; const uint64_t *qOff;
-  uint8_t *t; const uint64_t *tOff;       // t is re-encoded in place to base codes by prep
+  uint8_t *t; const uint64_t *tOff;       // t is re-encoded in place to base codes by prep (kept raw for BGPU_FN_IDS)
   const uint8_t *qual;
+  const uint8_t *insQV, *delQV, *subQV, *delTag, *subTag;   // IDSScoreFunction tracks (parallel to q), else NULL
   const bgpu_block *guide; const uint64_t *guideOff;
   const int32_t *band;
   JobGeom *geom;

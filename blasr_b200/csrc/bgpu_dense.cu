@@ -4,10 +4,11 @@
 //   KBandAlign  common/algorithms/alignment/KBandAlign.h:75-403  (+ SetKBoundedLengths :36-56)
 //   SWAlign     common/algorithms/alignment/SWAlign.h:18-389
 //
-// Both have constant gap costs on this path (DistanceMatrix / QualityValue score functions), so the
-// in-row dependency  S[t] = min(A[t], S[t-1] + del)  is the min-plus prefix scan
-//     S[t] = min_{j<=t} (A[j] + (t-j) del)
-// which a warp evaluates for 32 columns with five shuffles: one warp per job sweeps the matrix row by
+// The in-row dependency  S[t] = min(A[t], S[t-1] + del_t)  is the min-plus prefix scan
+//     S[t] = min_{j<=t} (A[j] - D[j]) + D[t],   D = prefix sum of the deletion costs of the row
+// (D[t] = t * del for the DistanceMatrix / QualityValue score functions; IDSScoreFunction's deletion cost depends on
+// the row's deletion tag and the column's base, so D comes from a warp prefix sum), which a warp evaluates for 32
+// columns with five shuffles: one warp per job sweeps the matrix row by
 // row, 32 columns per step, all lanes busy.  The previous row lives in an L1/L2-resident ping-pong
 // buffer indexed by absolute column; one traceback byte per cell is written row-major with the layout
 // the reference uses (SW: (|q|+1) x (|t|+1); k-band: (qLen+1) x (2k+1)), boundary cells included, so the
@@ -68,15 +69,18 @@ __global__ void __launch_bounds__(128) dense_prep_kernel(BatchDev B, ScoreParams
     if (((long long)qLength + 1) * ((long long)tLength + 1) > INT_MAX) status = BGPU_JOB_BAD_INPUT;
   }
   if (P.kind == BGPU_FN_QUALITY && !B.qual) status = BGPU_JOB_BAD_INPUT;
+  if (P.kind == BGPU_FN_IDS && (A.algo != BGPU_KBAND || !B.insQV || !B.subQV || !B.subTag)) status = BGPU_JOB_BAD_INPUT;
   {
     int mx = max(max(abs(P.ins), abs(P.del)), max(abs(A.bndIns), abs(A.bndDel)));
     if (P.kind == BGPU_FN_QUALITY) mx = max(mx, 255);
+    else if (P.kind == BGPU_FN_IDS) mx = max(max(mx, 255), max(abs(P.subPrior), abs(P.delPrior)));
     else for (int i = 0; i < 25; i++) mx = max(mx, abs(P.M[i]));
     if ((long long)mx * ((long long)qLength + tLength + 2) >= (1 << 28) || mx >= (1 << 15)) status = status ? status : BGPU_JOB_RANGE;
   }
   int bad = 0;
   uint8_t *tb = B.t + to; uint8_t *qb = B.q + qo;
-  for (uint32_t i = lane; i < tLen; i += 32) { const uint8_t c = lut[tb[i]]; if (c > 4) bad = 1; tb[i] = c; }
+  const bool keepRaw = P.kind == BGPU_FN_IDS;            // IDSScoreFunction compares raw bytes; base_code() is idempotent on codes
+  for (uint32_t i = lane; i < tLen; i += 32) { const uint8_t c = lut[tb[i]]; if (c > 4) bad = 1; if (!keepRaw) tb[i] = c; }
   for (uint32_t i = lane; i < qLen; i += 32) { const uint8_t c = lut[qb[i]]; if (c > 4) bad = 1; }
   bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
   if (bad && status == BGPU_JOB_OK) status = BGPU_JOB_BAD_INPUT;
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(128) dense_fill_kernel(BatchDev B, ScoreParams
   if (threadIdx.x < 25) Mtab[threadIdx.x] = P.M[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const bool sw = A.algo == BGPU_SW, qv = P.kind == BGPU_FN_QUALITY;
+  const bool sw = A.algo == BGPU_SW, qv = P.kind == BGPU_FN_QUALITY, ids = P.kind == BGPU_FN_IDS;
   const int at = P.alignType;
   for (;;) {
     uint32_t idx = 0;
@@ -109,6 +113,7 @@ __global__ void __launch_bounds__(128) dense_fill_kernel(BatchDev B, ScoreParams
     const int R = G.Qn, T = G.Tn, k = G.band;          // rows 0..R, columns 0..T (already k-bounded for KBandAlign)
     const uint8_t *qb = B.q + B.qOff[job], *tb = B.t + B.tOff[job];
     const uint8_t *qual = B.qual ? B.qual + B.qOff[job] : nullptr;
+    const size_t qo = (size_t)B.qOff[job];
     uint8_t *arrows = B.arrows + A.arrowOff[job];
     int *row0 = B.rowBuf + G.rowBufOff, *row1 = row0 + (T + 2);
     const int nCols = sw ? T + 1 : 2 * k + 1;           // arrow row pitch
@@ -163,32 +168,48 @@ __global__ void __launch_bounds__(128) dense_fill_kernel(BatchDev B, ScoreParams
       if (!sw) {
         for (int c = lane; c < nCols; c += 32) { const int t = r - k + c; if (t < 0 || t > T || (t == 0 && !c0in) ) arow[c] = DN_NONE; }
       }
-      const uint8_t qch = lut[qb[r - 1]];
+      const uint8_t qraw = qb[r - 1], qch = lut[qraw];
       const int qvv = qv ? (int)qual[r - 1] : 0;
+      // IDSScoreFunction.h:80-139: this row's tracks (KBandAlign passes the cell's own positions, KBandAlign.h:163-189)
+      int rowIns = ins, subTag = 0, subQ = 0, delTag = 0, delQ = 0; bool hasDel = false;
+      if (ids) {
+        rowIns = (int)B.insQV[qo + r - 1]; subTag = (int)B.subTag[qo + r - 1]; subQ = (int)B.subQV[qo + r - 1];
+        if (B.delQV) { hasDel = true; delTag = (int)B.delTag[qo + r - 1]; delQ = (int)B.delQV[qo + r - 1]; }
+      }
       int carry = (sw || tlo > r - k) ? c0v : DBIG;      // value left of column tlo (k-band: none at the band edge)
       if (!sw && tlo > 1) carry = DBIG;                   // tlo == r-k >= 2: left band edge, deletion not allowed (:155-157)
       for (int base = tlo; base <= thi; base += 32) {
         const int t = base + lane;
         const bool act = t <= thi;
         int ms = DBIG, is = DBIG;
-        int diag = 0;
+        int diag = 0, dcost = act ? del : 0;
         if (act) {
           diag = prev[t - 1];
-          const uint8_t tch = lut[tb[t - 1]];
+          const uint8_t traw = tb[t - 1], tch = lut[traw];
           int m;
-          if (qv) m = ((qch == tch && qch < 4) ? -1 : 1) * qvv; else m = Mtab[qch * 5 + tch];
+          if (ids) {
+            m = (qraw == traw) ? 0 : (subTag == (int)traw ? subQ : P.subPrior);
+            if (hasDel) dcost = (delTag != 'N' && delTag == (int)traw) ? delQ : P.delPrior;
+          }
+          else if (qv) m = ((qch == tch && qch < 4) ? -1 : 1) * qvv; else m = Mtab[qch * 5 + tch];
           ms = diag + m;
-          if (sw || t != r + k) is = prev[t] + ins;       // right band edge: no insertion (:182-184)
+          if (sw || t != r + k) is = prev[t] + rowIns;    // right band edge: no insertion (:182-184)
         }
         int a0 = min(ms, is);
         if (localFam) a0 = min(a0, 0);                    // reset-to-zero == an extra zero candidate
-        // S[t] = min_j (A[j] + (t-j) del)  and the chunk's left neighbour
-        int bv = act ? a0 - lane * del : DBIG;
+        // D = inclusive prefix sum of the deletion costs of this chunk's columns
+        int dpre = dcost;
+        if (ids) {
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, dpre, o); if (lane >= o) dpre += u; }
+        } else dpre = (lane + 1) * del;
+        // S[t] = min_j (A[j] - D[j]) + D[t]  and the chunk's left neighbour
+        int bv = act ? a0 - dpre : DBIG;
         bv = warp_prefix_min(bv, lane);
-        int s = min(bv + lane * del, carry >= DBIG ? DBIG : carry + (lane + 1) * del);
+        int s = min(bv + dpre, carry >= DBIG ? DBIG : carry + dpre);
         int left = __shfl_up_sync(0xffffffffu, s, 1);
         if (lane == 0) left = carry;
-        const int ds = left >= DBIG ? DBIG : left + del;
+        const int ds = left >= DBIG ? DBIG : left + dcost;
         const int best = min(min(ms, is), ds);            // the reference's minScore before any reset
         uint8_t arrow;
         if (sw) arrow = best == ms ? DN_DIAG : (best == is ? DN_UP : DN_LEFT);       // SWAlign.h:196-207

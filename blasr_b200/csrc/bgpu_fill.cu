@@ -25,7 +25,7 @@
 // load per row / column; per cell that leaves one LDS (the substitution score), two VIADDMNMX, the in-band test
 // and the tag split; one funnel shift appends the arrow to the lane's traceback word.  Words are
 // stored [d-block][16-step row][slot pair], 2 bits per cell for the linear aligner (8 for the affine one).
-// Blocks that touch the boundary row, a job's last block, the QV score function and very wide windows take the
+// Blocks that touch the boundary row, a job's last block, the QV / IDS score functions and very wide windows take the
 // generic path (run_block_gen), which reads its rows and columns from shared memory per cell.
 #include "bgpu_common.cuh"
 
@@ -42,14 +42,19 @@ struct FillConsts {
   int del0;              // row-0 step: (Global ? del : 0) << SH
   int k256, kacc;        // 256 and 1 << BITS held in registers the compiler cannot fold: keeps these
                          // multiply-adds on the FMA pipe (IMAD) instead of the busier ALU pipe
+  int subPrior, delPrior, del;   // IDSScoreFunction: unshifted substitutionPrior / globalDeletionPrior / del
 };
 
-template <int LPJ, int KM, bool QV>
+template <int LPJ, int KM, int FN>
 struct SubSmem {          // staging of one job: two d-blocks (current, next)
   int2 rows[2][KM * LPJ + 32];           // RowInfo as prep wrote it: {cd8, (width << 8) | qcode * 20}
   uint32_t colw[2][(KM * LPJ + 44) / 4]; // target codes (bytes), 4-byte chunks from an aligned-down address
   int shift[2 * KM * LPJ];               // window re-mapping scratch
-  int rowq[QV ? KM * LPJ + 32 : 2];      // QV of the current block's rows (QualityValueScoreFunction only)
+  // per-row score data of the current block: QualityValueScoreFunction: the QV; IDSScoreFunction: two words per row,
+  //   [r]      query byte | substitutionTag << 8 | substitutionQV << 16 | insertionQV << 24
+  //   [NR + r] deletionTag | deletionQV << 8 | (deletion tracks present) << 16
+  static constexpr int NR = KM * LPJ + 32;
+  int rowq[FN == 0 ? 2 : (FN == 1 ? NR : 2 * NR)];
 };
 
 template <bool AFFINE> struct Fmt {
@@ -77,10 +82,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // The min chain of one DP cell.
 template <bool AFFINE>
 __device__ __forceinline__ int dp_core(const int S, const int leftS, const int leftAD, const int upS, const int upAI,
-                                       const int m, const FillConsts &c, int &ai, int &ad) {
+                                       const int m, const int delT, const int insT, const FillConsts &c, int &ai, int &ad) {
   int cnd = S + m;                                         // Diagonal (tag 0)
-  cnd = __viaddmin_s32(leftS, c.delT, cnd);                // Left
-  cnd = __viaddmin_s32(upS, c.insT, cnd);                  // Up
+  cnd = __viaddmin_s32(leftS, delT, cnd);                  // Left
+  cnd = __viaddmin_s32(upS, insT, cnd);                    // Up
   if (AFFINE) {
     cnd = __viaddmin_s32(upAI, c.extT3, cnd);              // AffineInsClose
     cnd = __viaddmin_s32(leftAD, c.extT4, cnd);            // AffineDelClose
@@ -145,7 +150,7 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
           const int leftAD = AFFINE ? (g == 0 ? leftA0 : ADo[g - 1]) : 0;
           const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
           int ai = 0, ad = 0;
-          int cnd = dp_core<AFFINE>(Se[g], leftS, leftAD, So[g], AFFINE ? AIo[g] : 0, m, c, ai, ad);
+          int cnd = dp_core<AFFINE>(Se[g], leftS, leftAD, So[g], AFFINE ? AIo[g] : 0, m, c.delT, c.insT, c, ai, ad);
           const bool inb = (unsigned)(c.k256 * (2 * g) + rX[p]) <= (unsigned)rY[p];
           cnd = inb ? cnd : (BIG | F::NONE);
           Se[g] = cnd & ~F::TAGMASK;
@@ -165,7 +170,7 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
           const int upAI = AFFINE ? (g == KA - 1 ? upA0 : AIe[g + 1]) : 0;
           const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
           int ai = 0, ad = 0;
-          int cnd = dp_core<AFFINE>(So[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, m, c, ai, ad);
+          int cnd = dp_core<AFFINE>(So[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, m, c.delT, c.insT, c, ai, ad);
           const bool inb = (unsigned)(c.k256 * (2 * g + 1) + rX[p]) <= (unsigned)rY[p];
           cnd = inb ? cnd : (BIG | F::NONE);
           So[g] = cnd & ~F::TAGMASK;
@@ -191,7 +196,7 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
 // ---------------------------------------------------------------------------------------------------------------
 // Generic path: run-time k, rows / columns read from shared memory per cell, boundary row (first) and the early
 // stop of a job's last block (eLast) handled per cell.
-template <int LPJ, int KM, bool AFFINE, bool QV>
+template <int LPJ, int KM, bool AFFINE, int FN>
 __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
                                               int (&ADe)[KM], int (&ADo)[KM], const BlockView &bv, const int *rowq,
                                               const int mtabAddr, const FillConsts &c, const int k, const int sl,
@@ -206,10 +211,22 @@ __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int 
   auto cell = [&](int &S, int &AI, int &AD, const int leftS, const int leftAD, const int upS, const int upAI,
                   const int ridx, const int cidx, const int slot, const int e, uint32_t &a) {
     const int2 rv = bv.rows[ridx];
-    int m = lds32((uint32_t)(mtabAddr + (rv.y & 0xff) + (int)bv.cols[cidx] * 4));
-    if (QV) m *= rowq[ridx];                                // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+    int m, delT = c.delT, insT = c.insT;
+    if (FN == 2) {
+      // IDSScoreFunction.h:80-139 on the raw bytes: the row's tracks against the column's target byte
+      constexpr int NR = KM * LPJ + 32;
+      const int ra = rowq[ridx], rb = rowq[NR + ridx], tb = (int)bv.cols[cidx];
+      const int stag = (ra >> 8) & 0xff, dtag = rb & 0xff;
+      m = ((ra & 0xff) == tb) ? 0 : ((stag == tb ? ((ra >> 16) & 0xff) : c.subPrior) << F::SHv);
+      insT = (int)(((unsigned)ra >> 24) << F::SHv) | TB_UP;
+      const int dc = (rb >> 16) ? ((dtag != 'N' && dtag == tb) ? ((rb >> 8) & 0xff) : c.delPrior) : c.del;
+      delT = (dc << F::SHv) | TB_LEFT;
+    } else {
+      m = lds32((uint32_t)(mtabAddr + (rv.y & 0xff) + (int)bv.cols[cidx] * 4));
+      if (FN == 1) m *= rowq[ridx];                         // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+    }
     int ai = 0, ad = 0;
-    int cnd = dp_core<AFFINE>(S, leftS, leftAD, upS, upAI, m, c, ai, ad);
+    int cnd = dp_core<AFFINE>(S, leftS, leftAD, upS, upAI, m, delT, insT, c, ai, ad);
     if (first && bv.qlo + ridx == 0) {                      // boundary row (GuidedAlign.h:415-442)
       cnd = ((bv.tlo + cidx) * c.del0) | (AFFINE ? (TB_LEFT | TB_IOPEN | TB_DOPEN) : TL_LEFT);
       ai = c.open; ad = c.open;
@@ -287,13 +304,13 @@ struct RingDispatch<LPJ, KM, AFFINE, KM + 1> {
 
 // order[] holds warp groups: 32 / LPJ job indices each (NOJOB pads the last group); a warp sweeps its jobs in
 // lockstep from d-block 0, with k = the widest member's need per block.
-template <int LPJ, int KM, bool AFFINE, bool QV>
+template <int LPJ, int KM, bool AFFINE, int FN>
 __global__ void __launch_bounds__(KM <= KRING ? 128 : 32, KM <= 4 ? (AFFINE ? 4 : 5) : (KM <= KRING ? (AFFINE ? 3 : 4) : 1))
 fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nGroups, uint32_t *counter) {
   typedef Fmt<AFFINE> F;
-  typedef SubSmem<LPJ, KM, QV> Smem;
+  typedef SubSmem<LPJ, KM, FN> Smem;
   constexpr int NJ = 32 / LPJ;
-  constexpr bool RING = KM <= KRING && !QV;
+  constexpr bool RING = KM <= KRING && FN == 0;
   constexpr int UG = KM <= KRING ? KM : 1;
   constexpr int UNITW = (64 / F::SPW) * LPJ;                // words per arrow unit
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -302,7 +319,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
   const int sub = lane / LPJ, sl = lane % LPJ;
   Smem &sm = reinterpret_cast<Smem *>(smemRaw)[warp * NJ + sub];
   if (threadIdx.x < 25) {
-    if (QV) { const int r = threadIdx.x / 5, cc = threadIdx.x % 5; Mtab[threadIdx.x] = ((r == cc && r < 4) ? -1 : 1) << F::SHv; }  // ScoreMatrices.h:4-10
+    if (FN == 1) { const int r = threadIdx.x / 5, cc = threadIdx.x % 5; Mtab[threadIdx.x] = ((r == cc && r < 4) ? -1 : 1) << F::SHv; }  // ScoreMatrices.h:4-10
     else Mtab[threadIdx.x] = P.M[threadIdx.x] << F::SHv;
   }
   __syncthreads();
@@ -314,6 +331,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
   c.openI = (P.open << F::SHv) | TB_IOPEN; c.openD = (P.open << F::SHv) | TB_DOPEN;
   c.del0 = (P.alignType == BGPU_GLOBAL ? P.del : 0) << F::SHv;
   c.k256 = 256 + P.pad; c.kacc = (1 << F::BITS) + P.pad;    // P.pad is always 0
+  c.subPrior = P.subPrior; c.delPrior = P.delPrior; c.del = P.del;
 
   for (;;) {
     uint32_t grp = 0;
@@ -327,13 +345,15 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
     int Qn = 0, Tn = 0, C0 = 0, nDB = 0, hi0 = 0;
     const RowInfo *rows = nullptr; DBlock *dblk = nullptr; const uint8_t *tcodes = nullptr, *tJobLo = nullptr, *tJobHi = nullptr;
     const uint8_t *qualRow = nullptr;
+    size_t trackOff = 0;                                     // IDS: track index of row q' is trackOff + q'
     uint32_t *arrowsJob = nullptr;
     if (have) {
       Qn = G->Qn; Tn = G->Tn; C0 = G->C0; nDB = G->nDB; hi0 = G->hi0;
       rows = B.rows + G->rowOff; dblk = B.dblk + G->dblkOff;
       tJobLo = B.t + B.tOff[job]; tJobHi = B.t + B.tOff[job + 1];
       tcodes = tJobLo + G->tStart - 1;                       // tcodes[t'] for t' in [1,Tn]
-      if (QV) qualRow = B.qual + B.qOff[job] + G->qStart - 1; // qualRow[q'] for q' in [1,Qn]
+      if (FN == 1) qualRow = B.qual + B.qOff[job] + G->qStart - 1; // qualRow[q'] for q' in [1,Qn]
+      if (FN == 2) trackOff = (size_t)B.qOff[job] + (size_t)G->qStart - 1;
       arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
     }
     const int nDBw = __reduce_max_sync(0xffffffffu, nDB);
@@ -424,10 +444,23 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
       bv.cols = reinterpret_cast<const uint8_t *>(sm.colw[buf]) + (buf ? colShift1 : colShift0);
       bv.wbase8 = wbase << 8;
       bv.qlo = 32 * b + cq - (k * LPJ - 1); bv.tlo = 32 * b - cq;
-      if (QV) {
+      if (FN == 1) {
         for (int r = sl; r < k * LPJ + 32; r += LPJ) {
           const int qp = bv.qlo + r;
           sm.rowq[r] = (live && qp >= 1 && qp <= Qn) ? (int)qualRow[qp] : 0;
+        }
+        __syncwarp();
+      }
+      if (FN == 2) {
+        for (int r = sl; r < k * LPJ + 32; r += LPJ) {
+          const int qp = bv.qlo + r;
+          int ra = 0, rb = 0;
+          if (live && qp >= 1 && qp <= Qn) {
+            const size_t x = trackOff + (size_t)qp;
+            ra = (int)B.q[x] | ((int)B.subTag[x] << 8) | ((int)B.subQV[x] << 16) | ((int)B.insQV[x] << 24);
+            if (B.delQV) rb = (int)B.delTag[x] | ((int)B.delQV[x] << 8) | (1 << 16);
+          }
+          sm.rowq[r] = ra; sm.rowq[Smem::NR + r] = rb;
         }
         __syncwarp();
       }
@@ -438,7 +471,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
       if (RING && !__any_sync(0xffffffffu, first || last))
         RingDispatch<LPJ, KM, AFFINE, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
       else
-        run_block_gen<LPJ, KM, AFFINE, QV>(Se, So, AIe, AIo, ADe, ADo, bv, sm.rowq, mtabAddr, c, k, sl, first, eLast, aw, live);
+        run_block_gen<LPJ, KM, AFFINE, FN>(Se, So, AIe, AIo, ADe, ADo, bv, sm.rowq, mtabAddr, c, k, sl, first, eLast, aw, live);
       if (live && sl == 0) { dblk[b].k = k; dblk[b].arrowUnit = unit; }
       unit += (uint32_t)k;
       // ---- the end cell (Qn, Tn) sits on diagonal Tn-Qn+C0 and is the last cell written to its slot
@@ -460,12 +493,12 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
   }
 }
 
-template <int LPJ, int KM, bool AFFINE, bool QV>
+template <int LPJ, int KM, bool AFFINE, int FN>
 static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, uint32_t nGroups,
                        uint32_t *counter, int nSM, cudaStream_t s) {
   constexpr int WPC = KM <= KRING ? 4 : 1;          // warps per CTA
-  const size_t smem = sizeof(SubSmem<LPJ, KM, QV>) * (32 / LPJ) * WPC;
-  auto kern = fill_guided_kernel<LPJ, KM, AFFINE, QV>;
+  const size_t smem = sizeof(SubSmem<LPJ, KM, FN>) * (32 / LPJ) * WPC;
+  auto kern = fill_guided_kernel<LPJ, KM, AFFINE, FN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int perSM = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, WPC * 32, smem);
@@ -476,24 +509,30 @@ static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *
   if (grid) kern<<<grid, WPC * 32, smem, s>>>(B, P, order, nGroups, counter);
 }
 
-template <bool AFFINE, bool QV>
+template <bool AFFINE, int FN>
 static void launch_cls(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, uint32_t nGroups,
                        uint32_t *counter, int nSM, cudaStream_t s) {
-  if (cls == CLS_L8N) launch_one<8, 4, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
-  else if (cls == CLS_L8) launch_one<8, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
-  else if (cls == CLS_L16) launch_one<16, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
-  else if (cls == CLS_L32) launch_one<32, KRING, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
-  else launch_one<32, KWIDE, AFFINE, QV>(B, P, order, nGroups, counter, nSM, s);
+  if (cls == CLS_L8N) launch_one<8, 4, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
+  else if (cls == CLS_L8) launch_one<8, KRING, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
+  else if (cls == CLS_L16) launch_one<16, KRING, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
+  else if (cls == CLS_L32) launch_one<32, KRING, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
+  else launch_one<32, KWIDE, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
 }
 
 // cls: CLS_*; order: nGroups groups of 32 / cls_lpj(cls) job indices
 void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, uint32_t nGroups,
                         uint32_t *counter, int nSM, cudaStream_t s) {
-  const bool aff = P.affine != 0, qv = P.kind == BGPU_FN_QUALITY;
-  if (aff && qv) launch_cls<true, true>(B, P, cls, order, nGroups, counter, nSM, s);
-  else if (aff) launch_cls<true, false>(B, P, cls, order, nGroups, counter, nSM, s);
-  else if (qv) launch_cls<false, true>(B, P, cls, order, nGroups, counter, nSM, s);
-  else launch_cls<false, false>(B, P, cls, order, nGroups, counter, nSM, s);
+  const bool aff = P.affine != 0;
+  if (P.kind == BGPU_FN_IDS) {
+    if (aff) launch_cls<true, 2>(B, P, cls, order, nGroups, counter, nSM, s);
+    else launch_cls<false, 2>(B, P, cls, order, nGroups, counter, nSM, s);
+  } else if (P.kind == BGPU_FN_QUALITY) {
+    if (aff) launch_cls<true, 1>(B, P, cls, order, nGroups, counter, nSM, s);
+    else launch_cls<false, 1>(B, P, cls, order, nGroups, counter, nSM, s);
+  } else {
+    if (aff) launch_cls<true, 0>(B, P, cls, order, nGroups, counter, nSM, s);
+    else launch_cls<false, 0>(B, P, cls, order, nGroups, counter, nSM, s);
+  }
 }
 
 }  // namespace bgpu

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   {
     int mx = max(max(abs(P.ins), abs(P.del)), abs(P.open) + abs(P.ext));
     if (P.kind == BGPU_FN_QUALITY) mx = max(mx, 255);
+    else if (P.kind == BGPU_FN_IDS) mx = max(max(mx, 255), max(abs(P.subPrior), abs(P.delPrior)));
     else for (int i = 0; i < 25; i++) mx = max(mx, abs(P.M[i]));
     if ((long long)mx * (Qn + Tn + 2) >= (P.affine ? SCORE_LIMIT_AFF : SCORE_LIMIT_LIN) || mx >= (1 << 15)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }
   }
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
   // ---- encode + validate the target window in place (codes 0..4), and check the query bases
   uint8_t *tb = B.t + to;
   const uint8_t *qb = B.q + qo;
-  for (int i = tStart + lane; i < tEnd; i += 32) { uint8_t c = lut[tb[i]]; if (c > 4) bad = 1; tb[i] = c; }
+  const bool keepRaw = P.kind == BGPU_FN_IDS;           // IDSScoreFunction compares raw bytes (IDSScoreFunction.h:129-132)
+  for (int i = tStart + lane; i < tEnd; i += 32) { uint8_t c = lut[tb[i]]; if (c > 4) bad = 1; if (!keepRaw) tb[i] = c; }
   if (warp_or(bad)) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
 
   // ---- live-diagonal range per d-block.  The warp owns these arrays: contributions are reduced across the

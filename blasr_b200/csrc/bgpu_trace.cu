@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
   const uint32_t nRuns = G.nRuns, nBlocks = G.nBlocks;
   const uint32_t *runs = B.runs + G.runOff;
   const uint8_t *qb = B.q + B.qOff[job];
-  const uint8_t *tb = B.t + B.tOff[job];             // codes inside [tStart,tEnd)
+  const uint8_t *tb = B.t + B.tOff[job];             // codes inside [tStart,tEnd) (raw bytes for BGPU_FN_IDS)
+  const bool tRaw = P.kind == BGPU_FN_IDS;
   const long long qLenJ = (long long)(B.qOff[job + 1] - B.qOff[job]), tLenJ = (long long)(B.tOff[job + 1] - B.tOff[job]);
   int oob = 0;
   const uint32_t qPrefix = G.qPos - (uint32_t)G.qStart, tPrefix = G.tPos - (uint32_t)G.tStart;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
         // out of bounds, here the job is flagged instead
         if (q0 < 0 || t0 < 0 || q0 + len > qLenJ || t0 + len > tLenJ) oob = 1;
         else for (uint32_t i = 0; i < len; i++) {
-          const int qc = base_code(qq[i]), tc = tt[i];
+          const int qc = base_code(qq[i]), tc = tRaw ? (int)base_code(tt[i]) : (int)tt[i];
           if (qc == tc) nMatch++; else nMismatch++;
           score += P.M[qc * 5 + tc];                   // ComputeAlignmentScore :74 (row = query)
         }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BGPU_VERSION 100 /* 0.1.0 */
+#define BGPU_VERSION 101 /* 0.1.1 */
 
 /* ---- return codes (API level) ---- */
 enum {
@@ -54,7 +54,10 @@ typedef enum {
   BGPU_FRONTANCHORED = 5, BGPU_ENDANCHORED = 6, BGPU_FIT = 7, BGPU_TSUFFIXQPREFIX = 8, BGPU_TPREFIXQSUFFIX = 9
 } bgpu_align_type;
 typedef enum { BGPU_FN_DISTANCE = 0, /* DistanceMatrixScoreFunction.h:11 */
-               BGPU_FN_QUALITY = 1   /* QualityValueScoreFunction.h:9    */ } bgpu_fn_kind;
+               BGPU_FN_QUALITY = 1,  /* QualityValueScoreFunction.h:9    */
+               BGPU_FN_IDS = 2       /* IDSScoreFunction.h:21 (rich QV tracks: GuidedAlign, AffineGuidedAlign, KBandAlign;
+                                        SWAlign x IDS reads out of bounds in the reference, SWAlign.h:166-167 -> BGPU_E_INVALID) */
+             } bgpu_fn_kind;
 
 /* ---- PODs mirroring the reference's containers ---- */
 typedef struct { uint32_t qPos, tPos, length; } bgpu_block;   /* Block, datastructures/alignment/AlignmentBlock.h:17 */
@@ -66,6 +69,7 @@ typedef struct {
   int32_t ins, del;         /* BaseScoreFunction.h:6-7 */
   int32_t affineOpen, affineExtend; /* BaseScoreFunction.h:10-11 */
   int32_t kind;             /* bgpu_fn_kind */
+  int32_t substitutionPrior, globalDeletionPrior; /* BaseScoreFunction.h:8-9; IDSScoreFunction defaults 20 / 13 (:29-32) */
 } bgpu_scorefn;
 
 typedef struct {
@@ -88,6 +92,10 @@ typedef struct {
   const uint8_t  *qual;                             /* QVs parallel to qBases, or NULL (needed for BGPU_FN_QUALITY) */
   const bgpu_block *guide; const uint64_t *guideOff;/* nJobs+1 offsets; guided algos only, else NULL */
   const int32_t  *band;                             /* per-job band / k, or NULL -> params.band */
+  /* FASTQSequence's rich QV tracks (FASTQSequence.h:19-26), parallel to qBases; read by BGPU_FN_IDS only:
+   * insertionQV, substitutionQV, substitutionTag are required there, deletionQV + deletionTag are optional as a pair
+   * (without them Deletion() is the constant del, IDSScoreFunction.h:85-101).  mergeQV is never read (`if (false)`, :82). */
+  const uint8_t  *insQV, *delQV, *subQV, *delTag, *subTag;
 } bgpu_batch;
 
 /* One job in pointer form (what a per-candidate call site has in hand). */
@@ -97,6 +105,7 @@ typedef struct {
   const uint8_t *qual;                  /* nullable */
   const bgpu_block *guide; uint32_t nGuide;
   int32_t band;
+  const uint8_t *insQV, *delQV, *subQV, *delTag, *subTag;   /* nullable, qLen each (BGPU_FN_IDS) */
 } bgpu_job;
 
 typedef struct {

@@ -42,8 +42,10 @@ class Context {
 template <typename T_ScoreFn>
 inline bgpu_scorefn MakeScoreFn(const T_ScoreFn &fn, int kind = BGPU_FN_DISTANCE) {
   bgpu_scorefn s;
+  std::memset(&s, 0, sizeof s);
   for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) s.M[i * 5 + j] = fn.scoreMatrix[i][j];
   s.ins = fn.ins; s.del = fn.del; s.affineOpen = fn.affineOpen; s.affineExtend = fn.affineExtend; s.kind = kind;
+  s.substitutionPrior = fn.substitutionPrior; s.globalDeletionPrior = fn.globalDeletionPrior;   // BaseScoreFunction.h:8-9
   return s;
 }
 
@@ -73,6 +75,7 @@ class RefineBatch {
     p.bndIns = p.bndDel = 0; p.doStats = 1; p.statsAffine = affine ? 1 : 0;
     if (!qual_.empty()) qual_.resize(q_.size(), 0);
     bgpu_batch b;
+    std::memset(&b, 0, sizeof b);   // no rich QV tracks on this path (DistanceMatrixScoreFunction)
     b.nJobs = size(); b.qBases = q_.data(); b.qOff = qOff_.data(); b.tBases = t_.data(); b.tOff = tOff_.data();
     b.qual = qual_.empty() ? nullptr : qual_.data(); b.guide = guide_.data(); b.guideOff = gOff_.data(); b.band = nullptr;
     results_.resize(b.nJobs);

@@ -56,12 +56,36 @@ static inline int iabs(int a) { return a < 0 ? -a : a; }
  * (row = query code); QualityValueScoreFunction::Match, QualityValueScoreFunction.h:78-83 with
  * QVDistanceMatrix (ScoreMatrices.h:4-10): -qual on equal ACGT, +qual otherwise (N-N is +qual). */
 static inline int match_cost(const orc_scorefn *fn, const orc_job *j, uint32_t tpos, uint32_t qpos) {
+  if (fn->kind == ORC_FN_IDS) {
+    /* IDSScoreFunction<DNASequence,FASTQSequence>::Match, IDSScoreFunction.h:126-139: raw (case-sensitive) bytes */
+    if (j->q[qpos] == j->t[tpos]) return 0;
+    if (j->subTag[qpos] == j->t[tpos]) return (int)j->subQV[qpos];
+    return fn->substitutionPrior;
+  }
   int qc = g_code[j->q[qpos]], tc = g_code[j->t[tpos]];
   if (fn->kind == ORC_FN_QUALITY) {
     int sign = (qc == tc && qc < 4) ? -1 : 1;
     return sign * (int)j->qual[qpos];
   }
   return fn->M[qc * 5 + tc];
+}
+/* the 4-argument Insertion / Deletion the DP loops call.  Distance / QualityValue: the constants ins / del
+ * (DistanceMatrixScoreFunction.h:34-45, QualityValueScoreFunction.h:47-66).  IDS: insertionQV[q]
+ * (IDSScoreFunction.h:113-116) and the deletion-tag rule (:80-103; the mergeQV branch is `if (false)`). */
+static inline int ins_cost(const orc_scorefn *fn, const orc_job *j, uint32_t qpos) {
+  if (fn->kind == ORC_FN_IDS) return (int)j->insQV[qpos];
+  return fn->ins;
+}
+static inline int del_cost(const orc_scorefn *fn, const orc_job *j, uint32_t tpos, uint32_t qpos) {
+  if (fn->kind == ORC_FN_IDS) {
+    if (j->delQV && j->delTag) {
+      if (j->delTag[qpos] == 'N') return fn->globalDeletionPrior;
+      if (j->delTag[qpos] == j->t[tpos]) return (int)j->delQV[qpos];
+      return fn->globalDeletionPrior;
+    }
+    return fn->del;
+  }
+  return fn->del;
 }
 
 /* ---- growable output path ------------------------------------------------------ */
@@ -282,8 +306,8 @@ static int guided_align(const orc_scorefn *fn, const orc_job *j, int affine, orc
       if (t < -1 || t >= tEnd) continue;                             /* :502-503 */
       int64_t c = gidx(&m, row, t), dg = gidx(&m, row - 1, t - 1), up = gidx(&m, row - 1, t), lf = gidx(&m, row, t - 1);
       int ms = dg >= 0 ? wadd(m.S[dg], match_cost(fn, j, (uint32_t)t, (uint32_t)q)) : ORC_INF;
-      int is = up >= 0 ? wadd(m.S[up], fn->ins) : ORC_INF;
-      int ds = lf >= 0 ? wadd(m.S[lf], fn->del) : ORC_INF;
+      int is = up >= 0 ? wadd(m.S[up], ins_cost(fn, j, (uint32_t)q)) : ORC_INF;
+      int ds = lf >= 0 ? wadd(m.S[lf], del_cost(fn, j, (uint32_t)t, (uint32_t)q)) : ORC_INF;
       if (!affine) {
         int best = imin(ms, imin(is, ds));
         m.S[c] = best;
@@ -377,9 +401,9 @@ static int kband_align(const orc_scorefn *fn, const orc_job *j, orc_result *res,
   for (int q = 1; q <= (int)qLen; q++) {
     for (int t = q - k; t < q + k + 1; t++) {
       if (t < 1 || (uint32_t)t > tLen) continue;
-      int ds = (t == q - k) ? ORC_INF : wadd(S[KB(q, k + t - q - 1)], fn->del);        /* :155-164 */
+      int ds = (t == q - k) ? ORC_INF : wadd(S[KB(q, k + t - q - 1)], del_cost(fn, j, (uint32_t)t - 1, (uint32_t)q - 1));        /* :155-164 */
       int ms = wadd(S[KB(q - 1, k + t - q)], match_cost(fn, j, (uint32_t)t - 1, (uint32_t)q - 1)); /* :176-177 */
-      int is = (t == q + k) ? ORC_INF : wadd(S[KB(q - 1, k + t - q + 1)], fn->ins);   /* :182-190 */
+      int is = (t == q + k) ? ORC_INF : wadd(S[KB(q - 1, k + t - q + 1)], ins_cost(fn, j, (uint32_t)q - 1));   /* :182-190 */
       int best = imin(ms, imin(is, ds));
       S[KB(q, k + t - q)] = best;
       P[KB(q, k + t - q)] = best == ms ? A_DIAG : best == ds ? A_LEFT : A_UP;           /* :201-209 */
@@ -590,7 +614,11 @@ int orc_align(const orc_scorefn *fn, const orc_job *job, orc_result *res, uint32
   a.blocks = blocks; a.capBlocks = capBlocks; a.gapCounts = gapCounts; a.capGapLists = capGapLists;
   a.gaps = gaps; a.capGaps = capGaps;
   if (!check_bases(job->q, job->qLen) || !check_bases(job->t, job->tLen) ||
-      (fn->kind == ORC_FN_QUALITY && !job->qual)) { res->status = ORC_BAD_INPUT; return 0; }
+      (fn->kind == ORC_FN_QUALITY && !job->qual) ||
+      (fn->kind == ORC_FN_IDS && (!job->insQV || !job->subQV || !job->subTag || job->algo == ORC_SW))) {
+    /* SWAlign x IDS: the reference passes transposed positions (SWAlign.h:166-167) and reads out of bounds */
+    res->status = ORC_BAD_INPUT; return 0;
+  }
   switch (job->algo) {
     case ORC_GUIDED: guided_align(fn, job, 0, res, &a); break;
     case ORC_AFFINE_GUIDED: guided_align(fn, job, 1, res, &a); break;

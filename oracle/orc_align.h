@@ -24,7 +24,7 @@ extern "C" {
 /* algorithms (mirrors bgpu_algo in include/blasr_gpu.h) */
 enum { ORC_GUIDED = 0, ORC_AFFINE_GUIDED = 1, ORC_KBAND = 2, ORC_SW = 3 };
 /* score function kinds */
-enum { ORC_FN_DISTANCE = 0, ORC_FN_QUALITY = 1 };
+enum { ORC_FN_DISTANCE = 0, ORC_FN_QUALITY = 1, ORC_FN_IDS = 2 };
 /* AlignmentType ordinals, common/algorithms/alignment/AlignmentUtils.h:14-58 */
 enum { ORC_LOCAL = 0, ORC_GLOBAL = 1, ORC_QUERYFIT = 2, ORC_TARGETFIT = 3, ORC_OVERLAP = 4,
        ORC_FRONTANCHORED = 5, ORC_ENDANCHORED = 6, ORC_FIT = 7, ORC_TSUFFIXQPREFIX = 8,
@@ -37,6 +37,7 @@ typedef struct {
   int32_t ins, del;       /* BaseScoreFunction.h:6-7 */
   int32_t affineOpen, affineExtend; /* BaseScoreFunction.h:10-11 */
   int32_t kind;           /* ORC_FN_* */
+  int32_t substitutionPrior, globalDeletionPrior; /* BaseScoreFunction.h:8-9 (IDSScoreFunction defaults 20 / 13) */
 } orc_scorefn;
 
 typedef struct {
@@ -51,6 +52,9 @@ typedef struct {
   const uint8_t *qual;    /* qLen QVs or NULL (required for ORC_FN_QUALITY) */
   const uint32_t *guide;  /* nGuide x {qPos,tPos,length} */
   uint32_t nGuide;
+  /* rich QV tracks of FASTQSequence (FASTQSequence.h:19-26), qLen bytes each, used by ORC_FN_IDS:
+   * insQV, subQV, subTag are required; delQV + delTag are optional as a pair (IDSScoreFunction.h:85) */
+  const uint8_t *insQV, *delQV, *subQV, *delTag, *subTag;
 } orc_job;
 
 typedef struct {

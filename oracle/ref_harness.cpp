@@ -13,8 +13,9 @@
  *   SWAlign            common/algorithms/alignment/SWAlign.h:18
  *   ComputeAlignmentStats  common/algorithms/alignment/AlignmentUtils.h:535
  *   SDPAlign           common/algorithms/alignment/SDPAlign.h (guide producer, test inputs only)
- * each with DistanceMatrixScoreFunction<DNASequence,FASTQSequence> and
- * QualityValueScoreFunction<DNASequence,FASTQSequence>.
+ * each with DistanceMatrixScoreFunction<DNASequence,FASTQSequence>,
+ * QualityValueScoreFunction<DNASequence,FASTQSequence> and (all but SWAlign, whose transposed position
+ * arguments make it read out of bounds, SWAlign.h:166-167) IDSScoreFunction<DNASequence,FASTQSequence>.
  */
 #define _GLIBCXX_USE_CXX11_ABI 0
 #include "algorithms/alignment.h"
@@ -23,6 +24,7 @@
 #include "algorithms/alignment/SDPAlign.h"
 #include "algorithms/alignment/DistanceMatrixScoreFunction.h"
 #include "algorithms/alignment/QualityValueScoreFunction.h"
+#include "algorithms/alignment/IDSScoreFunction.h"
 #include "datastructures/alignment/AlignmentCandidate.h"
 #include "FASTQSequence.h"
 
@@ -52,6 +54,13 @@ static void FillDist(const orc_scorefn *fn, DistFn &f) {
 }
 static void FillQV(const orc_scorefn *fn, QVFn &f) {
   f.ins = fn->ins; f.del = fn->del;
+  f.affineOpen = fn->affineOpen; f.affineExtend = fn->affineExtend;
+}
+
+typedef IDSScoreFunction<DNASequence, FASTQSequence> IDSFn;
+static void FillIDS(const orc_scorefn *fn, IDSFn &f) {
+  f.ins = fn->ins; f.del = fn->del;
+  f.substitutionPrior = fn->substitutionPrior; f.globalDeletionPrior = fn->globalDeletionPrior;
   f.affineOpen = fn->affineOpen; f.affineExtend = fn->affineExtend;
 }
 
@@ -103,6 +112,15 @@ static int RunOne(const orc_scorefn *fn, const orc_job *job, orc_result *res, Sc
     if (!job->qual) { q.qual.data = NULL; res->status = ORC_BAD_INPUT; return 0; }
     QVFn qf; FillQV(fn, qf);
     score = RunAligner(job, qf, fn, q, t, aln, s);
+  } else if (fn->kind == ORC_FN_IDS) {
+    if (!job->insQV || !job->subQV || !job->subTag || job->algo == ORC_SW) { q.qual.data = NULL; res->status = ORC_BAD_INPUT; return 0; }
+    q.insertionQV.data = (QualityValue *)job->insQV; q.substitutionQV.data = (QualityValue *)job->subQV;
+    q.substitutionTag = (Nucleotide *)job->subTag;
+    if (job->delQV && job->delTag) { q.deletionQV.data = (QualityValue *)job->delQV; q.deletionTag = (Nucleotide *)job->delTag; }
+    IDSFn idf; FillIDS(fn, idf);
+    score = RunAligner(job, idf, fn, q, t, aln, s);
+    q.insertionQV.data = NULL; q.substitutionQV.data = NULL; q.deletionQV.data = NULL;   /* borrowed */
+    q.substitutionTag = NULL; q.deletionTag = NULL;
   } else {
     score = RunAligner(job, df, fn, q, t, aln, s);
   }

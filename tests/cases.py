@@ -17,6 +17,27 @@ def job_arrays(b: JobBatch, i: int):
     return q, t, g, qv
 
 
+def job_tracks(b: JobBatch, i: int):
+    lo, hi = int(b.qOff[i]), int(b.qOff[i + 1])
+    return {k: (getattr(b, k)[lo:hi] if getattr(b, k, None) is not None else None) for k in JobBatch.TRACKS}
+
+
+def add_ids_tracks(b: JobBatch, seed: int, with_del=True) -> JobBatch:
+    """bas.h5-style rich QV tracks: QVs ~ clamp(N(12,4),1,93); tags are a random base
+    (substitution) / a random base or 'N' (deletion), a few of them lower-case (the compares are raw bytes)."""
+    rng = np.random.default_rng(seed)
+    n = len(b.q)
+    qv = lambda: np.clip(np.rint(rng.normal(12, 4, n)), 1, 93).astype(np.uint8)
+    b.insQV, b.subQV = qv(), qv()
+    st = ACGT[rng.integers(0, 4, n)].copy(); st[rng.random(n) < 0.05] |= 0x20
+    b.subTag = st
+    if with_del:
+        b.delQV = qv()
+        dt = ACGT[rng.integers(0, 4, n)].copy(); dt[rng.random(n) < 0.3] = ord("N"); dt[rng.random(n) < 0.05] |= 0x20
+        b.delTag = dt
+    return b
+
+
 def drop_blocks(guide: np.ndarray, rng, p_drop: float, run: int = 1) -> np.ndarray:
     """Adversarial guide: delete runs of interior blocks (keeps first and last), leaving real gaps."""
     n = len(guide)
@@ -102,6 +123,6 @@ def oracle_batch(which: str, b: JobBatch, fn: O.OrcScoreFn, algo: int, alignType
     for i in range(b.n):
         q, t, g, qv = job_arrays(b, i)
         bd = int(band[i]) if hasattr(band, "__len__") else int(band)
-        j, keep = O.make_job(algo, alignType, bd, q, t, g, qv, bndIns, bndDel, doStats, statsAffine)
+        j, keep = O.make_job(algo, alignType, bd, q, t, g, qv, bndIns, bndDel, doStats, statsAffine, tracks=job_tracks(b, i))
         out.append(O.align(which, fn, j))
     return out

@@ -20,14 +20,17 @@ REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libblasr_ref.so")
 
 class OrcScoreFn(C.Structure):
     _fields_ = [("M", C.c_int32 * 25), ("ins", C.c_int32), ("del_", C.c_int32), ("affineOpen", C.c_int32),
-                ("affineExtend", C.c_int32), ("kind", C.c_int32)]
+                ("affineExtend", C.c_int32), ("kind", C.c_int32), ("substitutionPrior", C.c_int32),
+                ("globalDeletionPrior", C.c_int32)]
 
 
 class OrcJob(C.Structure):
     _fields_ = [("algo", C.c_int32), ("alignType", C.c_int32), ("band", C.c_int32), ("bndIns", C.c_int32),
                 ("bndDel", C.c_int32), ("doStats", C.c_int32), ("statsAffine", C.c_int32),
                 ("q", C.c_void_p), ("qLen", C.c_uint32), ("t", C.c_void_p), ("tLen", C.c_uint32),
-                ("qual", C.c_void_p), ("guide", C.c_void_p), ("nGuide", C.c_uint32)]
+                ("qual", C.c_void_p), ("guide", C.c_void_p), ("nGuide", C.c_uint32),
+                ("insQV", C.c_void_p), ("delQV", C.c_void_p), ("subQV", C.c_void_p), ("delTag", C.c_void_p),
+                ("subTag", C.c_void_p)]
 
 
 class OrcResult(C.Structure):
@@ -72,18 +75,19 @@ def have_ref() -> bool:
     return _load("ref") is not None
 
 
-def score_fn(M, ins, del_, affineOpen=0, affineExtend=0, kind=0) -> OrcScoreFn:
+def score_fn(M, ins, del_, affineOpen=0, affineExtend=0, kind=0, substitutionPrior=20, globalDeletionPrior=13) -> OrcScoreFn:
     f = OrcScoreFn()
     m = np.asarray(M, dtype=np.int32).reshape(25)
     for i in range(25):
         f.M[i] = int(m[i])
     f.ins, f.del_, f.affineOpen, f.affineExtend, f.kind = ins, del_, affineOpen, affineExtend, kind
+    f.substitutionPrior, f.globalDeletionPrior = substitutionPrior, globalDeletionPrior
     return f
 
 
 def make_job(algo, alignType, band, q: np.ndarray, t: np.ndarray, guide=None, qual=None, bndIns=0, bndDel=0, doStats=1,
-             statsAffine=0):
-    """Returns (OrcJob, keepalive)."""
+             statsAffine=0, tracks=None):
+    """Returns (OrcJob, keepalive).  tracks: dict of the rich QV tracks (insQV, delQV, subQV, delTag, subTag)."""
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     keep = [q, t]
     j = OrcJob()
@@ -94,6 +98,9 @@ def make_job(algo, alignType, band, q: np.ndarray, t: np.ndarray, guide=None, qu
     if guide is not None and len(guide):
         guide = np.ascontiguousarray(guide, np.uint32).reshape(-1, 3); keep.append(guide)
         j.guide, j.nGuide = guide.ctypes.data, len(guide)
+    for name, arr in (tracks or {}).items():
+        if arr is not None:
+            arr = np.ascontiguousarray(arr, np.uint8); keep.append(arr); setattr(j, name, arr.ctypes.data)
     return j, keep
 
 

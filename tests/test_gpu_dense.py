@@ -3,7 +3,7 @@ gap lists, stats), all end conditions, DistanceMatrix and QualityValue score fun
 import numpy as np
 import pytest
 
-from blasr_b200 import DistanceMatrixScoreFunction, JobBatch, QualityValueScoreFunction, SMRTDistanceMatrix, capi
+from blasr_b200 import DistanceMatrixScoreFunction, IDSScoreFunction, JobBatch, QualityValueScoreFunction, SMRTDistanceMatrix, capi
 from . import cases, oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -24,7 +24,8 @@ def _check(res, b, ofn, algo, at, bands, bndIns, bndDel, doStats, fields):
     n_ok = 0
     for i in range(b.n):
         q, t, _, qv = cases.job_arrays(b, i)
-        j, keep = O.make_job(algo, at, int(bands[i]) if bands is not None else 0, q, t, None, qv, bndIns, bndDel, int(doStats), 0)
+        j, keep = O.make_job(algo, at, int(bands[i]) if bands is not None else 0, q, t, None, qv, bndIns, bndDel, int(doStats), 0,
+                             tracks=cases.job_tracks(b, i))
         # the reference itself is undefined for some inputs (see oracle/orc_align.c); ask the C port first
         pre = O.align("orc", ofn, j)
         got = cases.gpu_to_dict(res, i)
@@ -58,6 +59,25 @@ def test_kband(aligner, at, kind):
     ofn = O.score_fn(fn.scoreMatrix, fn.ins, fn.del_, kind=kind)
     fields = cases.GPU_FIELDS if doStats else ["status", "score", "qPos", "tPos", "nCells", "nBlocks", "nGapLists", "nGaps"]
     assert _check(res, b, ofn, 2, at, bands, bi, bd, doStats, fields) > 100
+
+
+@pytest.mark.parametrize("at", [1, 2, 3, 7])
+def test_kband_ids(aligner, at):
+    """KBandAlign x IDSScoreFunction: per-row insertion cost, per-cell deletion cost (prefix-sum scan)."""
+    b, rng = _pairs(1500 + at, 120, 4, 400, False)
+    cases.add_ids_tracks(b, 33 + at, with_del=(at != 2))
+    bands = rng.integers(1, 48, b.n).astype(np.int32)
+    if at in (3, 7):
+        tl = np.diff(b.tOff.astype(np.int64)); ql = np.diff(b.qOff.astype(np.int64))
+        bands = np.maximum(1, np.minimum(bands, np.minimum(tl, ql))).astype(np.int32)
+    b.band = bands
+    fn = IDSScoreFunction(SMRTDistanceMatrix.copy(), int(rng.integers(1, 8)), int(rng.integers(1, 8)))
+    bi, bd = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+    res = aligner.KBandAlign(b, fn, bi, bd, 0, alignType=at, computeStats=(at == 1))
+    ofn = O.score_fn(fn.scoreMatrix, fn.ins, fn.del_, kind=2, substitutionPrior=fn.substitutionPrior,
+                     globalDeletionPrior=fn.globalDeletionPrior)
+    fields = cases.GPU_FIELDS if at == 1 else ["status", "score", "qPos", "tPos", "nCells", "nBlocks", "nGapLists", "nGaps"]
+    assert _check(res, b, ofn, 2, at, bands, bi, bd, at == 1, fields) > 80
 
 
 def test_kband_long(aligner):

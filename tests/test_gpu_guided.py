@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from blasr_b200 import DistanceMatrixScoreFunction, QualityValueScoreFunction, SMRTDistanceMatrix
+from blasr_b200 import DistanceMatrixScoreFunction, IDSScoreFunction, QualityValueScoreFunction, SMRTDistanceMatrix
 from blasr_b200 import capi
 from . import cases, oracle as O
 
@@ -16,7 +16,8 @@ def _run(aligner, b, algo, fn, band, at=1):
         res = aligner.AffineGuidedAlign(b, fn, band, alignType=at)
     else:
         res = aligner.GuidedAlign(b, fn, band, alignType=at)
-    ofn = O.score_fn(fn.scoreMatrix, fn.ins, fn.del_, fn.affineOpen, fn.affineExtend, fn.kind)
+    ofn = O.score_fn(fn.scoreMatrix, fn.ins, fn.del_, fn.affineOpen, fn.affineExtend, fn.kind, fn.substitutionPrior,
+                     fn.globalDeletionPrior)
     bd = b.band if b.band is not None else band
     want = cases.oracle_batch(WHICH, b, ofn, algo, at, bd, statsAffine=algo)
     nbad = 0
@@ -69,6 +70,33 @@ def test_quality_value_score_function(aligner):
     fn = QualityValueScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
     _run(aligner, b, 0, fn, 16)
     _run(aligner, b, 1, fn, 16)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("with_del", [True, False])
+def test_ids_score_function(aligner, algo, with_del):
+    """BASELINE configs[3]: rich QV tracks (ins/del/sub QVs + tags) through IDSScoreFunction, function-level parity."""
+    rng = np.random.default_rng(17 + algo)
+    for rep in range(3):
+        b = cases.guided_batch(seed=520 + rep, n=16, lo=100, hi=2500, n_rate=0.01, lower=(rep == 1),
+                               adversarial=0.3 if rep == 2 else 0.0, run=10)
+        cases.add_ids_tracks(b, 77 + rep, with_del)
+        fn = IDSScoreFunction(ins=int(rng.integers(1, 9)), del_=int(rng.integers(1, 9)), affineOpen=int(rng.choice([0, 5, 30])),
+                              affineExtend=int(rng.choice([0, 1, 3])), substitutionPrior=int(rng.choice([20, 7])),
+                              globalDeletionPrior=int(rng.choice([13, 4])))
+        for at in (0, 1):
+            res, _ = _run(aligner, b, algo, fn, int(rng.choice([8, 16, 32])), at)
+            assert (res.results["status"] == 0).sum() >= b.n - 2
+
+
+def test_ids_needs_tracks(aligner):
+    from blasr_b200 import BgpuError
+    b = cases.guided_batch(seed=1, n=2, lo=100, hi=200)
+    with pytest.raises(BgpuError):
+        aligner.GuidedAlign(b, IDSScoreFunction(), 16)
+    cases.add_ids_tracks(b, 1)
+    with pytest.raises(BgpuError):   # SWAlign x IDS reads out of bounds in the reference (SWAlign.h:166-167)
+        aligner.SWAlign(b, IDSScoreFunction())
 
 
 def test_edge_cases(aligner):

@@ -4,7 +4,7 @@ absent (it is built from /root/reference by oracle/Makefile and travels to the G
 import numpy as np
 import pytest
 
-from blasr_b200 import SMRTDistanceMatrix
+from blasr_b200 import JobBatch, SMRTDistanceMatrix
 from . import cases, oracle as O
 
 pytestmark = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libblasr_ref.so not built")
@@ -54,6 +54,46 @@ def test_guided_quality():
     fn = O.score_fn(SMRTDistanceMatrix, 5, 5, 50, 0, kind=1)
     _check(b, fn, 0, 1, 16)
     _check(b, fn, 1, 1, 16, statsAffine=1)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("with_del", [True, False])
+def test_guided_ids(algo, with_del):
+    """IDSScoreFunction (rich QV tracks): per-row insertion cost, tag-dependent deletion / substitution costs."""
+    rng = np.random.default_rng(3 + algo)
+    for rep in range(4):
+        b = cases.guided_batch(seed=300 + rep, n=3, lo=150, hi=1100, n_rate=0.01, lower=(rep % 2 == 1),
+                               adversarial=0.3 if rep == 3 else 0.0, run=10)
+        cases.add_ids_tracks(b, 900 + rep, with_del)
+        fn = O.score_fn(SMRTDistanceMatrix, int(rng.integers(1, 9)), int(rng.integers(1, 9)), int(rng.choice([0, 5, 30])),
+                        int(rng.choice([0, 1, 3])), kind=2, substitutionPrior=int(rng.choice([20, 7])),
+                        globalDeletionPrior=int(rng.choice([13, 4])))
+        for at in (0, 1):
+            _check(b, fn, algo, at, int(rng.choice([8, 16, 32])), statsAffine=algo)
+
+
+@pytest.mark.parametrize("at", [1, 2, 3, 7])
+def test_kband_ids(at):
+    rng = np.random.default_rng(140 + at)
+    fn = O.score_fn(SMRTDistanceMatrix, 4, 6, kind=2)
+    n = 0
+    for rep in range(40):
+        q, t = cases.random_pair(rng, 5, 200, err=0.2, n_rate=0.01)
+        k = int(rng.integers(1, 40))
+        if at in (3, 7) and k > min(len(t), len(q) + k):
+            k = max(1, min(k, len(t), len(q)))
+        b = JobBatch.from_lists([q.tobytes()], [t.tobytes()])
+        cases.add_ids_tracks(b, 500 + rep, with_del=(rep % 3 != 0))
+        j, keep = O.make_job(2, at, k, q, t, None, None, int(rng.integers(1, 9)), int(rng.integers(1, 9)), 1, 0,
+                             tracks=cases.job_tracks(b, 0))
+        a = O.align("orc", fn, j)
+        if a["status"] != 0:
+            continue
+        r = O.align("ref", fn, j)
+        bad = cases.compare(a, r)
+        assert not bad, f"rep {rep} k={k} |q|={len(q)} |t|={len(t)}: {bad}"
+        n += 1
+    assert n > 20
 
 
 def test_guide_rows():
