@@ -21,7 +21,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import capi
-from .capi import (AFFINE_GUIDED, FN_DISTANCE, FN_IDS, FN_QUALITY, GLOBAL, GUIDED, KBAND, SW, BgpuError)
+from .capi import (AFFINE_GUIDED, AFFINE_KBAND, FN_DISTANCE, FN_IDS, FN_QUALITY, GLOBAL, GUIDED, KBAND, SW, BgpuError)
 
 # ScoreMatrices.h:20-26
 SMRTDistanceMatrix = np.array([[-5, 6, 6, 6, 0], [6, -5, 6, 6, 0], [6, 6, -5, 6, 0], [6, 6, 6, -5, 0],
@@ -201,7 +201,8 @@ class Aligner:
 
     # ---- low level: ticket API ----
     def submit(self, batch: JobBatch, fn: DistanceMatrixScoreFunction, algo: int, alignType: int = GLOBAL, band: int = 16,
-               bndIns: int = 0, bndDel: int = 0, doStats: bool = True, statsAffine: Optional[bool] = None):
+               bndIns: int = 0, bndDel: int = 0, doStats: bool = True, statsAffine: Optional[bool] = None,
+               affineKBand: Sequence[int] = (0, 0, 0, 0)):
         keep = dict(q=np.ascontiguousarray(batch.q, np.uint8), qOff=np.ascontiguousarray(batch.qOff, np.uint64),
                     t=np.ascontiguousarray(batch.t, np.uint8), tOff=np.ascontiguousarray(batch.tOff, np.uint64))
         n = batch.n
@@ -222,7 +223,7 @@ class Aligner:
                        *[_ptr(keep.get(name)) for name in JobBatch.TRACKS])
         if statsAffine is None:
             statsAffine = algo == AFFINE_GUIDED
-        p = capi.Params(algo, alignType, band, bndIns, bndDel, int(doStats), int(statsAffine))
+        p = capi.Params(algo, alignType, band, bndIns, bndDel, int(doStats), int(statsAffine), *[int(x) for x in affineKBand])
         f = fn.c_struct()
         tk = C.c_void_p()
         rc = self._lib.bgpu_submit(self._ctx, C.byref(f), C.byref(p), C.byref(b), C.byref(tk))
@@ -299,6 +300,15 @@ class Aligner:
         """KBandAlign.h:75; ins/del are the boundary-cost *parameters*, the fill uses scoreFn.ins/del."""
         return self._run(batch, scoreFn, KBAND, alignType=alignType, band=k, bndIns=ins, bndDel=del_, doStats=computeStats,
                          statsAffine=False)
+
+    def AffineKBandAlign(self, batch: JobBatch, matchMat, hpInsOpen: int, hpInsExtend: int, insOpen: int, insExtend: int,
+                         del_: int, k: int, alignType: int = GLOBAL, computeStats: bool = False, scoreFn=None) -> BatchResult:
+        """AffineKBandAlign.h:12 (argument order of Blasr.cpp:1067-1076): matchMat[5][5] (row = query), the five int gap
+        parameters, k.  Global and QueryFit.  scoreFn is only used by the optional stats pass."""
+        fn = scoreFn if scoreFn is not None else DistanceMatrixScoreFunction()
+        fn = DistanceMatrixScoreFunction(np.asarray(matchMat, np.int32).copy(), fn.ins, fn.del_, fn.affineOpen, fn.affineExtend)
+        return self._run(batch, fn, AFFINE_KBAND, alignType=alignType, band=k, bndDel=del_, doStats=computeStats,
+                         statsAffine=False, affineKBand=(hpInsOpen, hpInsExtend, insOpen, insExtend))
 
     def SWAlign(self, batch: JobBatch, scoreFn, alignType: int = capi.LOCAL, computeStats: bool = False) -> BatchResult:
         """SWAlign.h:18."""

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libblasr_gpu.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 # --- enums (mirror include/blasr_gpu.h) ---
-GUIDED, AFFINE_GUIDED, KBAND, SW = 0, 1, 2, 3
+GUIDED, AFFINE_GUIDED, KBAND, SW, AFFINE_KBAND = 0, 1, 2, 3, 4
 LOCAL, GLOBAL, QUERYFIT, TARGETFIT, OVERLAP, FRONTANCHORED, ENDANCHORED, FIT, TSUFFIXQPREFIX, TPREFIXQSUFFIX = range(10)
 FN_DISTANCE, FN_QUALITY, FN_IDS = 0, 1, 2
 JOB_OK, JOB_EMPTY_GUIDE, JOB_PATH_AWRY, JOB_BAD_INPUT, JOB_REF_UNDEFINED, JOB_TOO_WIDE, JOB_RANGE = range(7)
@@ -37,7 +37,8 @@ class ScoreFn(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [("algo", C.c_int32), ("alignType", C.c_int32), ("band", C.c_int32), ("bndIns", C.c_int32),
-                ("bndDel", C.c_int32), ("doStats", C.c_int32), ("statsAffine", C.c_int32)]
+                ("bndDel", C.c_int32), ("doStats", C.c_int32), ("statsAffine", C.c_int32), ("hpInsOpen", C.c_int32),
+                ("hpInsExtend", C.c_int32), ("insOpen", C.c_int32), ("insExtend", C.c_int32)]
 
 
 class Batch(C.Structure):

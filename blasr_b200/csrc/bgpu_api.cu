@@ -209,6 +209,7 @@ static void fill_score_params(ScoreParams &sp, const bgpu_scorefn *fn, const bgp
 // reference then reads past the ends of the tracks, so that combination is refused.
 static int check_ids_tracks(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b) {
   if (fn->kind != BGPU_FN_IDS) return BGPU_OK;
+  if (p->algo == BGPU_AFFINE_KBAND) { ctx->err = "AffineKBandAlign takes a match matrix, not a score function (AffineKBandAlign.h:13)"; return BGPU_E_INVALID; }
   if (p->algo == BGPU_SW) { ctx->err = "SWAlign x BGPU_FN_IDS is undefined in the reference (out-of-bounds track reads)"; return BGPU_E_INVALID; }
   if (b->nJobs && (!b->insQV || !b->subQV || !b->subTag)) { ctx->err = "BGPU_FN_IDS needs batch.insQV, subQV and subTag"; return BGPU_E_INVALID; }
   if ((b->delQV == nullptr) != (b->delTag == nullptr)) { ctx->err = "BGPU_FN_IDS: delQV and delTag come as a pair"; return BGPU_E_INVALID; }
@@ -519,13 +520,15 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
   fill_score_params(t->sp, fn, p);
   t->dense = true;
   t->dargs.algo = p->algo; t->dargs.defaultBand = p->band; t->dargs.bndIns = p->bndIns; t->dargs.bndDel = p->bndDel;
+  t->dargs.hpInsOpen = p->hpInsOpen; t->dargs.hpInsExtend = p->hpInsExtend; t->dargs.insOpen = p->insOpen; t->dargs.insExtend = p->insExtend;
   BatchDev &B = t->B;
   B.nJobs = n;
   uint64_t *d_qOff, *d_tOff; uint8_t *d_q, *d_t, *d_qual = nullptr; int32_t *d_band = nullptr;
   RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16));
   RC(talloc_dev(ctx, t, &d_qOff, n + 1)); RC(talloc_dev(ctx, t, &d_tOff, n + 1));
   if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
-  if (b->band && p->algo == BGPU_KBAND) RC(talloc_dev(ctx, t, &d_band, std::max<uint32_t>(n, 1)));
+  const bool banded = p->algo == BGPU_KBAND || p->algo == BGPU_AFFINE_KBAND;
+  if (b->band && banded) RC(talloc_dev(ctx, t, &d_band, std::max<uint32_t>(n, 1)));
   RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
   RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));
   RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
@@ -541,7 +544,7 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
     const uint64_t ql = b->qOff[i + 1] - b->qOff[i], tl = b->tOff[i + 1] - b->tOff[i];
     uint32_t qb = (uint32_t)ql, tb = (uint32_t)tl;
     uint64_t bytes, cells;
-    if (p->algo == BGPU_KBAND) {
+    if (banded) {
       const int k = d_band ? b->band[i] : p->band;
       if (k >= 0) kbounded_host((uint32_t)tl, (uint32_t)ql, (uint32_t)k, tb, qb);
       bytes = k >= 0 ? ((uint64_t)qb + 1) * (2ull * (uint64_t)k + 1) : 16; cells = bytes;
@@ -549,7 +552,7 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
     if (bytes > (1ull << 31)) bytes = 16;          // rejected by the prep kernel (matrix size is an int in the reference)
     t->h_arrowBytes[i] = bytes; t->h_cellsMetric[i] = cells;
     h_off[i] = rbTot; h_off[n + i] = runTot;
-    rbTot += 2 * ((uint64_t)tb + 2); runTot += ql + tl + 2;
+    rbTot += (p->algo == BGPU_AFFINE_KBAND ? 6 : 2) * ((uint64_t)tb + 2); runTot += ql + tl + 2;   // ping-pong rows (x3 matrices)
   }
   RC(talloc_dev(ctx, t, &t->d_dblkOff, 2 * (size_t)n + 2));
   t->d_runOff = t->d_dblkOff + n;
@@ -566,7 +569,7 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
   if (!ctx) return BGPU_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!fn || !p || !b || !out) { ctx->err = "null argument"; return BGPU_E_INVALID; }
-  if (p->algo < BGPU_GUIDED || p->algo > BGPU_SW) { ctx->err = "unknown algo"; return BGPU_E_INVALID; }
+  if (p->algo < BGPU_GUIDED || p->algo > BGPU_AFFINE_KBAND) { ctx->err = "unknown algo"; return BGPU_E_INVALID; }
   if (fn->kind < BGPU_FN_DISTANCE || fn->kind > BGPU_FN_IDS) { ctx->err = "unknown score function kind"; return BGPU_E_INVALID; }
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return BGPU_E_CUDA; }
   const auto h0 = std::chrono::steady_clock::now();

@@ -102,8 +102,9 @@ struct BatchDev {         // device pointers of one submitted batch
 };
 
 struct DenseArgs {
-  int algo;            // BGPU_KBAND / BGPU_SW
+  int algo;            // BGPU_KBAND / BGPU_SW / BGPU_AFFINE_KBAND
   int defaultBand, bndIns, bndDel;
+  int hpInsOpen, hpInsExtend, insOpen, insExtend;   // AffineKBandAlign.h:14 (its `del` is bndDel)
   const uint64_t *arrowOff;   // per job byte offset into B.arrows
 };
 

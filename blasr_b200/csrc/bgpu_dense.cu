@@ -1,8 +1,9 @@
-// bgpu_dense.cu -- KBandAlign and SWAlign on the device.
+// bgpu_dense.cu -- KBandAlign, SWAlign and AffineKBandAlign on the device (8f N1).
 //
 // Reference semantics restated:
 //   KBandAlign  common/algorithms/alignment/KBandAlign.h:75-403  (+ SetKBoundedLengths :36-56)
 //   SWAlign     common/algorithms/alignment/SWAlign.h:18-389
+//   AffineKBandAlign  common/algorithms/alignment/AffineKBandAlign.h:12-401 (second half of this file)
 //
 // The in-row dependency  S[t] = min(A[t], S[t-1] + del_t)  is the min-plus prefix scan
 //     S[t] = min_{j<=t} (A[j] - D[j]) + D[t],   D = prefix sum of the deletion costs of the row
@@ -50,12 +51,26 @@ __global__ void __launch_bounds__(128) dense_prep_kernel(BatchDev B, ScoreParams
   JobGeom &G = B.geom[job];
   const uint64_t qo = B.qOff[job], to = B.tOff[job];
   const uint32_t qLength = (uint32_t)(B.qOff[job + 1] - qo), tLength = (uint32_t)(B.tOff[job + 1] - to);
-  const int k = A.algo == BGPU_KBAND ? (B.band ? B.band[job] : A.defaultBand) : 0;
+  const int k = A.algo != BGPU_SW ? (B.band ? B.band[job] : A.defaultBand) : 0;
   const int at = P.alignType;
   uint32_t qLen = qLength, tLen = tLength;
   int status = BGPU_JOB_OK;
   long long nCells = 0;
-  if (A.algo == BGPU_KBAND) {
+  if (A.algo == BGPU_AFFINE_KBAND) {
+    // AffineKBandAlign.h:12-401.  Global and QueryFit; TargetFit searches mirrored band columns (:322-330) and its
+    // traceback can spin on a NoArrow cell; other types leave the end cell outside the matrix.
+    if (k < 0 || (at != BGPU_GLOBAL && at != BGPU_QUERYFIT && at != BGPU_TARGETFIT)) status = BGPU_JOB_BAD_INPUT;
+    else if (at == BGPU_TARGETFIT) status = BGPU_JOB_REF_UNDEFINED;
+    else {
+      kbounded(tLength, qLength, (uint32_t)k, tLen, qLen);
+      nCells = ((long long)qLen + 1) * (2ll * k + 1);
+      if (nCells > INT_MAX) status = BGPU_JOB_BAD_INPUT;
+      else if (at == BGPU_QUERYFIT && (tLen == 0 || qLen == 0)) status = BGPU_JOB_REF_UNDEFINED;   // end search reads unwritten cells
+      // INF_SCORE = INT_MAX - 1000 (:30): larger costs overflow int in the reference
+      else if (max(max(abs(A.hpInsOpen), abs(A.hpInsExtend)), max(max(abs(A.insOpen), abs(A.insExtend)), abs(A.bndDel))) >= 1000) status = BGPU_JOB_RANGE;
+      nCells = 0;                                          // the reference never sets alignment.nCells here
+    }
+  } else if (A.algo == BGPU_KBAND) {
     if (k < 0 || at < 0 || at > BGPU_TPREFIXQSUFFIX) status = BGPU_JOB_BAD_INPUT;
     else {
       kbounded(tLength, qLength, (uint32_t)k, tLen, qLen);
@@ -85,7 +100,7 @@ __global__ void __launch_bounds__(128) dense_prep_kernel(BatchDev B, ScoreParams
   bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
   if (bad && status == BGPU_JOB_OK) status = BGPU_JOB_BAD_INPUT;
   if (lane == 0) {
-    G.status = status; G.Qn = (int)qLen; G.Tn = (int)tLen; G.band = k; G.nCells = A.algo == BGPU_KBAND ? (int)nCells : 0;
+    G.status = status; G.Qn = (int)qLen; G.Tn = (int)tLen; G.band = k; G.nCells = A.algo == BGPU_KBAND ? (int)nCells : 0;   // SWAlign / AffineKBandAlign never set it
     G.qStart = G.tStart = 0; G.C0 = 0; G.nDB = 0; G.kmax = 0; G.hi0 = 0; G.score = 0;
     G.rowOff = 0; G.dblkOff = 0; G.arrowBytes = 0; G.runOff = runOff[job]; G.rowBufOff = rowBufOff[job];
     G.nRuns = G.nBlocks = G.nGaps = G.nGapLists = 0; G.qPos = G.tPos = 0; G.startR = G.startC = 0;
@@ -349,6 +364,143 @@ __global__ void __launch_bounds__(64) dense_trace_kernel(BatchDev B, ScoreParams
   G.qPos = qPos; G.tPos = tPos; G.qStart = (int)qPos; G.tStart = (int)tPos;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// AffineKBandAlign (AffineKBandAlign.h:12-401): three band matrices -- main S, homopolymer-insertion H, insertion I.
+// H and I of a cell depend on the row above only, S adds the in-row linear deletion, so the row sweep is the same
+// min-plus scan as KBandAlign's.  One byte per cell: bits 0-1 main arrow, bit 2 / 3 = the I / H matrix arrow is Open
+// (else Up), 0x80 = NoArrow.  INF_SCORE (:30) is DBIG here: it only ever loses comparisons or ties with itself.
+enum { AK_DIAG = 0, AK_LEFT = 1, AK_ICLOSE = 2, AK_HCLOSE = 3, AK_IOPEN = 4, AK_HOPEN = 8, AK_NOARROW = 0x80 };
+
+__global__ void __launch_bounds__(128) affine_kband_fill_kernel(BatchDev B, ScoreParams P, DenseArgs A, const uint32_t *order,
+                                                                uint32_t nOrder, uint32_t *counter) {
+  __shared__ int Mtab[25];
+  __shared__ uint8_t lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = base_code((uint8_t)i);
+  if (threadIdx.x < 25) Mtab[threadIdx.x] = P.M[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int at = P.alignType;
+  const int hpO = A.hpInsOpen, hpE = A.hpInsExtend, inO = A.insOpen, inE = A.insExtend, del = A.bndDel;
+  for (;;) {
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(counter, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= nOrder) break;
+    const uint32_t job = order[idx];
+    JobGeom &G = B.geom[job];
+    if (G.status != BGPU_JOB_OK) continue;
+    const int R = G.Qn, T = G.Tn, k = G.band, nCols = 2 * k + 1;
+    const uint8_t *qb = B.q + B.qOff[job], *tb = B.t + B.tOff[job];
+    uint8_t *arrows = B.arrows + A.arrowOff[job];
+    const int W = T + 2;
+    int *pS = B.rowBuf + G.rowBufOff, *pH = pS + W, *pI = pH + W, *cS = pI + W, *cH = cS + W, *cI = cH + W;
+    // ---- row 0 (:93-141): S = t * del with Left arrows for t <= k, H = I = INF right of the origin
+    for (int t = lane; t <= T; t += 32) { pS[t] = t <= k ? t * del : 0; pH[t] = t ? DBIG : 0; pI[t] = t ? DBIG : 0; }
+    for (int c = lane; c < nCols; c += 32) arrows[c] = c > k ? AK_LEFT : (c == k ? (AK_NOARROW | AK_IOPEN | AK_HOPEN) : AK_NOARROW);
+    __syncwarp();
+    for (int r = 1; r <= R; r++) {
+      const int tlo = max(1, r - k), thi = min(T, r + k);
+      uint8_t *arow = arrows + (size_t)r * nCols;
+      for (int c = lane; c < nCols; c += 32) { const int t = r - k + c; if (t < 0 || t > T) arow[c] = AK_NOARROW; }   // t == 0: the boundary cell below
+      // boundary column t = 0 (band column k - r), rows r <= k (:96-99,122-125,134-137)
+      int carry = DBIG;                                    // S left of column tlo: none at the left band edge (:226-228)
+      if (r <= k) {
+        const int bI = r * inE + inO;
+        if (lane == 0) { cS[0] = bI; cI[0] = bI; cH[0] = r * hpE + hpO; arow[k - r] = AK_ICLOSE; }
+        carry = bI;
+      }
+      const uint8_t qraw = qb[r - 1];
+      const int qch = lut[qraw];
+      const bool hp = r > 1 && qraw == qb[r - 2];          // :180 (raw bytes)
+      for (int base = tlo; base <= thi; base += 32) {
+        const int t = base + lane;
+        const bool act = t <= thi;
+        int ms = DBIG, minI = DBIG, minH = DBIG; uint8_t flags = 0;
+        if (act) {
+          ms = pS[t - 1] + Mtab[qch * 5 + lut[tb[t - 1]]];                            // :248 (row = query)
+          const bool inBand = t < r + k;                   // the cell above exists (:169-172,204-211)
+          const int up = pS[t];
+          const int hOpen = inBand ? up + hpO : DBIG, hExt = (hp && inBand) ? pH[t] + hpE : DBIG;
+          if (hOpen < hExt) { flags |= AK_HOPEN; minH = hOpen; } else minH = hExt;   // strict '<': ties extend (:195-203)
+          const int iOpen = inBand ? up + inO : DBIG, iExt = inBand ? pI[t] + inE : DBIG;
+          if (iOpen < iExt) { flags |= AK_IOPEN; minI = iOpen; } else minI = iExt;   // :213-221
+        }
+        const int a0 = min(ms, min(minI, minH));
+        int bv = act ? a0 - lane * del : DBIG;
+        bv = warp_prefix_min(bv, lane);
+        const int s = min(bv + lane * del, carry >= DBIG ? DBIG : carry + (lane + 1) * del);
+        int left = __shfl_up_sync(0xffffffffu, s, 1);
+        if (lane == 0) left = carry;
+        const int ds = left >= DBIG ? DBIG : left + del;
+        const int best = min(a0, ds);
+        // tie order Diagonal > Left > AffineInsClose > AffineHPInsClose (:254-269)
+        const uint8_t arrow = best == ms ? AK_DIAG : (best == ds ? AK_LEFT : (best == minI ? AK_ICLOSE : AK_HCLOSE));
+        if (act) { cS[t] = s; cH[t] = minH; cI[t] = minI; arow[k + t - r] = arrow | flags; }
+        carry = __shfl_sync(0xffffffffu, s, 31);
+      }
+      __syncwarp();
+      int *x;
+      x = pS; pS = cS; cS = x; x = pH; pH = cH; cH = x; x = pI; pI = cI; cI = x;
+    }
+    // ---- end cell: Global corner (:292-295) or the first minimum of the last row (QueryFit :296-311)
+    int startC = k - (R - T), score = pS[T];
+    if (at == BGPU_QUERYFIT) {
+      const int lo = max(1, R - k), hi = min(T, R + k);
+      int bv = INT_MAX, bc = INT_MAX;
+      for (int t = lo + lane; t <= hi; t += 32) { const int v = pS[t]; if (v < bv) { bv = v; bc = t; } }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const int v = __shfl_xor_sync(0xffffffffu, bv, o), c = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (v < bv || (v == bv && c < bc)) { bv = v; bc = c; }
+      }
+      startC = k - (R - bc); score = bv;
+    }
+    if (lane == 0) { G.startR = R; G.startC = startC; G.score = score; }
+  }
+}
+
+// one thread per job: the three-matrix walk of AffineKBandAlign.h:338-395
+__global__ void __launch_bounds__(64) affine_kband_trace_kernel(BatchDev B, DenseArgs A, const uint32_t *order, uint32_t nOrder) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nOrder) return;
+  const uint32_t job = order[idx];
+  JobGeom &G = B.geom[job];
+  if (G.status != BGPU_JOB_OK) return;
+  const int k = G.band, nCols = 2 * k + 1;
+  const uint8_t *arrows = B.arrows + A.arrowOff[job];
+  uint32_t *runs = B.runs + G.runOff;
+  int q = G.startR, t = G.startC, mat = 0;                  // 0 Match, 1 AffineHPIns, 2 AffineIns
+  int runType = -1; uint32_t runLen = 0, nRuns = 0, nBlocks = 0, nGaps = 0, pendGaps = 0;
+  bool seenD = false, awry = false;
+  auto push = [&](int type) {
+    if (type == runType) { runLen++; return; }
+    if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
+    runType = type; runLen = 1;
+    if (type == RUN_D) { if (seenD) nGaps += pendGaps; pendGaps = 0; seenD = true; nBlocks++; }
+    else pendGaps++;
+  };
+  long guard = 4l * (G.Qn + 1) * nCols + 16;
+  while (q > 0 || (q == 0 && t > k)) {
+    if (t < 0 || t >= nCols || --guard < 0) { awry = true; break; }
+    const uint8_t a = arrows[(size_t)q * nCols + t];
+    if (mat == 0) {
+      if (a & AK_NOARROW) { awry = true; break; }           // the reference would never leave its loop here
+      const int m = a & 3;
+      if (m == AK_DIAG) { push(RUN_D); q--; }
+      else if (m == AK_LEFT) { push(RUN_L); t--; }
+      else mat = m == AK_ICLOSE ? 2 : 1;                    // closes change the matrix without moving
+    } else {
+ if (a & AK_NOARROW) { awry = true; break; }           // reference: assert(0)
+      if (a & (mat == 1 ? AK_HOPEN : AK_IOPEN)) mat = 0;
+      push(RUN_U); q--; t++;                                // every step inside an affine matrix emits Up (:363-390)
+    }
+  }
+  if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
+  if (awry) { G.status = BGPU_JOB_PATH_AWRY; G.nRuns = G.nBlocks = G.nGaps = G.nGapLists = 0; return; }
+  G.nRuns = nRuns; G.nBlocks = nBlocks; G.nGaps = seenD ? nGaps + pendGaps : 0; G.nGapLists = nRuns ? nBlocks + 1 : 0;
+  G.qPos = G.tPos = 0; G.qStart = G.tStart = 0;             // never set by the reference: the alignment starts at (0,0)
+}
+
 void kbounded_host(uint32_t tLength, uint32_t qLength, uint32_t k, uint32_t &tLen, uint32_t &qLen) { kbounded(tLength, qLength, k, tLen, qLen); }
 
 void launch_dense_prep(const BatchDev &B, const ScoreParams &P, const DenseArgs &A, const uint64_t *rowBufOff,
@@ -361,12 +513,16 @@ void launch_dense_fill(const BatchDev &B, const ScoreParams &P, const DenseArgs 
   unsigned grid = (unsigned)nSM * 8u;
   const unsigned need = (nOrder + 3) / 4;
   if (grid > need) grid = need;
-  if (grid) dense_fill_kernel<<<grid, 128, 0, s>>>(B, P, A, order, nOrder, counter);
+  if (!grid) return;
+  if (A.algo == BGPU_AFFINE_KBAND) affine_kband_fill_kernel<<<grid, 128, 0, s>>>(B, P, A, order, nOrder, counter);
+  else dense_fill_kernel<<<grid, 128, 0, s>>>(B, P, A, order, nOrder, counter);
 }
 void launch_dense_trace(const BatchDev &B, const ScoreParams &P, const DenseArgs &A, const uint32_t *order, uint32_t nOrder,
                         cudaStream_t s) {
   const unsigned grid = (nOrder + 31) / 32;
-  if (grid) dense_trace_kernel<<<grid, 32, 0, s>>>(B, P, A, order, nOrder);
+  if (!grid) return;
+  if (A.algo == BGPU_AFFINE_KBAND) affine_kband_trace_kernel<<<grid, 32, 0, s>>>(B, A, order, nOrder);
+  else dense_trace_kernel<<<grid, 32, 0, s>>>(B, P, A, order, nOrder);
 }
 
 }  // namespace bgpu

@@ -10,6 +10,7 @@
  *   GuidedAlign(...)         common/algorithms/alignment/GuidedAlign.h:278        called at alignment/Blasr.cpp:869
  *   KBandAlign(...)          common/algorithms/alignment/KBandAlign.h:75          called at alignment/Blasr.cpp:717,820
  *   SWAlign(...)             common/algorithms/alignment/SWAlign.h:18             called at common/algorithms/alignment/SDPAlign.h:440,503,563
+ *   AffineKBandAlign(...)    common/algorithms/alignment/AffineKBandAlign.h:12    called at alignment/Blasr.cpp:695,1067
  *   ComputeAlignmentStats    common/algorithms/alignment/AlignmentUtils.h:535     called at alignment/Blasr.cpp:740,875
  *
  * Plain pointers and sizes only; no C++/torch types.  All work runs in hand-written sm_100a
@@ -47,7 +48,8 @@ enum {
 };
 
 /* ---- enums mirrored from the reference ---- */
-typedef enum { BGPU_GUIDED = 0, BGPU_AFFINE_GUIDED = 1, BGPU_KBAND = 2, BGPU_SW = 3 } bgpu_algo;
+typedef enum { BGPU_GUIDED = 0, BGPU_AFFINE_GUIDED = 1, BGPU_KBAND = 2, BGPU_SW = 3,
+               BGPU_AFFINE_KBAND = 4   /* Global and QueryFit; see the note at bgpu_params */ } bgpu_algo;
 /* AlignmentType ordinals, AlignmentUtils.h:14-58 */
 typedef enum {
   BGPU_LOCAL = 0, BGPU_GLOBAL = 1, BGPU_QUERYFIT = 2, BGPU_TARGETFIT = 3, BGPU_OVERLAP = 4,
@@ -79,6 +81,12 @@ typedef struct {
   int32_t bndIns, bndDel;   /* KBandAlign's int ins/del *parameters* (boundary costs, KBandAlign.h:116,121) */
   int32_t doStats;          /* also run ComputeAlignmentStats (fills nMatch.. statsScore) */
   int32_t statsAffine;      /* its useAffineScore argument (blasr: params.affineAlign) */
+  /* AffineKBandAlign's int parameters (AffineKBandAlign.h:14-15; blasr passes indel+2, indel-3, indel+2, indel-1 and
+   * del = indel, Blasr.cpp:1067-1071).  Its `del` travels as bndDel, its matchMat is scorefn.M (row = query), k is band.
+   * Global and QueryFit are implemented; TargetFit -> BGPU_JOB_REF_UNDEFINED (the reference's end search reads mirrored
+   * band columns, :322-330, and its traceback then spins on NoArrow cells).  It returns blocks / gaps / score only:
+   * qPos, tPos and nCells are never set by the reference and come back 0. */
+  int32_t hpInsOpen, hpInsExtend, insOpen, insExtend;
 } bgpu_params;
 
 /* A batch in structure-of-arrays form.  Sequences are ASCII exactly as DNASequence::seq holds

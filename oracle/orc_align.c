@@ -456,6 +456,99 @@ static int kband_align(const orc_scorefn *fn, const orc_job *j, orc_result *res,
   return 0;
 }
 
+/* ---- AffineKBandAlign, AffineKBandAlign.h:12-401 -------------------------------- */
+/* Three (qLen+1) x (2k+1) matrices: main S, homopolymer-insertion H, insertion I (:82-87 zero / NoArrow fill).
+ * Deletions are linear (bndDel), insertions affine with a second, cheaper state that may only be extended
+ * while the query repeats its previous base (:180-188, raw bytes).  Global and QueryFit only: the TargetFit end
+ * search reads mirrored band columns (:322-330) and can start the traceback on a never-written NoArrow cell,
+ * where the traceback loop (:342-390) does not terminate; other types leave q,t past the matrix. */
+#define AK_INF (INT_MAX - 1000)                                        /* :30 */
+enum { AK_NONE = 0, AK_DIAG, AK_LEFT, AK_ICLOSE, AK_HCLOSE, AK_OPEN, AK_UP };
+static int affine_kband_align(const orc_scorefn *fn, const orc_job *j, orc_result *res, aln_t *aln) {
+  int k = j->band, at = j->alignType;
+  const int hpO = j->hpInsOpen, hpE = j->hpInsExtend, inO = j->insOpen, inE = j->insExtend, del = j->bndDel;
+  if (k < 0 || (at != ORC_GLOBAL && at != ORC_QUERYFIT)) { res->status = ORC_BAD_INPUT; return 0; }
+  if (iabs(hpO) >= 1000 || iabs(hpE) >= 1000 || iabs(inO) >= 1000 || iabs(inE) >= 1000 || iabs(del) >= 1000) {
+    res->status = ORC_BAD_INPUT; return 0;                             /* INF_SCORE + cost would overflow int */
+  }
+  uint32_t tLen, qLen; kbounded(j->tLen, j->qLen, (uint32_t)k, &tLen, &qLen);   /* :43 */
+  if (at == ORC_QUERYFIT && (tLen == 0 || qLen == 0)) { res->status = ORC_BAD_INPUT; return 0; } /* end search reads unwritten cells */
+  int64_t nCols = 2 * (int64_t)k + 1, total = ((int64_t)qLen + 1) * nCols;
+  if (total > INT_MAX) { res->status = ORC_BAD_INPUT; return 0; }
+  int *S = (int *)calloc((size_t)total, sizeof(int)), *H = (int *)calloc((size_t)total, sizeof(int)), *I = (int *)calloc((size_t)total, sizeof(int));
+  uint8_t *PS = (uint8_t *)calloc((size_t)total, 1), *PH = (uint8_t *)calloc((size_t)total, 1), *PI = (uint8_t *)calloc((size_t)total, 1);
+#define KB(q_, c_) ((int64_t)(q_) * nCols + (c_))
+  I[KB(0, k)] = 0; PI[KB(0, k)] = AK_OPEN;                             /* :93-94 */
+  H[KB(0, k)] = 0; PH[KB(0, k)] = AK_OPEN;                             /* :119-120 */
+  for (int q = 1; q <= k && q < (int64_t)qLen + 1; q++) {
+    I[KB(q, k - q)] = q * inE + inO; PI[KB(q, k - q)] = AK_UP;         /* :96-99 */
+    H[KB(q, k - q)] = q * hpE + hpO; PH[KB(q, k - q)] = AK_UP;         /* :122-125 */
+  }
+  for (int t = k + 1; t < nCols; t++) { H[KB(0, t)] = AK_INF; I[KB(0, t)] = AK_INF; }   /* :127-132 */
+  for (int q = 1; q <= k && q < (int64_t)qLen + 1; q++) { S[KB(q, k - q)] = I[KB(q, k - q)]; PS[KB(q, k - q)] = AK_ICLOSE; } /* :134-137 */
+  for (int t = 1; t <= k; t++) { S[KB(0, t + k)] = t * del; PS[KB(0, t + k)] = AK_LEFT; }  /* :138-141 (no t < tLen guard) */
+  for (int q = 1; q <= (int)qLen; q++) {
+    for (int t = q - k; t < q + k + 1; t++) {
+      if (t < 1) continue;
+      if ((uint32_t)t > tLen) break;                                   /* :159-164 */
+      int64_t upper = KB(q - 1, k + t - q + 1), cur = KB(q, k + t - q);
+      int inBand = t < q + k;
+      int hOpen = inBand ? wadd(S[upper], hpO) : AK_INF;               /* :169-172 */
+      int hExt = (q > 1 && j->q[q - 1] == j->q[q - 2] && inBand) ? wadd(H[upper], hpE) : AK_INF;   /* :180-188 */
+      int minH;
+      if (hOpen < hExt) { PH[cur] = AK_OPEN; minH = hOpen; } else { PH[cur] = AK_UP; minH = hExt; }   /* :195-203 */
+      H[cur] = minH;
+      int iOpen = inBand ? wadd(S[upper], inO) : AK_INF, iExt = inBand ? wadd(I[upper], inE) : AK_INF;  /* :204-211 */
+      int minI;
+      if (iOpen < iExt) { PI[cur] = AK_OPEN; minI = iOpen; } else { PI[cur] = AK_UP; minI = iExt; }   /* :213-221 */
+      I[cur] = minI;
+      int ds = (t == q - k) ? AK_INF : wadd(S[KB(q, k + t - q - 1)], del);                          /* :226-236 */
+      int ms = wadd(S[KB(q - 1, k + t - q)], fn->M[g_code[j->q[q - 1]] * 5 + g_code[j->t[t - 1]]]); /* :248 row = query */
+      int best = imin(ms, imin(ds, imin(minI, minH)));
+      S[cur] = best;
+      PS[cur] = best == ms ? AK_DIAG : best == ds ? AK_LEFT : best == minI ? AK_ICLOSE : AK_HCLOSE;   /* :254-269 */
+    }
+  }
+  int q = (int)qLen, t = k - ((int)qLen - (int)tLen);                  /* Global corner :292-295 */
+  if (at == ORC_QUERYFIT) {                                            /* :296-311 */
+    int best = q - k > 1 ? q - k : 1, minScore = S[KB(qLen, k + best - q)];
+    for (int t2 = q - k; t2 < q + k + 1; t2++) {
+      if (t2 < 1) continue;
+      if ((uint32_t)t2 > tLen) break;
+      if (S[KB(qLen, k + t2 - q)] < minScore) { best = t2; minScore = S[KB(qLen, k + t2 - q)]; }
+    }
+    t = k - ((int)qLen - best);
+  }
+  int opt = S[KB(q, t)];
+  path_t p = {0, 0, 0};
+  int mat = 0;                                                         /* 0 Match, 1 AffineHPIns, 2 AffineIns */
+  int64_t guard = 4 * total + 16;
+  while (q > 0 || (q == 0 && t > k)) {                                 /* :342-390 */
+    if (t < 0 || t >= nCols || --guard < 0) { res->status = ORC_PATH_AWRY; break; }
+    if (mat == 0) {
+      uint8_t a = PS[KB(q, t)];
+      if (a == AK_DIAG) { path_push(&p, A_DIAG); q--; }
+      else if (a == AK_LEFT) { path_push(&p, A_LEFT); t--; }
+      else if (a == AK_ICLOSE) mat = 2;                                /* closes change state only */
+      else if (a == AK_HCLOSE) mat = 1;
+      else { res->status = ORC_PATH_AWRY; break; }                     /* reference: spins forever on NoArrow */
+    } else {
+      uint8_t a = mat == 1 ? PH[KB(q, t)] : PI[KB(q, t)];
+      if (a == AK_OPEN) mat = 0;
+      else if (a != AK_UP) { res->status = ORC_PATH_AWRY; break; }     /* reference: assert(0) */
+      path_push(&p, A_UP); q--; t++;                                   /* every step inside an affine matrix emits Up :363-390 */
+    }
+  }
+  if (res->status == ORC_OK) {
+    path_reverse(&p);
+    arrows_to_alignment(aln, p.a, p.n);                                /* qPos / tPos / nCells / score stay untouched */
+  }
+  free(p.a); free(S); free(H); free(I); free(PS); free(PH); free(PI);
+#undef KB
+  res->score = opt; res->alnScore = 0;
+  return 0;
+}
+
 /* ---- SWAlign, SWAlign.h:18-389 -------------------------------------------------- */
 static int sw_align(const orc_scorefn *fn, const orc_job *j, orc_result *res, aln_t *aln) {
   int at = j->alignType;
@@ -624,6 +717,7 @@ int orc_align(const orc_scorefn *fn, const orc_job *job, orc_result *res, uint32
     case ORC_AFFINE_GUIDED: guided_align(fn, job, 1, res, &a); break;
     case ORC_KBAND: kband_align(fn, job, res, &a); break;
     case ORC_SW: sw_align(fn, job, res, &a); break;
+    case ORC_AFFINE_KBAND: affine_kband_align(fn, job, res, &a); break;
     default: res->status = ORC_BAD_INPUT;
   }
   res->qPos = a.qPos; res->tPos = a.tPos;

@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 /* algorithms (mirrors bgpu_algo in include/blasr_gpu.h) */
-enum { ORC_GUIDED = 0, ORC_AFFINE_GUIDED = 1, ORC_KBAND = 2, ORC_SW = 3 };
+enum { ORC_GUIDED = 0, ORC_AFFINE_GUIDED = 1, ORC_KBAND = 2, ORC_SW = 3, ORC_AFFINE_KBAND = 4 };
 /* score function kinds */
 enum { ORC_FN_DISTANCE = 0, ORC_FN_QUALITY = 1, ORC_FN_IDS = 2 };
 /* AlignmentType ordinals, common/algorithms/alignment/AlignmentUtils.h:14-58 */
@@ -55,6 +55,8 @@ typedef struct {
   /* rich QV tracks of FASTQSequence (FASTQSequence.h:19-26), qLen bytes each, used by ORC_FN_IDS:
    * insQV, subQV, subTag are required; delQV + delTag are optional as a pair (IDSScoreFunction.h:85) */
   const uint8_t *insQV, *delQV, *subQV, *delTag, *subTag;
+  /* AffineKBandAlign's int parameters (AffineKBandAlign.h:14-15); its `del` is bndDel, its matchMat is fn->M */
+  int32_t  hpInsOpen, hpInsExtend, insOpen, insExtend;
 } orc_job;
 
 typedef struct {

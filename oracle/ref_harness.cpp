@@ -11,6 +11,7 @@
  *   AffineGuidedAlign  common/algorithms/alignment/AffineGuidedAlign.h:31
  *   KBandAlign         common/algorithms/alignment/KBandAlign.h:75
  *   SWAlign            common/algorithms/alignment/SWAlign.h:18
+ *   AffineKBandAlign   common/algorithms/alignment/AffineKBandAlign.h:12 (Global / QueryFit; takes matchMat, no score function)
  *   ComputeAlignmentStats  common/algorithms/alignment/AlignmentUtils.h:535
  *   SDPAlign           common/algorithms/alignment/SDPAlign.h (guide producer, test inputs only)
  * each with DistanceMatrixScoreFunction<DNASequence,FASTQSequence>,
@@ -22,6 +23,7 @@
 #include "algorithms/alignment/GuidedAlign.h"
 #include "algorithms/alignment/AffineGuidedAlign.h"
 #include "algorithms/alignment/SDPAlign.h"
+#include "algorithms/alignment/AffineKBandAlign.h"
 #include "algorithms/alignment/DistanceMatrixScoreFunction.h"
 #include "algorithms/alignment/QualityValueScoreFunction.h"
 #include "algorithms/alignment/IDSScoreFunction.h"
@@ -66,6 +68,7 @@ static void FillIDS(const orc_scorefn *fn, IDSFn &f) {
 
 struct Scratch {
   vector<int> scoreMat; vector<Arrow> pathMat; vector<double> probMat, optPathProbMat;
+  vector<int> hpInsScoreMat, insScoreMat; vector<Arrow> hpInsPathMat, insPathMat;
   vector<float> a, b, c, d;
 };
 
@@ -96,6 +99,10 @@ static int RunAligner(const orc_job *job, T_Fn &f, const orc_scorefn *fn, FASTQS
                         false);
     case ORC_SW:
       return SWAlign(q, t, s.scoreMat, s.pathMat, aln, f, at);
+    case ORC_AFFINE_KBAND:   /* argument order of Blasr.cpp:1067-1076 */
+      return AffineKBandAlign(q, t, m, job->hpInsOpen, job->hpInsExtend, job->insOpen, job->insExtend, job->bndDel,
+                              (int)job->band, s.scoreMat, s.pathMat, s.hpInsScoreMat, s.hpInsPathMat, s.insScoreMat,
+                              s.insPathMat, aln, at);
   }
   return 0;
 }

@@ -30,7 +30,8 @@ class OrcJob(C.Structure):
                 ("q", C.c_void_p), ("qLen", C.c_uint32), ("t", C.c_void_p), ("tLen", C.c_uint32),
                 ("qual", C.c_void_p), ("guide", C.c_void_p), ("nGuide", C.c_uint32),
                 ("insQV", C.c_void_p), ("delQV", C.c_void_p), ("subQV", C.c_void_p), ("delTag", C.c_void_p),
-                ("subTag", C.c_void_p)]
+                ("subTag", C.c_void_p), ("hpInsOpen", C.c_int32), ("hpInsExtend", C.c_int32), ("insOpen", C.c_int32),
+                ("insExtend", C.c_int32)]
 
 
 class OrcResult(C.Structure):
@@ -86,7 +87,7 @@ def score_fn(M, ins, del_, affineOpen=0, affineExtend=0, kind=0, substitutionPri
 
 
 def make_job(algo, alignType, band, q: np.ndarray, t: np.ndarray, guide=None, qual=None, bndIns=0, bndDel=0, doStats=1,
-             statsAffine=0, tracks=None):
+             statsAffine=0, tracks=None, affineKBand=None):
     """Returns (OrcJob, keepalive).  tracks: dict of the rich QV tracks (insQV, delQV, subQV, delTag, subTag)."""
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     keep = [q, t]
@@ -98,6 +99,8 @@ def make_job(algo, alignType, band, q: np.ndarray, t: np.ndarray, guide=None, qu
     if guide is not None and len(guide):
         guide = np.ascontiguousarray(guide, np.uint32).reshape(-1, 3); keep.append(guide)
         j.guide, j.nGuide = guide.ctypes.data, len(guide)
+    if affineKBand is not None:   # (hpInsOpen, hpInsExtend, insOpen, insExtend); del travels as bndDel
+        j.hpInsOpen, j.hpInsExtend, j.insOpen, j.insExtend = [int(x) for x in affineKBand]
     for name, arr in (tracks or {}).items():
         if arr is not None:
             arr = np.ascontiguousarray(arr, np.uint8); keep.append(arr); setattr(j, name, arr.ctypes.data)

@@ -80,6 +80,44 @@ def test_kband_ids(aligner, at):
     assert _check(res, b, ofn, 2, at, bands, bi, bd, at == 1, fields) > 80
 
 
+@pytest.mark.parametrize("at", [1, 2])
+def test_affine_kband(aligner, at):
+    """AffineKBandAlign (the bulk DP of -alignContigs): blasr's parameter pattern and random ones."""
+    rng = np.random.default_rng(2400 + at)
+    for rep in range(3):
+        qs, ts = [], []
+        for i in range(200):
+            lo, hi = (2, 24) if i % 2 else (10, 300)
+            q, t = cases.random_pair(rng, lo, hi, err=float(rng.choice([0.05, 0.2, 0.35])), n_rate=0.01)
+            if i % 3 == 0:
+                q = np.repeat(q, rng.integers(1, 4, len(q)))   # homopolymer runs: the hp-insertion state matters
+            qs.append(q.tobytes()); ts.append(t.tobytes())
+        b = JobBatch.from_lists(qs, ts)
+        b.band = rng.integers(0 if at == 1 else 1, 30, b.n).astype(np.int32)
+        pr = (7, 2, 7, 4) if rep == 0 else tuple(int(x) for x in rng.integers(0, 12, 4))
+        d = 5 if rep == 0 else int(rng.integers(1, 10))
+        M = SMRTDistanceMatrix.copy() if rep < 2 else rng.integers(-6, 8, size=(5, 5)).astype(np.int32)
+        res = aligner.AffineKBandAlign(b, M, pr[0], pr[1], pr[2], pr[3], d, 0, alignType=at, computeStats=True)
+        ofn = O.score_fn(M, 5, 5)
+        n_ok = 0
+        for i in range(b.n):
+            q, t, _, _ = cases.job_arrays(b, i)
+            j, keep = O.make_job(4, at, int(b.band[i]), q, t, None, None, 0, d, 1, 0, affineKBand=pr)
+            pre = O.align("orc", ofn, j)
+            got = cases.gpu_to_dict(res, i)
+            if pre["status"] != 0:
+                assert got["status"] != 0
+                continue
+            want = O.align(WHICH, ofn, j)
+            bad = cases.compare(got, want, cases.GPU_FIELDS)
+            assert not bad, f"rep {rep} job {i} (|q|={len(q)}, |t|={len(t)}, k={b.band[i]}): {bad}"
+            n_ok += 1
+        assert n_ok > 150
+    # TargetFit: the reference's end search / traceback is undefined there
+    res = aligner.AffineKBandAlign(b, SMRTDistanceMatrix, 7, 2, 7, 4, 5, 10, alignType=3)
+    assert (res.results["status"] == capi.JOB_REF_UNDEFINED).all()
+
+
 def test_kband_long(aligner):
     b = cases.guided_batch(seed=71, n=8, lo=3000, hi=12000)
     b.guide = b.guideOff = None

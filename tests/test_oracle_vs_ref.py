@@ -96,6 +96,33 @@ def test_kband_ids(at):
     assert n > 20
 
 
+@pytest.mark.parametrize("at", [1, 2])
+def test_affine_kband(at):
+    """AffineKBandAlign: blasr's parameters (indel+2, indel-3, indel+2, indel-1, indel) and random ones,
+    homopolymer-rich queries so the hp-insertion state is exercised, tiny (-alignContigs-like) and longer jobs."""
+    rng = np.random.default_rng(240 + at)
+    n = 0
+    for rep in range(150):
+        lo, hi = (2, 24) if rep % 2 else (10, 300)
+        q, t = cases.random_pair(rng, lo, hi, err=float(rng.choice([0.05, 0.2, 0.35])), n_rate=0.01)
+        if rep % 3 == 0:   # stretch homopolymers in the query
+            q = np.repeat(q, rng.integers(1, 4, len(q)))
+        k = int(rng.integers(0 if at == 1 else 1, 30))
+        pr = (7, 2, 7, 4) if rep % 4 == 0 else tuple(int(x) for x in rng.integers(0, 12, 4))
+        d = 5 if rep % 4 == 0 else int(rng.integers(1, 10))
+        M = SMRTDistanceMatrix if rep % 5 else rng.integers(-6, 8, size=(5, 5)).astype(np.int32)
+        fn = O.score_fn(M, 5, 5)
+        j, keep = O.make_job(4, at, k, q, t, None, None, 0, d, 1, 0, affineKBand=pr)
+        a = O.align("orc", fn, j)
+        if a["status"] != 0:
+            continue
+        r = O.align("ref", fn, j)
+        bad = cases.compare(a, r)
+        assert not bad, f"rep {rep} k={k} |q|={len(q)} |t|={len(t)} params={pr},{d}: {bad}"
+        n += 1
+    assert n > 120
+
+
 def test_guide_rows():
     b = cases.guided_batch(seed=9, n=5, lo=300, hi=1500, adversarial=0.4, run=20)
     for i in range(b.n):
