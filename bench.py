@@ -167,11 +167,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    # the generator forks worker processes: run it before CUDA / NCCL are initialised in this process
+    batch = make_workload(args.jobs, args.seed + 1000 * rank)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     algo = capi.AFFINE_GUIDED if args.algo == "affine" else capi.GUIDED
-    batch = make_workload(args.jobs, args.seed + 1000 * rank)
     # inputs in pinned host memory (the library then DMA's straight from them)
     keep = []
     for name in ("q", "qOff", "t", "tOff", "guide", "guideOff", "band"):

@@ -372,7 +372,6 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
 
 static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t) {
   cudaStream_t s = ctx->stream;
-  CK(cudaMemsetAsync(t->d_gapCounts, 0, sizeof(uint32_t) * std::max<uint64_t>(t->totals[1], 1), s));
   launch_emit(t->B, t->sp, t->d_results, t->d_blocks, t->d_gapCounts, t->d_gaps, t->d_blockOff, t->d_listOff,
               t->d_gapOff, t->params.doStats, t->params.statsAffine, t->dense ? 1 : 0, s);
   t->timing.kernelLaunches++;

@@ -173,11 +173,23 @@ __device__ __forceinline__ uint32_t warp_excl_u32(uint32_t v, int lane, uint32_t
   return x - v;
 }
 
-// warp per job.  gapCounts must be zeroed beforehand.
-__global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine,
+// warp per job.  Every gapCounts entry of the job is written here (no zero-fill, no atomics): the lane holding block d
+// writes the number of kept gap runs between blocks d-1 and d, lane 0 the (always empty) list after the last block.
+// The per-base part of ComputeAlignmentStats is spread over the lanes by query position, not by run: the chunk's 32
+// run starts go to shared memory and every lane finds the run its position falls into with a 5-step search, so a
+// warp compares 32 consecutive query bases per step whatever the run lengths are.
+constexpr int EMIT_WARPS = 4;
+__global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine,
                                                    int keepLeading) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ uint8_t lut[256];
+  __shared__ int sM[64];
+  __shared__ uint32_t sQ[EMIT_WARPS][32];
+  __shared__ int sDelta[EMIT_WARPS][32];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = base_code((uint8_t)i);
+  if (threadIdx.x < 64) { const int r = threadIdx.x >> 3, c = threadIdx.x & 7; sM[threadIdx.x] = (r < 5 && c < 5) ? P.M[r * 5 + c] : 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t job = blockIdx.x * (blockDim.x >> 5) + warp;
   if (job >= B.nJobs) return;
   const JobGeom &G = B.geom[job];
   bgpu_result R;
@@ -190,10 +202,9 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
   R.nBlocks = G.nBlocks; R.nGapLists = G.nGapLists; R.nGaps = G.nGaps;
   const uint32_t nRuns = G.nRuns, nBlocks = G.nBlocks;
   const uint32_t *runs = B.runs + G.runOff;
-  const uint8_t *qb = B.q + B.qOff[job];
-  const uint8_t *tb = B.t + B.tOff[job];             // codes inside [tStart,tEnd) (raw bytes for BGPU_FN_IDS)
-  const bool tRaw = P.kind == BGPU_FN_IDS;
   const long long qLenJ = (long long)(B.qOff[job + 1] - B.qOff[job]), tLenJ = (long long)(B.tOff[job + 1] - B.tOff[job]);
+  const uint8_t *qb = B.q + B.qOff[job] + G.qStart;  // qb[x]: query base at path offset x
+  const uint8_t *tb = B.t + B.tOff[job] + G.tStart;  // codes inside [tStart,tEnd), raw bytes for BGPU_FN_IDS: the table maps both
   int oob = 0;
   const uint32_t qPrefix = G.qPos - (uint32_t)G.qStart, tPrefix = G.tPos - (uint32_t)G.tStart;
   bgpu_block *blocks = O.blocks + R.blockOff;
@@ -201,6 +212,7 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
   bgpu_gap *gaps = O.gaps + R.gapOff;
 
   uint32_t cq = 0, ct = 0, cD = 0, cG = 0;            // carries: q/t consumed, D runs seen, kept gap runs seen
+  uint32_t gAtPrevD = 0;                              // kept gap runs before the latest block seen so far
   int nMatch = 0, nMismatch = 0, nIns = 0, nDel = 0, score = 0; long long cols = 0;
   for (uint32_t base = 0; base < nRuns; base += 32) {
     const uint32_t f = base + lane;                   // forward run index
@@ -210,32 +222,31 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
     const uint32_t dq = (type == RUN_D || type == RUN_U) ? len : 0, dt = (type == RUN_D || type == RUN_L) ? len : 0;
     uint32_t totQ, totT, totD, totG;
     const uint32_t pq = cq + warp_excl_u32(dq, lane, totQ), pt = ct + warp_excl_u32(dt, lane, totT);
-    const uint32_t isD = act && type == RUN_D;
-    const uint32_t dBefore = cD + warp_excl_u32(isD, lane, totD);
+    const bool isD = act && type == RUN_D;
+    const uint32_t dBefore = cD + warp_excl_u32(isD ? 1u : 0u, lane, totD);
     // gap runs after the last block are dropped; the ones before the first block are folded into qPos/tPos by the
     // guided aligners (RemoveAlignmentPrefixGaps) and kept as gaps[0] by KBandAlign / SWAlign
     const bool kept = act && !isD && (keepLeading || dBefore >= 1) && dBefore < nBlocks;
     const uint32_t gBefore = cG + warp_excl_u32(kept ? 1u : 0u, lane, totG);
+    // kept gap runs before the previous block: from the nearest lower lane holding a block, else the carry
+    const uint32_t dMask = __ballot_sync(0xffffffffu, isD);
+    const uint32_t below = dMask & ((1u << lane) - 1u);
+    const uint32_t gPrevLane = __shfl_sync(0xffffffffu, gBefore, below ? 31 - __clz((int)below) : lane);
+    bool cmp = false;                                 // this lane's block takes part in the per-base pass
     if (isD) {
       bgpu_block bl; bl.qPos = pq - qPrefix; bl.tPos = pt - tPrefix; bl.length = len;
       blocks[dBefore] = bl;
+      gapCounts[dBefore] = gBefore - (below ? gPrevLane : gAtPrevD);
       if (doStats) {
         const long long q0 = (long long)G.qStart + pq, t0 = (long long)G.tStart + pt;
-        const uint8_t *qq = qb + q0, *tt = tb + t0;
         // KBandAlign can leave qPos/tPos pointing outside the sequences (KBandAlign.h:394-399); the reference then reads
         // out of bounds, here the job is flagged instead
-        if (q0 < 0 || t0 < 0 || q0 + len > qLenJ || t0 + len > tLenJ) oob = 1;
-        else for (uint32_t i = 0; i < len; i++) {
-          const int qc = base_code(qq[i]), tc = tRaw ? (int)base_code(tt[i]) : (int)tt[i];
-          if (qc == tc) nMatch++; else nMismatch++;
-          score += P.M[qc * 5 + tc];                   // ComputeAlignmentScore :74 (row = query)
-        }
+        if (q0 < 0 || t0 < 0 || q0 + len > qLenJ || t0 + len > tLenJ) oob = 1; else cmp = true;
         cols += len;
       }
     } else if (kept) {
       bgpu_gap g; g.seq = (type == RUN_L) ? 0 : 1; g.length = (int32_t)len;
       gaps[gBefore] = g;
-      atomicAdd(&gapCounts[dBefore], 1u);
       if (doStats) {
         if (type == RUN_L) nDel += (int)len; else nIns += (int)len;
         cols += len;
@@ -258,8 +269,31 @@ __global__ void __launch_bounds__(128) emit_kernel(BatchDev B, ScoreParams P, Em
         }
       }
     }
+    if (dMask) gAtPrevD = __shfl_sync(0xffffffffu, gBefore, 31 - __clz((int)dMask));
+    if (doStats) {
+      // ---- per-base pass over the query positions [cq, cq + totQ) of this chunk (ComputeAlignmentStats :546-560,
+      //      ComputeAlignmentScore :70-76): position x lies in the last run starting at or before x (runs that take no
+      //      query base share their start with the run after them, which is the one found)
+      const uint32_t cmpMask = __ballot_sync(0xffffffffu, cmp);
+      if (cmpMask) {
+        sQ[warp][lane] = pq; sDelta[warp][lane] = (int)(pt - pq);   // lanes past the last run hold pq = cq + totQ
+        __syncwarp();
+        for (uint32_t x = cq + lane; x < cq + totQ; x += 32) {
+          int r = 0;
+#pragma unroll
+          for (int st = 16; st; st >>= 1) if (sQ[warp][r + st] <= x) r += st;
+          if ((cmpMask >> r) & 1u) {
+            const int qc = lut[qb[x]] & 7, tc = lut[tb[(long long)x + sDelta[warp][r]]] & 7;
+            if (qc == tc) nMatch++; else nMismatch++;
+            score += sM[qc * 8 + tc];                    // ComputeAlignmentScore :74 (row = query)
+          }
+        }
+        __syncwarp();
+      }
+    }
     cq += totQ; ct += totT; cD += totD; cG += totG;
   }
+  if (lane == 0 && R.nGapLists) gapCounts[nBlocks] = 0;   // the list after the last block: its gap runs are dropped
   if (doStats) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -292,8 +326,8 @@ void launch_emit(const BatchDev &B, const ScoreParams &P, bgpu_result *results, 
                  uint32_t *gapCounts, bgpu_gap *gaps, const uint64_t *blockOff, const uint64_t *listOff,
                  const uint64_t *gapOff, int doStats, int statsAffine, int keepLeading, cudaStream_t s) {
   EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff};
-  const unsigned grid = (B.nJobs + 3) / 4;
-  if (grid) emit_kernel<<<grid, 128, 0, s>>>(B, P, O, doStats, statsAffine, keepLeading);
+  const unsigned grid = (B.nJobs + EMIT_WARPS - 1) / EMIT_WARPS;
+  if (grid) emit_kernel<<<grid, EMIT_WARPS * 32, 0, s>>>(B, P, O, doStats, statsAffine, keepLeading);
 }
 
 }  // namespace bgpu
