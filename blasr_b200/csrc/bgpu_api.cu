@@ -321,7 +321,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     }
     RC(talloc_dev(ctx, t, &t->d_order, std::max<size_t>(order.size(), 1)));
     RC(talloc_dev(ctx, t, &t->d_arrowOff, std::max<uint32_t>(n, 1)));
-    t->nCounters = (uint32_t)t->waves.size() * 8 + 8;
+    t->nCounters = (uint32_t)t->waves.size() * 16 + 16;          // per wave: [c] = work queue of class c's fill kernel
     RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
     uint8_t *arrows = nullptr;
     RC(talloc_dev(ctx, t, &arrows, std::max<size_t>(maxWaveBytes, 16)));
@@ -351,7 +351,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     for (int c = N_CLS - 1; c >= 0; c--)
       if (W.count[c]) {
         CK(cudaStreamWaitEvent(ctx->aux[c], ctx->evFork, 0));
-        launch_fill_guided(t->B, t->sp, c, t->d_order + W.begin[c], W.count[c], t->d_counters + 8 * w + c, ctx->nSM, ctx->aux[c]);
+        launch_fill_guided(t->B, t->sp, c, t->d_order + W.begin[c], W.count[c], t->d_counters + 16 * w + c, ctx->nSM, ctx->aux[c]);
         CK(cudaEventRecord(ctx->evJoin[c], ctx->aux[c]));
         CK(cudaStreamWaitEvent(s, ctx->evJoin[c], 0));
         t->timing.kernelLaunches++;

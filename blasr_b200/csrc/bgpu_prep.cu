@@ -28,10 +28,12 @@ __device__ __forceinline__ int warp_or(int v) { return __reduce_or_sync(0xffffff
 constexpr int MAX_BAND_SIZE = 250;  // GuidedAlign.h:29
 
 // rowOffIn / dblkOffIn / runOffIn are host-computed exclusive prefix sums of the per-job capacities.
-__global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParams P, int defaultBand,
+constexpr int PREP_WARPS = 4, PREP_WIN = 96;   // warps per CTA; guide blocks staged per warp
+__global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B, ScoreParams P, int defaultBand,
                                                           const uint64_t *rowOffIn, const uint64_t *dblkOffIn,
                                                           const uint64_t *runOffIn) {
   __shared__ uint8_t lut[256];
+  __shared__ bgpu_block sWin[PREP_WARPS][PREP_WIN];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = base_code((uint8_t)i);
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -130,30 +132,46 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
 
   int carryL = tStart - 1;                              // L_0
   int bcur = 0;                                         // guide block of the chunk's first row
+  // A window of the block list lives in shared memory (PREP_WIN blocks per warp, refilled as the rows advance): the
+  // 32 rows of a chunk find their blocks without searching -- lane j looks at block bcur+1+j, the starts that fall
+  // inside the chunk are OR-reduced into a 32-bit mask (blocks are ordered and hold >= 1 row each, so there are at
+  // most 32 of them) and row r lies in block bcur + popc(mask & bits[0..r]).
+  bgpu_block *win = sWin[threadIdx.x >> 5];
+  int wb = 0, we = 0;                                   // window = blocks [wb, we)
+  uint8_t qchNext = Qn >= 1 + lane ? qb[qStart + lane] : 0;
   for (int base = 1; base <= Qn; base += 32) {
     const int i = base + lane;
     const bool act = i <= Qn;
-    int t = 0, cap = 0, tPost = 0, x = INT_MIN, myB = bcur;
-    uint8_t qch = 0;
+    if (min(nB, bcur + 34) > we) {
+      __syncwarp();
+      wb = max(bcur - 1, 0); we = min(nB, wb + PREP_WIN);
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(blk + wb);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(win);
+      for (int w = lane; w < 3 * (we - wb); w += 32) dst[w] = src[w];
+      __syncwarp();
+    }
+    int t = 0, cap = 0, tPost = 0, x = INT_MIN;
+    const uint8_t qch = qchNext;
+    if (i + 32 <= Qn) qchNext = qb[qStart + i + 31];
+    const uint32_t q0 = (uint32_t)(qStart + base - 1);
+    const int cand = bcur + 1 + lane;
+    const uint32_t rel = cand < nB ? win[cand - wb].qPos - q0 : 0xffffffffu;
+    const uint32_t mask = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+    const int lo = bcur + __popc(mask & (0xffffffffu >> (31 - lane)));
     if (act) {
-      const uint32_t q = (uint32_t)(qStart + i - 1);
-      qch = qb[q];
-      // largest b with blk[b].qPos <= q; every block holds >= 1 row, so it lies within 32 of the previous chunk's last
-      int lo = bcur, hi = min(bcur + 32, nB - 1);
-      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (blk[mid].qPos <= q) lo = mid; else hi = mid - 1; }
-      myB = lo;
-      const bgpu_block c = blk[lo];
+      const uint32_t q = q0 + (uint32_t)lane;
+      const bgpu_block c = win[lo - wb];
       const uint32_t off = q - c.qPos;
       if (off < c.length) {
         t = (int)(c.tPos + off);
         if (off == 0) {                                 // first base of a block: :161-165
           int drift;
           if (lo == 0) drift = drift0;
-          else { bgpu_block p = blk[lo - 1]; drift = (int)(c.tPos - (p.tPos + p.length)) - (int)(c.qPos - (p.qPos + p.length)); }
+          else { const bgpu_block p = win[lo - 1 - wb]; drift = (int)(c.tPos - (p.tPos + p.length)) - (int)(c.qPos - (p.qPos + p.length)); }
           cap = INT_MAX; tPost = band + abs(drift);
         } else { cap = band; tPost = min(MAX_BAND_SIZE, band); }   // :170-174
       } else {                                          // gap rows after block lo: :213-250
-        const bgpu_block n = blk[lo + 1];
+        const bgpu_block n = win[lo + 1 - wb];
         const int g = (int)(off - c.length);
         const int qGap = (int)(n.qPos - (c.qPos + c.length)), tGap = (int)(n.tPos - (c.tPos + c.length));
         const int diag = min(qGap, tGap);
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
       }
       x = (cap == INT_MAX) ? INT_MIN : t - cap;
     }
-    bcur = __shfl_sync(0xffffffffu, myB, 31);
+    bcur += __popc(mask);
     int L = warp_incl_max(x, lane);
     L = max(L, carryL);
     carryL = __shfl_sync(0xffffffffu, L, 31);
@@ -225,7 +243,7 @@ __global__ void __launch_bounds__(128) prep_guided_kernel(BatchDev B, ScoreParam
 
 void launch_prep_guided(const BatchDev &B, const ScoreParams &P, int defaultBand, const uint64_t *rowOff,
                         const uint64_t *dblkOff, const uint64_t *runOff, cudaStream_t s) {
-  const int warpsPerBlock = 4;
+  const int warpsPerBlock = PREP_WARPS;
   const unsigned grid = (B.nJobs + warpsPerBlock - 1) / warpsPerBlock;
   if (grid) prep_guided_kernel<<<grid, warpsPerBlock * 32, 0, s>>>(B, P, defaultBand, rowOff, dblkOff, runOff);
 }

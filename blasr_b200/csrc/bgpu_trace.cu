@@ -1,6 +1,6 @@
 // bgpu_trace.cu -- device-side traceback and alignment emission.
 //
-//   trace_guided_kernel : (one thread per job) walks the traceback bytes of one job from (qEnd-1,tEnd-1) to the origin with the
+//   trace_guided_kernel : (one thread per job) walks the traceback words of one job from (qEnd-1,tEnd-1) to the origin with the
 //                         reference's 3-matrix state machine (GuidedAlign.h:626-663,
 //                         AffineGuidedAlign.h:377-468) and records the path as run-length runs (reversed).
 //   scan_counts_kernel  : exclusive scan of per-job block / gap-list / gap counts -> arena offsets.
@@ -16,13 +16,26 @@ enum { RUN_D = 0, RUN_U = 1, RUN_L = 2 };   // diagonal / up (insertion, Gap::Ta
 
 // One THREAD per job: a traceback is a serial pointer chase, so a warp walks 32 independent paths at once (jobs are
 // ordered longest-first, neighbouring threads have similar path lengths).  The fill kernels store the arrows
-// [d-block][row of 16 (linear) / 4 (affine) anti-diagonals][slot pair], so the walk, which only ever moves to lower
-// anti-diagonals and at most one diagonal sideways per step, stays inside one 32 B sector for many steps; the
-// sector two rows further down is prefetched.  Linear words hold 16 two-bit arrows of one slot pair: a run of
-// Diagonal arrows (every other field, the slot does not change) is consumed with one CLZ instead of one step each.
+// [d-block][row of 16 (linear) / 4 (affine) anti-diagonals][slot pair].  A walk only ever moves to lower
+// anti-diagonals and at most one diagonal sideways per step, so the words it is going to read are known well ahead:
+// each thread keeps a private window in shared memory -- chunk = 4 rows x 16 words (64 B of every row, centred on the
+// walk's current diagonal) -- and copies the chunk BEFORE the current one with cp.async while it walks the current
+// one, so a step costs a shared-memory load instead of an L2 round trip.  A walk that drifts out of its window
+// (more than ~12 diagonals sideways within two chunks) falls back to a global load for those steps.
+// Linear words hold 16 two-bit arrows of one slot pair: a run of Diagonal arrows (every other field, the slot does
+// not change) is consumed with one CLZ instead of one step each.
+constexpr int TR_THREADS = 64, TR_CR = 4, TR_WP = 4;     // threads per CTA; rows per chunk; 16-byte pieces per row window
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <bool AFFINE>
-__global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder) {
-  constexpr int BITS = AFFINE ? 8 : 2, SPW = 32 / BITS, ROWS = 64 / SPW;
+__global__ void __launch_bounds__(TR_THREADS) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder) {
+  constexpr int BITS = AFFINE ? 8 : 2, SPW = 32 / BITS, ROWS = 64 / SPW, CR = TR_CR, CPB = ROWS / CR, WP = TR_WP;
+  // piece (buffer bi, row r, piece pc) of thread tid: interleaved over the CTA's threads, 16 B each
+  __shared__ __align__(16) uint32_t win[2 * CR * WP * TR_THREADS * 4];
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nOrder) return;
   const uint32_t job = order[idx];
@@ -31,19 +44,17 @@ __global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uin
   if (G.status != BGPU_JOB_OK) return;
   const int Qn = G.Qn, Tn = G.Tn, C0 = G.C0;
   const int lpj = cls_lpj(G.cls);
-  const size_t unitBytes = (size_t)ROWS * lpj * 4;
+  const int unitW = ROWS * lpj;                          // words per arrow unit (one group of one d-block)
   const DBlock *dblk = B.dblk + G.dblkOff;
-  const uint8_t *arrows = B.arrows + B.arrowOff[job];
+  const uint32_t *arrows = reinterpret_cast<const uint32_t *>(B.arrows + B.arrowOff[job]);
   uint32_t *runs = B.runs + G.runOff;
+  uint32_t *mine = win + threadIdx.x * 4;
+  auto piece = [&](int bi, int r, int pc) { return mine + ((bi * CR + r) * WP + pc) * (TR_THREADS * 4); };
 
   int q = Qn, t = Tn, mat = 0;
-  int curB = -1, wbase = 0; size_t blkBase = 0, rowBytes = 0;
-  int pW = 0; size_t pBase = 0, pRowBytes = 0;          // previous d-block (next one the walk enters)
-  const uint8_t *curAddr = nullptr; uint32_t word = 0;
   int runType = -1; uint32_t runLen = 0, nRuns = 0;
   uint32_t nBlocks = 0, nGaps = 0, pendGaps = 0, pendQ = 0, pendT = 0;
   bool seenD = false, awry = false;
-
   auto push = [&](int type, uint32_t n) {
     if (type == runType) { runLen += n; return; }
     if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
@@ -51,61 +62,92 @@ __global__ void __launch_bounds__(128) trace_guided_kernel(BatchDev B, const uin
     if (type == RUN_D) { if (seenD) nGaps += pendGaps; pendGaps = 0; pendQ = pendT = 0; seenD = true; nBlocks++; }
     else pendGaps++;
   };
+  // window of a chunk: np pieces from piece p0 of every row, centred on the diagonal the walk is on right now
+  auto window = [&](const DBlock &db, int &p0, int &np) {
+    const int rowPieces = (db.k * lpj) >> 2;
+    np = min(WP, rowPieces);
+    const int sg = (t - q + C0 - db.wbase) >> 1;
+    p0 = max(0, min((sg - 6) >> 2, rowPieces - np));
+  };
+  auto stage = [&](int bi, int ci, const DBlock &db, int p0, int np) {
+    const int rowWords = db.k * lpj;
+    const uint32_t *src = arrows + (size_t)db.arrowUnit * unitW + (size_t)((ci % CPB) * CR) * rowWords + p0 * 4;
+#pragma unroll
+    for (int r = 0; r < CR; r++)
+#pragma unroll
+      for (int pc = 0; pc < WP; pc++)
+        if (pc < np) cp_async16(piece(bi, r, pc), src + (size_t)r * rowWords + pc * 4);
+  };
 
-  while (q >= 1 || t >= 1) {
-    if (q < 0 || t < 0) { awry = true; break; }
-    const int d = q + t, b = d >> 6, e = d & 63;
-    if (b != curB) {
-      const DBlock db = dblk[b]; wbase = db.wbase; rowBytes = (size_t)db.k * lpj * 4; blkBase = (size_t)db.arrowUnit * unitBytes; curB = b;
-      if (b > 0) { const DBlock pb = dblk[b - 1]; pW = pb.wbase; pRowBytes = (size_t)pb.k * lpj * 4; pBase = (size_t)pb.arrowUnit * unitBytes; }
-    }
-    const int cd = t - q + C0;
-    const int s = cd - wbase;
-    if (s < 0 || (size_t)(s >> 1) * 4 >= rowBytes) { awry = true; break; }
-    const int row = e / SPW;
-    const uint8_t *addr = arrows + blkBase + (size_t)row * rowBytes + (size_t)(s >> 1) * 4;
-    if (addr != curAddr) {
-      word = __ldg(reinterpret_cast<const uint32_t *>(addr)); curAddr = addr;
-      if (row >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(addr - 2 * rowBytes));
-      else if (b > 0) {
-        long sp = (cd - pW) >> 1; const long lim = (long)(pRowBytes >> 2) - 1;
-        sp = sp < 0 ? 0 : (sp > lim ? lim : sp);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(arrows + pBase + (size_t)(ROWS + row - 2) * pRowBytes + (size_t)sp * 4));
+  const int d0 = Qn + Tn;
+  int ci = (d0 >> 6) * CPB + ((d0 & 63) / SPW) / CR;     // chunk the walk starts in; it then visits ci-1, ci-2, ...
+  DBlock dbW = dblk[ci / CPB];
+  int p0W, npW;
+  window(dbW, p0W, npW);
+  stage(0, ci, dbW, p0W, npW);
+  cp_commit();
+  DBlock dbS = dblk[max(ci - 1, 0) / CPB];
+  int bi = 0;
+  for (;;) {
+    int p0S = 0, npS = 0;
+    if (ci >= 1) { window(dbS, p0S, npS); stage(bi ^ 1, ci - 1, dbS, p0S, npS); }
+    cp_commit();
+    const DBlock dbS2 = dblk[max(ci - 2, 0) / CPB];      // in flight while this chunk is walked
+    cp_wait<1>();
+    bool more = false;
+    {
+      const int bCur = ci / CPB, cCur = ci % CPB;
+      const int wbase = dbW.wbase, rowWords = dbW.k * lpj;
+      const uint32_t *gsrc = arrows + (size_t)dbW.arrowUnit * unitW;
+      while (q >= 1 || t >= 1) {
+        if (q < 0 || t < 0) { awry = true; break; }
+        const int d = q + t, e = d & 63, row = e / SPW;
+        if ((d >> 6) != bCur || row / CR != cCur) { more = true; break; }     // the walk has left this chunk
+        const int s = t - q + C0 - wbase;
+        if (s < 0 || (s >> 1) >= rowWords) { awry = true; break; }
+        const int wo = (s >> 1) - p0W * 4;
+        uint32_t word;
+        if ((unsigned)wo < (unsigned)(npW * 4)) word = piece(bi, row - cCur * CR, wo >> 2)[wo & 3];
+        else word = __ldg(gsrc + (size_t)row * rowWords + (s >> 1));
+        const int pos = e % SPW;                                   // the first step of a word sits in its lowest field
+        const uint32_t f = (word >> (BITS * pos)) & ((1u << BITS) - 1u);
+        if (!AFFINE) {
+          if (f == TL_DIAG) {
+            // earlier anti-diagonals of this slot sit in fields pos-2, pos-4, ...: take the whole run of Diagonal
+            // arrows inside the word at once
+            uint32_t x = word & (0x33333333u << (2 * (pos & 1)));
+            x &= 0xffffffffu >> (30 - 2 * pos);
+            int n = x == 0 ? (pos >> 1) + 1 : (pos - ((31 - __clz((int)x)) >> 1)) >> 1;
+            n = min(n, min(q, t));
+            if (n <= 0) { awry = true; break; }
+            push(RUN_D, (uint32_t)n); q -= n; t -= n;
+          }
+          else if (f == TL_UP) { push(RUN_U, 1); pendQ++; q--; }
+          else if (f == TL_LEFT) { push(RUN_L, 1); pendT++; t--; }
+          else { awry = true; break; }
+        } else {
+          const uint32_t tag = f & 7u;
+          if (tag == TB_NONE) { awry = true; break; }
+          if (mat == 0) {
+            if (tag == TB_DIAG) { push(RUN_D, 1); q--; t--; }
+            else if (tag == TB_UP) { push(RUN_U, 1); pendQ++; q--; }
+            else if (tag == TB_LEFT) { push(RUN_L, 1); pendT++; t--; }
+            else if (tag == TB_ICLOSE) { push(RUN_U, 1); pendQ++; mat = 1; q--; }
+            else if (tag == TB_DCLOSE) { push(RUN_L, 1); pendT++; mat = 2; t--; }
+            else { awry = true; break; }
+          } else if (mat == 1) {
+            if (f & TB_IOPEN) mat = 0; else { q--; push(RUN_U, 1); pendQ++; }
+          } else {
+            if (f & TB_DOPEN) mat = 0; else { t--; push(RUN_L, 1); pendT++; }
+          }
+        }
       }
     }
-    const int pos = e % SPW;                                   // the first step of a word sits in its lowest field
-    const uint32_t f = (word >> (BITS * pos)) & ((1u << BITS) - 1u);
-    if (!AFFINE) {
-      if (f == TL_DIAG) {
-        // earlier anti-diagonals of this slot sit in fields pos-2, pos-4, ...: take the whole run of Diagonal
-        // arrows inside the word at once
-        uint32_t x = word & (0x33333333u << (2 * (pos & 1)));
-        x &= 0xffffffffu >> (30 - 2 * pos);
-        int n = x == 0 ? (pos >> 1) + 1 : (pos - ((31 - __clz((int)x)) >> 1)) >> 1;
-        n = min(n, min(q, t));
-        if (n <= 0) { awry = true; break; }
-        push(RUN_D, (uint32_t)n); q -= n; t -= n;
-      }
-      else if (f == TL_UP) { push(RUN_U, 1); pendQ++; q--; }
-      else if (f == TL_LEFT) { push(RUN_L, 1); pendT++; t--; }
-      else { awry = true; break; }
-    } else {
-      const uint32_t tag = f & 7u;
-      if (tag == TB_NONE) { awry = true; break; }
-      if (mat == 0) {
-        if (tag == TB_DIAG) { push(RUN_D, 1); q--; t--; }
-        else if (tag == TB_UP) { push(RUN_U, 1); pendQ++; q--; }
-        else if (tag == TB_LEFT) { push(RUN_L, 1); pendT++; t--; }
-        else if (tag == TB_ICLOSE) { push(RUN_U, 1); pendQ++; mat = 1; q--; }
-        else if (tag == TB_DCLOSE) { push(RUN_L, 1); pendT++; mat = 2; t--; }
-        else { awry = true; break; }
-      } else if (mat == 1) {
-        if (f & TB_IOPEN) mat = 0; else { q--; push(RUN_U, 1); pendQ++; }
-      } else {
-        if (f & TB_DOPEN) mat = 0; else { t--; push(RUN_L, 1); pendT++; }
-      }
-    }
+    if (!more) break;
+    if (ci == 0) { awry = true; break; }
+    ci--; bi ^= 1; dbW = dbS; p0W = p0S; npW = npS; dbS = dbS2;
   }
+  cp_wait<0>();
   if (runType >= 0) runs[nRuns++] = ((uint32_t)runType << 30) | runLen;
   if (awry) { G.status = BGPU_JOB_PATH_AWRY; G.nRuns = 0; G.nBlocks = G.nGaps = G.nGapLists = 0; }
   else {
@@ -179,7 +221,7 @@ __device__ __forceinline__ uint32_t warp_excl_u32(uint32_t v, int lane, uint32_t
 // run starts go to shared memory and every lane finds the run its position falls into with a 5-step search, so a
 // warp compares 32 consecutive query bases per step whatever the run lengths are.
 constexpr int EMIT_WARPS = 4;
-__global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine,
+__global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine,
                                                    int keepLeading) {
   __shared__ uint8_t lut[256];
   __shared__ int sM[64];
@@ -214,11 +256,13 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(BatchDev B, Score
   uint32_t cq = 0, ct = 0, cD = 0, cG = 0;            // carries: q/t consumed, D runs seen, kept gap runs seen
   uint32_t gAtPrevD = 0;                              // kept gap runs before the latest block seen so far
   int nMatch = 0, nMismatch = 0, nIns = 0, nDel = 0, score = 0; long long cols = 0;
+  uint32_t runNext = (uint32_t)lane < nRuns ? runs[nRuns - 1 - lane] : 0;
   for (uint32_t base = 0; base < nRuns; base += 32) {
     const uint32_t f = base + lane;                   // forward run index
     const bool act = f < nRuns;
     uint32_t type = 3, len = 0;
-    if (act) { const uint32_t r = runs[nRuns - 1 - f]; type = r >> 30; len = r & 0x3fffffffu; }
+    if (act) { const uint32_t r = runNext; type = r >> 30; len = r & 0x3fffffffu; }
+    if (f + 32 < nRuns) runNext = runs[nRuns - 33 - f];   // the next chunk's run, in flight during this chunk
     const uint32_t dq = (type == RUN_D || type == RUN_U) ? len : 0, dt = (type == RUN_D || type == RUN_L) ? len : 0;
     uint32_t totQ, totT, totD, totG;
     const uint32_t pq = cq + warp_excl_u32(dq, lane, totQ), pt = ct + warp_excl_u32(dt, lane, totT);
@@ -278,15 +322,23 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(BatchDev B, Score
       if (cmpMask) {
         sQ[warp][lane] = pq; sDelta[warp][lane] = (int)(pt - pq);   // lanes past the last run hold pq = cq + totQ
         __syncwarp();
-        for (uint32_t x = cq + lane; x < cq + totQ; x += 32) {
-          int r = 0;
+        const uint32_t xEnd = cq + totQ;
+        const uint32_t *sq = sQ[warp]; const int *sd = sDelta[warp];
+        auto find = [&](uint32_t x) { int r = 0;
 #pragma unroll
-          for (int st = 16; st; st >>= 1) if (sQ[warp][r + st] <= x) r += st;
-          if ((cmpMask >> r) & 1u) {
-            const int qc = lut[qb[x]] & 7, tc = lut[tb[(long long)x + sDelta[warp][r]]] & 7;
-            if (qc == tc) nMatch++; else nMismatch++;
-            score += sM[qc * 8 + tc];                    // ComputeAlignmentScore :74 (row = query)
-          }
+          for (int st = 16; st; st >>= 1) if (sq[r + st] <= x) r += st;
+          return r; };
+        auto tally = [&](int qc, int tc) { if (qc == tc) nMatch++; else nMismatch++; score += sM[qc * 8 + tc]; };   // ComputeAlignmentScore :74 (row = query)
+        // two positions per step: both searches, then all four byte loads, are in flight together
+        for (uint32_t x = cq + lane; x < xEnd; x += 64) {
+          const uint32_t y = x + 32; const bool hasY = y < xEnd;
+          const int r0 = find(x), r1 = find(hasY ? y : x);
+          const bool c0 = (cmpMask >> r0) & 1u, c1 = hasY && ((cmpMask >> r1) & 1u);
+          uint8_t q0b = 0, t0b = 0, q1b = 0, t1b = 0;
+          if (c0) { q0b = qb[x]; t0b = tb[(long long)x + sd[r0]]; }
+          if (c1) { q1b = qb[y]; t1b = tb[(long long)y + sd[r1]]; }
+          if (c0) tally(lut[q0b] & 7, lut[t0b] & 7);
+          if (c1) tally(lut[q1b] & 7, lut[t1b] & 7);
         }
         __syncwarp();
       }
@@ -310,7 +362,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(BatchDev B, Score
 }
 
 void launch_trace_guided(const BatchDev &B, bool affine, const uint32_t *order, uint32_t nOrder, cudaStream_t s) {
-  const unsigned block = 32;   // one warp per CTA spreads the (few, long) walks over all SMs
+  const unsigned block = TR_THREADS;   // small CTAs spread the (few, long) walks over all SMs
   const unsigned grid = (nOrder + block - 1) / block;
   if (!grid) return;
   if (affine) trace_guided_kernel<true><<<grid, block, 0, s>>>(B, order, nOrder);

@@ -1,0 +1,19 @@
+"""Top lines of an `ncu --page source --csv` export by executed instructions and by stall samples."""
+import csv, sys
+fn = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+rows = list(csv.reader(open(fn)))
+hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+h = rows[hi]; data = rows[hi + 1:]
+ci = {k: h.index(k) for k in ("Source", "# Samples", "Instructions Executed", "Avg. Threads Executed")}
+def num(x):
+    try: return float(x)
+    except Exception: return 0.0
+tot_i = sum(num(r[ci["Instructions Executed"]]) for r in data); tot_s = sum(num(r[ci["# Samples"]]) for r in data)
+print("total inst %.3g samples %.3g lines %d" % (tot_i, tot_s, len(data)))
+stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
+for key in ("Instructions Executed", "# Samples"):
+    print("---- top by", key)
+    for r in sorted(data, key=lambda r: -num(r[ci[key]]))[:n]:
+        st = sorted(((num(r[h.index(k)]), k) for k in stalls), reverse=True)[:2]
+        print("%5.1f%% i %5.1f%% s thr %4.1f  %-70s %s" % (100 * num(r[ci["Instructions Executed"]]) / max(tot_i, 1), 100 * num(r[ci["# Samples"]]) / max(tot_s, 1),
+              num(r[ci["Avg. Threads Executed"]]), r[ci["Source"]][:70], " ".join("%s:%d" % (k[6:], v) for v, k in st if v)))
