@@ -44,8 +44,8 @@ def parse():
     ap.add_argument("--algo", default="guided", choices=["guided", "affine"])
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
-    ap.add_argument("--e2e-threads", type=int, default=3, help="host threads (one context each) of the e2e measurement")
-    ap.add_argument("--e2e-chunks", type=int, default=12, help="sub-batches the shard is cut into for the e2e measurement")
+    ap.add_argument("--e2e-threads", type=int, default=5, help="host threads (one context each) of the e2e measurement")
+    ap.add_argument("--e2e-chunks", type=int, default=10, help="sub-batches the shard is cut into for the e2e measurement")
     return ap.parse_args()
 
 

@@ -12,7 +12,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblasr_gpu.so")
+# BGPU_LIB_PATH points experiments at a variant build of the same library (kernel A/B timing); default = the in-tree build
+LIB_PATH = os.environ.get("BGPU_LIB_PATH") or os.path.join(_HERE, "libblasr_gpu.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 # --- enums (mirror include/blasr_gpu.h) ---

@@ -7,6 +7,7 @@
 // No CPU implementation of any aligner exists here: without a CUDA device every entry point fails.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -33,6 +34,28 @@ extern double g_peakByMode[4];
 }  // namespace bgpu
 
 using namespace bgpu;
+
+// ---- phase gates.  Several host threads, each with its own context, drive one GPU (blasr's MapReads pthreads).  Left
+// alone they fall into lockstep -- all copy in, then all compute, then all copy out -- and nothing overlaps.  One gate
+// per device and phase (H2D, kernels, D2H) admits a bounded number of tickets at a time, so while one ticket computes
+// the next one copies in and the previous one copies out.  BGPU_GATES="h,c,d" sets the three widths (0 = no gate).
+struct Gate {
+  std::mutex mu; std::condition_variable cv; int width = 1, held = 0;
+  void acquire() { if (width <= 0) return; std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return held < width; }); held++; }
+  void release() { if (width <= 0) return; { std::lock_guard<std::mutex> lk(mu); held--; } cv.notify_one(); }
+};
+enum { GATE_H2D = 0, GATE_COMPUTE = 1, GATE_D2H = 2 };
+static Gate g_gates[64][3];
+static std::once_flag g_gateOnce;
+static Gate &gate(int device, int phase) {
+  std::call_once(g_gateOnce, [] {
+    int w[3] = {1, 3, 1};   // measured best on B200 / PCIe gen5: a few tickets' kernels overlap each other's tails
+    if (const char *e = getenv("BGPU_GATES")) sscanf(e, "%d,%d,%d", &w[0], &w[1], &w[2]);
+    for (auto &d : g_gates) for (int p = 0; p < 3; p++) d[p].width = w[p];
+  });
+  return g_gates[device & 63][phase];
+}
+static void CUDART_CB gate_release_cb(void *g) { static_cast<Gate *>(g)->release(); }
 
 struct bgpu_ctx {
   int device = 0, nSM = 0;
@@ -111,6 +134,8 @@ struct bgpu_ticket_s {
   std::vector<Wave> waves;
   uint32_t nCounters = 0;
   bool arenaReady = false, collected = false, dense = false;
+  bool holdsH2D = false;      // the ticket is inside the H2D gate and its release has not been queued on the stream yet
+  bool holdsCompute = false;  // ... inside the kernel gate and its release has not been queued on the stream yet
   cudaEvent_t ev[6] = {};     // start, prepEnd, fillTraceEnd(unused), scanEnd, emitEnd
   std::vector<cudaEvent_t> waveEv;   // per wave: fillStart, fillEnd, traceEnd
   bgpu_timing timing{};
@@ -340,6 +365,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     t->timing.cells = cells;
     t->timing.fillCells = laneSteps;
   }
+  if (firstRun) { gate(ctx->device, GATE_COMPUTE).acquire(); t->holdsCompute = true; }   // released by the stream itself once the last kernel is done
   CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
   CK(cudaMemsetAsync(t->d_totals + 3, 0, sizeof(uint64_t), s));
   t->B.cellSlots = reinterpret_cast<unsigned long long *>(t->d_totals + 3);
@@ -366,6 +392,10 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   launch_scan_counts(t->B, t->d_blockOff, t->d_listOff, t->d_gapOff, t->d_totals, s);
   t->timing.kernelLaunches++;
   CK(cudaEventRecord(t->ev[3], s));
+  if (firstRun) {
+    if (gate(ctx->device, GATE_COMPUTE).width > 0) CK(cudaLaunchHostFunc(s, gate_release_cb, &gate(ctx->device, GATE_COMPUTE)));
+    t->holdsCompute = false;
+  }
   CK(cudaGetLastError());
   return BGPU_OK;
 }
@@ -409,6 +439,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   RC(talloc_dev(ctx, t, &d_guide, totG + 1));
   if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
   if (b->band) RC(talloc_dev(ctx, t, &d_band, n));
+  gate(ctx->device, GATE_H2D).acquire(); t->holdsH2D = true;   // until the uploads below are done
   RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
   RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));
   RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
@@ -430,6 +461,9 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   RC(talloc_dev(ctx, t, &t->d_rowOff, 3 * (size_t)n + 3));
   t->d_dblkOff = t->d_rowOff + n; t->d_runOff = t->d_rowOff + 2 * (size_t)n;
   CK(cudaMemcpyAsync(t->d_rowOff, h_off, sizeof(uint64_t) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+  // the stream leaves the H2D gate as soon as the last input byte has landed
+  if (gate(ctx->device, GATE_H2D).width > 0) CK(cudaLaunchHostFunc(ctx->stream, gate_release_cb, &gate(ctx->device, GATE_H2D)));
+  t->holdsH2D = false;
   RC(talloc_dev(ctx, t, &B.geom, n)); RC(talloc_dev(ctx, t, &B.rows, rowTot + 1)); RC(talloc_dev(ctx, t, &B.dblk, dbTot + 1));
   RC(talloc_dev(ctx, t, &B.dmin, dbTot + 1)); RC(talloc_dev(ctx, t, &B.dmax, dbTot + 1)); RC(talloc_dev(ctx, t, &B.runs, runTot + 1));
   RC(talloc_dev(ctx, t, &t->d_blockOff, 3 * (size_t)n + 3));
@@ -580,6 +614,8 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
   else rc = submit_dense(ctx, fn, p, b, t);
   if (rc != BGPU_OK) {
     cudaStreamSynchronize(ctx->stream);
+    if (t->holdsH2D) { gate(ctx->device, GATE_H2D).release(); t->holdsH2D = false; }
+    if (t->holdsCompute) { gate(ctx->device, GATE_COMPUTE).release(); t->holdsCompute = false; }
     for (void *v : t->dev) dev_free(ctx, v);
     for (void *v : t->pin) pin_free(ctx, v);
     for (auto &e : t->ev) cudaEventDestroy(e);
@@ -647,6 +683,7 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
   const auto h0 = std::chrono::steady_clock::now();
   if (!t->collected) {
     RC(ensure_arena(ctx, t));
+    struct Hold { Gate &g; Hold(Gate &x) : g(x) { g.acquire(); } ~Hold() { g.release(); } } hold(gate(ctx->device, GATE_D2H));
     RC(enqueue_emit(ctx, t));
     CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
