@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--jobs", type=int, default=int(os.environ.get("BGPU_BENCH_JOBS", 100000)), help="pairs per GPU")
     ap.add_argument("--algo", default="guided", choices=["guided", "affine"])
+    ap.add_argument("--scorefn", default="distance", choices=["distance", "quality"],
+                    help="distance = configs[1] (the headline); quality = configs[3]-style QualityValueScoreFunction over a simulated QV track")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--e2e-threads", type=int, default=5, help="host threads (one context each) of the e2e measurement")
@@ -49,30 +51,34 @@ def parse():
     return ap.parse_args()
 
 
-def make_workload(n_jobs, seed):
+def make_workload(n_jobs, seed, with_qual=False):
     from blasr_b200 import synth
-    return synth.simulate_pairs(n_jobs, LEN_LO, LEN_HI, err=0.15, seed=seed, bands=BANDS)
+    return synth.simulate_pairs(n_jobs, LEN_LO, LEN_HI, err=0.15, seed=seed, bands=BANDS, with_qual=with_qual)
 
 
 def config_dict(args, n_jobs):
-    return {"workload": "configs[1]: GuidedAlign microbench, read/window pairs 1-20 kb, band 16/32/64, "
-                        "DistanceMatrixScoreFunction(SMRTDistanceMatrix, ins=5, del=5)",
+    wl = ("configs[1]: GuidedAlign microbench, read/window pairs 1-20 kb, band 16/32/64, "
+          "DistanceMatrixScoreFunction(SMRTDistanceMatrix, ins=5, del=5)")
+    if args.scorefn == "quality":
+        wl = ("configs[3]-style: the configs[1] pairs with a simulated QV track (clamp(N(12,4),1,93)), "
+              "QualityValueScoreFunction(ins=5, del=5)")
+    return {"workload": wl,
             "pairs_per_gpu": n_jobs, "algo": "AffineGuidedAlign" if args.algo == "affine" else "GuidedAlign",
             "error_rate": 0.15, "guide": "all diagonal runs of the simulated alignment (detailed-SDP-like)",
             "l2": "inputs_larger_than_L2", "parallelism": f"read-shard x{args.gpus}, no collective"}
 
 
 # ---------------------------------------------------------------- CPU side (reference / port)
-def cpu_replay(batch, algo, n_threads, target_seconds, est_gcups_per_core=0.05):
+def cpu_replay(batch, algo, n_threads, target_seconds, est_gcups_per_core=0.05, quality=False):
     """Replays a bounded prefix of the batch through oracle/_ref (or the C port) on n_threads; returns dict."""
     from tests import cases, oracle as O
     which = "ref" if O.have_ref() else "orc"
-    fn = O.score_fn(__import__("blasr_b200").SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0)
+    fn = O.score_fn(__import__("blasr_b200").SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0, kind=1 if quality else 0)
     target_cells = target_seconds * n_threads * est_gcups_per_core * 1e9 * (0.5 if algo else 1.0)
     jobs, keep, est = [], [], 0
     for i in range(batch.n):
         q, t, g, qv = cases.job_arrays(batch, i)
-        j, k = O.make_job(algo, 1, int(batch.band[i]), q, t, g, None, 0, 0, 0, 0)
+        j, k = O.make_job(algo, 1, int(batch.band[i]), q, t, g, qv if quality else None, 0, 0, 0, 0)
         jobs.append(j); keep.append(k)
         est += len(q) * (2 * int(batch.band[i]) + 2)
         if est >= target_cells and len(jobs) >= n_threads:
@@ -92,13 +98,14 @@ def run_reference(args):
     n_threads = os.cpu_count() or 1
     algo = 1 if args.algo == "affine" else 0
     # a shard prefix is enough: the sample is bounded by CPU time, not by the 100k pairs
-    batch = make_workload(min(args.jobs, max(256, n_threads * 32)), args.seed)
+    quality = args.scorefn == "quality"
+    batch = make_workload(min(args.jobs, max(256, n_threads * 32)), args.seed, with_qual=quality)
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        cpu_replay(batch, algo, n_threads, min(per_step, 2.0))
+        cpu_replay(batch, algo, n_threads, min(per_step, 2.0), quality=quality)
     vals, ms = [], []
     for _ in range(args.steps):
-        r = cpu_replay(batch, algo, n_threads, per_step)
+        r = cpu_replay(batch, algo, n_threads, per_step, quality=quality)
         vals.append(r["value"]); ms.append(r["_seconds"] * 1e3)
     v = float(np.mean(vals))
     cb = {k: r[k] for k in ("unit", "cores", "kind", "sample")}
@@ -162,22 +169,23 @@ def range_view(batch, a, b):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from blasr_b200 import Aligner, DistanceMatrixScoreFunction, capi
+    from blasr_b200 import Aligner, DistanceMatrixScoreFunction, QualityValueScoreFunction, capi
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     # the generator forks worker processes: run it before CUDA / NCCL are initialised in this process
-    batch = make_workload(args.jobs, args.seed + 1000 * rank)
+    batch = make_workload(args.jobs, args.seed + 1000 * rank, with_qual=args.scorefn == "quality")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     algo = capi.AFFINE_GUIDED if args.algo == "affine" else capi.GUIDED
     # inputs in pinned host memory (the library then DMA's straight from them)
     keep = []
-    for name in ("q", "qOff", "t", "tOff", "guide", "guideOff", "band"):
+    for name in ("q", "qOff", "t", "tOff", "guide", "guideOff", "band") + (("qual",) if batch.qual is not None else ()):
         v, t = pinned_copy(getattr(batch, name)); setattr(batch, name, v); keep.append(t)
-    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50 if algo == capi.AFFINE_GUIDED else 0, affineExtend=0)
+    fn_cls = QualityValueScoreFunction if args.scorefn == "quality" else DistanceMatrixScoreFunction
+    fn = fn_cls(ins=5, del_=5, affineOpen=50 if algo == capi.AFFINE_GUIDED else 0, affineExtend=0)
     al = Aligner(local)
 
     def barrier():
@@ -317,7 +325,7 @@ def run_ours(args):
     }
     if rank == 0 and world == 1:
         try:
-            cb = cpu_replay(batch, a, os.cpu_count() or 1, args.cpu_seconds)
+            cb = cpu_replay(batch, a, os.cpu_count() or 1, args.cpu_seconds, quality=args.scorefn == "quality")
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}

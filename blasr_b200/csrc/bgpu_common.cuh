@@ -39,7 +39,8 @@ enum { TB_DIAG = 0, TB_LEFT = 1, TB_UP = 2, TB_ICLOSE = 3, TB_DCLOSE = 4, TB_NON
 enum { TL_DIAG = 0, TL_LEFT = 1, TL_UP = 2, TL_NONE = 3 };
 
 struct alignas(8) RowInfo {  // 8 B per guide row in HBM, consumed as is by the fill kernels
-  int32_t cd8;            // (diagonal of the row's first in-band cell) << 8, diagonal = t' - q' + C0
+  int32_t cd8;            // (diagonal of the row's first in-band cell) << 8, diagonal = t' - q' + C0;
+                          // low byte: the row's QV for BGPU_FN_QUALITY, else 0
   uint32_t packed;        // bits 8-27: hi'-lo' (cells in the row - 1), bits 0-7: query base code * 20
 };
 

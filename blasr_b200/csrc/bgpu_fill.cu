@@ -25,7 +25,7 @@
 // load per row / column; per cell that leaves one LDS (the substitution score), two VIADDMNMX, the in-band test
 // and the tag split; one funnel shift appends the arrow to the lane's traceback word.  Words are
 // stored [d-block][16-step row][slot pair], 2 bits per cell for the linear aligner (8 for the affine one).
-// Blocks that touch the boundary row, a job's last block, the QV / IDS score functions and very wide windows take the
+// Blocks that touch the boundary row, a job's last block, the IDS score function and very wide windows take the
 // generic path (run_block_gen), which reads its rows and columns from shared memory per cell.
 #include "bgpu_common.cuh"
 
@@ -50,11 +50,12 @@ struct SubSmem {          // staging of one job: two d-blocks (current, next)
   int2 rows[2][KM * LPJ + 32];           // RowInfo as prep wrote it: {cd8, (width << 8) | qcode * 20}
   uint32_t colw[2][(KM * LPJ + 44) / 4]; // target codes (bytes), 4-byte chunks from an aligned-down address
   int shift[2 * KM * LPJ];               // window re-mapping scratch
-  // per-row score data of the current block: QualityValueScoreFunction: the QV; IDSScoreFunction: two words per row,
+  // per-row score data of the current block (QualityValueScoreFunction needs none: the QV rides in RowInfo::cd8);
+  // IDSScoreFunction: two words per row,
   //   [r]      query byte | substitutionTag << 8 | substitutionQV << 16 | insertionQV << 24
   //   [NR + r] deletionTag | deletionQV << 8 | (deletion tracks present) << 16
   static constexpr int NR = KM * LPJ + 32;
-  int rowq[FN == 0 ? 2 : (FN == 1 ? NR : 2 * NR)];
+  int rowq[FN == 2 ? 2 * NR : 2];
 };
 
 template <bool AFFINE> struct Fmt {
@@ -114,7 +115,7 @@ struct BlockView {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fast path: KA groups per lane (compile time), rows / columns in register rings, no boundary row, full 64 steps.
-template <int LPJ, int KM, int KA, bool AFFINE>
+template <int LPJ, int KM, int KA, bool AFFINE, int FN>
 __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
                                                int (&ADe)[KM], int (&ADo)[KM], const BlockView &bv,
                                                const int mtabAddr, const FillConsts &c, const int sl,
@@ -125,11 +126,13 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
   const uint8_t *cp = bv.cols + kL;                          // cp[i + g]: column of group g on the even step of pair i
   const int s08 = bv.wbase8 + ((2 * kL) << 8);
   int rX[KA], rY[KA], rQ[KA], cT[KA];
+  int rV[FN == 1 ? KA : 1];                                  // QualityValueScoreFunction: the rows' QVs
   uint32_t acc[KA];
 #pragma unroll
   for (int m = 0; m < KA; m++) {
     const int2 v = rp[m];
-    rX[m] = s08 - v.x; rY[m] = v.y; rQ[m] = v.y & 0xff;
+    if (FN == 1) { rV[m] = v.x & 0xff; rX[m] = s08 - v.x + rV[m]; } else rX[m] = s08 - v.x;
+    rY[m] = v.y; rQ[m] = v.y & 0xff;
     cT[m] = (int)cp[m] * 4 + mtabAddr;
     acc[m] = 0;
   }
@@ -148,7 +151,8 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
           const int p = (j + KA - 1 - g) % KA, cs = (j + g) % KA;
           const int leftS = g == 0 ? left0 : So[g - 1];
           const int leftAD = AFFINE ? (g == 0 ? leftA0 : ADo[g - 1]) : 0;
-          const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
+          int m = lds32((uint32_t)(rQ[p] + cT[cs]));
+          if (FN == 1) m *= rV[p];                            // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
           int ai = 0, ad = 0;
           int cnd = dp_core<AFFINE>(Se[g], leftS, leftAD, So[g], AFFINE ? AIo[g] : 0, m, c.delT, c.insT, c, ai, ad);
           const bool inb = (unsigned)(c.k256 * (2 * g) + rX[p]) <= (unsigned)rY[p];
@@ -168,7 +172,8 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
           const int p = (j + KA - 1 - g) % KA, cs = (j + 1 + g) % KA;
           const int upS = g == KA - 1 ? up0 : Se[g + 1];
           const int upAI = AFFINE ? (g == KA - 1 ? upA0 : AIe[g + 1]) : 0;
-          const int m = lds32((uint32_t)(rQ[p] + cT[cs]));
+          int m = lds32((uint32_t)(rQ[p] + cT[cs]));
+          if (FN == 1) m *= rV[p];
           int ai = 0, ad = 0;
           int cnd = dp_core<AFFINE>(So[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, m, c.delT, c.insT, c, ai, ad);
           const bool inb = (unsigned)(c.k256 * (2 * g + 1) + rX[p]) <= (unsigned)rY[p];
@@ -180,7 +185,8 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
       }
       {                                                       // row baseR + i + KA replaces row baseR + i
         const int2 v = rp[i0 + j + KA];
-        rX[j] = s08 - v.x; rY[j] = v.y; rQ[j] = v.y & 0xff;
+        if (FN == 1) { rV[j] = v.x & 0xff; rX[j] = s08 - v.x + rV[j]; } else rX[j] = s08 - v.x;
+        rY[j] = v.y; rQ[j] = v.y & 0xff;
       }
       if (((i0 + j) & (F::SPW / 2 - 1)) == F::SPW / 2 - 1) {  // a traceback word is complete
         if (live) {
@@ -223,7 +229,7 @@ __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int 
       delT = (dc << F::SHv) | TB_LEFT;
     } else {
       m = lds32((uint32_t)(mtabAddr + (rv.y & 0xff) + (int)bv.cols[cidx] * 4));
-      if (FN == 1) m *= rowq[ridx];                         // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+      if (FN == 1) m *= rv.x & 0xff;                        // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
     }
     int ai = 0, ad = 0;
     int cnd = dp_core<AFFINE>(S, leftS, leftAD, upS, upAI, m, delT, insT, c, ai, ad);
@@ -231,7 +237,7 @@ __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int 
       cnd = ((bv.tlo + cidx) * c.del0) | (AFFINE ? (TB_LEFT | TB_IOPEN | TB_DOPEN) : TL_LEFT);
       ai = c.open; ad = c.open;
     }
-    const bool inb = (unsigned)(bv.wbase8 + (slot << 8) - rv.x) <= (unsigned)rv.y;
+    const bool inb = (unsigned)(bv.wbase8 + (slot << 8) - (FN == 1 ? (rv.x & ~0xff) : rv.x)) <= (unsigned)rv.y;
     cnd = inb ? cnd : (BIG | F::NONE);
     if (e <= eLast) {
       S = cnd & ~F::TAGMASK;
@@ -286,17 +292,17 @@ __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int 
   }
 }
 
-template <int LPJ, int KM, bool AFFINE, int KA>
+template <int LPJ, int KM, bool AFFINE, int FN, int KA>
 struct RingDispatch {
   static __device__ __forceinline__ void run(const int k, int (&Se)[KM], int (&So)[KM], int (&AIe)[KM], int (&AIo)[KM],
                                              int (&ADe)[KM], int (&ADo)[KM], const BlockView &bv, const int mtabAddr,
                                              const FillConsts &c, const int sl, uint32_t *aw, const bool live) {
-    if (k == KA) run_block_ring<LPJ, KM, KA, AFFINE>(Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
-    else RingDispatch<LPJ, KM, AFFINE, KA + 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
+    if (k == KA) run_block_ring<LPJ, KM, KA, AFFINE, FN>(Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
+    else RingDispatch<LPJ, KM, AFFINE, FN, KA + 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
   }
 };
-template <int LPJ, int KM, bool AFFINE>
-struct RingDispatch<LPJ, KM, AFFINE, KM + 1> {
+template <int LPJ, int KM, bool AFFINE, int FN>
+struct RingDispatch<LPJ, KM, AFFINE, FN, KM + 1> {
   static __device__ __forceinline__ void run(const int, int (&)[KM], int (&)[KM], int (&)[KM], int (&)[KM], int (&)[KM],
                                              int (&)[KM], const BlockView &, const int, const FillConsts &, const int,
                                              uint32_t *, const bool) {}
@@ -310,7 +316,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
   typedef Fmt<AFFINE> F;
   typedef SubSmem<LPJ, KM, FN> Smem;
   constexpr int NJ = 32 / LPJ;
-  constexpr bool RING = KM <= KRING && FN == 0;
+  constexpr bool RING = KM <= KRING && FN <= 1;
   constexpr int UG = KM <= KRING ? KM : 1;
   constexpr int UNITW = (64 / F::SPW) * LPJ;                // words per arrow unit
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -344,7 +350,6 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
     if (have && G->status != BGPU_JOB_OK) have = false;
     int Qn = 0, Tn = 0, C0 = 0, nDB = 0, hi0 = 0;
     const RowInfo *rows = nullptr; DBlock *dblk = nullptr; const uint8_t *tcodes = nullptr, *tJobLo = nullptr, *tJobHi = nullptr;
-    const uint8_t *qualRow = nullptr;
     size_t trackOff = 0;                                     // IDS: track index of row q' is trackOff + q'
     uint32_t *arrowsJob = nullptr;
     if (have) {
@@ -352,7 +357,6 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
       rows = B.rows + G->rowOff; dblk = B.dblk + G->dblkOff;
       tJobLo = B.t + B.tOff[job]; tJobHi = B.t + B.tOff[job + 1];
       tcodes = tJobLo + G->tStart - 1;                       // tcodes[t'] for t' in [1,Tn]
-      if (FN == 1) qualRow = B.qual + B.qOff[job] + G->qStart - 1; // qualRow[q'] for q' in [1,Qn]
       if (FN == 2) trackOff = (size_t)B.qOff[job] + (size_t)G->qStart - 1;
       arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
     }
@@ -444,13 +448,6 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
       bv.cols = reinterpret_cast<const uint8_t *>(sm.colw[buf]) + (buf ? colShift1 : colShift0);
       bv.wbase8 = wbase << 8;
       bv.qlo = 32 * b + cq - (k * LPJ - 1); bv.tlo = 32 * b - cq;
-      if (FN == 1) {
-        for (int r = sl; r < k * LPJ + 32; r += LPJ) {
-          const int qp = bv.qlo + r;
-          sm.rowq[r] = (live && qp >= 1 && qp <= Qn) ? (int)qualRow[qp] : 0;
-        }
-        __syncwarp();
-      }
       if (FN == 2) {
         for (int r = sl; r < k * LPJ + 32; r += LPJ) {
           const int qp = bv.qlo + r;
@@ -469,7 +466,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
       const bool last = live && (b == nDB - 1);
       const int eLast = last ? ((nD - 1) & 63) : 63;
       if (RING && !__any_sync(0xffffffffu, first || last))
-        RingDispatch<LPJ, KM, AFFINE, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
+        RingDispatch<LPJ, KM, AFFINE, FN, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
       else
         run_block_gen<LPJ, KM, AFFINE, FN>(Se, So, AIe, AIo, ADe, ADo, bv, sm.rowq, mtabAddr, c, k, sl, first, eLast, aw, live);
       if (live && sl == 0) { dblk[b].k = k; dblk[b].arrowUnit = unit; }

@@ -139,6 +139,9 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   bgpu_block *win = sWin[threadIdx.x >> 5];
   int wb = 0, we = 0;                                   // window = blocks [wb, we)
   uint8_t qchNext = Qn >= 1 + lane ? qb[qStart + lane] : 0;
+  // QualityValueScoreFunction: the row's QV rides in the low byte of RowInfo::cd8 (the fill kernels multiply by it)
+  const uint8_t *qvb = (P.kind == BGPU_FN_QUALITY && B.qual) ? B.qual + qo : nullptr;
+  uint8_t qvNext = (qvb && Qn >= 1 + lane) ? qvb[qStart + lane] : 0;
   for (int base = 1; base <= Qn; base += 32) {
     const int i = base + lane;
     const bool act = i <= Qn;
@@ -151,8 +154,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
       __syncwarp();
     }
     int t = 0, cap = 0, tPost = 0, x = INT_MIN;
-    const uint8_t qch = qchNext;
-    if (i + 32 <= Qn) qchNext = qb[qStart + i + 31];
+    const uint8_t qch = qchNext, qv = qvNext;
+    if (i + 32 <= Qn) { qchNext = qb[qStart + i + 31]; if (qvb) qvNext = qvb[qStart + i + 31]; }
     const uint32_t q0 = (uint32_t)(qStart + base - 1);
     const int cand = bcur + 1 + lane;
     const uint32_t rel = cand < nB ? win[cand - wb].qPos - q0 : 0xffffffffu;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
       if (w >= (1 << ROW_W_BITS)) wide = 1;
       const uint32_t qc = lut[qch];
       if (qc > 4) bad = 1;
-      RowInfo r; r.cd8 = (lop - i + C0) << 8; r.packed = (((uint32_t)w & ((1u << ROW_W_BITS) - 1)) << 8) | ((qc & 7u) * 20u);
+      RowInfo r; r.cd8 = ((lop - i + C0) << 8) | (int)qv; r.packed = (((uint32_t)w & ((1u << ROW_W_BITS) - 1)) << 8) | ((qc & 7u) * 20u);
       rows[i] = r;
       if (bad || wide) { lop = 1; hip = 0; }
     }

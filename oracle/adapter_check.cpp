@@ -19,6 +19,7 @@
 #include "algorithms/alignment/DistanceMatrixScoreFunction.h"
 #include "datastructures/alignment/AlignmentCandidate.h"
 #include "FASTQSequence.h"
+#include "algorithms/alignment/printers/SAMPrinter.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +67,24 @@ static int Diff(const A &a, const B &b, int job, const char *what) {
   return bad;
 }
 
+/* What the reference prints from a refined candidate: the SAM CIGAR core (printers/SAMPrinter.h:203-293, '=' / 'X' / 'I' / 'D'
+ * ops) and the three m5 strings (AlignmentUtils.h:390-533, printed by printers/CompareSequencesAlignmentPrinter.h:17-89),
+ * produced by the reference's own printers from whatever the aligner stored into the candidate. */
+static std::string PrintedForm(T_AlignmentCandidate &a, FASTQSequence &q, DNASequence &t) {
+  a.qAlignedSeq.ReferenceSubstring(q, 0, q.length); a.tAlignedSeq.ReferenceSubstring(t, 0, t.length);
+  a.qAlignedSeqPos = 0; a.tAlignedSeqPos = 0; a.qLength = q.length; a.tLength = t.length;
+  std::string out;
+  if (a.blocks.size()) {
+    vector<int> opSize; vector<char> opChar; std::string cigar;
+    SAMOutput::CreateNoClippingCigarOps(a, a.qPos + a.blocks[0].qPos, a.tPos + a.blocks[0].tPos, opSize, opChar);
+    SAMOutput::CigarOpsToString(opSize, opChar, cigar);
+    out += cigar;
+  }
+  std::string qs, as, ts;
+  CreateAlignmentStrings(a, q.seq, t.seq, ts, as, qs, q.length, t.length);
+  return out + "|" + qs + "|" + as + "|" + ts;
+}
+
 int main(int argc, char **argv) {
   const int nJobs = argc > 1 ? atoi(argv[1]) : 48;
   const int maxLen = argc > 2 ? atoi(argv[2]) : 6000;
@@ -86,6 +105,7 @@ int main(int argc, char **argv) {
   }
 
   int bad = 0;
+  size_t printedBytes = 0;
   for (int affine = 1; affine >= 0; affine--) {
     const int band = affine ? 16 : 10;                                       /* bandSize / guidedAlignBandSize */
     blasr_gpu::Context ctx(0);
@@ -112,7 +132,12 @@ int main(int argc, char **argv) {
       ComputeAlignmentStats(refRefined, qs[i].seq, ts[i].seq, fn, affine != 0);
       batch.Store(j, gpuRefined);
       bad += Diff(refRefined, gpuRefined, i, affine ? "AffineGuidedAlign" : "GuidedAlign");
+      const std::string pr = PrintedForm(refRefined, qs[i], ts[i]), pg = PrintedForm(gpuRefined, qs[i], ts[i]);
+      if (pr != pg) { printf("job %d: printed CIGAR / m5 strings differ\n", i); bad++; }
+      printedBytes += pr.size();
     }
+    printf("adapter_check: %zu bytes of SAM CIGAR + m5 alignment strings printed by the reference's printers: %s\n", printedBytes,
+           bad ? "MISMATCH" : "identical");
     printf("adapter_check: %s x%zu candidates through blasr_gpu::RefineBatch: %s\n", affine ? "AffineGuidedAlign" : "GuidedAlign",
            jobOf.size(), bad ? "MISMATCH" : "identical to the reference call site");
   }

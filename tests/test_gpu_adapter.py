@@ -18,6 +18,8 @@ def test_adapter_matches_reference_call_site():
     r = subprocess.run([BIN, "64", "8000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("identical to the reference call site") == 2, r.stdout
+    # SAM CIGAR ('=' / 'X' / 'I' / 'D') and the m5 strings, printed by the reference's own printers from both candidates
+    assert r.stdout.count("printed by the reference's printers: identical") == 2, r.stdout
 
 
 @needs_bin

@@ -72,6 +72,17 @@ def test_quality_value_score_function(aligner):
     _run(aligner, b, 1, fn, 16)
 
 
+def test_quality_value_all_classes(aligner):
+    """The QV rides in RowInfo::cd8 through the register-ring kernels of every job class (bands 8..64, reads up to 6 kb)."""
+    b = cases.guided_batch(seed=53, n=48, lo=300, hi=6000, with_qual=True)
+    b.band = np.random.default_rng(2).choice([8, 16, 32, 64], size=b.n).astype(np.int32)
+    b.qual[::7] = 0; b.qual[3::11] = 255            # extreme QVs: zero-cost and maximal-cost mismatches
+    fn = QualityValueScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    for at in (0, 1):
+        _run(aligner, b, 0, fn, 16, at)
+        _run(aligner, b, 1, fn, 16, at)
+
+
 @pytest.mark.parametrize("algo", [0, 1])
 @pytest.mark.parametrize("with_del", [True, False])
 def test_ids_score_function(aligner, algo, with_del):

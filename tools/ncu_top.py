@@ -1,9 +1,13 @@
 """Top lines of an `ncu --page source --csv` export by executed instructions and by stall samples."""
 import csv, sys
 fn = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+sec = int(sys.argv[3]) if len(sys.argv) > 3 else 0        # which kernel of a multi-kernel export
 rows = list(csv.reader(open(fn)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-h = rows[hi]; data = rows[hi + 1:]
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+hi = his[sec]; h = rows[hi]
+end = next((i for i in range(hi + 1, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))
+data = [r for r in rows[hi + 1:end] if len(r) == len(h)]
+print(rows[hi - 1][:2] if hi else "")
 ci = {k: h.index(k) for k in ("Source", "# Samples", "Instructions Executed", "Avg. Threads Executed")}
 def num(x):
     try: return float(x)
