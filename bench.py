@@ -295,6 +295,14 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     a = 1 if algo == capi.AFFINE_GUIDED else 0
+    # DRAM bytes of the fill kernels from the committed ncu --set full capture of this very workload (same pairs, same seed)
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))[args.algo]
+        if tr["pairs"] == args.jobs and tr["seed"] == args.seed and tr["scorefn"] == args.scorefn:
+            traffic, traffic_src = tr["dram_bytes_per_step"], tr["source"]
+    except Exception:  # noqa: BLE001
+        pass
     fill_s = float(np.mean(ms_fill)) * 1e-3
     fill_gcups = cells / fill_s / 1e9
     out = {
@@ -312,7 +320,8 @@ def run_ours(args):
         "stage_ms": {"prep": float(np.mean(ms_prep)), "fill": float(np.mean(ms_fill)), "trace": float(np.mean(ms_trace)),
                      "emit": float(np.mean(ms_emit)), "wall_per_step": wall / args.steps * 1e3},
         "roofline": {"bound": "hbm", "kernel": "fill_guided_kernel", "achieved": cells * BYTES_PER_CELL[a] / fill_s / 1e9, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": cells * BYTES_PER_CELL[a] / fill_s / 1e9 / hbm_peak, "traffic": None,
+                     "unit": "GB/s", "frac": cells * BYTES_PER_CELL[a] / fill_s / 1e9 / hbm_peak, "traffic": traffic,
+                     "algorithmic_bytes": cells * BYTES_PER_CELL[a], "traffic_source": traffic_src,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                      "note": "integer DP: the HBM roofline is not the binding one, see int_roofline"},
         "int_roofline": {"bound": "int32 ALU issue", "fill_gcups": fill_gcups, "ops_per_cell": OPS_PER_CELL[a],

@@ -82,7 +82,16 @@ struct bgpu_ctx {
     }                                                                                             \
   } while (0)
 
-static size_t round_up(size_t n) { const size_t g = 1u << 16; return n == 0 ? g : (n + g - 1) / g * g; }
+// Allocation size classes: eight per octave (<= 12.5 % slack), so the sub-batches of a stream of similar tickets keep
+// hitting the cached blocks instead of growing the cache with cudaMalloc / cudaHostAlloc calls in steady state.
+static size_t round_up(size_t n) {
+  const size_t g = 1u << 16;
+  if (n <= g) return g;
+  int e = 0;
+  while ((size_t(2) << e) < n) e++;                       // 2^e < n <= 2^(e+1)
+  const size_t step = std::max<size_t>((size_t(1) << e) / 8, g);
+  return (n + step - 1) / step * step;
+}
 
 static int dev_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
   bytes = round_up(bytes);
@@ -200,7 +209,7 @@ extern "C" int bgpu_create(bgpu_ctx **out, int device) {
   if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
   size_t freeB = 0, totalB = 0;
   cudaMemGetInfo(&freeB, &totalB);
-  ctx->arrowPoolCap = freeB / 3;
+  ctx->arrowPoolCap = freeB / 5 * 3;   // one wave holds ~100 GB of affine arrows (100k pairs of 1-20 kb): a B200 has the HBM for it
   const char *env = getenv("BGPU_ARROW_POOL_MB");
   if (env) ctx->arrowPoolCap = (size_t)atoll(env) << 20;
   *out = ctx;

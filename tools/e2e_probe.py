@@ -9,11 +9,13 @@ jobs = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 C = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 STAG = float(sys.argv[4]) * 1e-3 if len(sys.argv) > 4 else 0.0
-batch = bench.make_workload(jobs, 1)
+QUAL = os.environ.get("SCOREFN") == "quality"
+batch = bench.make_workload(jobs, 1, with_qual=QUAL)
 keep = []
-for name in ("q", "qOff", "t", "tOff", "guide", "guideOff", "band"):
+for name in ("q", "qOff", "t", "tOff", "guide", "guideOff", "band") + (("qual",) if QUAL else ()):
     v, t = bench.pinned_copy(getattr(batch, name)); setattr(batch, name, v); keep.append(t)
-fn = DistanceMatrixScoreFunction(ins=5, del_=5)
+from blasr_b200 import QualityValueScoreFunction
+fn = QualityValueScoreFunction(ins=5, del_=5) if QUAL else DistanceMatrixScoreFunction(ins=5, del_=5)
 bounds = np.linspace(0, batch.n, C + 1).astype(np.int64)
 chunks = [bench.range_view(batch, int(bounds[i]), int(bounds[i + 1])) for i in range(C)]
 workers = [Aligner(0) for _ in range(T)]
