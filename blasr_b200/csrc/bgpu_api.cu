@@ -291,12 +291,12 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     for (int c = 0; c < N_CLS; c++) {
       auto &v = byCls[c];
       auto kt = [&](uint32_t i) { const JobGeom &g = t->h_geom[i]; return (g.ksum + g.nDB / 2) / std::max(g.nDB, 1); };
-      std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) {
-        const int ka = kt(a), kb = kt(b);
-        if (ka != kb) return ka > kb;
-        const int da = t->h_geom[a].nDB, db = t->h_geom[b].nDB;
-        return da != db ? da > db : a < b;
-      });
+      {   // (typical width, d-blocks) descending, index ascending -- sorted on packed keys, not through the geometry array
+        std::vector<std::pair<uint64_t, uint32_t>> keyed; keyed.reserve(v.size());
+        for (uint32_t i : v) keyed.emplace_back(~(((uint64_t)(uint32_t)kt(i) << 32) | (uint32_t)t->h_geom[i].nDB), i);
+        std::sort(keyed.begin(), keyed.end());
+        for (size_t i = 0; i < keyed.size(); i++) v[i] = keyed[i].second;
+      }
       const uint32_t lpj = (uint32_t)cls_lpj(c), nj = 32 / lpj;
       for (size_t i0 = 0; i0 < v.size(); i0 += nj) {
         const size_t i1 = std::min(v.size(), i0 + nj);
@@ -346,7 +346,12 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
       w.traceBegin = (uint32_t)order.size();
       std::vector<uint32_t> tl;
       for (size_t gi = g0; gi < g1; gi++) for (uint32_t j = 0; j < groups[gi].count; j++) tl.push_back(sorted[groups[gi].first + j]);
-      std::sort(tl.begin(), tl.end(), [&](uint32_t a, uint32_t b) { const int da = t->h_geom[a].nDB, db = t->h_geom[b].nDB; return da != db ? da > db : a < b; });
+      {
+        std::vector<std::pair<uint64_t, uint32_t>> keyed; keyed.reserve(tl.size());
+        for (uint32_t i : tl) keyed.emplace_back(~(uint64_t)(uint32_t)t->h_geom[i].nDB, i);
+        std::sort(keyed.begin(), keyed.end());
+        for (size_t i = 0; i < keyed.size(); i++) tl[i] = keyed[i].second;
+      }
       order.insert(order.end(), tl.begin(), tl.end());
       w.traceCount = (uint32_t)tl.size();
       maxWaveBytes = std::max(maxWaveBytes, off);
@@ -495,8 +500,16 @@ static int enqueue_dense(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     CK(cudaStreamSynchronize(s));
     const uint32_t n = t->nJobs;
     std::vector<uint32_t> idx; idx.reserve(n);
-    for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) idx.push_back(i);
-    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { uint64_t ca = t->h_arrowBytes[a], cb = t->h_arrowBytes[b]; return ca != cb ? ca > cb : a < b; });
+    uint64_t maxBytes = 0;
+    for (uint32_t i = 0; i < n; i++) if (t->h_geom[i].status == BGPU_JOB_OK) { idx.push_back(i); maxBytes = std::max(maxBytes, t->h_arrowBytes[i]); }
+    // largest matrices first, so the queue's tail is made of small jobs; batches of small gap fills (every matrix under
+    // 64 KiB: the ~80-cell AffineKBandAlign jobs of -alignContigs) keep their order, a sort would cost more than it saves
+    if (maxBytes > (64u << 10)) {
+      std::vector<std::pair<uint64_t, uint32_t>> keyed; keyed.reserve(idx.size());
+      for (uint32_t i : idx) keyed.emplace_back(~t->h_arrowBytes[i], i);      // ascending (~bytes, index) = bytes descending, index ascending
+      std::sort(keyed.begin(), keyed.end());
+      for (size_t i = 0; i < keyed.size(); i++) idx[i] = keyed[i].second;
+    }
     std::vector<uint64_t> arrowOff(n, 0);
     std::vector<uint32_t> order; order.reserve(idx.size());
     size_t maxWaveBytes = 0, i0 = 0;
