@@ -18,13 +18,17 @@ enum { RUN_D = 0, RUN_U = 1, RUN_L = 2 };   // diagonal / up (insertion, Gap::Ta
 // ordered longest-first, neighbouring threads have similar path lengths).  The fill kernels store the arrows
 // [d-block][row of 16 (linear) / 4 (affine) anti-diagonals][slot pair].  A walk only ever moves to lower
 // anti-diagonals and at most one diagonal sideways per step, so the words it is going to read are known well ahead:
-// each thread keeps a private window in shared memory -- chunk = 4 rows x 16 words (64 B of every row, centred on the
-// walk's current diagonal) -- and copies the chunk BEFORE the current one with cp.async while it walks the current
-// one, so a step costs a shared-memory load instead of an L2 round trip.  A walk that drifts out of its window
-// (more than ~12 diagonals sideways within two chunks) falls back to a global load for those steps.
+// each thread keeps a private window in shared memory -- chunk = 4 rows x 16 words (linear) or 8 rows x 8 words (affine) centred on the
+// walk's current diagonal; see TrGeom) -- and copies the chunk BEFORE the current one with cp.async while it walks the
+// current one, so a step costs a shared-memory load instead of an L2 round trip.  A walk that drifts out of its window
+// (more than ~12 (linear) / ~6 (affine) diagonals sideways within two chunks) falls back to a global load for those steps.
 // Linear words hold 16 two-bit arrows of one slot pair: a run of Diagonal arrows (every other field, the slot does
 // not change) is consumed with one CLZ instead of one step each.
-constexpr int TR_THREADS = 64, TR_CR = 4, TR_WP = 4;     // threads per CTA; rows per chunk; 16-byte pieces per row window
+constexpr int TR_THREADS = 64;                           // threads per CTA
+// rows per chunk / 16-byte pieces per row window (512 B of shared memory per walker, two chunks).  Measured on 100k pairs:
+// linear (CR, WP) = (4,4) 7.95 ms, (4,2) 8.7, (2,4) 10.8; affine (4,4) 20.5 ms, (4,2) 17.6, (8,2) 15.7 -- chunk changes
+// are the expensive part of a walk, and an affine chunk of 4 rows is only 16 anti-diagonals.
+template <bool AFFINE> struct TrGeom { static constexpr int CR = AFFINE ? 8 : 4, WP = AFFINE ? 2 : 4; };
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
@@ -33,7 +37,7 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 
 template <bool AFFINE>
 __global__ void __launch_bounds__(TR_THREADS) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder) {
-  constexpr int BITS = AFFINE ? 8 : 2, SPW = 32 / BITS, ROWS = 64 / SPW, CR = TR_CR, CPB = ROWS / CR, WP = TR_WP;
+  constexpr int BITS = AFFINE ? 8 : 2, SPW = 32 / BITS, ROWS = 64 / SPW, CR = TrGeom<AFFINE>::CR, CPB = ROWS / CR, WP = TrGeom<AFFINE>::WP;
   // piece (buffer bi, row r, piece pc) of thread tid: interleaved over the CTA's threads, 16 B each
   __shared__ __align__(16) uint32_t win[2 * CR * WP * TR_THREADS * 4];
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_guided_kernel(BatchDev B, co
     const int rowPieces = (db.k * lpj) >> 2;
     np = min(WP, rowPieces);
     const int sg = (t - q + C0 - db.wbase) >> 1;
-    p0 = max(0, min((sg - 6) >> 2, rowPieces - np));
+    p0 = max(0, min((sg - (2 * WP - 2)) >> 2, rowPieces - np));   // the walk's word sits in the middle of the window
   };
   auto stage = [&](int bi, int ci, const DBlock &db, int p0, int np) {
     const int rowWords = db.k * lpj;
