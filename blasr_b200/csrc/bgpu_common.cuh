@@ -18,7 +18,8 @@ constexpr int BIG = 1 << 30;           // "invalid neighbour" in the shifted dom
 constexpr int SCORE_LIMIT_AFF = 1 << 24;  // |score| bounds that keep (score << SH) clear of BIG
 constexpr int SCORE_LIMIT_LIN = 1 << 27;
 constexpr int DBLK = 64;               // anti-diagonals per d-block
-constexpr int KRING = 8;               // most diagonal groups per lane in the register-ring kernels
+constexpr int KRING = 6;               // most diagonal groups per lane in the register-ring kernels (6: the ring state still
+                                       // fits 5 linear / 4 affine resident CTAs per SM; 8 and 5 measured slower)
 constexpr int KWIDE = 128;             // groups per lane of the wide fallback kernel (32 lanes x 2 x 128 = 8192 diagonals)
 constexpr int ROW_W_BITS = 20;
 
