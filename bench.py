@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--algo", default="guided", choices=["guided", "affine"])
     ap.add_argument("--scorefn", default="distance", choices=["distance", "quality"],
                     help="distance = configs[1] (the headline); quality = configs[3]-style QualityValueScoreFunction over a simulated QV track")
+    ap.add_argument("--len-lo", type=int, default=LEN_LO); ap.add_argument("--len-hi", type=int, default=LEN_HI)
+    ap.add_argument("--bands", default=",".join(str(b) for b in BANDS), help="band sizes drawn per job (configs[1]: 16,32,64; blasr's default -bandSize: 16)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--e2e-threads", type=int, default=5, help="host threads (one context each) of the e2e measurement")
@@ -51,14 +53,21 @@ def parse():
     return ap.parse_args()
 
 
-def make_workload(n_jobs, seed, with_qual=False):
+def make_workload(n_jobs, seed, with_qual=False, len_lo=LEN_LO, len_hi=LEN_HI, bands=BANDS):
     from blasr_b200 import synth
-    return synth.simulate_pairs(n_jobs, LEN_LO, LEN_HI, err=0.15, seed=seed, bands=BANDS, with_qual=with_qual)
+    return synth.simulate_pairs(n_jobs, len_lo, len_hi, err=0.15, seed=seed, bands=bands, with_qual=with_qual)
+
+
+def workload_args(args):
+    return dict(len_lo=args.len_lo, len_hi=args.len_hi, bands=tuple(int(x) for x in args.bands.split(",")))
 
 
 def config_dict(args, n_jobs):
     wl = ("configs[1]: GuidedAlign microbench, read/window pairs 1-20 kb, band 16/32/64, "
           "DistanceMatrixScoreFunction(SMRTDistanceMatrix, ins=5, del=5)")
+    if (args.len_lo, args.len_hi, args.bands) != (LEN_LO, LEN_HI, ",".join(str(b) for b in BANDS)):
+        wl = (f"configs[1] generator at read/window pairs {args.len_lo}-{args.len_hi} b, band {args.bands} "
+              "(10 kb / band 16 = the refinement jobs of configs[0]), DistanceMatrixScoreFunction(SMRTDistanceMatrix, ins=5, del=5)")
     if args.scorefn == "quality":
         wl = ("configs[3]-style: the configs[1] pairs with a simulated QV track (clamp(N(12,4),1,93)), "
               "QualityValueScoreFunction(ins=5, del=5)")
@@ -99,7 +108,7 @@ def run_reference(args):
     algo = 1 if args.algo == "affine" else 0
     # a shard prefix is enough: the sample is bounded by CPU time, not by the 100k pairs
     quality = args.scorefn == "quality"
-    batch = make_workload(min(args.jobs, max(256, n_threads * 32)), args.seed, with_qual=quality)
+    batch = make_workload(min(args.jobs, max(256, n_threads * 32)), args.seed, with_qual=quality, **workload_args(args))
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_replay(batch, algo, n_threads, min(per_step, 2.0), quality=quality)
@@ -175,7 +184,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     # the generator forks worker processes: run it before CUDA / NCCL are initialised in this process
-    batch = make_workload(args.jobs, args.seed + 1000 * rank, with_qual=args.scorefn == "quality")
+    batch = make_workload(args.jobs, args.seed + 1000 * rank, with_qual=args.scorefn == "quality", **workload_args(args))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -299,7 +308,8 @@ def run_ours(args):
     traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))[args.algo]
-        if tr["pairs"] == args.jobs and tr["seed"] == args.seed and tr["scorefn"] == args.scorefn:
+        default_wl = (args.len_lo, args.len_hi, args.bands) == (LEN_LO, LEN_HI, ",".join(str(b) for b in BANDS))
+        if tr["pairs"] == args.jobs and tr["seed"] == args.seed and tr["scorefn"] == args.scorefn and default_wl:
             traffic, traffic_src = tr["dram_bytes_per_step"], tr["source"]
     except Exception:  # noqa: BLE001
         pass
