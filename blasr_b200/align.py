@@ -133,6 +133,14 @@ class JobBatch:
         return out
 
 
+CIGAR_CHARS = "MIDNSHP=X"
+
+
+def cigar_string(ops) -> str:
+    """BAM-packed ops -> the text CigarOpsToString prints (SAMPrinter.h:318-327)."""
+    return "".join(f"{int(o) >> 4}{CIGAR_CHARS[int(o) & 15]}" for o in ops)
+
+
 @dataclass
 class Alignment:
     """The fields of the reference's Alignment the DP fills (datastructures/alignment/Alignment.h:17-41)."""
@@ -250,6 +258,19 @@ class Aligner:
         return BatchResult(res, view(arena.blocks, arena.nBlocks, capi.BLOCK_DTYPE),
                            view(arena.gapCounts, arena.nGapLists, np.dtype("<u4")),
                            view(arena.gaps, arena.nGaps, capi.GAP_DTYPE), self.timing(ticket))
+
+    def cigar(self, ticket):
+        """SAM CIGAR core of every alignment of a collected guided ticket (bgpu_cigar; SAMPrinter.h:203-293): returns
+        (ops, off) -- BAM-packed uint32 ops (length << 4 | code) and nJobs+1 offsets, copied out of the library's arena."""
+        tk, n = ticket
+        ops, off = C.c_void_p(), C.c_void_p()
+        rc = self._lib.bgpu_cigar(self._ctx, tk, C.byref(ops), C.byref(off))
+        if rc != 0:
+            self._err(rc, "bgpu_cigar")
+        o = np.frombuffer((C.c_ubyte * (8 * (n + 1))).from_address(off.value), dtype="<u8").copy()
+        tot = int(o[-1])
+        c = np.frombuffer((C.c_ubyte * (4 * tot)).from_address(ops.value), dtype="<u4").copy() if tot else np.zeros(0, "<u4")
+        return c, o
 
     def rerun(self, ticket):
         rc = self._lib.bgpu_rerun(self._ctx, ticket[0])

@@ -29,6 +29,8 @@ void launch_dense_prep(const BatchDev &, const ScoreParams &, const DenseArgs &,
 void launch_dense_fill(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, uint32_t *, int,
                        cudaStream_t);
 void launch_dense_trace(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, cudaStream_t);
+void launch_cigar_count(const BatchDev &, uint32_t *, cudaStream_t);
+void launch_cigar_write(const BatchDev &, const uint64_t *, uint32_t *, cudaStream_t);
 double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz);
 extern double g_peakByMode[4];
 }  // namespace bgpu
@@ -151,6 +153,7 @@ struct bgpu_ticket_s {
   DenseArgs dargs{};
   std::vector<uint64_t> h_arrowBytes;   // dense: host-computed traceback bytes per job
   std::vector<uint64_t> h_cellsMetric;  // dense: SURVEY 8(d) cell count per job
+  uint32_t *h_cigar = nullptr; uint64_t *h_cigarOff = nullptr;   // bgpu_cigar results (pinned), once built
 };
 
 template <typename T>
@@ -447,8 +450,8 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   fill_score_params(t->sp, fn, p);
   BatchDev &B = t->B;
   B.nJobs = n;
-  uint64_t *d_qOff, *d_tOff, *d_gOff; uint8_t *d_q, *d_t, *d_qual = nullptr; bgpu_block *d_guide; int32_t *d_band = nullptr;
-  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16));
+  uint64_t *d_qOff, *d_tOff, *d_gOff; uint8_t *d_q, *d_t, *d_tc, *d_qual = nullptr; bgpu_block *d_guide; int32_t *d_band = nullptr;
+  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16)); RC(talloc_dev(ctx, t, &d_tc, totT + 16));
   RC(talloc_dev(ctx, t, &d_qOff, n + 1)); RC(talloc_dev(ctx, t, &d_tOff, n + 1)); RC(talloc_dev(ctx, t, &d_gOff, n + 1));
   RC(talloc_dev(ctx, t, &d_guide, totG + 1));
   if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
@@ -461,7 +464,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   RC(upload(ctx, t, d_guide, b->guide, sizeof(bgpu_block) * totG));
   if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
   if (b->band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
-  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tOff = d_tOff; B.qual = d_qual; B.guide = d_guide; B.guideOff = d_gOff; B.band = d_band;
+  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tc = d_tc; B.tOff = d_tOff; B.qual = d_qual; B.guide = d_guide; B.guideOff = d_gOff; B.band = d_band;
   RC(upload_ids_tracks(ctx, t, fn, b, totQ));
   // capacities from sequence lengths (upper bounds of the guide extents)
   uint64_t *h_off = nullptr;
@@ -578,8 +581,8 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
   t->dargs.hpInsOpen = p->hpInsOpen; t->dargs.hpInsExtend = p->hpInsExtend; t->dargs.insOpen = p->insOpen; t->dargs.insExtend = p->insExtend;
   BatchDev &B = t->B;
   B.nJobs = n;
-  uint64_t *d_qOff, *d_tOff; uint8_t *d_q, *d_t, *d_qual = nullptr; int32_t *d_band = nullptr;
-  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16));
+  uint64_t *d_qOff, *d_tOff; uint8_t *d_q, *d_t, *d_tc, *d_qual = nullptr; int32_t *d_band = nullptr;
+  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16)); RC(talloc_dev(ctx, t, &d_tc, totT + 16));
   RC(talloc_dev(ctx, t, &d_qOff, n + 1)); RC(talloc_dev(ctx, t, &d_tOff, n + 1));
   if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
   const bool banded = p->algo == BGPU_KBAND || p->algo == BGPU_AFFINE_KBAND;
@@ -589,7 +592,7 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
   RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
   if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
   if (d_band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
-  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tOff = d_tOff; B.qual = d_qual; B.guide = nullptr; B.guideOff = nullptr; B.band = d_band;
+  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tc = d_tc; B.tOff = d_tOff; B.qual = d_qual; B.guide = nullptr; B.guideOff = nullptr; B.band = d_band;
   RC(upload_ids_tracks(ctx, t, fn, b, totQ));
   uint64_t *h_off = nullptr;
   RC(talloc_pin(ctx, t, &h_off, 2 * (size_t)n + 2));
@@ -724,6 +727,37 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
     arena->gapCounts = t->h_gapCounts; arena->nGapLists = t->totals[1];
     arena->gaps = t->h_gaps; arena->nGaps = t->totals[2];
   }
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, const uint64_t **cigarOff) {
+  if (!ctx || !t || !ops || !cigarOff) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!t->collected) { ctx->err = "bgpu_cigar needs a collected ticket"; return BGPU_E_BUSY; }
+  if (t->dense) { ctx->err = "bgpu_cigar: GuidedAlign / AffineGuidedAlign tickets only"; return BGPU_E_INVALID; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  if (!t->h_cigarOff) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = t->nJobs;
+    uint32_t *d_cnt = nullptr, *h_cnt = nullptr; uint64_t *d_off = nullptr, *h_off = nullptr;
+    RC(talloc_dev(ctx, t, &d_cnt, (size_t)n + 1)); RC(talloc_pin(ctx, t, &h_cnt, (size_t)n + 1));
+    RC(talloc_dev(ctx, t, &d_off, (size_t)n + 1)); RC(talloc_pin(ctx, t, &h_off, (size_t)n + 1));
+    launch_cigar_count(t->B, d_cnt, s);                                   // pass 1: ops per job
+    CK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < n; i++) { h_off[i] = tot; tot += h_cnt[i]; }
+    h_off[n] = tot;
+    uint32_t *d_ops = nullptr, *h_ops = nullptr;
+    RC(talloc_dev(ctx, t, &d_ops, tot + 1)); RC(talloc_pin(ctx, t, &h_ops, tot + 1));
+    CK(cudaMemcpyAsync(d_off, h_off, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, s));
+    launch_cigar_write(t->B, d_off, d_ops, s);                            // pass 2: the ops themselves
+    CK(cudaMemcpyAsync(h_ops, d_ops, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    t->h_cigar = h_ops; t->h_cigarOff = h_off;
+  }
+  *ops = t->h_cigar; *cigarOff = t->h_cigarOff;
   return BGPU_OK;
 }
 

@@ -85,7 +85,9 @@ struct ScoreParams {      // kernel argument (by value)
 struct BatchDev {         // device pointers of one submitted batch
   uint32_t nJobs;
   uint8_t *q; const uint64_t *qOff;
-  uint8_t *t; const uint64_t *tOff;       // t is re-encoded in place to base codes by prep (kept raw for BGPU_FN_IDS)
+  const uint8_t *t; const uint64_t *tOff; // raw bytes as the caller passed them (emit / cigar compare these)
+  uint8_t *tc;                            // the target as the fill kernels read it, written by prep: base codes 0..4
+                                          // (raw bytes for BGPU_FN_IDS), indexed like t
   const uint8_t *qual;
   const uint8_t *insQV, *delQV, *subQV, *delTag, *subTag;   // IDSScoreFunction tracks (parallel to q), else NULL
   const bgpu_block *guide; const uint64_t *guideOff;

@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(128) dense_prep_kernel(BatchDev B, ScoreParams
     if ((long long)mx * ((long long)qLength + tLength + 2) >= (1 << 28) || mx >= (1 << 15)) status = status ? status : BGPU_JOB_RANGE;
   }
   int bad = 0;
-  uint8_t *tb = B.t + to; uint8_t *qb = B.q + qo;
+  const uint8_t *tb = B.t + to; uint8_t *tcb = B.tc + to; uint8_t *qb = B.q + qo;
   const bool keepRaw = P.kind == BGPU_FN_IDS;            // IDSScoreFunction compares raw bytes; base_code() is idempotent on codes
-  for (uint32_t i = lane; i < tLen; i += 32) { const uint8_t c = lut[tb[i]]; if (c > 4) bad = 1; if (!keepRaw) tb[i] = c; }
+  for (uint32_t i = lane; i < tLen; i += 32) { const uint8_t r = tb[i], c = lut[r]; if (c > 4) bad = 1; tcb[i] = keepRaw ? r : c; }
   for (uint32_t i = lane; i < qLen; i += 32) { const uint8_t c = lut[qb[i]]; if (c > 4) bad = 1; }
   bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
   if (bad && status == BGPU_JOB_OK) status = BGPU_JOB_BAD_INPUT;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) dense_fill_kernel(BatchDev B, ScoreParams
     JobGeom &G = B.geom[job];
     if (G.status != BGPU_JOB_OK) continue;
     const int R = G.Qn, T = G.Tn, k = G.band;          // rows 0..R, columns 0..T (already k-bounded for KBandAlign)
-    const uint8_t *qb = B.q + B.qOff[job], *tb = B.t + B.tOff[job];
+    const uint8_t *qb = B.q + B.qOff[job], *tb = B.tc + B.tOff[job];
     const uint8_t *qual = B.qual ? B.qual + B.qOff[job] : nullptr;
     const size_t qo = (size_t)B.qOff[job];
     uint8_t *arrows = B.arrows + A.arrowOff[job];
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(128) affine_kband_fill_kernel(BatchDev B, Scor
     JobGeom &G = B.geom[job];
     if (G.status != BGPU_JOB_OK) continue;
     const int R = G.Qn, T = G.Tn, k = G.band, nCols = 2 * k + 1;
-    const uint8_t *qb = B.q + B.qOff[job], *tb = B.t + B.tOff[job];
+    const uint8_t *qb = B.q + B.qOff[job], *tb = B.tc + B.tOff[job];
     uint8_t *arrows = B.arrows + A.arrowOff[job];
     const int W = T + 2;
     int *pS = B.rowBuf + G.rowBufOff, *pH = pS + W, *pI = pH + W, *cS = pI + W, *cH = cS + W, *cI = cH + W;

@@ -355,7 +355,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
     if (have) {
       Qn = G->Qn; Tn = G->Tn; C0 = G->C0; nDB = G->nDB; hi0 = G->hi0;
       rows = B.rows + G->rowOff; dblk = B.dblk + G->dblkOff;
-      tJobLo = B.t + B.tOff[job]; tJobHi = B.t + B.tOff[job + 1];
+      tJobLo = B.tc + B.tOff[job]; tJobHi = B.tc + B.tOff[job + 1];
       tcodes = tJobLo + G->tStart - 1;                       // tcodes[t'] for t' in [1,Tn]
       if (FN == 2) trackOff = (size_t)B.qOff[job] + (size_t)G->qStart - 1;
       arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);

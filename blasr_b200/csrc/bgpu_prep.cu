@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
     if ((long long)mx * (Qn + Tn + 2) >= (P.affine ? SCORE_LIMIT_AFF : SCORE_LIMIT_LIN) || mx >= (1 << 15)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }
   }
 
-  // ---- encode + validate the target window in place (codes 0..4), and check the query bases
-  uint8_t *tb = B.t + to;
+  // ---- encode + validate the target window (codes 0..4 into B.tc), and check the query bases
+  const uint8_t *tb = B.t + to;
+  uint8_t *tcb = B.tc + to;
   const uint8_t *qb = B.q + qo;
   const bool keepRaw = P.kind == BGPU_FN_IDS;           // IDSScoreFunction compares raw bytes (IDSScoreFunction.h:129-132)
-  for (int i = tStart + lane; i < tEnd; i += 32) { uint8_t c = lut[tb[i]]; if (c > 4) bad = 1; if (!keepRaw) tb[i] = c; }
+  for (int i = tStart + lane; i < tEnd; i += 32) { const uint8_t r = tb[i], c = lut[r]; if (c > 4) bad = 1; tcb[i] = keepRaw ? r : c; }
   if (warp_or(bad)) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
 
   // ---- live-diagonal range per d-block.  The warp owns these arrays: contributions are reduced across the

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
   const uint32_t *runs = B.runs + G.runOff;
   const long long qLenJ = (long long)(B.qOff[job + 1] - B.qOff[job]), tLenJ = (long long)(B.tOff[job + 1] - B.tOff[job]);
   const uint8_t *qb = B.q + B.qOff[job] + G.qStart;  // qb[x]: query base at path offset x
-  const uint8_t *tb = B.t + B.tOff[job] + G.tStart;  // codes inside [tStart,tEnd), raw bytes for BGPU_FN_IDS: the table maps both
+  const uint8_t *tb = B.t + B.tOff[job] + G.tStart;  // raw bytes, mapped through the same table as the query's
   int oob = 0;
   const uint32_t qPrefix = G.qPos - (uint32_t)G.qStart, tPrefix = G.tPos - (uint32_t)G.tStart;
   bgpu_block *blocks = O.blocks + R.blockOff;

@@ -169,6 +169,15 @@ int  bgpu_release(bgpu_ctx *ctx, bgpu_ticket t);
 int  bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t);
 int  bgpu_timing_of(bgpu_ctx *ctx, bgpu_ticket t, bgpu_timing *out);
 
+/* ---- SAM CIGAR core of every alignment of a collected GuidedAlign / AffineGuidedAlign ticket, built on the device.
+ * Replaces SAMOutput::CreateNoClippingCigarOps (common/algorithms/alignment/printers/SAMPrinter.h:203-293, with AddGaps
+ * :120-137 and AddUngappedOperations :138-166): per block, maximal runs of unequal / equal RAW bytes as 'X' / '=', every
+ * stored Gap as 'D' (Gap::Query) or 'I' (Gap::Target), nothing merged; clipping ops and the strand reversal stay with
+ * the caller (CreateCIGARString :330-400 wraps this core).  ops are BAM-packed (length << 4 | code; '=' 7, 'X' 8, 'I' 1,
+ * 'D' 2); job i owns ops[cigarOff[i] .. cigarOff[i+1]) (empty for jobs without blocks).  Both arrays are pinned host
+ * memory owned by the library until bgpu_release(). */
+int  bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, const uint64_t **cigarOff);
+
 /* ---- synchronous one-shot: submit + collect; arena valid until the next call on ctx ---- */
 int  bgpu_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b,
                 bgpu_result *results, bgpu_arena *arena);

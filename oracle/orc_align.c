@@ -755,3 +755,46 @@ int64_t orc_replay(const orc_scorefn *fn, const orc_job *jobs, uint32_t n, int n
   free(th); free(w);
   return cells;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * SAM CIGAR core, restated from printers/SAMPrinter.h:203-293 for alignments whose gap lists are filled (the
+ * `nGaps > 0` branch): AddGaps(gaps[0]) (:120-137: Gap::Query -> 'D' and tPos += length, Gap::Target -> 'I' and
+ * qPos += length), then per block AddUngappedOperations (:138-166: alternating maximal runs of unequal 'X' and equal '='
+ * RAW bytes of the two aligned sequences, qPos / tPos being running counters, not the block's own coordinates) and
+ * AddGaps(gaps[b+1]).  q / t are the sequences the candidate's qAlignedSeq / tAlignedSeq reference. */
+static int cig_push(uint32_t *ops, uint32_t cap, uint32_t *n, uint32_t len, uint32_t code) {
+  if (*n >= cap) return -1;
+  ops[(*n)++] = (len << 4) | code;
+  return 0;
+}
+int orc_cigar_from(const uint8_t *q, const uint8_t *t, uint32_t qPos, uint32_t tPos,
+                   const uint32_t *blocks, uint32_t nBlocks, const uint32_t *gapCounts, uint32_t nGapLists,
+                   const int32_t *gaps, uint32_t *ops, uint32_t capOps) {
+  uint32_t n = 0, g = 0, b, i, j;
+  if (nBlocks == 0) return 0;
+  qPos += blocks[0]; tPos += blocks[1];                     /* CreateCIGARString :362-363 */
+  for (b = 0; b <= nBlocks; b++) {
+    if (b > 0) {                                            /* AddUngappedOperations(b-1) */
+      const uint32_t len = blocks[3 * (b - 1) + 2];
+      i = 0;
+      while (i < len) {
+        uint32_t s0 = i;
+        while (i < len && q[qPos + i] != t[tPos + i]) i++;
+        if (i > s0 && cig_push(ops, capOps, &n, i - s0, 8)) return -1;
+        s0 = i;
+        while (i < len && q[qPos + i] == t[tPos + i]) i++;
+        if (i > s0 && cig_push(ops, capOps, &n, i - s0, 7)) return -1;
+      }
+      qPos += len; tPos += len;
+    }
+    if (b < nGapLists) {                                    /* AddGaps(b) */
+      for (j = 0; j < gapCounts[b]; j++, g++) {
+        const int32_t seq = gaps[2 * g], len = gaps[2 * g + 1];
+        if (seq == 0) { if (cig_push(ops, capOps, &n, (uint32_t)len, 2)) return -1; tPos += (uint32_t)len; }
+        else if (seq == 1) { if (cig_push(ops, capOps, &n, (uint32_t)len, 1)) return -1; qPos += (uint32_t)len; }
+      }
+    }
+  }
+  return (int)n;
+}

@@ -89,6 +89,16 @@ int ref_align(const orc_scorefn *fn, const orc_job *job, orc_result *res,
               uint32_t *blocks, uint32_t capBlocks, uint32_t *gapCounts, uint32_t capGapLists,
               int32_t *gaps, uint32_t capGaps);
 
+/* SAM CIGAR core (printers/SAMPrinter.h:203-293, CreateNoClippingCigarOps with AddGaps :120-137 and
+ * AddUngappedOperations :138-166), BAM-packed: length << 4 | code, '=' 7, 'X' 8, 'I' 1, 'D' 2.
+ *   ref_cigar       runs the job's aligner and then the reference's own printer code on the result;
+ *   orc_cigar_from  the C restatement, from a stored alignment (blocks / gap lists as ref_align / orc_align return them).
+ * Both return the number of ops (0 for an alignment without blocks), -1 when capOps is too small. */
+int ref_cigar(const orc_scorefn *fn, const orc_job *job, uint32_t *ops, uint32_t capOps);
+int orc_cigar_from(const uint8_t *q, const uint8_t *t, uint32_t qPos, uint32_t tPos,
+                   const uint32_t *blocks, uint32_t nBlocks, const uint32_t *gapCounts, uint32_t nGapLists,
+                   const int32_t *gaps, uint32_t *ops, uint32_t capOps);
+
 /* Guide rows exactly as AlignmentToGuide builds them (GuidedAlign.h:104-259):
  * rows[i] = {q, t, tPre, tPost}; returns number of rows (0 for an empty guide),
  * -1 if capRows is too small. nCells = sum(tPre+tPost+1) (GuidedAlign.h:83-92). */

@@ -29,6 +29,7 @@
 #include "algorithms/alignment/IDSScoreFunction.h"
 #include "datastructures/alignment/AlignmentCandidate.h"
 #include "FASTQSequence.h"
+#include "algorithms/alignment/printers/SAMPrinter.h"
 
 #include <thread>
 #include <atomic>
@@ -169,6 +170,25 @@ extern "C" int ref_align(const orc_scorefn *fn, const orc_job *job, orc_result *
     }
   }
   return 0;
+}
+
+extern "C" int ref_cigar(const orc_scorefn *fn, const orc_job *job, uint32_t *ops, uint32_t capOps) {
+  Scratch s; T_AlignmentCandidate cand; orc_result res;
+  RunOne(fn, job, &res, s, cand);
+  if (res.status != ORC_OK || cand.blocks.size() == 0) return 0;
+  /* the printer reads the aligned sequences through the candidate (SAMPrinter.h:146-147) */
+  DNASequence t; t.seq = (Nucleotide *)job->t; t.length = job->tLen;
+  FASTQSequence q; q.seq = (Nucleotide *)job->q; q.length = job->qLen;
+  cand.qAlignedSeq.ReferenceSubstring(q, 0, q.length); cand.tAlignedSeq.ReferenceSubstring(t, 0, t.length);
+  vector<int> opSize; vector<char> opChar;
+  SAMOutput::CreateNoClippingCigarOps(cand, cand.qPos + cand.blocks[0].qPos, cand.tPos + cand.blocks[0].tPos, opSize, opChar);
+  if (opSize.size() > capOps) return -1;
+  for (size_t i = 0; i < opSize.size(); i++) {
+    const char c = opChar[i];
+    const uint32_t code = c == '=' ? 7 : c == 'X' ? 8 : c == 'I' ? 1 : c == 'D' ? 2 : 15;
+    ops[i] = ((uint32_t)opSize[i] << 4) | code;
+  }
+  return (int)opSize.size();
 }
 
 extern "C" int ref_guide_rows(const uint32_t *guide, uint32_t nGuide, int band, int32_t *rows, uint32_t capRows,

@@ -66,8 +66,12 @@ def _load(which: str):
     rp.argtypes = [C.POINTER(OrcScoreFn), C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_int64)]
     rp.restype = C.c_int64
     if which == "ref":
+        L.ref_cigar.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p, C.c_uint32]
         L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                     C.c_int, C.c_float, C.c_void_p, C.c_uint32]
+    else:
+        L.orc_cigar_from.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
     _libs[which] = L
     return L
 
@@ -126,6 +130,33 @@ def align(which: str, fn: OrcScoreFn, job: OrcJob):
         gl.append([(int(a), int(b)) for a, b in gaps[p:p + int(cnt[i])]]); p += int(cnt[i])
     out["gaps"] = gl
     return out
+
+
+def ref_cigar(fn: OrcScoreFn, job: OrcJob) -> np.ndarray:
+    """The job's aligner, then the reference's own CreateNoClippingCigarOps on its result: BAM-packed ops."""
+    L = _load("ref")
+    cap = int(job.qLen) + int(job.tLen) + 8
+    ops = np.zeros(cap, np.uint32)
+    n = L.ref_cigar(C.byref(fn), C.byref(job), ops.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("ref_cigar overflow")
+    return ops[:n].copy()
+
+
+def orc_cigar_from(q: np.ndarray, t: np.ndarray, aln: dict) -> np.ndarray:
+    """C restatement of the printer, from an alignment dict as align() returns it."""
+    L = _load("orc")
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    blocks = np.ascontiguousarray(aln["blocks"], np.uint32).reshape(-1, 3)
+    cnt = np.asarray([len(g) for g in aln["gaps"]], np.uint32)
+    flat = np.asarray([x for g in aln["gaps"] for x in g], np.int32).reshape(-1, 2)
+    cap = len(q) + len(t) + 8
+    ops = np.zeros(cap, np.uint32)
+    n = L.orc_cigar_from(q.ctypes.data, t.ctypes.data, int(aln["qPos"]), int(aln["tPos"]), blocks.ctypes.data, len(blocks),
+                         cnt.ctypes.data, len(cnt), flat.ctypes.data, ops.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("orc_cigar_from overflow")
+    return ops[:n].copy()
 
 
 def guide_rows(which: str, guide: np.ndarray, band: int):

@@ -1,0 +1,71 @@
+"""SAM CIGAR core: the reference's own printer code (oracle/_ref: CreateNoClippingCigarOps run on the result of
+the reference aligner) against the C restatement (CPU) and against bgpu_cigar (GPU), op for op."""
+import numpy as np
+import pytest
+
+from blasr_b200 import DistanceMatrixScoreFunction, SMRTDistanceMatrix, align as A
+from tests import cases, oracle as O
+
+needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+
+
+def _mixed_case_batch(seed, n, lo, hi):
+    """Pairs with lower-case stretches and N's: the printer compares raw bytes, the aligner base codes."""
+    b = cases.guided_batch(seed=seed, n=n, lo=lo, hi=hi, n_rate=0.01, lower=True)
+    return b
+
+
+@needs_ref
+@pytest.mark.parametrize("algo", [0, 1])
+def test_restatement_matches_reference_printer(algo):
+    b = _mixed_case_batch(90 + algo, 12, 60, 900)
+    fn = O.score_fn(SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0)
+    n_ops = 0
+    for i in range(b.n):
+        q, t, g, _ = cases.job_arrays(b, i)
+        j, keep = O.make_job(algo, 1, 12, q, t, g, None, 0, 0, 0, 0)
+        want = O.ref_cigar(fn, j)
+        aln = O.align("ref", fn, j)
+        got = O.orc_cigar_from(q, t, aln)
+        assert np.array_equal(got, want), (i, A.cigar_string(got)[:80], A.cigar_string(want)[:80])
+        # the ops account for every aligned base of both sequences
+        qlen = sum(int(o) >> 4 for o in want if int(o) & 15 in (1, 7, 8)); tlen = sum(int(o) >> 4 for o in want if int(o) & 15 in (2, 7, 8))
+        if len(aln["blocks"]):
+            last = aln["blocks"][-1]
+            assert qlen == int(last[0] + last[2] - aln["blocks"][0][0]) and tlen == int(last[1] + last[2] - aln["blocks"][0][1])
+        n_ops += len(want)
+    assert n_ops > 100
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", [0, 1])
+def test_gpu_cigar_matches_reference_printer(aligner, algo):
+    b = _mixed_case_batch(190 + algo, 40, 50, 5000)
+    b.band = np.random.default_rng(3).choice([8, 16, 32, 64], size=b.n).astype(np.int32)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50 if algo else 0, affineExtend=0)
+    tk = aligner.submit(b, fn, algo, band=16)
+    res = aligner.collect(tk)
+    ops, off = aligner.cigar(tk)
+    ofn = O.score_fn(SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0)
+    n_ops = 0
+    for i in range(b.n):
+        q, t, g, _ = cases.job_arrays(b, i)
+        j, keep = O.make_job(algo, 1, int(b.band[i]), q, t, g, None, 0, 0, 0, 0)
+        want = O.ref_cigar(ofn, j)
+        got = ops[int(off[i]):int(off[i + 1])]
+        assert np.array_equal(got, want), (i, A.cigar_string(got)[:80], A.cigar_string(want)[:80])
+        n_ops += len(want)
+    assert n_ops > 1000
+    aligner.release(tk)
+
+
+@pytest.mark.gpu
+def test_gpu_cigar_refuses_dense_tickets(aligner):
+    from blasr_b200 import BgpuError, JobBatch, capi
+    b = JobBatch.from_lists([b"ACGTACGT"], [b"ACGAACGT"])
+    tk = aligner.submit(b, DistanceMatrixScoreFunction(), capi.SW, alignType=capi.GLOBAL)
+    aligner.collect(tk)
+    with pytest.raises(BgpuError):
+        aligner.cigar(tk)
+    aligner.release(tk)
