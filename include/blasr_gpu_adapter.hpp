@@ -79,8 +79,25 @@ class RefineBatch {
     b.nJobs = size(); b.qBases = q_.data(); b.qOff = qOff_.data(); b.tBases = t_.data(); b.tOff = tOff_.data();
     b.qual = qual_.empty() ? nullptr : qual_.data(); b.guide = guide_.data(); b.guideOff = gOff_.data(); b.band = nullptr;
     results_.resize(b.nJobs);
-    int rc = bgpu_align(ctx.get(), &s, &p, &b, results_.data(), &arena_);
+    Release();
+    int rc = bgpu_submit(ctx.get(), &s, &p, &b, &ticket_);
+    if (rc == BGPU_OK) { owner_ = ctx.get(); rc = bgpu_collect(owner_, ticket_, results_.data(), &arena_); }
     if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
+    cigarOps_ = nullptr; cigarOff_ = nullptr;
+  }
+  ~RefineBatch() { Release(); }
+
+  // The SAM CIGAR core of job i as CreateNoClippingCigarOps + CigarOpsToString print it (SAMPrinter.h:203-293,318-327):
+  // '=' / 'X' runs per block, 'I' / 'D' per stored gap.  Clipping ops and the tStrand reversal stay with the caller
+  // (CreateCIGARString :366-397).  Built on the device for the whole batch at the first call.
+  std::string Cigar(uint32_t i) {
+    if (!cigarOps_) {
+      int rc = bgpu_cigar(owner_, ticket_, &cigarOps_, &cigarOff_);
+      if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(owner_));
+    }
+    std::string out;
+    for (uint64_t k = cigarOff_[i]; k < cigarOff_[i + 1]; k++) { out += std::to_string(cigarOps_[k] >> 4); out += "MIDNSHP=X"[cigarOps_[k] & 15]; }
+    return out;
   }
 
   const bgpu_result &Result(uint32_t i) const { return results_[i]; }
@@ -115,7 +132,8 @@ class RefineBatch {
     out.pctSimilarity = r.pctSimilarity; out.score = r.statsScore;   // ComputeAlignmentStats overwrites score, AlignmentUtils.h:578
   }
 
-  void Clear() { q_.clear(); t_.clear(); qual_.clear(); guide_.clear(); qOff_.assign(1, 0); tOff_.assign(1, 0); gOff_.assign(1, 0); results_.clear(); }
+  void Release() { if (ticket_) { bgpu_release(owner_, ticket_); ticket_ = nullptr; } }
+  void Clear() { Release(); q_.clear(); t_.clear(); qual_.clear(); guide_.clear(); qOff_.assign(1, 0); tOff_.assign(1, 0); gOff_.assign(1, 0); results_.clear(); }
 
  private:
   std::vector<uint8_t> q_, t_, qual_;
@@ -123,6 +141,8 @@ class RefineBatch {
   std::vector<uint64_t> qOff_{0}, tOff_{0}, gOff_{0};
   std::vector<bgpu_result> results_;
   bgpu_arena arena_{};
+  bgpu_ctx *owner_ = nullptr; bgpu_ticket ticket_ = nullptr;       // results and the arena live until Release()
+  const uint32_t *cigarOps_ = nullptr; const uint64_t *cigarOff_ = nullptr;
 };
 
 }  // namespace blasr_gpu

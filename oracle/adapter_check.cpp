@@ -134,6 +134,8 @@ int main(int argc, char **argv) {
       bad += Diff(refRefined, gpuRefined, i, affine ? "AffineGuidedAlign" : "GuidedAlign");
       const std::string pr = PrintedForm(refRefined, qs[i], ts[i]), pg = PrintedForm(gpuRefined, qs[i], ts[i]);
       if (pr != pg) { printf("job %d: printed CIGAR / m5 strings differ\n", i); bad++; }
+      /* the CIGAR built on the device (bgpu_cigar) against the reference printer's text */
+      if (batch.Cigar(j) != pr.substr(0, pr.find('|'))) { printf("job %d: device CIGAR differs from the reference printer's\n", i); bad++; }
       printedBytes += pr.size();
     }
     printf("adapter_check: %zu bytes of SAM CIGAR + m5 alignment strings printed by the reference's printers: %s\n", printedBytes,
