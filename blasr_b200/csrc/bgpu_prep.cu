@@ -91,7 +91,23 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   uint8_t *tcb = B.tc + to;
   const uint8_t *qb = B.q + qo;
   const bool keepRaw = P.kind == BGPU_FN_IDS;           // IDSScoreFunction compares raw bytes (IDSScoreFunction.h:129-132)
-  for (int i = tStart + lane; i < tEnd; i += 32) { const uint8_t r = tb[i], c = lut[r]; if (c > 4) bad = 1; tcb[i] = keepRaw ? r : c; }
+  {
+    // t and tc share their offsets, so one word grid is aligned for both: bytes up to the first 4-byte boundary, whole
+    // words (four table look-ups per load / store), then the tail bytes
+    const int head = min((int)((4u - (unsigned)((uintptr_t)(tb + tStart) & 3u)) & 3u), Tn);
+    const int nW = (Tn - head) >> 2, tail0 = tStart + head + 4 * nW;
+    auto one = [&](int i) { const uint8_t r = tb[i], c = lut[r]; if (c > 4) bad = 1; tcb[i] = keepRaw ? r : c; };
+    if (lane < head) one(tStart + lane);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(tb + tStart + head);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(tcb + tStart + head);
+    for (int w = lane; w < nW; w += 32) {
+      const uint32_t v = src[w];
+      const uint32_t c0 = lut[v & 0xff], c1 = lut[(v >> 8) & 0xff], c2 = lut[(v >> 16) & 0xff], c3 = lut[v >> 24];
+      if (max(max(c0, c1), max(c2, c3)) > 4) bad = 1;
+      dst[w] = keepRaw ? v : (c0 | (c1 << 8) | (c2 << 16) | (c3 << 24));
+    }
+    if (tail0 + lane < tEnd) one(tail0 + lane);
+  }
   if (warp_or(bad)) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
 
   // ---- live-diagonal range per d-block.  The warp owns these arrays: contributions are reduced across the
