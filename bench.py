@@ -156,6 +156,25 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------- GPU side
+def bind_to_gpu_cpus(index):
+    """Binds this process (and the host threads it starts) to the CPUs NVML reports as local to GPU `index`, so the
+    pinned input / result buffers are allocated on that GPU's NUMA node and the copies do not cross sockets.
+    Returns the number of CPUs bound to, or None when NVML gives no answer."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def pinned_copy(a):
     import torch
     a = np.ascontiguousarray(a)
@@ -186,6 +205,8 @@ def run_ours(args):
     # the generator forks worker processes: run it before CUDA / NCCL are initialised in this process
     batch = make_workload(args.jobs, args.seed + 1000 * rank, with_qual=args.scorefn == "quality", **workload_args(args))
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_cpus(local)     # before any pinned allocation: first touch then lands on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     algo = capi.AFFINE_GUIDED if args.algo == "affine" else capi.GUIDED
@@ -340,11 +361,12 @@ def run_ours(args):
                          "lane_steps_per_cell": float(tm.fillCells) / max(1, cells),
                          "peak_by_mix_tops": {k: v / 1e12 for k, v in al.int_peak_modes.items()},
                          "peak_source": "bgpu_measure_int_peak: best of add / min / mad / add+mad chains on this device"},
-        "clocks": sampler.summary(), "jobs_ok": int(jobs_all),
+        "clocks": sampler.summary(), "jobs_ok": int(jobs_all), "host_cpus_bound_per_rank": numa,
     }
     if rank == 0 and world == 1:
         try:
-            cb = cpu_replay(batch, a, os.cpu_count() or 1, args.cpu_seconds, quality=args.scorefn == "quality")
+            os.sched_setaffinity(0, all_cpus)            # the CPU baseline gets every host core back
+            cb = cpu_replay(batch, a, len(all_cpus), args.cpu_seconds, quality=args.scorefn == "quality")
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}

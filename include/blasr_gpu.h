@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BGPU_VERSION 101 /* 0.1.1 */
+#define BGPU_VERSION 102 /* 0.1.2: + bgpu_cigar */
 
 /* ---- return codes (API level) ---- */
 enum {
