@@ -147,3 +147,35 @@ def test_long_reads_properties(aligner):
         # leading/trailing gaps (first guide block at (0,0), last at the ends)
         if al.qPos == 0 and al.tPos == 0 and blk[-1, 0] + blk[-1, 2] == b.qOff[i + 1] - b.qOff[i]:
             assert al.statsScore == al.score
+
+
+def test_concurrent_contexts_match_single_context(aligner):
+    """Host threads with their own contexts (blasr's MapReads pthreads) behind the per-device phase gates: every sub-batch
+    comes back exactly as the single-context run returns it."""
+    import threading
+    from blasr_b200 import Aligner
+    b = cases.guided_batch(seed=77, n=96, lo=200, hi=4000)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    want = aligner.AffineGuidedAlign(b, fn, 16)
+    parts = [list(range(i, b.n, 8)) for i in range(8)]
+    got, errs = {}, []
+
+    def work(a, mine):
+        try:
+            for p in mine:
+                got[p] = a.AffineGuidedAlign(b.slice(parts[p]), fn, 16)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    workers = [Aligner(0) for _ in range(4)]
+    th = [threading.Thread(target=work, args=(a, [w, w + 4])) for w, a in enumerate(workers)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for a in workers:
+        a.close()
+    assert not errs, errs
+    for p, idx in enumerate(parts):
+        for k, i in enumerate(idx):
+            bad = cases.compare(cases.gpu_to_dict(got[p], k), cases.gpu_to_dict(want, i), cases.GPU_FIELDS)
+            assert not bad, (p, i, bad)
