@@ -59,6 +59,19 @@ static Gate &gate(int device, int phase) {
 }
 static void CUDART_CB gate_release_cb(void *g) { static_cast<Gate *>(g)->release(); }
 
+// BGPU_TRACE=1: every collected ticket prints the device-side times of its stages relative to one process-wide reference
+// event (diagnostic for the pipelining of concurrent contexts; stderr, one line per ticket).
+static cudaEvent_t g_refEvent = nullptr;
+static std::once_flag g_refOnce;
+static bool g_trace = false;
+static void trace_init(cudaStream_t s) {
+  std::call_once(g_refOnce, [&] {
+    const char *e = getenv("BGPU_TRACE");
+    g_trace = e && *e && *e != '0';
+    if (g_trace) { cudaEventCreate(&g_refEvent); cudaEventRecord(g_refEvent, s); cudaEventSynchronize(g_refEvent); }
+  });
+}
+
 struct bgpu_ctx {
   int device = 0, nSM = 0;
   cudaStream_t stream = nullptr;
@@ -215,6 +228,7 @@ extern "C" int bgpu_create(bgpu_ctx **out, int device) {
   ctx->arrowPoolCap = freeB / 5 * 3;   // one wave holds ~100 GB of affine arrows (100k pairs of 1-20 kb): a B200 has the HBM for it
   const char *env = getenv("BGPU_ARROW_POOL_MB");
   if (env) ctx->arrowPoolCap = (size_t)atoll(env) << 20;
+  trace_init(ctx->stream);
   *out = ctx;
   return BGPU_OK;
 }
@@ -708,16 +722,25 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
   const auto h0 = std::chrono::steady_clock::now();
   if (!t->collected) {
     RC(ensure_arena(ctx, t));
+    RC(enqueue_emit(ctx, t));                          // a kernel: outside the D2H gate, which only covers the copies
     struct Hold { Gate &g; Hold(Gate &x) : g(x) { g.acquire(); } ~Hold() { g.release(); } } hold(gate(ctx->device, GATE_D2H));
-    RC(enqueue_emit(ctx, t));
     CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(t->ev[5], s));
     CK(cudaStreamSynchronize(s));
     t->timing.d2hBytes = sizeof(bgpu_result) * (uint64_t)t->nJobs + sizeof(bgpu_block) * t->totals[0] +
                          sizeof(uint32_t) * t->totals[1] + sizeof(bgpu_gap) * t->totals[2];
     gather_timing(t);
+    if (g_trace) {
+      auto at = [&](cudaEvent_t e) { float ms = -1; if (e) cudaEventElapsedTime(&ms, g_refEvent, e); return ms; };
+      fprintf(stderr, "BGPU_TRACE ctx %p jobs %u start %.2f prepEnd %.2f fill0 %.2f fillEnd %.2f traceEnd %.2f scanEnd %.2f emitEnd %.2f d2hEnd %.2f\n",
+              (void *)ctx, t->nJobs, at(t->ev[0]), at(t->ev[1]), t->waveEv.empty() ? -1.f : at(t->waveEv[0]),
+              t->waveEv.empty() ? -1.f : at(t->waveEv[t->waveEv.size() - 2]), t->waveEv.empty() ? -1.f : at(t->waveEv.back()),
+              at(t->ev[3]), at(t->ev[4]), at(t->ev[5]));
+      cudaGetLastError();
+    }
     t->collected = true;
   }
   if (results && t->nJobs) memcpy(results, t->h_results, sizeof(bgpu_result) * t->nJobs);
