@@ -77,6 +77,7 @@ struct bgpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux[N_CLS] = {};                  // one per job class: the class kernels of a wave run concurrently
   cudaEvent_t evFork = nullptr, evJoin[N_CLS] = {};
+  cudaEvent_t evSync = nullptr;                  // blocking-sync event: waiting host threads sleep instead of spinning
   std::string err;
   std::mutex mu;
   size_t arrowPoolCap = 0;                       // max bytes of traceback pool per wave
@@ -99,6 +100,17 @@ struct bgpu_ctx {
 
 // Allocation size classes: eight per octave (<= 12.5 % slack), so the sub-batches of a stream of similar tickets keep
 // hitting the cached blocks instead of growing the cache with cudaMalloc / cudaHostAlloc calls in steady state.
+// Waits for everything queued on the context's stream.  By default the wait spins (lowest latency: 5 host threads x 10
+// sub-batches of 100k pairs pass in 131-140 ms against 140-150 ms with sleeping waits).  BGPU_BLOCKING_SYNC=1 makes waiting
+// threads sleep on an event created with cudaEventBlockingSync instead: for hosts that run more waiting threads than
+// they have cores (blasr's one pthread per core, several GPUs per box).
+static bool blocking_sync() { static const bool on = [] { const char *e = getenv("BGPU_BLOCKING_SYNC"); return e && *e && *e != '0'; }(); return on; }
+static cudaError_t wait_stream(bgpu_ctx *ctx) {
+  if (!blocking_sync()) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->evSync, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->evSync);
+}
+
 static size_t round_up(size_t n) {
   const size_t g = 1u << 16;
   if (n <= g) return g;
@@ -222,7 +234,8 @@ extern "C" int bgpu_create(bgpu_ctx **out, int device) {
     if (cudaStreamCreateWithFlags(&ctx->aux[c], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evJoin[c], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
   }
-  if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
+  if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->evSync, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
   size_t freeB = 0, totalB = 0;
   cudaMemGetInfo(&freeB, &totalB);
   ctx->arrowPoolCap = freeB / 5 * 3;   // one wave holds ~100 GB of affine arrows (100k pairs of 1-20 kb): a B200 has the HBM for it
@@ -241,7 +254,7 @@ extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
   for (auto &kv : ctx->devFree) cudaFree(kv.second);
   for (auto &kv : ctx->pinFree) cudaFreeHost(kv.second);
   for (int c = 0; c < N_CLS; c++) { cudaStreamDestroy(ctx->aux[c]); cudaEventDestroy(ctx->evJoin[c]); }
-  cudaEventDestroy(ctx->evFork);
+  cudaEventDestroy(ctx->evFork); cudaEventDestroy(ctx->evSync);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -292,7 +305,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   if (firstRun) {
     // geometry back to the host: class lists, warp groups and wave cutting need it
     CK(cudaMemcpyAsync(t->h_geom, t->B.geom, sizeof(JobGeom) * t->nJobs, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(ctx));
     const uint32_t n = t->nJobs;
     const bool affine = t->sp.affine != 0;
     const uint64_t rowsPerBlock = affine ? 16 : 4;             // 64 anti-diagonals / steps per traceback word
@@ -514,7 +527,7 @@ static int enqueue_dense(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   CK(cudaEventRecord(t->ev[1], s));
   if (firstRun) {
     CK(cudaMemcpyAsync(t->h_geom, t->B.geom, sizeof(JobGeom) * t->nJobs, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(ctx));
     const uint32_t n = t->nJobs;
     std::vector<uint32_t> idx; idx.reserve(n);
     uint64_t maxBytes = 0;
@@ -703,7 +716,7 @@ extern "C" int bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgp
 static int ensure_arena(bgpu_ctx *ctx, bgpu_ticket t) {
   if (t->arenaReady) return BGPU_OK;
   CK(cudaMemcpyAsync(t->h_totals, t->d_totals, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(wait_stream(ctx));
   for (int i = 0; i < 3; i++) t->totals[i] = t->h_totals[i];
   if (!t->dense) t->timing.fillCells = t->h_totals[3];
   RC(talloc_dev(ctx, t, &t->d_blocks, t->totals[0] + 1)); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->totals[1] + 1));
@@ -729,7 +742,7 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
     CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(t->ev[5], s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(ctx));
     t->timing.d2hBytes = sizeof(bgpu_result) * (uint64_t)t->nJobs + sizeof(bgpu_block) * t->totals[0] +
                          sizeof(uint32_t) * t->totals[1] + sizeof(bgpu_gap) * t->totals[2];
     gather_timing(t);
@@ -767,7 +780,7 @@ extern "C" int bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, co
     RC(talloc_dev(ctx, t, &d_off, (size_t)n + 1)); RC(talloc_pin(ctx, t, &h_off, (size_t)n + 1));
     launch_cigar_count(t->B, d_cnt, s);                                   // pass 1: ops per job
     CK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(ctx));
     uint64_t tot = 0;
     for (uint32_t i = 0; i < n; i++) { h_off[i] = tot; tot += h_cnt[i]; }
     h_off[n] = tot;
@@ -776,7 +789,7 @@ extern "C" int bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, co
     CK(cudaMemcpyAsync(d_off, h_off, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, s));
     launch_cigar_write(t->B, d_off, d_ops, s);                            // pass 2: the ops themselves
     CK(cudaMemcpyAsync(h_ops, d_ops, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(ctx));
     CK(cudaGetLastError());
     t->h_cigar = h_ops; t->h_cigarOff = h_off;
   }
@@ -791,7 +804,7 @@ extern "C" int bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t) {
   if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
   if (t->dense) RC(enqueue_dense(ctx, t, false)); else RC(enqueue_guided(ctx, t, false));
   RC(enqueue_emit(ctx, t));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(wait_stream(ctx));
   gather_timing(t);
   return BGPU_OK;
 }
