@@ -38,6 +38,20 @@ def test_restatement_matches_reference_printer(algo):
 
 
 @needs_ref
+def test_restatement_on_anchor_only_and_local_guides():
+    """Guides with real gaps between their blocks (min_block 8) and Local alignments (qPos / tPos past the guide start)."""
+    b = cases.guided_batch(seed=93, n=10, lo=80, hi=700, min_block=8)
+    fn = O.score_fn(SMRTDistanceMatrix, 4, 6, 0, 0)
+    for at in (0, 1):
+        for i in range(b.n):
+            q, t, g, _ = cases.job_arrays(b, i)
+            j, keep = O.make_job(0, at, 20, q, t, g, None, 0, 0, 0, 0)
+            want = O.ref_cigar(fn, j)
+            got = O.orc_cigar_from(q, t, O.align("ref", fn, j))
+            assert np.array_equal(got, want), (at, i)
+
+
+@needs_ref
 @pytest.mark.gpu
 @pytest.mark.parametrize("algo", [0, 1])
 def test_gpu_cigar_matches_reference_printer(aligner, algo):
