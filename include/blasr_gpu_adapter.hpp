@@ -9,7 +9,8 @@
 // and against the small stand-ins of tests/cpp/adapter_check.cpp; it contains no alignment arithmetic.
 //
 // Replaces, per batch of candidates instead of per candidate:
-//   AffineGuidedAlign / GuidedAlign + ComputeAlignmentStats      alignment/Blasr.cpp:863-878
+//   AffineGuidedAlign / GuidedAlign + ComputeAlignmentStats      alignment/Blasr.cpp:863-878   (RefineBatch)
+//   KBandAlign / AffineKBandAlign / SWAlign                      Blasr.cpp:717-730,820-824,1067-1076; SDPAlign.h:440,503,563   (DenseBatch)
 #ifndef BLASR_GPU_ADAPTER_HPP_
 #define BLASR_GPU_ADAPTER_HPP_
 #include <cstdint>
@@ -143,6 +144,100 @@ class RefineBatch {
   bgpu_arena arena_{};
   bgpu_ctx *owner_ = nullptr; bgpu_ticket ticket_ = nullptr;       // results and the arena live until Release()
   const uint32_t *cigarOps_ = nullptr; const uint64_t *cigarOff_ = nullptr;
+};
+
+// The other per-candidate DP call sites: jobs without a guide.
+//   KBandAlign        alignment/Blasr.cpp:820-824 (-global), :717-730 (PairwiseLocalAlign, Fit)       KBandAlign.h:75
+//   AffineKBandAlign  Blasr.cpp:1067-1076 (AlignSubstring, the gap fills of -alignContigs), :695-705   AffineKBandAlign.h:12
+//   SWAlign           common/algorithms/alignment/SDPAlign.h:440,503,563 (gap fills of a detailed SDPAlign)  SWAlign.h:18
+class DenseBatch {
+ public:
+  // k < 0: use the k passed to Run*()
+  void Add(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int k = -1) {
+    q_.insert(q_.end(), q, q + qLen); t_.insert(t_.end(), t, t + tLen);
+    qOff_.push_back(q_.size()); tOff_.push_back(t_.size()); band_.push_back(k); anyBand_ = anyBand_ || k >= 0;
+  }
+  uint32_t size() const { return (uint32_t)qOff_.size() - 1; }
+
+  // KBandAlign(q, t, matchMat, ins, del, k, scoreMat, pathMat, alignment, alignType, scoreFn): ins / del are the int
+  // boundary-cost parameters, the fill uses scoreFn's (KBandAlign.h:116,121 vs :196-244)
+  template <typename T_ScoreFn>
+  void RunKBand(Context &ctx, const T_ScoreFn &fn, int ins, int del, int k, int alignType) {
+    bgpu_params p = Params(BGPU_KBAND, alignType, k); p.bndIns = ins; p.bndDel = del;
+    Run(ctx, MakeScoreFn(fn), p);
+  }
+  // SWAlign(q, t, scoreMat, pathMat, alignment, scoreFn, alignType)
+  template <typename T_ScoreFn>
+  void RunSW(Context &ctx, const T_ScoreFn &fn, int alignType) { Run(ctx, MakeScoreFn(fn), Params(BGPU_SW, alignType, 0)); }
+  // AffineKBandAlign(q, t, matchMat, hpInsOpen, hpInsExtend, insOpen, insExtend, del, k, ..., alignment, alignType)
+  void RunAffineKBand(Context &ctx, const int matchMat[5][5], int hpInsOpen, int hpInsExtend, int insOpen, int insExtend,
+                      int del, int k, int alignType) {
+    bgpu_scorefn s; std::memset(&s, 0, sizeof s);
+    for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) s.M[i * 5 + j] = matchMat[i][j];
+    s.kind = BGPU_FN_DISTANCE;
+    bgpu_params p = Params(BGPU_AFFINE_KBAND, alignType, k);
+    p.bndDel = del; p.hpInsOpen = hpInsOpen; p.hpInsExtend = hpInsExtend; p.insOpen = insOpen; p.insExtend = insExtend;
+    Run(ctx, s, p);
+  }
+  ~DenseBatch() { Release(); }
+
+  const bgpu_result &Result(uint32_t i) const { return results_[i]; }
+
+  // Writes what the aligner stores into `alignment` -- blocks, gaps, and (KBandAlign, SWAlign) qPos / tPos; AffineKBandAlign
+  // never sets qPos / tPos, so they are left alone -- and returns the aligner's return value (its score).
+  template <typename T_Alignment>
+  int Store(uint32_t i, T_Alignment &out) const {
+    const bgpu_result &r = results_[i];
+    if (r.status != BGPU_JOB_OK) throw Error(r.status, "blasr_gpu: job rejected");
+    out.blocks.resize(r.nBlocks);
+    for (uint32_t k = 0; k < r.nBlocks; k++) {
+      const bgpu_block &bk = arena_.blocks[r.blockOff + k];
+      out.blocks[k].qPos = bk.qPos; out.blocks[k].tPos = bk.tPos; out.blocks[k].length = bk.length;
+    }
+    out.gaps.clear(); out.gaps.resize(r.nGapLists);
+    uint64_t g = r.gapOff;
+    for (uint32_t k = 0; k < r.nGapLists; k++) {
+      const uint32_t c = arena_.gapCounts[r.gapListOff + k];
+      out.gaps[k].resize(c);
+      for (uint32_t x = 0; x < c; x++, g++) {
+        typedef decltype(out.gaps[k][x].seq) seq_t;
+        out.gaps[k][x].seq = (seq_t)arena_.gaps[g].seq; out.gaps[k][x].length = arena_.gaps[g].length;
+      }
+    }
+    if (algo_ != BGPU_AFFINE_KBAND) { out.qPos = r.qPos; out.tPos = r.tPos; }
+    return r.score;
+  }
+
+  void Release() { if (ticket_) { bgpu_release(owner_, ticket_); ticket_ = nullptr; } }
+  void Clear() { Release(); q_.clear(); t_.clear(); band_.clear(); anyBand_ = false; qOff_.assign(1, 0); tOff_.assign(1, 0); results_.clear(); }
+
+ private:
+  static bgpu_params Params(int algo, int alignType, int k) {
+    bgpu_params p; std::memset(&p, 0, sizeof p);
+    p.algo = algo; p.alignType = alignType; p.band = k;
+    return p;
+  }
+  void Run(Context &ctx, const bgpu_scorefn &s, const bgpu_params &p) {
+    bgpu_batch b; std::memset(&b, 0, sizeof b);
+    b.nJobs = size(); b.qBases = q_.data(); b.qOff = qOff_.data(); b.tBases = t_.data(); b.tOff = tOff_.data();
+    std::vector<int32_t> band(band_);
+    for (size_t i = 0; i < band.size(); i++) if (band[i] < 0) band[i] = p.band;
+    b.band = anyBand_ ? band.data() : nullptr;
+    results_.resize(b.nJobs);
+    Release();
+    algo_ = p.algo;
+    int rc = bgpu_submit(ctx.get(), &s, &p, &b, &ticket_);
+    if (rc == BGPU_OK) { owner_ = ctx.get(); rc = bgpu_collect(owner_, ticket_, results_.data(), &arena_); }
+    if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
+  }
+  std::vector<uint8_t> q_, t_;
+  std::vector<int32_t> band_;
+  bool anyBand_ = false;
+  std::vector<uint64_t> qOff_{0}, tOff_{0};
+  std::vector<bgpu_result> results_;
+  bgpu_arena arena_{};
+  bgpu_ctx *owner_ = nullptr; bgpu_ticket ticket_ = nullptr;
+  int algo_ = BGPU_KBAND;
 };
 
 }  // namespace blasr_gpu

@@ -16,6 +16,7 @@
 #include "algorithms/alignment/GuidedAlign.h"
 #include "algorithms/alignment/AffineGuidedAlign.h"
 #include "algorithms/alignment/SDPAlign.h"
+#include "algorithms/alignment/AffineKBandAlign.h"
 #include "algorithms/alignment/DistanceMatrixScoreFunction.h"
 #include "datastructures/alignment/AlignmentCandidate.h"
 #include "FASTQSequence.h"
@@ -85,6 +86,72 @@ static std::string PrintedForm(T_AlignmentCandidate &a, FASTQSequence &q, DNASeq
   return out + "|" + qs + "|" + as + "|" + ts;
 }
 
+/* What KBandAlign / SWAlign / AffineKBandAlign leave in the alignment: blocks, gaps, qPos / tPos and the return value. */
+template <typename A, typename B>
+static int DiffDense(const A &a, int sa, const B &b, int sb, int job, const char *what, bool pos) {
+  int bad = 0;
+  if (sa != sb) { printf("job %d %s: return value differs (%d vs %d)\n", job, what, sa, sb); bad++; }
+  if (pos && (a.qPos != b.qPos || a.tPos != b.tPos)) { printf("job %d %s: qPos/tPos differ\n", job, what); bad++; }
+  if (a.blocks.size() != b.blocks.size()) { printf("job %d %s: %zu vs %zu blocks\n", job, what, a.blocks.size(), b.blocks.size()); return bad + 1; }
+  for (size_t i = 0; i < a.blocks.size(); i++)
+    if (a.blocks[i].qPos != b.blocks[i].qPos || a.blocks[i].tPos != b.blocks[i].tPos || a.blocks[i].length != b.blocks[i].length) { printf("job %d %s: block %zu differs\n", job, what, i); return bad + 1; }
+  if (a.gaps.size() != b.gaps.size()) { printf("job %d %s: %zu vs %zu gap lists\n", job, what, a.gaps.size(), b.gaps.size()); return bad + 1; }
+  for (size_t i = 0; i < a.gaps.size(); i++) {
+    if (a.gaps[i].size() != b.gaps[i].size()) { printf("job %d %s: gap list %zu size differs\n", job, what, i); return bad + 1; }
+    for (size_t j = 0; j < a.gaps[i].size(); j++)
+      if (a.gaps[i][j].seq != b.gaps[i][j].seq || a.gaps[i][j].length != b.gaps[i][j].length) { printf("job %d %s: gap %zu/%zu differs\n", job, what, i, j); return bad + 1; }
+  }
+  return bad;
+}
+
+/* The guide-less call sites through blasr_gpu::DenseBatch against the reference's own templates, called the way blasr calls
+ * them: KBandAlign Global (-global, Blasr.cpp:820-824) and Fit (PairwiseLocalAlign, :717-730), SWAlign Global on short gap
+ * fragments (SDPAlign.h:440,503,563), AffineKBandAlign Global with AlignSubstring's parameter pattern (Blasr.cpp:1067-1076). */
+static int CheckDense(std::vector<Pair> &pairs, DistFn &fn) {
+  int bad = 0;
+  std::mt19937 rng(99);
+  blasr_gpu::Context ctx(0);
+  const int n = (int)std::min<size_t>(pairs.size(), 24);
+  std::vector<FASTQSequence> qs(n); std::vector<DNASequence> ts(n);
+  std::vector<std::string> qstr(n), tstr(n);
+  int mat[5][5];
+  for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) mat[i][j] = SMRTDistanceMatrix[i][j];
+  for (int mode = 0; mode < 4; mode++) {
+    const char *what = mode == 0 ? "KBandAlign Global" : mode == 1 ? "KBandAlign Fit" : mode == 2 ? "SWAlign Global" : "AffineKBandAlign Global";
+    blasr_gpu::DenseBatch batch;
+    for (int i = 0; i < n; i++) {
+      /* short fragments for the gap-fill shapes, longer slices for the k-band ones */
+      const size_t len = mode >= 2 ? 4 + rng() % 28 : 200 + rng() % 700;
+      qstr[i] = pairs[i].q.substr(0, std::min(pairs[i].q.size(), len));
+      tstr[i] = pairs[i].t.substr(0, std::min(pairs[i].t.size(), mode >= 2 ? 4 + rng() % 28 : len));
+      qs[i].seq = (Nucleotide *)qstr[i].data(); qs[i].length = qstr[i].size();
+      ts[i].seq = (Nucleotide *)tstr[i].data(); ts[i].length = tstr[i].size();
+      batch.Add(qs[i].seq, qs[i].length, ts[i].seq, ts[i].length);
+    }
+    const int k = mode == 3 ? 6 : 15, indel = 5;
+    if (mode == 0) batch.RunKBand(ctx, fn, indel, indel, k, BGPU_GLOBAL);
+    else if (mode == 1) batch.RunKBand(ctx, fn, indel, indel, k, BGPU_FIT);
+    else if (mode == 2) batch.RunSW(ctx, fn, BGPU_GLOBAL);
+    else batch.RunAffineKBand(ctx, mat, indel + 2, indel - 3, indel + 2, indel - 1, indel, k, BGPU_GLOBAL);
+    int checked = 0;
+    for (int i = 0; i < n; i++) {
+      if (batch.Result(i).status != BGPU_JOB_OK) continue;   /* shapes on which the reference itself is undefined */
+      T_AlignmentCandidate ref, gpu;
+      vector<int> scoreMat, hpS, insS; vector<Arrow> pathMat, hpP, insP;
+      int sr;
+      if (mode == 0) sr = KBandAlign(qs[i], ts[i], mat, indel, indel, k, scoreMat, pathMat, ref, Global, fn, false);
+      else if (mode == 1) sr = KBandAlign(qs[i], ts[i], mat, indel, indel, k, scoreMat, pathMat, ref, Fit, fn, false);
+      else if (mode == 2) sr = SWAlign(qs[i], ts[i], scoreMat, pathMat, ref, fn, Global);
+      else sr = AffineKBandAlign(qs[i], ts[i], mat, indel + 2, indel - 3, indel + 2, indel - 1, indel, k, scoreMat, pathMat, hpS, hpP, insS, insP, ref, Global);
+      const int sg = batch.Store(i, gpu);
+      bad += DiffDense(ref, sr, gpu, sg, i, what, mode != 3);
+      checked++;
+    }
+    printf("adapter_check: %s x%d jobs through blasr_gpu::DenseBatch: %s\n", what, checked, bad ? "MISMATCH" : "identical to the reference call site");
+  }
+  return bad;
+}
+
 int main(int argc, char **argv) {
   const int nJobs = argc > 1 ? atoi(argv[1]) : 48;
   const int maxLen = argc > 2 ? atoi(argv[2]) : 6000;
@@ -103,6 +170,8 @@ int main(int argc, char **argv) {
     /* the candidate AlignIntervals hands to RefineAlignment: SDPAlign(Local, detailed), Blasr.cpp:1716-1722 */
     SDPAlign(q, t, fn, 11, 5, 10, 0.30f, cands[i], Local, true, false, 50, 2, 1000);
   }
+
+  if (argc > 3 && std::string(argv[3]) == "dense") return CheckDense(pairs, fn) ? 1 : 0;   /* the guide-less call sites */
 
   int bad = 0;
   size_t printedBytes = 0;

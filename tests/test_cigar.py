@@ -58,20 +58,21 @@ def test_gpu_cigar_matches_reference_printer(aligner, algo):
     b = _mixed_case_batch(190 + algo, 40, 50, 5000)
     b.band = np.random.default_rng(3).choice([8, 16, 32, 64], size=b.n).astype(np.int32)
     fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50 if algo else 0, affineExtend=0)
-    tk = aligner.submit(b, fn, algo, band=16)
-    res = aligner.collect(tk)
-    ops, off = aligner.cigar(tk)
     ofn = O.score_fn(SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0)
     n_ops = 0
-    for i in range(b.n):
-        q, t, g, _ = cases.job_arrays(b, i)
-        j, keep = O.make_job(algo, 1, int(b.band[i]), q, t, g, None, 0, 0, 0, 0)
-        want = O.ref_cigar(ofn, j)
-        got = ops[int(off[i]):int(off[i + 1])]
-        assert np.array_equal(got, want), (i, A.cigar_string(got)[:80], A.cigar_string(want)[:80])
-        n_ops += len(want)
+    for at in (1, 0):                                   # Global, Local
+        tk = aligner.submit(b, fn, algo, alignType=at, band=16)
+        aligner.collect(tk)
+        ops, off = aligner.cigar(tk)
+        for i in range(b.n):
+            q, t, g, _ = cases.job_arrays(b, i)
+            j, keep = O.make_job(algo, at, int(b.band[i]), q, t, g, None, 0, 0, 0, 0)
+            want = O.ref_cigar(ofn, j)
+            got = ops[int(off[i]):int(off[i + 1])]
+            assert np.array_equal(got, want), (at, i, A.cigar_string(got)[:80], A.cigar_string(want)[:80])
+            n_ops += len(want)
+        aligner.release(tk)
     assert n_ops > 1000
-    aligner.release(tk)
 
 
 @pytest.mark.gpu

@@ -23,6 +23,16 @@ def test_adapter_matches_reference_call_site():
 
 
 @needs_bin
+@pytest.mark.gpu
+def test_dense_adapter_matches_reference_call_sites():
+    """KBandAlign (Global, Fit), SWAlign (Global) and AffineKBandAlign (Global) through blasr_gpu::DenseBatch against the
+    reference's templates called with blasr's own argument patterns."""
+    r = subprocess.run([BIN, "32", "3000", "dense"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("through blasr_gpu::DenseBatch: identical to the reference call site") == 4, r.stdout
+
+
+@needs_bin
 def test_adapter_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
