@@ -99,6 +99,15 @@ int orc_cigar_from(const uint8_t *q, const uint8_t *t, uint32_t qPos, uint32_t t
                    const uint32_t *blocks, uint32_t nBlocks, const uint32_t *gapCounts, uint32_t nGapLists,
                    const int32_t *gaps, uint32_t *ops, uint32_t capOps);
 
+/* The chaining step of SDPAlign (next scope row): SDPLongestCommonSubsequence
+ * (sdp/SparseDynamicProgramming.h:71-322) over a fragment set with unique (x, y).
+ * frags: n x {x, y, length, weight}.  chain: indices into the set sorted by (x, y), first fragment first.
+ * Returns the chain length, -1 when capChain is too small.  alignType: ORC_GLOBAL or ORC_LOCAL. */
+int orc_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLength, uint32_t fragmentLength,
+                  int insertion, int deletion, int match, int alignType, int32_t *chain, uint32_t capChain);
+int ref_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLength, uint32_t fragmentLength,
+                  int insertion, int deletion, int match, int alignType, int32_t *chain, uint32_t capChain);
+
 /* Guide rows exactly as AlignmentToGuide builds them (GuidedAlign.h:104-259):
  * rows[i] = {q, t, tPre, tPost}; returns number of rows (0 for an empty guide),
  * -1 if capRows is too small. nCells = sum(tPre+tPost+1) (GuidedAlign.h:83-92). */

@@ -191,6 +191,22 @@ extern "C" int ref_cigar(const orc_scorefn *fn, const orc_job *job, uint32_t *op
   return (int)opSize.size();
 }
 
+extern "C" int ref_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLength, uint32_t fragmentLength,
+                             int insertion, int deletion, int match, int alignType, int32_t *chain, uint32_t capChain) {
+  vector<Fragment> fragmentSet;
+  for (uint32_t i = 0; i < n; i++) {
+    Fragment f(frags[4 * i], frags[4 * i + 1], (int)frags[4 * i + 3]);
+    f.length = frags[4 * i + 2];
+    fragmentSet.push_back(f);
+  }
+  vector<int> maxFragmentChain;
+  SDPLongestCommonSubsequence(queryLength, fragmentSet, fragmentLength, insertion, deletion, match, maxFragmentChain,
+                              (AlignmentType)alignType);
+  if (maxFragmentChain.size() > capChain) return -1;
+  for (size_t i = 0; i < maxFragmentChain.size(); i++) chain[i] = maxFragmentChain[i];
+  return (int)maxFragmentChain.size();
+}
+
 extern "C" int ref_guide_rows(const uint32_t *guide, uint32_t nGuide, int band, int32_t *rows, uint32_t capRows,
                               int64_t *nCells) {
   Alignment a; a.blocks.resize(nGuide);

@@ -65,6 +65,8 @@ def _load(which: str):
     rp = getattr(L, f"{which}_replay")
     rp.argtypes = [C.POINTER(OrcScoreFn), C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_int64)]
     rp.restype = C.c_int64
+    sc = getattr(L, f"{which}_sdp_chain")
+    sc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     if which == "ref":
         L.ref_cigar.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p, C.c_uint32]
         L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
@@ -157,6 +159,20 @@ def orc_cigar_from(q: np.ndarray, t: np.ndarray, aln: dict) -> np.ndarray:
     if n < 0:
         raise RuntimeError("orc_cigar_from overflow")
     return ops[:n].copy()
+
+
+def sdp_chain(which: str, frags: np.ndarray, queryLength: int, fragmentLength: int, ins: int, del_: int, match: int,
+              alignType: int) -> np.ndarray:
+    """SDPLongestCommonSubsequence over frags (n x {x, y, length, weight}, unique (x, y)): chain of indices into the
+    (x, y)-sorted set."""
+    L = _load(which)
+    frags = np.ascontiguousarray(frags, np.uint32).reshape(-1, 4)
+    chain = np.zeros(len(frags) + 1, np.int32)
+    n = getattr(L, f"{which}_sdp_chain")(frags.ctypes.data, len(frags), queryLength, fragmentLength, ins, del_, match, alignType,
+                                         chain.ctypes.data, len(chain))
+    if n < 0:
+        raise RuntimeError("sdp_chain overflow")
+    return chain[:n].copy()
 
 
 def guide_rows(which: str, guide: np.ndarray, band: int):
