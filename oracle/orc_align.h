@@ -108,6 +108,17 @@ int orc_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLength, uint3
 int ref_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLength, uint32_t fragmentLength,
                   int insertion, int deletion, int match, int alignType, int32_t *chain, uint32_t capChain);
 
+/* The fragment set SDPAlign hands to the chain (SDPAlign.h:133-262): prefix / middle / suffix k-mer matches, sorted by
+ * (x, y), de-duplicated.  frags: n x {x, y, length, weight}.  Returns n, -1 when capFrags is too small, -2 when the
+ * restated std::sort would have to fall back to heapsort (not restated: result unpinned for that input).
+ *   ref_sdp_fragments runs the reference's SDPAlign (no detailed alignment, no recursion) and returns the fragment set
+ *   it left in its buffers, plus its chain (indices into that set). */
+int orc_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize, int sdpPrefixLength,
+                      uint32_t *frags, uint32_t capFrags);
+int ref_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, const orc_scorefn *fn, int wordSize,
+                      int sdpIns, int sdpDel, int alignType, uint32_t *frags, uint32_t capFrags,
+                      int32_t *chain, uint32_t capChain, int32_t *nChain);
+
 /* Guide rows exactly as AlignmentToGuide builds them (GuidedAlign.h:104-259):
  * rows[i] = {q, t, tPre, tPost}; returns number of rows (0 for an empty guide),
  * -1 if capRows is too small. nCells = sum(tPre+tPost+1) (GuidedAlign.h:83-92). */

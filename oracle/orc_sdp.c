@@ -187,3 +187,193 @@ int orc_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLength, uint3
   free(f); free(cols); free(sw);
   return (int)len;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The fragment set SDPAlign builds in front of the chain (common/algorithms/alignment/SDPAlign.h:133-262):
+ *   - the target's first / last sdpPrefixLength bases and the whole target are turned into (tuple, pos) lists
+ *     (SequenceToTupleList, tuples/DNATuple.h:309-358: every k-mer of every ACGT-only span; tuples are read right to
+ *     left, :55-83) with word sizes small = min(wordSize, SDP_DETAILED_WORD_SIZE = 5), small, wordSize, and sorted by
+ *     (tuple, pos) -- a unique key;
+ *   - every valid k-mer of the query's first / last sdpPrefixLength bases and of the whole query is looked up
+ *     (StoreMatchingPositions, tuples/TupleMatching.h:37-62; FindAll, tuples/TupleList.h:88-101: all positions of an
+ *     equal tuple, ascending);
+ *   - weights are wordSize everywhere, lengths small / wordSize (:204-215); suffix matches are shifted to absolute
+ *     coordinates (:223-230); the three sets are concatenated prefix, middle, suffix (:235-236), sorted by (x, y) with
+ *     std::sort and de-duplicated keeping the FIRST of equal (x, y) (:249-262).
+ * The same (x, y) regularly arrives from the prefix set (length 5) and from the middle set (length 11): which one
+ * survives is decided by the order std::sort leaves equal keys in.  The reference is built with libstdc++ (GCC 13), so
+ * that algorithm is restated here -- introsort: median-of-three quicksort down to 16 elements, then insertion sort
+ * (bits/stl_algo.h: __introsort_loop, __unguarded_partition_pivot, __move_median_to_first, __final_insertion_sort).
+ * including its heapsort escape past a recursion depth of 2 * log2(n), which the nearly sorted concatenation does reach. */
+#define ORC_SDP_UNPINNED (-2)
+
+typedef struct { uint32_t x, y, length, weight; } Frag4;
+static int f4_less(const Frag4 *a, const Frag4 *b) { return a->x < b->x || (a->x == b->x && a->y < b->y); }   /* LessThanXY */
+static void f4_swap(Frag4 *a, Frag4 *b) { const Frag4 t = *a; *a = *b; *b = t; }
+
+static void move_median_to_first(Frag4 *result, Frag4 *a, Frag4 *b, Frag4 *c) {
+  if (f4_less(a, b)) {
+    if (f4_less(b, c)) f4_swap(result, b);
+    else if (f4_less(a, c)) f4_swap(result, c);
+    else f4_swap(result, a);
+  } else if (f4_less(a, c)) f4_swap(result, a);
+  else if (f4_less(b, c)) f4_swap(result, c);
+  else f4_swap(result, b);
+}
+static Frag4 *unguarded_partition(Frag4 *first, Frag4 *last, Frag4 *pivot) {
+  for (;;) {
+    while (f4_less(first, pivot)) ++first;
+    --last;
+    while (f4_less(pivot, last)) --last;
+    if (!(first < last)) return first;
+    f4_swap(first, last);
+    ++first;
+  }
+}
+/* the heapsort escape: std::__partial_sort(first, last, last) = __make_heap + __sort_heap (bits/stl_heap.h) */
+static void push_heap_(Frag4 *first, long hole, long top, Frag4 value) {
+  long parent = (hole - 1) / 2;
+  while (hole > top && f4_less(first + parent, &value)) { first[hole] = first[parent]; hole = parent; parent = (hole - 1) / 2; }
+  first[hole] = value;
+}
+static void adjust_heap(Frag4 *first, long hole, long len, Frag4 value) {
+  const long top = hole;
+  long child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (f4_less(first + child, first + (child - 1))) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  push_heap_(first, hole, top, value);
+}
+static void heap_sort(Frag4 *first, Frag4 *last) {
+  const long len = last - first;
+  long parent;
+  if (len >= 2) for (parent = (len - 2) / 2;; parent--) { adjust_heap(first, parent, len, first[parent]); if (parent == 0) break; }
+  while (last - first > 1) { --last; { const Frag4 value = *last; *last = *first; adjust_heap(first, 0, last - first, value); } }
+}
+static int introsort_loop(Frag4 *first, Frag4 *last, long depth) {
+  while (last - first > 16) {
+    if (depth == 0) { heap_sort(first, last); return 0; }
+    --depth;
+    Frag4 *mid = first + (last - first) / 2;
+    move_median_to_first(first, first + 1, mid, last - 1);
+    Frag4 *cut = unguarded_partition(first + 1, last, first);
+    if (introsort_loop(cut, last, depth)) return ORC_SDP_UNPINNED;
+    last = cut;
+  }
+  return 0;
+}
+static void unguarded_linear_insert(Frag4 *last) {
+  const Frag4 val = *last;
+  Frag4 *next = last - 1;
+  while (f4_less(&val, next)) { *last = *next; last = next; --next; }
+  *last = val;
+}
+static void insertion_sort(Frag4 *first, Frag4 *last) {
+  Frag4 *i;
+  if (first == last) return;
+  for (i = first + 1; i != last; ++i) {
+    if (f4_less(i, first)) { const Frag4 val = *i; memmove(first + 1, first, sizeof(Frag4) * (size_t)(i - first)); *first = val; }
+    else unguarded_linear_insert(i);
+  }
+}
+static int std_sort_xy(Frag4 *first, Frag4 *last) {
+  Frag4 *i;
+  long n = last - first, lg = 0;
+  if (first == last) return 0;
+  while ((1L << (lg + 1)) <= n) lg++;                      /* std::__lg */
+  if (introsort_loop(first, last, lg * 2)) return ORC_SDP_UNPINNED;
+  if (last - first > 16) { insertion_sort(first, first + 16); for (i = first + 16; i != last; ++i) unguarded_linear_insert(i); }
+  else insertion_sort(first, last);
+  return 0;
+}
+
+static int base2(uint8_t c) {                               /* TwoBit where ThreeBit <= 3 (NucConversion.h:7-84), else -1 */
+  switch (c) {
+    case 0: case 'A': case 'a': return 0;
+    case 1: case 'C': case 'c': return 1;
+    case 2: case 'G': case 'g': return 2;
+    case 3: case 'T': case 't': return 3;
+    default: return -1;
+  }
+}
+typedef struct { uint64_t tuple; uint32_t pos; } TPos;
+static int tpos_cmp(const void *a, const void *b) {
+  const TPos *p = (const TPos *)a, *q = (const TPos *)b;
+  if (p->tuple != q->tuple) return p->tuple < q->tuple ? -1 : 1;
+  return p->pos < q->pos ? -1 : (p->pos > q->pos ? 1 : 0);
+}
+/* every k-mer of every ACGT-only span of s, read right to left (the leftmost base in the lowest two bits) */
+static uint32_t tuple_list(const uint8_t *s, uint32_t len, int k, TPos *out) {
+  uint32_t n = 0, i, run = 0;
+  if (k <= 0 || len < (uint32_t)k) return 0;
+  for (i = 0; i < len; i++) {
+    run = base2(s[i]) >= 0 ? run + 1 : 0;
+    if (run >= (uint32_t)k) {
+      uint64_t v = 0; int j;
+      for (j = k - 1; j >= 0; j--) v = (v << 2) | (uint64_t)base2(s[i - (uint32_t)(k - 1) + (uint32_t)j]);
+      out[n].tuple = v; out[n].pos = i - (uint32_t)(k - 1); n++;
+    }
+  }
+  qsort(out, n, sizeof(TPos), tpos_cmp);
+  return n;
+}
+/* StoreMatchingPositions with maxMatches = 0: (s, pos) for every target position holding the query's k-mer at s */
+static uint32_t match_positions(const uint8_t *q, uint32_t qLen, int k, const TPos *list, uint32_t nList,
+                                uint32_t xOff, uint32_t yOff, uint32_t length, uint32_t weight, Frag4 *out, uint32_t n, uint32_t cap) {
+  uint32_t s, run = 0;
+  if (k <= 0 || qLen < (uint32_t)k) return n;
+  for (s = 0; s + (uint32_t)k <= qLen + 0u; s++) {
+    /* validity of the window [s, s + k): recomputed per position, which is what the res state machine amounts to */
+    uint64_t v = 0; int j, ok = 1;
+    for (j = k - 1; j >= 0; j--) { const int b = base2(q[s + (uint32_t)j]); if (b < 0) { ok = 0; break; } v = (v << 2) | (uint64_t)b; }
+    (void)run;
+    if (!ok) continue;
+    uint32_t lo = 0, hi = nList;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (list[mid].tuple < v) lo = mid + 1; else hi = mid; }
+    for (; lo < nList && list[lo].tuple == v; lo++) {
+      if (n < cap) { out[n].x = s + xOff; out[n].y = list[lo].pos + yOff; out[n].length = length; out[n].weight = weight; }
+      n++;
+    }
+  }
+  return n;
+}
+
+int orc_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize, int sdpPrefixLength,
+                      uint32_t *frags, uint32_t capFrags) {
+  const int small = wordSize < 5 ? wordSize : 5;                                   /* SDP_DETAILED_WORD_SIZE */
+  const uint32_t P = (uint32_t)sdpPrefixLength;
+  const uint32_t prefixLength = tLen < P ? tLen : P, suffixLength = (tLen - prefixLength) < P ? (tLen - prefixLength) : P;
+  const uint32_t suffixPos = tLen - suffixLength;                                  /* prefix + middle lengths */
+  const uint32_t qPrefixLength = qLen < P ? qLen : P, qSuffixLength = (qLen - qPrefixLength) < P ? (qLen - qPrefixLength) : P;
+  const uint32_t qSuffixPos = qLen - qSuffixLength;
+  TPos *lp = (TPos *)malloc(sizeof(TPos) * (prefixLength + 1)), *ls = (TPos *)malloc(sizeof(TPos) * (suffixLength + 1));
+  TPos *lm = (TPos *)malloc(sizeof(TPos) * ((size_t)tLen + 1));
+  const uint32_t np = tuple_list(t, prefixLength, small, lp), ns = tuple_list(t + suffixPos, suffixLength, small, ls);
+  const uint32_t nm = tuple_list(t, tLen, wordSize, lm);
+  uint32_t cap = capFrags, n = 0, i, m;
+  Frag4 *all = (Frag4 *)malloc(sizeof(Frag4) * ((size_t)cap + 1));
+  n = match_positions(q, qPrefixLength, small, lp, np, 0, 0, (uint32_t)small, (uint32_t)wordSize, all, n, cap);
+  n = match_positions(q, qLen, wordSize, lm, nm, 0, 0, (uint32_t)wordSize, (uint32_t)wordSize, all, n, cap);
+  n = match_positions(q + qSuffixPos, qSuffixLength, small, ls, ns, qSuffixPos, suffixPos, (uint32_t)small, (uint32_t)wordSize, all, n, cap);
+  free(lp); free(ls); free(lm);
+  if (n > cap) { free(all); return -1; }
+  if (std_sort_xy(all, all + n)) { free(all); return ORC_SDP_UNPINNED; }
+  m = 0;
+  for (i = 0; i < n;) {                                                            /* keep the first of equal (x, y) */
+    uint32_t j = i;
+    all[m] = all[i];
+    while (j < n && all[j].x == all[m].x && all[j].y == all[m].y) j++;
+    m++; i = j;
+  }
+  for (i = 0; i < m; i++) { frags[4 * i] = all[i].x; frags[4 * i + 1] = all[i].y; frags[4 * i + 2] = all[i].length; frags[4 * i + 3] = all[i].weight; }
+  free(all);
+  return (int)m;
+}

@@ -207,6 +207,31 @@ extern "C" int ref_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLe
   return (int)maxFragmentChain.size();
 }
 
+extern "C" int ref_sdp_fragments(const uint8_t *qs, uint32_t qLen, const uint8_t *ts, uint32_t tLen, const orc_scorefn *fn,
+                                 int wordSize, int sdpIns, int sdpDel, int alignType, uint32_t *frags, uint32_t capFrags,
+                                 int32_t *chain, uint32_t capChain, int32_t *nChain) {
+  FASTQSequence q; DNASequence t;
+  q.seq = (Nucleotide *)qs; q.length = qLen; t.seq = (Nucleotide *)ts; t.length = tLen;
+  DistFn df; FillDist(fn, df);
+  Alignment sdp;
+  vector<Fragment> fragmentSet, prefixFragmentSet, suffixFragmentSet;
+  TupleList<PositionDNATuple> targetTupleList, targetPrefixTupleList, targetSuffixTupleList;
+  vector<int> maxFragmentChain;
+  /* detailedAlignment = false, extendFrontByLocalAlignment = false, recurse = 0, noRecurseUnder = 0: nothing after the
+   * chain touches the buffers again (the recursive calls of SDPAlign.h:445-456,505-520,565-580 reuse them) */
+  SDPAlign(q, t, df, wordSize, sdpIns, sdpDel, 0.30f, sdp, fragmentSet, prefixFragmentSet, suffixFragmentSet,
+           targetTupleList, targetPrefixTupleList, targetSuffixTupleList, maxFragmentChain,
+           (AlignmentType)alignType, false, false, 50, 0, 0);
+  *nChain = (int32_t)maxFragmentChain.size();
+  if (fragmentSet.size() > capFrags || maxFragmentChain.size() > capChain) return -1;
+  for (size_t i = 0; i < fragmentSet.size(); i++) {
+    frags[4 * i] = fragmentSet[i].x; frags[4 * i + 1] = fragmentSet[i].y;
+    frags[4 * i + 2] = fragmentSet[i].length; frags[4 * i + 3] = fragmentSet[i].weight;
+  }
+  for (size_t i = 0; i < maxFragmentChain.size(); i++) chain[i] = maxFragmentChain[i];
+  return (int)fragmentSet.size();
+}
+
 extern "C" int ref_guide_rows(const uint32_t *guide, uint32_t nGuide, int band, int32_t *rows, uint32_t capRows,
                               int64_t *nCells) {
   Alignment a; a.blocks.resize(nGuide);

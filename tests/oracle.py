@@ -68,10 +68,13 @@ def _load(which: str):
     sc = getattr(L, f"{which}_sdp_chain")
     sc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     if which == "ref":
+        L.ref_sdp_fragments.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]
         L.ref_cigar.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p, C.c_uint32]
         L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                     C.c_int, C.c_float, C.c_void_p, C.c_uint32]
     else:
+        L.orc_sdp_fragments.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
         L.orc_cigar_from.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
     _libs[which] = L
@@ -173,6 +176,33 @@ def sdp_chain(which: str, frags: np.ndarray, queryLength: int, fragmentLength: i
     if n < 0:
         raise RuntimeError("sdp_chain overflow")
     return chain[:n].copy()
+
+
+def ref_sdp_fragments(q: np.ndarray, t: np.ndarray, fn: OrcScoreFn, wordSize=11, sdpIns=5, sdpDel=10, alignType=0):
+    """The fragment set the reference's SDPAlign leaves in its buffers (sorted, de-duplicated) and its chain."""
+    L = _load("ref")
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    cap = 64 * (len(q) + len(t)) + 4096
+    frags = np.zeros((cap, 4), np.uint32); chain = np.zeros(len(q) + len(t) + 8, np.int32); nc = C.c_int32(0)
+    n = L.ref_sdp_fragments(q.ctypes.data, len(q), t.ctypes.data, len(t), C.byref(fn), wordSize, sdpIns, sdpDel, alignType,
+                            frags.ctypes.data, cap, chain.ctypes.data, len(chain), C.byref(nc))
+    if n < 0:
+        raise RuntimeError("ref_sdp_fragments overflow")
+    return frags[:n].copy(), chain[:nc.value].copy()
+
+
+def orc_sdp_fragments(q: np.ndarray, t: np.ndarray, wordSize=11, sdpPrefixLength=50):
+    """C restatement of the fragment-set construction; None when the restated std::sort is unpinned for this input."""
+    L = _load("orc")
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    cap = 64 * (len(q) + len(t)) + 4096
+    frags = np.zeros((cap, 4), np.uint32)
+    n = L.orc_sdp_fragments(q.ctypes.data, len(q), t.ctypes.data, len(t), wordSize, sdpPrefixLength, frags.ctypes.data, cap)
+    if n == -2:
+        return None
+    if n < 0:
+        raise RuntimeError("orc_sdp_fragments overflow")
+    return frags[:n].copy()
 
 
 def guide_rows(which: str, guide: np.ndarray, band: int):

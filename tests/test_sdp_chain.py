@@ -79,3 +79,29 @@ def test_chain_matches_reference_on_random_fragments():
             want = O.sdp_chain("ref", fr, span + 3, k, 5, 10, -5, at)
             got = O.sdp_chain("orc", fr, span + 3, k, 5, 10, -5, at)
             assert np.array_equal(got, want), (rep, at, len(fr))
+
+
+@needs_ref
+def test_fragment_set_and_chain_match_reference_sdpalign():
+    """End to end over the deterministic front half: the fragment set (prefix / middle / suffix k-mer matches, sorted with
+    the restated libstdc++ std::sort, de-duplicated) and the chain over it, against what the reference's SDPAlign leaves
+    in its own buffers -- including which of two equal (x, y) fragments (length 5 vs 11) survives."""
+    from blasr_b200 import SMRTDistanceMatrix
+    from tests import cases
+    fn = O.score_fn(SMRTDistanceMatrix, 5, 5)
+    n_dup_len5 = n_frag = 0
+    for seed, lo, hi, n_rate, lower in ((1, 30, 400, 0.0, False), (2, 100, 3000, 0.01, True), (3, 2000, 6000, 0.0, False)):
+        b = cases.guided_batch(seed=300 + seed, n=8, lo=lo, hi=hi, n_rate=n_rate, lower=lower)
+        for i in range(b.n):
+            q, t, _, _ = cases.job_arrays(b, i)
+            for word, at in ((11, 0), (11, 1), (8, 1), (5, 0)):
+                want, want_chain = O.ref_sdp_fragments(q, t, fn, word, 5, 10, at)
+                got = O.orc_sdp_fragments(q, t, word)
+                assert got is not None
+                assert np.array_equal(got, want), (seed, i, word, len(got), len(want))
+                if len(want):
+                    match = int(fn.M[0])
+                    chain = O.sdp_chain("orc", got, len(q), word, 5, 10, match, at)
+                    assert np.array_equal(chain, want_chain), (seed, i, word, at)
+                n_frag += len(want); n_dup_len5 += int(((want[:, 2] == 5) & (want[:, 3] == 11)).sum())
+    assert n_frag > 10000 and n_dup_len5 > 100
