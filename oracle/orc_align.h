@@ -119,6 +119,13 @@ int ref_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_
                       int sdpIns, int sdpDel, int alignType, uint32_t *frags, uint32_t capFrags,
                       int32_t *chain, uint32_t capChain, int32_t *nChain);
 
+/* SDPAlign as a whole (SDPAlign.h:95-637), the call that produces the guide of the refinement (Blasr.cpp:1716-1722 passes
+ * Local, detailed, no front extension, prefix 50, recurse 2, noRecurseUnder 1000): blocks relative to (*qPos, *tPos).
+ * Returns nBlocks, -1 when capBlocks is too small.  The reference counterpart is ref_sdp_guide below. */
+int orc_sdp_align(const orc_scorefn *fn, const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize,
+                  int sdpIns, int sdpDel, float indelRate, int alignType, int detailed, int extendFront, int sdpPrefixLength,
+                  int recurse, int noRecurseUnder, uint32_t *blocks, uint32_t capBlocks, uint32_t *qPos, uint32_t *tPos);
+
 /* Guide rows exactly as AlignmentToGuide builds them (GuidedAlign.h:104-259):
  * rows[i] = {q, t, tPre, tPost}; returns number of rows (0 for an empty guide),
  * -1 if capRows is too small. nCells = sum(tPre+tPost+1) (GuidedAlign.h:83-92). */

@@ -327,7 +327,8 @@ static uint32_t tuple_list(const uint8_t *s, uint32_t len, int k, TPos *out) {
 }
 /* StoreMatchingPositions with maxMatches = 0: (s, pos) for every target position holding the query's k-mer at s */
 static uint32_t match_positions(const uint8_t *q, uint32_t qLen, int k, const TPos *list, uint32_t nList,
-                                uint32_t xOff, uint32_t yOff, uint32_t length, uint32_t weight, Frag4 *out, uint32_t n, uint32_t cap) {
+                                uint32_t xOff, uint32_t yOff, uint32_t length, uint32_t weight, Frag4 *out, uint32_t n, uint32_t cap,
+                                int maxMatches) {
   uint32_t s, run = 0;
   if (k <= 0 || qLen < (uint32_t)k) return n;
   for (s = 0; s + (uint32_t)k <= qLen + 0u; s++) {
@@ -338,6 +339,11 @@ static uint32_t match_positions(const uint8_t *q, uint32_t qLen, int k, const TP
     if (!ok) continue;
     uint32_t lo = 0, hi = nList;
     while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (list[mid].tuple < v) lo = mid + 1; else hi = mid; }
+    if (maxMatches != 0) {                                   /* positions with more matches than that are skipped (:50) */
+      uint32_t e = lo;
+      while (e < nList && list[e].tuple == v) e++;
+      if ((long)(e - lo) > (long)maxMatches) continue;
+    }
     for (; lo < nList && list[lo].tuple == v; lo++) {
       if (n < cap) { out[n].x = s + xOff; out[n].y = list[lo].pos + yOff; out[n].length = length; out[n].weight = weight; }
       n++;
@@ -346,8 +352,8 @@ static uint32_t match_positions(const uint8_t *q, uint32_t qLen, int k, const TP
   return n;
 }
 
-int orc_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize, int sdpPrefixLength,
-                      uint32_t *frags, uint32_t capFrags) {
+static int sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize, int sdpPrefixLength,
+                         int maxMatches, uint32_t *frags, uint32_t capFrags) {
   const int small = wordSize < 5 ? wordSize : 5;                                   /* SDP_DETAILED_WORD_SIZE */
   const uint32_t P = (uint32_t)sdpPrefixLength;
   const uint32_t prefixLength = tLen < P ? tLen : P, suffixLength = (tLen - prefixLength) < P ? (tLen - prefixLength) : P;
@@ -360,9 +366,9 @@ int orc_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_
   const uint32_t nm = tuple_list(t, tLen, wordSize, lm);
   uint32_t cap = capFrags, n = 0, i, m;
   Frag4 *all = (Frag4 *)malloc(sizeof(Frag4) * ((size_t)cap + 1));
-  n = match_positions(q, qPrefixLength, small, lp, np, 0, 0, (uint32_t)small, (uint32_t)wordSize, all, n, cap);
-  n = match_positions(q, qLen, wordSize, lm, nm, 0, 0, (uint32_t)wordSize, (uint32_t)wordSize, all, n, cap);
-  n = match_positions(q + qSuffixPos, qSuffixLength, small, ls, ns, qSuffixPos, suffixPos, (uint32_t)small, (uint32_t)wordSize, all, n, cap);
+  n = match_positions(q, qPrefixLength, small, lp, np, 0, 0, (uint32_t)small, (uint32_t)wordSize, all, n, cap, maxMatches);
+  n = match_positions(q, qLen, wordSize, lm, nm, 0, 0, (uint32_t)wordSize, (uint32_t)wordSize, all, n, cap, maxMatches);
+  n = match_positions(q + qSuffixPos, qSuffixLength, small, ls, ns, qSuffixPos, suffixPos, (uint32_t)small, (uint32_t)wordSize, all, n, cap, maxMatches);
   free(lp); free(ls); free(lm);
   if (n > cap) { free(all); return -1; }
   if (std_sort_xy(all, all + n)) { free(all); return ORC_SDP_UNPINNED; }
@@ -376,4 +382,155 @@ int orc_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_
   for (i = 0; i < m; i++) { frags[4 * i] = all[i].x; frags[4 * i + 1] = all[i].y; frags[4 * i + 2] = all[i].length; frags[4 * i + 3] = all[i].weight; }
   free(all);
   return (int)m;
+}
+
+int orc_sdp_fragments(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize, int sdpPrefixLength,
+                      uint32_t *frags, uint32_t capFrags) {
+  return sdp_fragments(q, qLen, t, tLen, wordSize, sdpPrefixLength, 0, frags, capFrags);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * SDPAlign as a whole (SDPAlign.h:95-637): fragment set, chain, chain -> blocks (:308-407), and the detailed part --
+ * front extension (:409-474), SWAlign / recursive SDPAlign between chained blocks (:481-535), the last block and the tail
+ * (:536-601), the Local shift (:604-612).  Blocks come back relative to (*qPos, *tPos) as the reference leaves them. */
+typedef struct { uint32_t q, t, len; } Blk;
+typedef struct { Blk *b; uint32_t n, cap; } BlkVec;
+static void bv_push(BlkVec *v, Blk x) {
+  if (v->n == v->cap) { v->cap = v->cap ? 2 * v->cap : 64; v->b = (Blk *)realloc(v->b, sizeof(Blk) * v->cap); }
+  v->b[v->n++] = x;
+}
+/* SWAlign(qFragment, tFragment, ..., scoreFn, Global) through the restatement in orc_align.c; blocks appended raw */
+static void sw_global(const orc_scorefn *fn, const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, BlkVec *out,
+                      uint32_t *qPos, uint32_t *tPos) {
+  orc_job j; orc_result r;
+  const uint32_t cap = qLen + tLen + 8;
+  uint32_t *bl = (uint32_t *)malloc(sizeof(uint32_t) * 3 * cap), *gc = (uint32_t *)malloc(sizeof(uint32_t) * (cap + 1)), i;
+  int32_t *gp = (int32_t *)malloc(sizeof(int32_t) * 4 * cap);
+  memset(&j, 0, sizeof j);
+  j.algo = ORC_SW; j.alignType = ORC_GLOBAL; j.q = q; j.qLen = qLen; j.t = t; j.tLen = tLen;
+  orc_align(fn, &j, &r, bl, cap, gc, cap + 1, gp, 2 * cap);
+  for (i = 0; i < r.nBlocks; i++) { Blk x; x.q = bl[3 * i]; x.t = bl[3 * i + 1]; x.len = bl[3 * i + 2]; bv_push(out, x); }
+  *qPos = r.qPos; *tPos = r.tPos;
+  free(bl); free(gc); free(gp);
+}
+
+static int sdp_align(const orc_scorefn *fn, const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize,
+                     int sdpIns, int sdpDel, float indelRate, int alignType, int detailed, int extendFront, int sdpPrefixLength,
+                     int recurse, int noRecurseUnder, int maxMatches, BlkVec *out, uint32_t *qPos, uint32_t *tPos) {
+  *qPos = 0; *tPos = 0;
+  const uint32_t capF = 64u * (qLen + tLen) + 4096u;
+  uint32_t *fr = (uint32_t *)malloc(sizeof(uint32_t) * 4 * (size_t)capF);
+  const int nF = sdp_fragments(q, qLen, t, tLen, wordSize, sdpPrefixLength, maxMatches, fr, capF);
+  if (nF < 0) { free(fr); return nF; }
+  if (nF == 0) { free(fr); return 0; }                       /* :264-269: needs at least one seed */
+  int32_t *chain = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nF + 1));
+  const int nC = orc_sdp_chain(fr, (uint32_t)nF, qLen, (uint32_t)wordSize, sdpIns, sdpDel, fn->M[0], alignType, chain, (uint32_t)nF + 1);
+  BlkVec ch = {0, 0, 0};
+  int f;
+  uint32_t b;
+  /* :308-335 condense runs of fragments that advance by one in both sequences */
+  for (f = 0; f < nC; f++) {
+    const int startF = f;
+    while (f < nC - 1 && fr[4 * chain[f]] == fr[4 * chain[f + 1]] - 1 && fr[4 * chain[f] + 1] == fr[4 * chain[f + 1] + 1] - 1) f++;
+    Blk x; x.q = fr[4 * chain[startF]]; x.t = fr[4 * chain[startF] + 1];
+    x.len = fr[4 * chain[f]] + fr[4 * chain[f] + 2] - fr[4 * chain[startF]];
+    bv_push(&ch, x);
+  }
+  free(fr); free(chain);
+  /* :349-358 a block may not run into the next one */
+  for (b = 0; b + 1 < ch.n; b++) {
+    if (ch.b[b].q + ch.b[b].len > ch.b[b + 1].q) ch.b[b].len = ch.b[b + 1].q - ch.b[b].q;
+    if (ch.b[b].t + ch.b[b].len > ch.b[b + 1].t) ch.b[b].len = ch.b[b + 1].t - ch.b[b].t;
+  }
+  /* :373-407 drop empty blocks and blocks that sit off the diagonal of both neighbours */
+  {
+    uint8_t *good = (uint8_t *)malloc(ch.n + 1);
+    uint32_t m = 0;
+    for (b = 0; b < ch.n; b++) good[b] = ch.b[b].len != 0;
+    for (b = 1; b + 1 < ch.n; b++) {
+      const int prevDiag = abs(((int)ch.b[b].t - (int)ch.b[b].q) - ((int)ch.b[b - 1].t - (int)ch.b[b - 1].q));
+      const uint32_t pdt = ch.b[b].t - ch.b[b - 1].t, pdq = ch.b[b].q - ch.b[b - 1].q;
+      const int prevDist = (int)(pdt < pdq ? pdt : pdq);
+      const int nextDiag = abs(((int)ch.b[b + 1].t - (int)ch.b[b + 1].q) - ((int)ch.b[b].t - (int)ch.b[b].q));
+      const uint32_t ndt = ch.b[b + 1].t - ch.b[b].t, ndq = ch.b[b + 1].q - ch.b[b].q;
+      const int nextDist = (int)(ndt < ndq ? ndt : ndq);
+      if (prevDist * indelRate < prevDiag && nextDist * indelRate < nextDiag) good[b] = 0;
+    }
+    for (b = 0; b < ch.n; b++) if (good[b]) ch.b[m++] = ch.b[b];
+    ch.n = m;
+    free(good);
+  }
+  if (ch.n > 0) {
+    const int sub = wordSize - 4 > 5 ? wordSize - 4 : 5;     /* max(wordSize-4, 5) */
+    /* :412-474 front extension */
+    if (ch.b[0].q > 0 && ch.b[0].t > 0 && (alignType == ORC_GLOBAL || extendFront)) {
+      BlkVec fa = {0, 0, 0};
+      uint32_t fq = 0, ft = 0, i;
+      if (recurse == 0 && (uint32_t)(ch.b[0].q * ch.b[0].t) < (uint32_t)noRecurseUnder) sw_global(fn, q, ch.b[0].q, t, ch.b[0].t, &fa, &fq, &ft);
+      else if (recurse != 0)
+        /* as the reference (:456): smithWatermanAlignType (EndAnchored = 6) lands in the maxMatchesPerPosition slot */
+        sdp_align(fn, q, ch.b[0].q, t, ch.b[0].t, sub, sdpIns, sdpDel, indelRate, ORC_GLOBAL, detailed, extendFront, sdpPrefixLength,
+                  recurse - 1, noRecurseUnder, ORC_ENDANCHORED, &fa, &fq, &ft);
+      for (i = 0; i < fa.n; i++) { Blk x = fa.b[i]; x.t += ft; x.q += fq; bv_push(out, x); }
+      free(fa.b);
+    }
+    /* :481-535 the chained blocks and what lies between them */
+    for (b = 0; b + 1 < ch.n; b++) {
+      bv_push(out, ch.b[b]);
+      const uint32_t qo = ch.b[b].q + ch.b[b].len, to = ch.b[b].t + ch.b[b].len;
+      const uint32_t ql = ch.b[b + 1].q - qo, tl = ch.b[b + 1].t - to;
+      if (ql > 0 && tl > 0 && detailed) {
+        BlkVec fa = {0, 0, 0};
+        uint32_t fq = 0, ft = 0, i;
+        if ((uint32_t)(ql * tl) < (uint32_t)noRecurseUnder) sw_global(fn, q + qo, ql, t + to, tl, &fa, &fq, &ft);
+        else if (recurse != 0)
+          sdp_align(fn, q + qo, ql, t + to, tl, sub, sdpIns, sdpDel, indelRate, ORC_GLOBAL, detailed, 0, 0, recurse - 1, noRecurseUnder, 0,
+                    &fa, &fq, &ft);
+        /* :523-524 the fragment's own qPos / tPos are reset, its blocks are used as they are */
+        for (i = 0; i < fa.n; i++) { Blk x = fa.b[i]; x.q += qo; x.t += to; bv_push(out, x); }
+        free(fa.b);
+      }
+    }
+    /* :536-601 the last block, and the tail when front extension is on */
+    if (alignType == ORC_GLOBAL || alignType == ORC_LOCAL) {
+      const Blk last = ch.b[ch.n - 1];
+      bv_push(out, last);
+      if (alignType == ORC_GLOBAL || extendFront) {
+        const uint32_t qo = last.q + last.len, to = last.t + last.len;
+        const uint32_t ql = qLen - qo, tl = tLen - to;
+        if (ql > 0 && tl > 0 && extendFront) {
+          BlkVec fa = {0, 0, 0};
+          uint32_t fq = 0, ft = 0, i;
+          const int half = wordSize / 2 > 5 ? wordSize / 2 : 5;
+          if (recurse == 0 && (uint32_t)(ql * tl) < (uint32_t)noRecurseUnder) sw_global(fn, q + qo, ql, t + to, tl, &fa, &fq, &ft);
+          else if (recurse != 0)
+            sdp_align(fn, q + qo, ql, t + to, tl, half, sdpIns, sdpDel, indelRate, ORC_GLOBAL, detailed, extendFront, sdpPrefixLength,
+                      recurse - 1, noRecurseUnder, maxMatches, &fa, &fq, &ft);
+          for (i = 0; i < fa.n; i++) { Blk x = fa.b[i]; x.q += qo; x.t += to; bv_push(out, x); }
+          free(fa.b);
+        }
+      }
+    }
+  }
+  free(ch.b);
+  return 0;
+}
+
+int orc_sdp_align(const orc_scorefn *fn, const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, int wordSize,
+                  int sdpIns, int sdpDel, float indelRate, int alignType, int detailed, int extendFront, int sdpPrefixLength,
+                  int recurse, int noRecurseUnder, uint32_t *blocks, uint32_t capBlocks, uint32_t *qPos, uint32_t *tPos) {
+  BlkVec out = {0, 0, 0};
+  uint32_t i;
+  const int rc = sdp_align(fn, q, qLen, t, tLen, wordSize, sdpIns, sdpDel, indelRate, alignType, detailed, extendFront, sdpPrefixLength,
+                           recurse, noRecurseUnder, 0, &out, qPos, tPos);
+  if (rc < 0) { free(out.b); return rc; }
+  if (alignType == ORC_LOCAL && out.n > 0) {                 /* :604-612 */
+    *tPos = out.b[0].t; *qPos = out.b[0].q;
+    for (i = 0; i < out.n; i++) { out.b[i].q -= *qPos; out.b[i].t -= *tPos; }
+  }
+  if (out.n > capBlocks) { free(out.b); return -1; }
+  for (i = 0; i < out.n; i++) { blocks[3 * i] = out.b[i].q; blocks[3 * i + 1] = out.b[i].t; blocks[3 * i + 2] = out.b[i].len; }
+  i = out.n;
+  free(out.b);
+  return (int)i;
 }

@@ -74,6 +74,9 @@ def _load(which: str):
         L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                     C.c_int, C.c_float, C.c_void_p, C.c_uint32]
     else:
+        L.orc_sdp_align.argtypes = [C.POINTER(OrcScoreFn), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                    C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_sdp_fragments.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
         L.orc_cigar_from.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
@@ -203,6 +206,21 @@ def orc_sdp_fragments(q: np.ndarray, t: np.ndarray, wordSize=11, sdpPrefixLength
     if n < 0:
         raise RuntimeError("orc_sdp_fragments overflow")
     return frags[:n].copy()
+
+
+def orc_sdp_guide(q: np.ndarray, t: np.ndarray, fn: OrcScoreFn, tupleSize=11, sdpIns=5, sdpDel=10, indelRate=0.9):
+    """C restatement of SDPAlign with blasr's argument pattern (Blasr.cpp:1716-1722): absolute blocks, like sdp_guide()."""
+    L = _load("orc")
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    cap = len(q) + len(t) + 8
+    blocks = np.zeros((cap, 3), np.uint32); qp = C.c_uint32(0); tp = C.c_uint32(0)
+    n = L.orc_sdp_align(C.byref(fn), q.ctypes.data, len(q), t.ctypes.data, len(t), tupleSize, sdpIns, sdpDel, C.c_float(indelRate),
+                        0, 1, 0, 50, 2, 1000, blocks.ctypes.data, cap, C.byref(qp), C.byref(tp))
+    if n < 0:
+        raise RuntimeError(f"orc_sdp_align rc={n}")
+    out = blocks[:n].copy()
+    out[:, 0] += qp.value; out[:, 1] += tp.value
+    return out
 
 
 def guide_rows(which: str, guide: np.ndarray, band: int):

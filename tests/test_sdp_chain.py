@@ -105,3 +105,23 @@ def test_fragment_set_and_chain_match_reference_sdpalign():
                     assert np.array_equal(chain, want_chain), (seed, i, word, at)
                 n_frag += len(want); n_dup_len5 += int(((want[:, 2] == 5) & (want[:, 3] == 11)).sum())
     assert n_frag > 10000 and n_dup_len5 > 100
+
+
+@needs_ref
+def test_whole_sdpalign_matches_reference():
+    """SDPAlign as blasr calls it (Local, detailed, prefix 50, recurse 2, noRecurseUnder 1000; Blasr.cpp:1716-1722): fragment
+    set, chain, chain -> blocks, SWAlign / recursive SDPAlign gap fills -- the guide the refinement receives, block for block."""
+    from blasr_b200 import SMRTDistanceMatrix, synth
+    from tests import cases
+    fn = O.score_fn(SMRTDistanceMatrix, 5, 5)
+    n_blocks = 0
+    for seed, (lo, hi, err) in enumerate([(20, 60, 0.15), (50, 600, 0.30), (500, 3000, 0.25), (3000, 7000, 0.15), (200, 2000, 0.05)]):
+        b = synth.simulate_pairs(6, lo, hi, err=err, seed=1300 + seed, n_rate=0.004 if seed == 2 else 0.0)
+        for i in range(b.n):
+            q, t, _, _ = cases.job_arrays(b, i)
+            for word, rate in ((11, 0.30), (8, 0.9), (13, 0.30)):
+                want = O.sdp_guide(q, t, fn, word, 5, 10, rate)
+                got = O.orc_sdp_guide(q, t, fn, word, 5, 10, rate)
+                assert np.array_equal(got, want), (seed, i, word, rate, len(got), len(want))
+                n_blocks += len(want)
+    assert n_blocks > 5000
