@@ -798,3 +798,69 @@ int orc_cigar_from(const uint8_t *q, const uint8_t *t, uint32_t qPos, uint32_t t
   }
   return (int)n;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The three strings of the m5 / stick printers, restated from CreateAlignmentStrings (AlignmentUtils.h:390-533) and
+ * AppendGapCharacters (:366-387).  q / t are the sequences the alignment indexes (positions start at qPos / tPos).
+ * With gap lists: gaps[0] columns carry '*' in the middle string, block columns '|' or '*' by TwoBit equality (every
+ * non-ACGT byte maps to 255 there, so N pairs with any other ambiguity code as a match), gaps[b+1] columns ' '.
+ * Without gap lists (SDPAlign output): leading offsets of block 0 and the gaps between blocks are laid out as
+ * :409-447 / :497-529 do.  out* need room for capOut bytes each; returns the common length, -1 on overflow. */
+static int two_bit(uint8_t c) {
+  if (c <= 7) return c & 3;
+  switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 255; }
+}
+#define STR_PUSH(tc, ac, qc) do { if (n >= capOut) return -1; textStr[n] = (char)(tc); alignStr[n] = (char)(ac); queryStr[n] = (char)(qc); n++; } while (0)
+int orc_alignment_strings(const uint8_t *query, const uint8_t *text, uint32_t qPos, uint32_t tPos,
+                          const uint32_t *blocks, uint32_t nBlocks, const uint32_t *gapCounts, uint32_t nGapLists,
+                          const int32_t *gaps, char *textStr, char *alignStr, char *queryStr, uint32_t capOut) {
+  uint32_t q = qPos, t = tPos, n = 0, b, bl, g = 0, gi, p;
+  if (nBlocks == 0) return 0;
+  if (nGapLists == 0) {                                     /* :409-447 */
+    if (blocks[0] > 0 || blocks[1] > 0) {
+      uint32_t qp = blocks[0], tp = blocks[1];
+      int common = (int)qp;
+      if ((uint32_t)common > tp) common = (int)tp;
+      for (p = 0; p < (uint32_t)common; p++) { STR_PUSH(text[t], '*', query[q]); t++; q++; }
+      tp -= (uint32_t)common; qp -= (uint32_t)common;
+      for (p = 0; p < tp; p++) { STR_PUSH(text[t], ' ', '-'); t++; }
+      for (p = 0; p < qp; p++) { STR_PUSH('-', ' ', query[q]); q++; }
+    }
+  } else {                                                  /* :453-460: the list before the first block */
+    for (gi = 0; gi < gapCounts[0]; gi++, g++) {
+      int k;
+      for (k = 0; k < gaps[2 * g + 1]; k++) {
+        if (gaps[2 * g] == 0) { STR_PUSH(text[t], '*', '-'); t++; }
+        else if (gaps[2 * g] == 1) { STR_PUSH('-', '*', query[q]); q++; }
+      }
+    }
+  }
+  for (b = 0; b < nBlocks; b++) {
+    for (bl = 0; bl < blocks[3 * b + 2]; bl++) {
+      STR_PUSH(text[t], two_bit(query[q]) != two_bit(text[t]) ? '*' : '|', query[q]);
+      q++; t++;
+    }
+    if (b == nBlocks - 1) continue;
+    if (nGapLists > 0) {
+      for (gi = 0; gi < gapCounts[b + 1]; gi++, g++) {
+        int k;
+        for (k = 0; k < gaps[2 * g + 1]; k++) {
+          if (gaps[2 * g] == 0) { STR_PUSH(text[t], ' ', '-'); t++; }
+          else if (gaps[2 * g] == 1) { STR_PUSH('-', ' ', query[q]); q++; }
+        }
+      }
+    } else {                                                /* :497-529 */
+      int queryGapLen = (int)(blocks[3 * (b + 1)] - blocks[3 * b] - blocks[3 * b + 2]);
+      int textGapLen = (int)(blocks[3 * (b + 1) + 1] - blocks[3 * b + 1] - blocks[3 * b + 2]);
+      if (queryGapLen > 0 || textGapLen > 0) {
+        int common = queryGapLen, k;
+        if (queryGapLen > textGapLen) common = textGapLen;
+        textGapLen -= common; queryGapLen -= common;
+        for (k = 0; k < queryGapLen; k++, q++) STR_PUSH('-', ' ', query[q]);
+        for (k = 0; k < textGapLen; k++, t++) STR_PUSH(text[t], ' ', '-');
+        for (k = 0; k < common; k++) { STR_PUSH(text[t], ' ', query[q]); t++; q++; }
+      }
+    }
+  }
+  return (int)n;
+}

@@ -99,6 +99,17 @@ int orc_cigar_from(const uint8_t *q, const uint8_t *t, uint32_t qPos, uint32_t t
                    const uint32_t *blocks, uint32_t nBlocks, const uint32_t *gapCounts, uint32_t nGapLists,
                    const int32_t *gaps, uint32_t *ops, uint32_t capOps);
 
+/* The three strings the m5 / stick printers print (CreateAlignmentStrings, AlignmentUtils.h:390-533): text, match pattern,
+ * query, each capOut bytes at most; returns their common length (0 without blocks), -1 on overflow.
+ *   ref_alignment_strings runs the job's aligner first and prints from its result;
+ *   orc_alignment_strings prints from a stored alignment (nGapLists == 0: the block-only form SDPAlign returns). */
+int ref_alignment_strings(const orc_scorefn *fn, const orc_job *job, char *textStr, char *alignStr, char *queryStr, uint32_t capOut);
+int ref_block_strings(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, const uint32_t *blocks, uint32_t nBlocks,
+                      char *textStr, char *alignStr, char *queryStr, uint32_t capOut);   /* a block-only alignment at qPos = tPos = 0 */
+int orc_alignment_strings(const uint8_t *query, const uint8_t *text, uint32_t qPos, uint32_t tPos,
+                          const uint32_t *blocks, uint32_t nBlocks, const uint32_t *gapCounts, uint32_t nGapLists,
+                          const int32_t *gaps, char *textStr, char *alignStr, char *queryStr, uint32_t capOut);
+
 /* The chaining step of SDPAlign (next scope row): SDPLongestCommonSubsequence
  * (sdp/SparseDynamicProgramming.h:71-322) over a fragment set with unique (x, y).
  * frags: n x {x, y, length, weight}.  chain: indices into the set sorted by (x, y), first fragment first.

@@ -191,6 +191,33 @@ extern "C" int ref_cigar(const orc_scorefn *fn, const orc_job *job, uint32_t *op
   return (int)opSize.size();
 }
 
+extern "C" int ref_alignment_strings(const orc_scorefn *fn, const orc_job *job, char *textStr, char *alignStr, char *queryStr,
+                                     uint32_t capOut) {
+  Scratch s; Alignment aln; orc_result res;
+  RunOne(fn, job, &res, s, aln);
+  if (res.status != ORC_OK) return 0;
+  std::string ts, as, qs;
+  Nucleotide *q = (Nucleotide *)job->q, *t = (Nucleotide *)job->t;
+  CreateAlignmentStrings(aln, q, t, ts, as, qs, job->qLen, job->tLen);
+  if (ts.size() > capOut) return -1;
+  memcpy(textStr, ts.data(), ts.size()); memcpy(alignStr, as.data(), as.size()); memcpy(queryStr, qs.data(), qs.size());
+  return (int)ts.size();
+}
+
+extern "C" int ref_block_strings(const uint8_t *qs, uint32_t qLen, const uint8_t *ts, uint32_t tLen, const uint32_t *blocks,
+                                 uint32_t nBlocks, char *textStr, char *alignStr, char *queryStr, uint32_t capOut) {
+  Alignment aln;                                   /* blocks only, no gap lists: the form SDPAlign returns */
+  aln.qPos = 0; aln.tPos = 0;
+  aln.blocks.resize(nBlocks);
+  for (uint32_t i = 0; i < nBlocks; i++) { aln.blocks[i].qPos = blocks[3 * i]; aln.blocks[i].tPos = blocks[3 * i + 1]; aln.blocks[i].length = blocks[3 * i + 2]; }
+  std::string t3, a3, q3;
+  Nucleotide *q = (Nucleotide *)qs, *t = (Nucleotide *)ts;
+  CreateAlignmentStrings(aln, q, t, t3, a3, q3, qLen, tLen);
+  if (t3.size() > capOut) return -1;
+  memcpy(textStr, t3.data(), t3.size()); memcpy(alignStr, a3.data(), a3.size()); memcpy(queryStr, q3.data(), q3.size());
+  return (int)t3.size();
+}
+
 extern "C" int ref_sdp_chain(const uint32_t *frags, uint32_t n, uint32_t queryLength, uint32_t fragmentLength,
                              int insertion, int deletion, int match, int alignType, int32_t *chain, uint32_t capChain) {
   vector<Fragment> fragmentSet;

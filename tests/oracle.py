@@ -68,12 +68,17 @@ def _load(which: str):
     sc = getattr(L, f"{which}_sdp_chain")
     sc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     if which == "ref":
+        L.ref_block_strings.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_uint32]
+        L.ref_alignment_strings.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.ref_sdp_fragments.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]
         L.ref_cigar.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p, C.c_uint32]
         L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                     C.c_int, C.c_float, C.c_void_p, C.c_uint32]
     else:
+        L.orc_alignment_strings.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                            C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_sdp_align.argtypes = [C.POINTER(OrcScoreFn), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -138,6 +143,45 @@ def align(which: str, fn: OrcScoreFn, job: OrcJob):
         gl.append([(int(a), int(b)) for a, b in gaps[p:p + int(cnt[i])]]); p += int(cnt[i])
     out["gaps"] = gl
     return out
+
+
+def ref_alignment_strings(fn: OrcScoreFn, job: OrcJob):
+    """(text, pattern, query) strings of CreateAlignmentStrings on the result of the job's reference aligner."""
+    L = _load("ref")
+    cap = int(job.qLen) + int(job.tLen) + 8
+    bufs = [C.create_string_buffer(cap) for _ in range(3)]
+    n = L.ref_alignment_strings(C.byref(fn), C.byref(job), bufs[0], bufs[1], bufs[2], cap)
+    if n < 0:
+        raise RuntimeError("ref_alignment_strings overflow")
+    return tuple(b.raw[:n] for b in bufs)
+
+
+def ref_block_strings(q: np.ndarray, t: np.ndarray, blocks: np.ndarray):
+    L = _load("ref")
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    blocks = np.ascontiguousarray(blocks, np.uint32).reshape(-1, 3)
+    cap = len(q) + len(t) + 8
+    bufs = [C.create_string_buffer(cap) for _ in range(3)]
+    n = L.ref_block_strings(q.ctypes.data, len(q), t.ctypes.data, len(t), blocks.ctypes.data, len(blocks), bufs[0], bufs[1], bufs[2], cap)
+    if n < 0:
+        raise RuntimeError("ref_block_strings overflow")
+    return tuple(b.raw[:n] for b in bufs)
+
+
+def orc_alignment_strings(q: np.ndarray, t: np.ndarray, aln: dict, with_gaps=True):
+    L = _load("orc")
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    blocks = np.ascontiguousarray(aln["blocks"], np.uint32).reshape(-1, 3)
+    gl = aln["gaps"] if with_gaps else []
+    cnt = np.asarray([len(g) for g in gl], np.uint32)
+    flat = np.asarray([x for g in gl for x in g], np.int32).reshape(-1, 2)
+    cap = len(q) + len(t) + 8
+    bufs = [C.create_string_buffer(cap) for _ in range(3)]
+    n = L.orc_alignment_strings(q.ctypes.data, t.ctypes.data, int(aln["qPos"]), int(aln["tPos"]), blocks.ctypes.data, len(blocks),
+                                cnt.ctypes.data, len(cnt), flat.ctypes.data, bufs[0], bufs[1], bufs[2], cap)
+    if n < 0:
+        raise RuntimeError("orc_alignment_strings overflow")
+    return tuple(b.raw[:n] for b in bufs)
 
 
 def ref_cigar(fn: OrcScoreFn, job: OrcJob) -> np.ndarray:

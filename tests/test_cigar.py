@@ -84,3 +84,42 @@ def test_gpu_cigar_refuses_dense_tickets(aligner):
     with pytest.raises(BgpuError):
         aligner.cigar(tk)
     aligner.release(tk)
+
+
+@needs_ref
+def test_m5_strings_restatement_matches_reference():
+    """CreateAlignmentStrings (the qalignedseq / matchpattern / talignedseq columns of -m 5) restated in C against the
+    reference, on refined alignments (gap lists) of mixed-case / N inputs and on KBandAlign / SWAlign results."""
+    fn = O.score_fn(SMRTDistanceMatrix, 5, 5, 50, 0)
+    b = _mixed_case_batch(290, 16, 60, 1500)
+    total = 0
+    for i in range(b.n):
+        q, t, g, _ = cases.job_arrays(b, i)
+        for algo, at, band in ((1, 1, 16), (0, 0, 10), (2, 1, 12), (3, 1, 0)):
+            qq, tt = (q, t) if algo < 3 else (q[:60], t[:70])
+            j, keep = O.make_job(algo, at, band, qq, tt, g if algo < 2 else None, None, 5, 5, 0, 0)
+            aln = O.align("ref", fn, j)
+            if aln["status"] != 0:
+                continue
+            want = O.ref_alignment_strings(fn, j)
+            got = O.orc_alignment_strings(qq, tt, aln)
+            assert got == want, (i, algo, got[1][:60], want[1][:60])
+            total += len(want[0])
+    assert total > 20000
+
+
+@needs_ref
+def test_m5_strings_of_block_only_alignments():
+    """The branch without gap lists (what SDPAlign returns): leading offsets and inter-block gaps laid out from the block
+    coordinates alone."""
+    fn = O.score_fn(SMRTDistanceMatrix, 5, 5)
+    b = cases.guided_batch(seed=295, n=10, lo=80, hi=1500)
+    total = 0
+    for i in range(b.n):
+        q, t, _, _ = cases.job_arrays(b, i)
+        blocks = O.sdp_guide(q, t, fn)
+        want = O.ref_block_strings(q, t, blocks)
+        got = O.orc_alignment_strings(q, t, {"blocks": blocks, "gaps": [], "qPos": 0, "tPos": 0}, with_gaps=False)
+        assert got == want, (i, got[1][:60], want[1][:60])
+        total += len(want[0])
+    assert total > 5000
