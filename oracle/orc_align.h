@@ -99,6 +99,12 @@ int orc_cigar_from(const uint8_t *q, const uint8_t *t, uint32_t qPos, uint32_t t
                    const uint32_t *blocks, uint32_t nBlocks, const uint32_t *gapCounts, uint32_t nGapLists,
                    const int32_t *gaps, uint32_t *ops, uint32_t capOps);
 
+/* CPU model of the next fill kernel's number format (oracle/orc_s16.c): the linear GuidedAlign sweep with 16-bit slots
+ * relative to an offset re-based every 64 anti-diagonals, next to the same sweep in 32 bits.  out[9]: cells compared,
+ * arrow mismatches, score mismatches, end score (32-bit), end score (16-bit + offset), min / max legit relative value
+ * (shifted by 2), max unreachable value, re-bases.  Returns 0, -1 on unsupported input. */
+int orc_guided_s16_model(const orc_scorefn *fn, const orc_job *job, int64_t *out);
+
 /* The three strings the m5 / stick printers print (CreateAlignmentStrings, AlignmentUtils.h:390-533): text, match pattern,
  * query, each capOut bytes at most; returns their common length (0 without blocks), -1 on overflow.
  *   ref_alignment_strings runs the job's aligner first and prints from its result;

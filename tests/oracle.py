@@ -77,6 +77,7 @@ def _load(which: str):
         L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                     C.c_int, C.c_float, C.c_void_p, C.c_uint32]
     else:
+        L.orc_guided_s16_model.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p]
         L.orc_alignment_strings.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                             C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_sdp_align.argtypes = [C.POINTER(OrcScoreFn), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
@@ -143,6 +144,16 @@ def align(which: str, fn: OrcScoreFn, job: OrcJob):
         gl.append([(int(a), int(b)) for a, b in gaps[p:p + int(cnt[i])]]); p += int(cnt[i])
     out["gaps"] = gl
     return out
+
+
+def guided_s16_model(fn: OrcScoreFn, job: OrcJob):
+    """oracle/orc_s16.c: dict of the model's counters, or None on unsupported input."""
+    L = _load("orc")
+    out = np.zeros(9, np.int64)
+    if L.orc_guided_s16_model(C.byref(fn), C.byref(job), out.ctypes.data) != 0:
+        return None
+    keys = ("cells", "arrow_mismatches", "score_mismatches", "end32", "end16", "min_rel", "max_rel", "max_big", "rebases")
+    return dict(zip(keys, (int(x) for x in out)))
 
 
 def ref_alignment_strings(fn: OrcScoreFn, job: OrcJob):
