@@ -216,6 +216,7 @@ extern "C" int bgpu_device_count(void) {
   return n;
 }
 extern "C" int bgpu_version(void) { return BGPU_VERSION; }
+extern "C" int bgpu_base_code(int c) { return bgpu::base_code((uint8_t)c); }
 
 extern "C" int bgpu_create(bgpu_ctx **out, int device) {
   if (!out) return BGPU_E_INVALID;
@@ -483,6 +484,9 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   RC(talloc_dev(ctx, t, &d_guide, totG + 1));
   if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
   if (b->band) RC(talloc_dev(ctx, t, &d_band, n));
+  // prep writes tc only inside [tStart, tEnd) of each job, the fill kernels also stage the boundary column t' = 0 and the
+  // columns past the guide's end: those bytes must be valid codes (0), not whatever the cached allocation last held
+  CK(cudaMemsetAsync(d_tc, 0, totT + 16, ctx->stream));
   gate(ctx->device, GATE_H2D).acquire(); t->holdsH2D = true;   // until the uploads below are done
   RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
   RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));

@@ -112,18 +112,19 @@ struct DenseArgs {
   const uint64_t *arrowOff;   // per job byte offset into B.arrows
 };
 
-__device__ __forceinline__ uint8_t base_code(uint8_t c) {
-  // NucConversion.h:48-84 (ThreeBit), restated as arithmetic: ACGT/acgt and raw 0..3 -> 0..3,
-  // IUPAC ambiguity letters (and raw 4) -> 4, '$' -> 5, everything else 255.
+__host__ __device__ __forceinline__ uint8_t base_code(uint8_t c) {
+  // NucConversion.h:48-84 (ThreeBit), restated as arithmetic: ACGT/acgt and raw 0..3 -> 0..3, raw 4, the IUPAC
+  // ambiguity letters in either case, 'x', 'y' (but not 'X') and '_' -> 4, '$' -> 5, everything else 255.
+  // tests/test_host_cpu.py::test_base_code_table pins all 256 entries against the reference's own table.
   if (c <= 4) return c;
-  uint8_t u = c & 0xDF;  // fold case
+  const uint8_t u = c & 0xDF;  // fold case
   switch (u) {
     case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
     case 'B': case 'D': case 'H': case 'K': case 'M': case 'N': case 'R': case 'S':
-    case 'U': case 'V': case 'W': case 'Y': return ((c == u) || (c == (u | 0x20))) ? 4 : 255;
+    case 'U': case 'V': case 'W': case 'Y': return 4;
     default: break;
   }
-  if (c == 'x') return 4;   // the table maps 'x' (but not 'X') to N
+  if (c == 'x' || c == '_') return 4;   // the table maps 'x' (but not 'X') and '_' to N
   if (c == '$') return 5;
   return 255;
 }

@@ -77,14 +77,15 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   const int C0 = Qn + (Qn & 1);
   const int nD = Qn + Tn + 1, nDB = (nD + DBLK - 1) / DBLK;
   if (nD >= (1 << 21)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }   // diagonals are carried << 8
-  // score range the shifted-domain kernels can carry
-  {
-    int mx = max(max(abs(P.ins), abs(P.del)), abs(P.open) + abs(P.ext));
-    if (P.kind == BGPU_FN_QUALITY) mx = max(mx, 255);
-    else if (P.kind == BGPU_FN_IDS) mx = max(max(mx, 255), max(abs(P.subPrior), abs(P.delPrior)));
-    else for (int i = 0; i < 25; i++) mx = max(mx, abs(P.M[i]));
-    if ((long long)mx * (Qn + Tn + 2) >= (P.affine ? SCORE_LIMIT_AFF : SCORE_LIMIT_LIN) || mx >= (1 << 15)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }
-  }
+  // score range the shifted-domain kernels can carry.  Every in-band cell is reachable by Diagonal / Left / Up moves
+  // alone (they stay candidates of the affine 5-way min), so |S| <= steps * max(|M|, |ins|, |del|, |ext|); the affine
+  // matrices sit at most one open above S.  QualityValueScoreFunction: |Match| <= the largest QV of this job's rows
+  // (reduced below), IDSScoreFunction: <= 255 or a prior.
+  int mxStep = max(max(abs(P.ins), abs(P.del)), abs(P.ext));
+  if (P.kind == BGPU_FN_IDS) mxStep = max(max(mxStep, 255), max(abs(P.subPrior), abs(P.delPrior)));
+  else if (P.kind == BGPU_FN_DISTANCE) for (int i = 0; i < 25; i++) mxStep = max(mxStep, abs(P.M[i]));
+  if (P.open < 0) mxStep = max(mxStep, abs(P.open) + abs(P.ext));   // a negative open could be collected once per step
+  if (mxStep >= (1 << 15) || abs(P.open) >= (1 << 20)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }
 
   // ---- encode + validate the target window (codes 0..4 into B.tc), and check the query bases
   const uint8_t *tb = B.t + to;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   // QualityValueScoreFunction: the row's QV rides in the low byte of RowInfo::cd8 (the fill kernels multiply by it)
   const uint8_t *qvb = (P.kind == BGPU_FN_QUALITY && B.qual) ? B.qual + qo : nullptr;
   uint8_t qvNext = (qvb && Qn >= 1 + lane) ? qvb[qStart + lane] : 0;
+  int maxQV = 0;
   for (int base = 1; base <= Qn; base += 32) {
     const int i = base + lane;
     const bool act = i <= Qn;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
     }
     int t = 0, cap = 0, tPost = 0, x = INT_MIN;
     const uint8_t qch = qchNext, qv = qvNext;
+    maxQV = max(maxQV, (int)qv);
     if (i + 32 <= Qn) { qchNext = qb[qStart + i + 31]; if (qvb) qvNext = qvb[qStart + i + 31]; }
     const uint32_t q0 = (uint32_t)(qStart + base - 1);
     const int cand = bcur + 1 + lane;
@@ -223,6 +226,11 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   }
   cells = warp_sum_ll(cells);
   if (warp_or(bad) || cells > INT_MAX) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
+  if (P.kind == BGPU_FN_QUALITY) mxStep = max(mxStep, __reduce_max_sync(0xffffffffu, maxQV));
+  if ((long long)mxStep * (Qn + Tn + 2) + abs(P.open) >= (P.affine ? SCORE_LIMIT_AFF : SCORE_LIMIT_LIN)) {
+    if (lane == 0) G.status = BGPU_JOB_RANGE;
+    return;
+  }
   __threadfence(); __syncwarp();
 
   // ---- per d-block window [mn-1, mx+1] aligned down to an even diagonal (the edge slots stay dead, see

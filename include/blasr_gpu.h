@@ -154,6 +154,9 @@ int  bgpu_create(bgpu_ctx **ctx, int device);       /* binds to one GPU; one ctx
 void bgpu_destroy(bgpu_ctx *ctx);
 const char *bgpu_last_error(const bgpu_ctx *ctx);
 int  bgpu_version(void);
+/* The base -> code table every kernel uses: ThreeBit[] of common/NucConversion.h:48-84 (0..3 ACGT, 4 = N / IUPAC,
+ * 5 = '$', 255 = not a base -> BGPU_JOB_BAD_INPUT).  Host-callable so that the table can be pinned without a GPU. */
+int  bgpu_base_code(int asciiByte);
 
 /* ---- asynchronous batch API ---- */
 /* Copies the batch into pinned staging, enqueues H2D + all kernels on the ctx stream, returns at once. */

@@ -317,3 +317,6 @@ extern "C" int64_t ref_replay(const orc_scorefn *fn, const orc_job *jobs, uint32
   if (scoreSum) *scoreSum = ssum;
   return cells;
 }
+
+/* The reference's own base -> code table (NucConversion.h:48-84), entry by entry. */
+extern "C" int ref_three_bit(int c) { return ThreeBit[c & 255]; }

@@ -117,3 +117,23 @@ def test_two_rank_gloo_sharding(tmp_path):
                           "127.0.0.1", "--master-port", "29677", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+# ThreeBit[] of the reference (common/NucConversion.h:48-84) as (code -> bytes); generated here from
+# oracle/_ref (ref_three_bit) and re-checked against it whenever the reference build is present.
+_THREE_BIT = {0: b"\x00Aa", 1: b"\x01Cc", 2: b"\x02Gg", 3: b"\x03Tt", 4: b"\x04BDHKMNRSUVWY_bdhkmnrsuvwxy", 5: b"$"}
+
+
+def test_base_code_table():
+    """All 256 entries of the kernels' base table (bgpu_base_code) equal the reference's ThreeBit[]."""
+    from blasr_b200 import capi
+    from . import oracle as O
+    lib = capi.lib()
+    want = np.full(256, 255, np.int64)
+    for code, chars in _THREE_BIT.items():
+        want[list(chars)] = code
+    got = np.array([lib.bgpu_base_code(c) for c in range(256)])
+    assert np.array_equal(got, want), np.nonzero(got != want)
+    if O.have_ref():
+        L = O._load("ref")
+        assert [L.ref_three_bit(c) for c in range(256)] == want.tolist()
