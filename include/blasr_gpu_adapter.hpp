@@ -6,15 +6,20 @@
 //   DNASequence            common/DNASequence.h            (seq, length)
 //   Block / Gap / GapList  common/datastructures/alignment/AlignmentBlock.h:9-41, AlignmentGapList.h:9-24
 //   DistanceMatrixScoreFunction  common/algorithms/alignment/DistanceMatrixScoreFunction.h:11
-// and against the small stand-ins of tests/cpp/adapter_check.cpp; it contains no alignment arithmetic.
+// (oracle/adapter_check.cpp and baseline/gpu_refine.hpp compile it that way) and against any stand-in with the same members;
+// it contains no alignment arithmetic.
 //
 // Replaces, per batch of candidates instead of per candidate:
 //   AffineGuidedAlign / GuidedAlign + ComputeAlignmentStats      alignment/Blasr.cpp:863-878   (RefineBatch)
 //   KBandAlign / AffineKBandAlign / SWAlign                      Blasr.cpp:717-730,820-824,1067-1076; SDPAlign.h:440,503,563   (DenseBatch)
 #ifndef BLASR_GPU_ADAPTER_HPP_
 #define BLASR_GPU_ADAPTER_HPP_
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -50,8 +55,18 @@ inline bgpu_scorefn MakeScoreFn(const T_ScoreFn &fn, int kind = BGPU_FN_DISTANCE
   return s;
 }
 
+// A ticket shared by the RefineBatch objects whose jobs RefineService merged into one submission: released when the
+// last of them lets go.
+struct SharedTicket {
+  bgpu_ctx *ctx; bgpu_ticket ticket; int refs; std::mutex mu;
+  SharedTicket(bgpu_ctx *c, bgpu_ticket t, int r) : ctx(c), ticket(t), refs(r) {}
+};
+
+class RefineService;
+
 // Collects the per-candidate slices RefineAlignment builds (Blasr.cpp:850-859) and runs them as one batch.
 class RefineBatch {
+  friend class RefineService;
  public:
   // q/t: the slices handed to (Affine)GuidedAlign; blocks: candidate.blocks (used raw as the guide).
   template <typename T_BlockVector>
@@ -84,7 +99,7 @@ class RefineBatch {
     int rc = bgpu_submit(ctx.get(), &s, &p, &b, &ticket_);
     if (rc == BGPU_OK) { owner_ = ctx.get(); rc = bgpu_collect(owner_, ticket_, results_.data(), &arena_); }
     if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
-    cigarOps_ = nullptr; cigarOff_ = nullptr;
+    cigarOps_ = nullptr; cigarOff_ = nullptr; base_ = 0;
   }
   ~RefineBatch() { Release(); }
 
@@ -93,10 +108,11 @@ class RefineBatch {
   // (CreateCIGARString :366-397).  Built on the device for the whole batch at the first call.
   std::string Cigar(uint32_t i) {
     if (!cigarOps_) {
-      int rc = bgpu_cigar(owner_, ticket_, &cigarOps_, &cigarOff_);
+      int rc = bgpu_cigar(owner_, shared_ ? shared_->ticket : ticket_, &cigarOps_, &cigarOff_);
       if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(owner_));
     }
     std::string out;
+    i += base_;                                   // position of this batch's first job inside a merged ticket
     for (uint64_t k = cigarOff_[i]; k < cigarOff_[i + 1]; k++) { out += std::to_string(cigarOps_[k] >> 4); out += "MIDNSHP=X"[cigarOps_[k] & 15]; }
     return out;
   }
@@ -133,10 +149,20 @@ class RefineBatch {
     out.pctSimilarity = r.pctSimilarity; out.score = r.statsScore;   // ComputeAlignmentStats overwrites score, AlignmentUtils.h:578
   }
 
-  void Release() { if (ticket_) { bgpu_release(owner_, ticket_); ticket_ = nullptr; } }
+  void Release() {
+    if (shared_) {
+      bool last;
+      { std::lock_guard<std::mutex> lk(shared_->mu); last = --shared_->refs == 0; }
+      if (last) { bgpu_release(shared_->ctx, shared_->ticket); delete shared_; }
+      shared_ = nullptr; ticket_ = nullptr;
+    }
+    if (ticket_) { bgpu_release(owner_, ticket_); ticket_ = nullptr; }
+  }
   void Clear() { Release(); q_.clear(); t_.clear(); qual_.clear(); guide_.clear(); qOff_.assign(1, 0); tOff_.assign(1, 0); gOff_.assign(1, 0); results_.clear(); }
 
  private:
+  SharedTicket *shared_ = nullptr;                                 // set when the jobs ran inside a merged submission
+  uint32_t base_ = 0;                                              // ... and the index of this batch's first job in it
   std::vector<uint8_t> q_, t_, qual_;
   std::vector<bgpu_block> guide_;
   std::vector<uint64_t> qOff_{0}, tOff_{0}, gOff_{0};
@@ -144,6 +170,107 @@ class RefineBatch {
   bgpu_arena arena_{};
   bgpu_ctx *owner_ = nullptr; bgpu_ticket ticket_ = nullptr;       // results and the arena live until Release()
   const uint32_t *cigarOps_ = nullptr; const uint64_t *cigarOff_ = nullptr;
+};
+
+// Cross-thread batching for blasr's thread driver.  MapReads (Blasr.cpp:3193) runs one pthread per -nproc, and each
+// calls RefineAlignments synchronously with the handful of candidates of ONE read -- far too few jobs to fill a GPU.
+// RefineService keeps that structure untouched: every pthread hands its RefineBatch to Run() and blocks; the first
+// waiter becomes the leader, gathers the batches of the other threads until every client that is not already being
+// served has arrived (or a short window closes), submits them as ONE ticket and hands each thread its slice of the
+// results.  Two or more contexts let the next merged ticket copy in while the previous one computes.
+class RefineService {
+ public:
+  RefineService(int device, int nClients, int maxWaitUs = 300, int nContexts = 2)
+      : nClients_(nClients < 1 ? 1 : nClients), maxWaitUs_(maxWaitUs) {
+    for (int i = 0; i < (nContexts < 1 ? 1 : nContexts); i++) ctxs_.push_back(std::unique_ptr<Context>(new Context(device)));
+  }
+
+  template <typename T_ScoreFn>
+  void Run(RefineBatch &batch, const T_ScoreFn &fn, int bandSize, bool affine, int alignType = BGPU_GLOBAL) {
+    Request r;
+    r.batch = &batch; r.fn = MakeScoreFn(fn);
+    std::memset(&r.p, 0, sizeof r.p);
+    r.p.algo = affine ? BGPU_AFFINE_GUIDED : BGPU_GUIDED; r.p.alignType = alignType; r.p.band = bandSize;
+    r.p.doStats = 1; r.p.statsAffine = affine ? 1 : 0;
+    batch.Release();
+    std::unique_lock<std::mutex> lk(mu_);
+    pending_.push_back(&r);
+    cv_.notify_all();
+    while (!r.done) {
+      if (leaderActive_) { cv_.wait(lk); continue; }
+      leaderActive_ = true;
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(maxWaitUs_);
+      while ((int)pending_.size() + inflight_ < nClients_)
+        if (cv_.wait_until(lk, deadline) == std::cv_status::timeout) break;
+      std::vector<Request *> mine, rest;          // one ticket = one (score function, parameters) pair
+      for (Request *x : pending_)
+        (std::memcmp(&x->fn, &r.fn, sizeof r.fn) == 0 && std::memcmp(&x->p, &r.p, sizeof r.p) == 0 ? mine : rest).push_back(x);
+      pending_.swap(rest);
+      inflight_ += (int)mine.size();
+      Context &ctx = *ctxs_[next_++ % ctxs_.size()];
+      leaderActive_ = false;
+      cv_.notify_all();
+      lk.unlock();
+      Execute(ctx, mine);
+      lk.lock();
+      inflight_ -= (int)mine.size();
+      for (Request *x : mine) x->done = true;
+      cv_.notify_all();
+    }
+    lk.unlock();
+    if (r.rc != BGPU_OK) throw Error(r.rc, "blasr_gpu: " + r.err);
+  }
+
+  uint64_t Tickets() const { return tickets_; }
+  uint64_t Jobs() const { return jobs_; }
+
+ private:
+  struct Request { RefineBatch *batch; bgpu_scorefn fn; bgpu_params p; bool done = false; int rc = BGPU_OK; std::string err; };
+
+  void Execute(Context &ctx, std::vector<Request *> &reqs) {
+    std::vector<uint8_t> q, t, qual; std::vector<bgpu_block> guide; std::vector<uint64_t> qOff(1, 0), tOff(1, 0), gOff(1, 0);
+    bool anyQual = false;
+    for (Request *x : reqs) anyQual = anyQual || !x->batch->qual_.empty();
+    for (Request *x : reqs) {
+      RefineBatch &b = *x->batch;
+      const uint64_t q0 = q.size(), t0 = t.size(), g0 = guide.size();
+      q.insert(q.end(), b.q_.begin(), b.q_.end()); t.insert(t.end(), b.t_.begin(), b.t_.end());
+      guide.insert(guide.end(), b.guide_.begin(), b.guide_.end());
+      if (anyQual) { qual.resize(q0, 0); qual.insert(qual.end(), b.qual_.begin(), b.qual_.end()); qual.resize(q.size(), 0); }
+      for (uint32_t i = 1; i <= b.size(); i++) { qOff.push_back(q0 + b.qOff_[i]); tOff.push_back(t0 + b.tOff_[i]); gOff.push_back(g0 + b.gOff_[i]); }
+    }
+    bgpu_batch mb; std::memset(&mb, 0, sizeof mb);
+    mb.nJobs = (uint32_t)qOff.size() - 1; mb.qBases = q.data(); mb.qOff = qOff.data(); mb.tBases = t.data(); mb.tOff = tOff.data();
+    mb.qual = anyQual ? qual.data() : nullptr; mb.guide = guide.data(); mb.guideOff = gOff.data();
+    std::vector<bgpu_result> res(mb.nJobs);
+    bgpu_arena arena; std::memset(&arena, 0, sizeof arena);
+    bgpu_ticket tk = nullptr;
+    int rc = mb.nJobs ? bgpu_submit(ctx.get(), &reqs[0]->fn, &reqs[0]->p, &mb, &tk) : BGPU_OK;
+    if (rc == BGPU_OK && tk) rc = bgpu_collect(ctx.get(), tk, res.data(), &arena);
+    if (rc != BGPU_OK) {
+      const std::string e = bgpu_last_error(ctx.get());
+      if (tk) bgpu_release(ctx.get(), tk);
+      for (Request *x : reqs) { x->rc = rc; x->err = e; }
+      return;
+    }
+    tickets_++; jobs_ += mb.nJobs;
+    SharedTicket *sh = tk ? new SharedTicket(ctx.get(), tk, (int)reqs.size()) : nullptr;
+    uint32_t at = 0;
+    for (Request *x : reqs) {
+      RefineBatch &b = *x->batch;
+      b.results_.assign(res.begin() + at, res.begin() + at + b.size());
+      b.base_ = at;
+      at += b.size();
+      b.arena_ = arena; b.owner_ = ctx.get(); b.ticket_ = nullptr; b.shared_ = sh; b.cigarOps_ = nullptr; b.cigarOff_ = nullptr;
+    }
+  }
+
+  const int nClients_, maxWaitUs_;
+  std::mutex mu_; std::condition_variable cv_;
+  std::vector<Request *> pending_;
+  bool leaderActive_ = false; int inflight_ = 0; size_t next_ = 0;
+  std::vector<std::unique_ptr<Context>> ctxs_;
+  uint64_t tickets_ = 0, jobs_ = 0;
 };
 
 // The other per-candidate DP call sites: jobs without a guide.
