@@ -15,8 +15,12 @@
 #include "blasr_gpu_adapter.hpp"
 
 static blasr_gpu::RefineService &BgpuService(int nProc) {
+  // MapReads runs more pthreads than the host has cores once the GPU takes the refinement: waiting threads must sleep
+  static const int once = setenv("BGPU_BLOCKING_SYNC", "1", 0);
+  (void)once;
   static blasr_gpu::RefineService svc(getenv("BGPU_DEVICE") ? atoi(getenv("BGPU_DEVICE")) : 0, nProc,
-                                      getenv("BGPU_BATCH_WAIT_US") ? atoi(getenv("BGPU_BATCH_WAIT_US")) : 300);
+                                      getenv("BGPU_BATCH_WAIT_US") ? atoi(getenv("BGPU_BATCH_WAIT_US")) : 300,
+                                      getenv("BGPU_SERVICE_CONTEXTS") ? atoi(getenv("BGPU_SERVICE_CONTEXTS")) : 3);
   return svc;
 }
 

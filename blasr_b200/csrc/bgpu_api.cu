@@ -19,12 +19,14 @@
 namespace bgpu {
 void launch_prep_guided(const BatchDev &, const ScoreParams &, int, const uint64_t *, const uint64_t *,
                         const uint64_t *, cudaStream_t);
-void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32_t *, uint32_t, uint32_t *, int,
+void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32_t *, const PlanHead *, uint32_t, uint32_t *, int,
                         cudaStream_t);
-void launch_trace_guided(const BatchDev &, bool, const uint32_t *, uint32_t, cudaStream_t);
+void launch_trace_guided(const BatchDev &, bool, const uint32_t *, const PlanHead *, uint32_t, cudaStream_t);
+void launch_plan_guided(const BatchDev &, bool, PlanHead *, uint32_t *, uint32_t *, uint64_t *, unsigned long long, cudaStream_t);
+size_t plan_scratch_words(uint32_t);
 void launch_scan_counts(const BatchDev &, uint64_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
 void launch_emit(const BatchDev &, const ScoreParams &, bgpu_result *, bgpu_block *, uint32_t *, bgpu_gap *,
-                 const uint64_t *, const uint64_t *, const uint64_t *, int, int, int, cudaStream_t);
+                 const uint64_t *, const uint64_t *, const uint64_t *, int, int, int, PlanHead *, cudaStream_t);
 void launch_dense_prep(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint64_t *, const uint64_t *, cudaStream_t);
 void launch_dense_fill(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, uint32_t *, int,
                        cudaStream_t);
@@ -72,6 +74,21 @@ static void trace_init(cudaStream_t s) {
   });
 }
 
+// ---- memory.  A ticket makes ~40 allocations whose sizes follow the batch; a stream of blasr-sized tickets (the candidates
+// of a few reads) never repeats a size, so a per-size cache keeps missing and every miss is a cudaMalloc / cudaHostAlloc
+// (measured: 5-45 ms per ticket).  Instead each context keeps SLABS: a ticket takes whole slabs from the free list
+// (smallest one that holds the request and the ticket's size hint), bump-allocates inside them and gives them back on
+// release.  After a few tickets the free list covers the working set and allocation is pointer arithmetic.
+struct Slab { char *base; size_t cap; };
+struct SlabPool {
+  bool pinned;
+  std::vector<Slab> free_;
+  size_t lastCap = 0;
+  uint32_t nAlloc = 0;                           // cudaMalloc / cudaHostAlloc calls so far
+  explicit SlabPool(bool p) : pinned(p) {}
+};
+struct TicketMem { std::vector<Slab> owned; size_t used = 0, hint = 0; };
+
 struct bgpu_ctx {
   int device = 0, nSM = 0;
   cudaStream_t stream = nullptr;
@@ -81,10 +98,8 @@ struct bgpu_ctx {
   std::string err;
   std::mutex mu;
   size_t arrowPoolCap = 0;                       // max bytes of traceback pool per wave
-  std::multimap<size_t, void *> devFree, pinFree; // cached allocations by size
-  std::map<void *, size_t> devSize, pinSize;
+  SlabPool devPool{false}, pinPool{true};        // cached device / pinned slabs, handed to tickets whole
   bgpu_ticket lastSync = nullptr;                // ticket owned by bgpu_align
-  uint32_t nDevAlloc = 0, nPinAlloc = 0;         // cudaMalloc / cudaHostAlloc calls so far (cache misses)
 };
 
 #define CK(call)                                                                                  \
@@ -98,8 +113,6 @@ struct bgpu_ctx {
     }                                                                                             \
   } while (0)
 
-// Allocation size classes: eight per octave (<= 12.5 % slack), so the sub-batches of a stream of similar tickets keep
-// hitting the cached blocks instead of growing the cache with cudaMalloc / cudaHostAlloc calls in steady state.
 // Waits for everything queued on the context's stream.  By default the wait spins (lowest latency: 5 host threads x 10
 // sub-batches of 100k pairs pass in 131-140 ms against 140-150 ms with sleeping waits).  BGPU_BLOCKING_SYNC=1 makes waiting
 // threads sleep on an event created with cudaEventBlockingSync instead: for hosts that run more waiting threads than
@@ -111,43 +124,53 @@ static cudaError_t wait_stream(bgpu_ctx *ctx) {
   return e != cudaSuccess ? e : cudaEventSynchronize(ctx->evSync);
 }
 
-static size_t round_up(size_t n) {
-  const size_t g = 1u << 16;
-  if (n <= g) return g;
-  int e = 0;
-  while ((size_t(2) << e) < n) e++;                       // 2^e < n <= 2^(e+1)
-  const size_t step = std::max<size_t>((size_t(1) << e) / 8, g);
-  return (n + step - 1) / step * step;
+static cudaError_t raw_alloc(bool pinned, void **p, size_t bytes) {
+  return pinned ? cudaHostAlloc(p, bytes, cudaHostAllocDefault) : cudaMalloc(p, bytes);
 }
+static void raw_free(bool pinned, void *p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
 
-static int dev_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
-  bytes = round_up(bytes);
-  auto it = ctx->devFree.lower_bound(bytes);
-  if (it != ctx->devFree.end() && it->first <= bytes + bytes / 4 + (1u << 20)) { *p = it->second; ctx->devFree.erase(it); return BGPU_OK; }
-  ctx->nDevAlloc++;
-  cudaError_t e = cudaMalloc(p, bytes);
-  if (e != cudaSuccess) {   // drop the cache and retry once
-    for (auto &kv : ctx->devFree) { cudaFree(kv.second); ctx->devSize.erase(kv.second); }
-    ctx->devFree.clear();
-    cudaGetLastError();
-    e = cudaMalloc(p, bytes);
+static int slab_alloc(bgpu_ctx *ctx, SlabPool &pool, TicketMem &tm, void **p, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (!tm.owned.empty() && tm.used + bytes <= tm.owned.back().cap) {
+    *p = tm.owned.back().base + tm.used; tm.used += bytes; return BGPU_OK;
   }
-  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); return BGPU_E_OOM; }
-  ctx->devSize[*p] = bytes;
+  // a new slab: the smallest free one that holds this request plus what the ticket still expects to ask for
+  const size_t minSlab = pool.pinned ? (1u << 20) : (4u << 20);
+  const size_t want = std::max(bytes + std::min(tm.hint, (size_t)1 << 30), minSlab);
+  int best = -1, fits = -1;
+  for (int i = 0; i < (int)pool.free_.size(); i++) {
+    const size_t c = pool.free_[i].cap;
+    if (c >= want && (best < 0 || c < pool.free_[best].cap)) best = i;
+    if (c >= bytes && (fits < 0 || c > pool.free_[fits].cap)) fits = i;       // else the largest one that holds the request
+  }
+  if (best < 0) best = fits;
+  Slab sl{};
+  if (best >= 0) { sl = pool.free_[best]; pool.free_.erase(pool.free_.begin() + best); }
+  else {
+    size_t cap = std::max(want, std::min(2 * pool.lastCap, (size_t)1 << 30));
+    cap = (cap + 0xfffff) & ~(size_t)0xfffff;
+    void *v = nullptr;
+    pool.nAlloc++;
+    cudaError_t e = raw_alloc(pool.pinned, &v, cap);
+    if (e != cudaSuccess && cap > bytes) { cudaGetLastError(); cap = (bytes + 0xfffff) & ~(size_t)0xfffff; e = raw_alloc(pool.pinned, &v, cap); }
+    if (e != cudaSuccess) {   // drop the cache and retry once
+      cudaGetLastError();
+      for (auto &f : pool.free_) raw_free(pool.pinned, f.base);
+      pool.free_.clear();
+      e = raw_alloc(pool.pinned, &v, cap);
+    }
+    if (e != cudaSuccess) { ctx->err = std::string(pool.pinned ? "cudaHostAlloc: " : "cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); return BGPU_E_OOM; }
+    sl.base = (char *)v; sl.cap = cap; pool.lastCap = cap;
+  }
+  tm.hint = tm.hint > sl.cap - bytes ? tm.hint - (sl.cap - bytes) : 0;
+  tm.owned.push_back(sl); tm.used = bytes;
+  *p = sl.base;
   return BGPU_OK;
 }
-static void dev_free(bgpu_ctx *ctx, void *p) { if (p) ctx->devFree.emplace(ctx->devSize[p], p); }
-static int pin_alloc(bgpu_ctx *ctx, void **p, size_t bytes) {
-  bytes = round_up(bytes);
-  auto it = ctx->pinFree.lower_bound(bytes);
-  if (it != ctx->pinFree.end() && it->first <= 2 * bytes + (1u << 20)) { *p = it->second; ctx->pinFree.erase(it); return BGPU_OK; }
-  ctx->nPinAlloc++;
-  cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
-  if (e != cudaSuccess) { ctx->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); return BGPU_E_OOM; }
-  ctx->pinSize[*p] = bytes;
-  return BGPU_OK;
+static void slab_release(SlabPool &pool, TicketMem &tm) {
+  for (auto &sl : tm.owned) pool.free_.push_back(sl);
+  tm.owned.clear(); tm.used = 0; tm.hint = 0;
 }
-static void pin_free(bgpu_ctx *ctx, void *p) { if (p) ctx->pinFree.emplace(ctx->pinSize[p], p); }
 
 struct Wave { uint32_t begin[N_CLS], count[N_CLS]; uint32_t traceBegin, traceCount; };  // index by job class
 
@@ -156,8 +179,7 @@ struct bgpu_ticket_s {
   bgpu_params params{};
   ScoreParams sp{};
   BatchDev B{};
-  // device buffers (everything in `dev` is returned to the cache on release)
-  std::vector<void *> dev, pin;
+  TicketMem dev, pin;         // the slabs this ticket allocates from (returned to the context's pools on release)
   uint64_t *d_rowOff = nullptr, *d_dblkOff = nullptr, *d_runOff = nullptr, *d_arrowOff = nullptr;
   uint32_t *d_order = nullptr, *d_counters = nullptr;
   uint64_t *d_blockOff = nullptr, *d_listOff = nullptr, *d_gapOff = nullptr, *d_totals = nullptr;
@@ -179,17 +201,25 @@ struct bgpu_ticket_s {
   std::vector<uint64_t> h_arrowBytes;   // dense: host-computed traceback bytes per job
   std::vector<uint64_t> h_cellsMetric;  // dense: SURVEY 8(d) cell count per job
   uint32_t *h_cigar = nullptr; uint64_t *h_cigarOff = nullptr;   // bgpu_cigar results (pinned), once built
+  // asynchronous guided path: the schedule is built on the device (bgpu_plan.cu), one wave, speculative sizes
+  bool fast = false;            // submit enqueued everything without waiting for the device
+  bool gated = false;           // large ticket: goes through the H2D / kernel / D2H phase gates
+  bool arenaInline = false;     // the (small) result arena was copied back by submit already
+  PlanHead *d_plan = nullptr;   // device: one head per wave (the asynchronous path has exactly one)
+  PlanHead *h_planInit = nullptr, *h_plan = nullptr;   // pinned: the head as uploaded / as read back after the kernels
+  uint32_t *d_planScratch = nullptr;
+  uint64_t poolBytes = 0, arenaCap[3] = {0, 0, 0};
 };
 
 template <typename T>
 static int talloc_dev(bgpu_ctx *ctx, bgpu_ticket t, T **p, size_t n) {
-  void *v = nullptr; int rc = dev_alloc(ctx, &v, n * sizeof(T)); if (rc) return rc;
-  t->dev.push_back(v); *p = (T *)v; return BGPU_OK;
+  void *v = nullptr; int rc = slab_alloc(ctx, ctx->devPool, t->dev, &v, n * sizeof(T)); if (rc) return rc;
+  *p = (T *)v; return BGPU_OK;
 }
 template <typename T>
 static int talloc_pin(bgpu_ctx *ctx, bgpu_ticket t, T **p, size_t n) {
-  void *v = nullptr; int rc = pin_alloc(ctx, &v, n * sizeof(T)); if (rc) return rc;
-  t->pin.push_back(v); *p = (T *)v; return BGPU_OK;
+  void *v = nullptr; int rc = slab_alloc(ctx, ctx->pinPool, t->pin, &v, n * sizeof(T)); if (rc) return rc;
+  *p = (T *)v; return BGPU_OK;
 }
 #define RC(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
@@ -252,8 +282,8 @@ extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->lastSync) bgpu_release(ctx, ctx->lastSync);
   cudaStreamSynchronize(ctx->stream);
-  for (auto &kv : ctx->devFree) cudaFree(kv.second);
-  for (auto &kv : ctx->pinFree) cudaFreeHost(kv.second);
+  for (auto &sl : ctx->devPool.free_) cudaFree(sl.base);
+  for (auto &sl : ctx->pinPool.free_) cudaFreeHost(sl.base);
   for (int c = 0; c < N_CLS; c++) { cudaStreamDestroy(ctx->aux[c]); cudaEventDestroy(ctx->evJoin[c]); }
   cudaEventDestroy(ctx->evFork); cudaEventDestroy(ctx->evSync);
   cudaStreamDestroy(ctx->stream);
@@ -391,6 +421,17 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     }
     RC(talloc_dev(ctx, t, &t->d_order, std::max<size_t>(order.size(), 1)));
     RC(talloc_dev(ctx, t, &t->d_arrowOff, std::max<uint32_t>(n, 1)));
+    {   // the kernels read their part of the schedule from a device-resident head per wave
+      const size_t nw = std::max<size_t>(t->waves.size(), 1);
+      PlanHead *h_heads = nullptr;
+      RC(talloc_dev(ctx, t, &t->d_plan, nw)); RC(talloc_pin(ctx, t, &h_heads, nw));
+      memset(h_heads, 0, sizeof(PlanHead) * nw);
+      for (size_t w = 0; w < t->waves.size(); w++) {
+        for (int c = 0; c < N_CLS; c++) { h_heads[w].nGroups[c] = t->waves[w].count[c]; h_heads[w].orderBegin[c] = t->waves[w].begin[c]; }
+        h_heads[w].traceBegin = t->waves[w].traceBegin; h_heads[w].traceCount = t->waves[w].traceCount;
+      }
+      CK(cudaMemcpyAsync(t->d_plan, h_heads, sizeof(PlanHead) * nw, cudaMemcpyHostToDevice, s));
+    }
     t->nCounters = (uint32_t)t->waves.size() * 16 + 16;          // per wave: [c] = work queue of class c's fill kernel
     RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
     uint8_t *arrows = nullptr;
@@ -410,7 +451,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     t->timing.cells = cells;
     t->timing.fillCells = laneSteps;
   }
-  if (firstRun) { gate(ctx->device, GATE_COMPUTE).acquire(); t->holdsCompute = true; }   // released by the stream itself once the last kernel is done
+  if (firstRun && t->gated) { gate(ctx->device, GATE_COMPUTE).acquire(); t->holdsCompute = true; }   // released by the stream itself once the last kernel is done
   CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
   CK(cudaMemsetAsync(t->d_totals + 3, 0, sizeof(uint64_t), s));
   t->B.cellSlots = reinterpret_cast<unsigned long long *>(t->d_totals + 3);
@@ -422,14 +463,14 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     for (int c = N_CLS - 1; c >= 0; c--)
       if (W.count[c]) {
         CK(cudaStreamWaitEvent(ctx->aux[c], ctx->evFork, 0));
-        launch_fill_guided(t->B, t->sp, c, t->d_order + W.begin[c], W.count[c], t->d_counters + 16 * w + c, ctx->nSM, ctx->aux[c]);
+        launch_fill_guided(t->B, t->sp, c, t->d_order, t->d_plan + w, W.count[c], t->d_counters + 16 * w + c, ctx->nSM, ctx->aux[c]);
         CK(cudaEventRecord(ctx->evJoin[c], ctx->aux[c]));
         CK(cudaStreamWaitEvent(s, ctx->evJoin[c], 0));
         t->timing.kernelLaunches++;
       }
     CK(cudaEventRecord(t->waveEv[3 * w + 1], s));
     if (W.traceCount) {
-      launch_trace_guided(t->B, t->sp.affine != 0, t->d_order + W.traceBegin, W.traceCount, s);
+      launch_trace_guided(t->B, t->sp.affine != 0, t->d_order, t->d_plan + w, W.traceCount, s);
       t->timing.kernelLaunches++;
     }
     CK(cudaEventRecord(t->waveEv[3 * w + 2], s));
@@ -437,9 +478,64 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   launch_scan_counts(t->B, t->d_blockOff, t->d_listOff, t->d_gapOff, t->d_totals, s);
   t->timing.kernelLaunches++;
   CK(cudaEventRecord(t->ev[3], s));
-  if (firstRun) {
+  if (firstRun && t->holdsCompute) {
     if (gate(ctx->device, GATE_COMPUTE).width > 0) CK(cudaLaunchHostFunc(s, gate_release_cb, &gate(ctx->device, GATE_COMPUTE)));
     t->holdsCompute = false;
+  }
+  CK(cudaGetLastError());
+  return BGPU_OK;
+}
+
+static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t);
+
+// ---- the asynchronous schedule of a guided ticket: nothing here waits for the device.  prep -> planner kernels (classes,
+// warp groups, dispatch order, traceback offsets: bgpu_plan.cu) -> the fill kernel of every class (each reads its share of
+// the schedule from the device-resident PlanHead; empty classes exit at once) -> traceback -> count scan -> emit into an
+// arena sized from the batch -> the copies back.  The traceback pool and the arena are sized BEFORE the device knows the
+// exact needs; the kernels check, flag PLAN_OVF_* and skip, and bgpu_collect then re-plans that ticket on the host path.
+static int enqueue_guided_fast(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = t->nJobs;
+  CK(cudaEventRecord(t->ev[0], s));
+  launch_prep_guided(t->B, t->sp, t->params.band, t->d_rowOff, t->d_dblkOff, t->d_runOff, s);
+  CK(cudaEventRecord(t->ev[1], s));
+  CK(cudaMemcpyAsync(t->d_plan, t->h_planInit, sizeof(PlanHead), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(t->d_counters, 0, sizeof(uint32_t) * t->nCounters, s));
+  CK(cudaMemsetAsync(t->d_totals + 3, 0, sizeof(uint64_t), s));
+  t->B.cellSlots = reinterpret_cast<unsigned long long *>(t->d_totals + 3);
+  launch_plan_guided(t->B, t->sp.affine != 0, t->d_plan, t->d_planScratch, t->d_order, t->d_arrowOff, t->poolBytes, s);
+  if (firstRun && t->gated) { gate(ctx->device, GATE_COMPUTE).acquire(); t->holdsCompute = true; }
+  CK(cudaEventRecord(t->waveEv[0], s));
+  CK(cudaEventRecord(ctx->evFork, s));
+  t->timing.kernelLaunches = 2;
+  for (int c = N_CLS - 1; c >= 0; c--) {
+    CK(cudaStreamWaitEvent(ctx->aux[c], ctx->evFork, 0));
+    launch_fill_guided(t->B, t->sp, c, t->d_order, t->d_plan, n + N_CLS, t->d_counters + c, ctx->nSM, ctx->aux[c]);
+    CK(cudaEventRecord(ctx->evJoin[c], ctx->aux[c]));
+    CK(cudaStreamWaitEvent(s, ctx->evJoin[c], 0));
+    t->timing.kernelLaunches++;
+  }
+  CK(cudaEventRecord(t->waveEv[1], s));
+  launch_trace_guided(t->B, t->sp.affine != 0, t->d_order, t->d_plan, n, s);
+  CK(cudaEventRecord(t->waveEv[2], s));
+  launch_scan_counts(t->B, t->d_blockOff, t->d_listOff, t->d_gapOff, reinterpret_cast<uint64_t *>(&t->d_plan->totals[0]), s);
+  t->timing.kernelLaunches += 2;
+  CK(cudaEventRecord(t->ev[3], s));
+  if (t->arenaReady) RC(enqueue_emit(ctx, t));
+  if (firstRun && t->holdsCompute) {
+    if (gate(ctx->device, GATE_COMPUTE).width > 0) CK(cudaLaunchHostFunc(s, gate_release_cb, &gate(ctx->device, GATE_COMPUTE)));
+    t->holdsCompute = false;
+  }
+  if (firstRun) {
+    // the head (flags, totals, cell counts), the per-job results and -- when it is small -- the arena itself go back now
+    CK(cudaMemcpyAsync(t->h_plan, t->d_plan, sizeof(PlanHead), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(t->h_totals, t->d_totals, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, s));
+    if (t->arenaReady) CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * n, cudaMemcpyDeviceToHost, s));
+    if (t->arenaInline) {
+      CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->arenaCap[0], cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->arenaCap[1], cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->arenaCap[2], cudaMemcpyDeviceToHost, s));
+    }
   }
   CK(cudaGetLastError());
   return BGPU_OK;
@@ -448,7 +544,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
 static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t) {
   cudaStream_t s = ctx->stream;
   launch_emit(t->B, t->sp, t->d_results, t->d_blocks, t->d_gapCounts, t->d_gaps, t->d_blockOff, t->d_listOff,
-              t->d_gapOff, t->params.doStats, t->params.statsAffine, t->dense ? 1 : 0, s);
+              t->d_gapOff, t->params.doStats, t->params.statsAffine, t->dense ? 1 : 0, t->fast ? t->d_plan : nullptr, s);
   t->timing.kernelLaunches++;
   CK(cudaEventRecord(t->ev[4], s));
   CK(cudaGetLastError());
@@ -476,6 +572,9 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   RC(check_ids_tracks(ctx, fn, p, b));
   const uint64_t totQ = b->qOff[n], totT = b->tOff[n], totG = b->guideOff[n];
   fill_score_params(t->sp, fn, p);
+  // what this ticket is going to ask for besides the traceback pool (sequences, band table, runs, job tables, results)
+  t->dev.hint = 17 * totQ + 7 * totT + 12 * totG + 512ull * n + (1u << 16);
+  t->pin.hint = 4 * totQ + totT + 12 * totG + 320ull * n + (1u << 16);
   BatchDev &B = t->B;
   B.nJobs = n;
   uint64_t *d_qOff, *d_tOff, *d_gOff; uint8_t *d_q, *d_t, *d_tc, *d_qual = nullptr; bgpu_block *d_guide; int32_t *d_band = nullptr;
@@ -487,7 +586,10 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   // prep writes tc only inside [tStart, tEnd) of each job, the fill kernels also stage the boundary column t' = 0 and the
   // columns past the guide's end: those bytes must be valid codes (0), not whatever the cached allocation last held
   CK(cudaMemsetAsync(d_tc, 0, totT + 16, ctx->stream));
-  gate(ctx->device, GATE_H2D).acquire(); t->holdsH2D = true;   // until the uploads below are done
+  // the phase gates keep LARGE tickets of concurrent contexts pipelined (copy in / compute / copy out); small tickets
+  // (the candidates of a few reads) would only pay their host round trips
+  t->gated = totQ + totT + sizeof(bgpu_block) * totG > (32u << 20);
+  if (t->gated) { gate(ctx->device, GATE_H2D).acquire(); t->holdsH2D = true; }   // until the uploads below are done
   RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
   RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));
   RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
@@ -500,25 +602,64 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   // capacities from sequence lengths (upper bounds of the guide extents)
   uint64_t *h_off = nullptr;
   RC(talloc_pin(ctx, t, &h_off, 3 * (size_t)n + 3));
-  uint64_t rowTot = 0, dbTot = 0, runTot = 0;
+  uint64_t rowTot = 0, dbTot = 0, runTot = 0, poolEst = 0;
+  const uint64_t rowsPerBlock = t->sp.affine ? 16 : 4;
   for (uint32_t i = 0; i < n; i++) {
     const uint64_t ql = b->qOff[i + 1] - b->qOff[i], tl = b->tOff[i + 1] - b->tOff[i];
     h_off[i] = rowTot; h_off[n + i] = dbTot; h_off[2 * (size_t)n + i] = runTot;
     rowTot += ql + 1; dbTot += (ql + tl + 1) / 64 + 2; runTot += ql + tl + 2;
+    // traceback bytes this job is expected to reserve: d-blocks x rows per block x words per row (window of the band plus
+    // drift and class quantisation) -- an estimate, the planner kernels check the real sum against the pool
+    const int64_t bd = std::max<int64_t>(b->band ? b->band[i] : p->band, 0);
+    poolEst += ((((ql + tl + 1) / 64 + 2) * rowsPerBlock * (uint64_t)(bd + 49) * 4ull) + 255ull) & ~255ull;
   }
   RC(talloc_dev(ctx, t, &t->d_rowOff, 3 * (size_t)n + 3));
   t->d_dblkOff = t->d_rowOff + n; t->d_runOff = t->d_rowOff + 2 * (size_t)n;
   CK(cudaMemcpyAsync(t->d_rowOff, h_off, sizeof(uint64_t) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
   // the stream leaves the H2D gate as soon as the last input byte has landed
-  if (gate(ctx->device, GATE_H2D).width > 0) CK(cudaLaunchHostFunc(ctx->stream, gate_release_cb, &gate(ctx->device, GATE_H2D)));
-  t->holdsH2D = false;
+  if (t->holdsH2D) {
+    if (gate(ctx->device, GATE_H2D).width > 0) CK(cudaLaunchHostFunc(ctx->stream, gate_release_cb, &gate(ctx->device, GATE_H2D)));
+    t->holdsH2D = false;
+  }
   RC(talloc_dev(ctx, t, &B.geom, n)); RC(talloc_dev(ctx, t, &B.rows, rowTot + 1)); RC(talloc_dev(ctx, t, &B.dblk, dbTot + 1));
   RC(talloc_dev(ctx, t, &B.dmin, dbTot + 1)); RC(talloc_dev(ctx, t, &B.dmax, dbTot + 1)); RC(talloc_dev(ctx, t, &B.runs, runTot + 1));
   RC(talloc_dev(ctx, t, &t->d_blockOff, 3 * (size_t)n + 3));
   t->d_listOff = t->d_blockOff + n; t->d_gapOff = t->d_blockOff + 2 * (size_t)n;
   RC(talloc_dev(ctx, t, &t->d_totals, 4)); RC(talloc_dev(ctx, t, &t->d_results, n));
   RC(talloc_pin(ctx, t, &t->h_geom, n)); RC(talloc_pin(ctx, t, &t->h_totals, 4)); RC(talloc_pin(ctx, t, &t->h_results, n));
-  return enqueue_guided(ctx, t, true);
+  static const bool hostPlan = [] { const char *e = getenv("BGPU_HOST_PLAN"); return e && *e && *e != '0'; }();
+  if (hostPlan || n == 0 || poolEst > ctx->arrowPoolCap) return enqueue_guided(ctx, t, true);   // multi-wave: planned on the host
+  // ---- asynchronous path
+  t->fast = true;
+  t->poolBytes = poolEst;
+  uint8_t *arrows = nullptr;
+  RC(talloc_dev(ctx, t, &t->d_order, 2 * (size_t)n + 64)); RC(talloc_dev(ctx, t, &t->d_arrowOff, n));
+  t->nCounters = 16;
+  RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
+  RC(talloc_dev(ctx, t, &t->d_plan, 1)); RC(talloc_dev(ctx, t, &t->d_planScratch, plan_scratch_words(n)));
+  RC(talloc_pin(ctx, t, &t->h_planInit, 1)); RC(talloc_pin(ctx, t, &t->h_plan, 1));
+  RC(talloc_dev(ctx, t, &arrows, std::max<uint64_t>(poolEst, 16)));
+  B.arrows = arrows; B.arrowOff = t->d_arrowOff; B.order = t->d_order; B.counters = t->d_counters;
+  memset(t->h_planInit, 0, sizeof(PlanHead));
+  // result arena sized from the batch (a block needs a matching base, gap runs sit between blocks): speculative when that
+  // is small enough to keep around, else sized exactly by bgpu_collect once the counts are known
+  t->arenaCap[0] = totQ / 4 + 2ull * n + 16; t->arenaCap[1] = t->arenaCap[0] + n; t->arenaCap[2] = 2 * t->arenaCap[0];
+  const uint64_t arenaBytes = sizeof(bgpu_block) * t->arenaCap[0] + sizeof(uint32_t) * t->arenaCap[1] + sizeof(bgpu_gap) * t->arenaCap[2];
+  if (arenaBytes <= (64u << 20)) {
+    RC(talloc_dev(ctx, t, &t->d_blocks, t->arenaCap[0])); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->arenaCap[1]));
+    RC(talloc_dev(ctx, t, &t->d_gaps, t->arenaCap[2]));
+    RC(talloc_pin(ctx, t, &t->h_blocks, t->arenaCap[0])); RC(talloc_pin(ctx, t, &t->h_gapCounts, t->arenaCap[1]));
+    RC(talloc_pin(ctx, t, &t->h_gaps, t->arenaCap[2]));
+    t->arenaReady = true;
+    t->arenaInline = arenaBytes <= (1u << 20);
+    for (int k = 0; k < 3; k++) t->h_planInit->caps[k] = t->arenaCap[k];
+  } else {
+    for (int k = 0; k < 3; k++) t->h_planInit->caps[k] = ~0ull;
+  }
+  t->waves.assign(1, Wave{});
+  t->waveEv.resize(3);
+  for (auto &e : t->waveEv) CK(cudaEventCreate(&e));
+  return enqueue_guided_fast(ctx, t, true);
 }
 
 
@@ -607,6 +748,8 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
   RC(check_ids_tracks(ctx, fn, p, b));
   const uint64_t totQ = b->qOff[n], totT = b->tOff[n];
   fill_score_params(t->sp, fn, p);
+  t->dev.hint = 8 * totQ + 32 * totT + 512ull * n + (1u << 16);
+  t->pin.hint = 4 * totQ + 4 * totT + 320ull * n + (1u << 16);
   t->dense = true;
   t->dargs.algo = p->algo; t->dargs.defaultBand = p->band; t->dargs.bndIns = p->bndIns; t->dargs.bndDel = p->bndDel;
   t->dargs.hpInsOpen = p->hpInsOpen; t->dargs.hpInsExtend = p->hpInsExtend; t->dargs.insOpen = p->insOpen; t->dargs.insExtend = p->insExtend;
@@ -672,8 +815,7 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
     cudaStreamSynchronize(ctx->stream);
     if (t->holdsH2D) { gate(ctx->device, GATE_H2D).release(); t->holdsH2D = false; }
     if (t->holdsCompute) { gate(ctx->device, GATE_COMPUTE).release(); t->holdsCompute = false; }
-    for (void *v : t->dev) dev_free(ctx, v);
-    for (void *v : t->pin) pin_free(ctx, v);
+    slab_release(ctx->devPool, t->dev); slab_release(ctx->pinPool, t->pin);
     for (auto &e : t->ev) cudaEventDestroy(e);
     for (auto &e : t->waveEv) cudaEventDestroy(e);
     delete t;
@@ -738,15 +880,54 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
   cudaStream_t s = ctx->stream;
   const auto h0 = std::chrono::steady_clock::now();
   if (!t->collected) {
-    RC(ensure_arena(ctx, t));
-    RC(enqueue_emit(ctx, t));                          // a kernel: outside the D2H gate, which only covers the copies
-    struct Hold { Gate &g; Hold(Gate &x) : g(x) { g.acquire(); } ~Hold() { g.release(); } } hold(gate(ctx->device, GATE_D2H));
-    CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(t->ev[5], s));
-    CK(wait_stream(ctx));
+    bool copied = false;
+    if (t->fast) {
+      CK(wait_stream(ctx));                              // everything bgpu_submit enqueued
+      if (t->h_plan->overflow & PLAN_OVF_ARROWS) {
+        // the traceback pool was under-estimated (adversarial guides): plan this ticket on the host, in waves
+        t->fast = false; t->arenaReady = false; t->arenaInline = false;
+        for (auto &e : t->waveEv) cudaEventDestroy(e);
+        t->waveEv.clear(); t->waves.clear();
+        t->d_blocks = nullptr;
+        RC(enqueue_guided(ctx, t, true));
+      } else {
+        for (int i = 0; i < 3; i++) t->totals[i] = t->h_plan->totals[i];
+        t->timing.cells = t->h_plan->cells; t->timing.fillCells = t->h_totals[3];
+        const bool emitted = t->arenaReady && !(t->h_plan->overflow & PLAN_OVF_ARENA);
+        if (!emitted) {                                  // no speculative arena, or it was too small: exact sizes now
+          t->fast = false;                               // (emit without the capacity check)
+          RC(talloc_dev(ctx, t, &t->d_blocks, t->totals[0] + 1)); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->totals[1] + 1));
+          RC(talloc_dev(ctx, t, &t->d_gaps, t->totals[2] + 1));
+          RC(talloc_pin(ctx, t, &t->h_blocks, t->totals[0] + 1)); RC(talloc_pin(ctx, t, &t->h_gapCounts, t->totals[1] + 1));
+          RC(talloc_pin(ctx, t, &t->h_gaps, t->totals[2] + 1));
+          t->arenaReady = true; t->arenaInline = false;
+          for (int k = 0; k < 3; k++) t->h_planInit->caps[k] = ~0ull;   // a later bgpu_rerun emits into this exact-size arena
+          RC(enqueue_emit(ctx, t));
+          t->fast = true;
+        }
+        if (!t->arenaInline) {
+          struct Hold { Gate *g; Hold(Gate *x) : g(x) { if (g) g->acquire(); } ~Hold() { if (g) g->release(); } } hold(t->gated ? &gate(ctx->device, GATE_D2H) : nullptr);
+          if (!emitted) CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
+          CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
+          CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
+          CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
+          CK(cudaEventRecord(t->ev[5], s));
+          CK(wait_stream(ctx));
+        }
+        copied = true;
+      }
+    }
+    if (!copied) {
+      RC(ensure_arena(ctx, t));
+      RC(enqueue_emit(ctx, t));                          // a kernel: outside the D2H gate, which only covers the copies
+      struct Hold { Gate *g; Hold(Gate *x) : g(x) { if (g) g->acquire(); } ~Hold() { if (g) g->release(); } } hold(t->gated || t->dense ? &gate(ctx->device, GATE_D2H) : nullptr);
+      CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
+      CK(cudaEventRecord(t->ev[5], s));
+      CK(wait_stream(ctx));
+    }
     t->timing.d2hBytes = sizeof(bgpu_result) * (uint64_t)t->nJobs + sizeof(bgpu_block) * t->totals[0] +
                          sizeof(uint32_t) * t->totals[1] + sizeof(bgpu_gap) * t->totals[2];
     gather_timing(t);
@@ -806,8 +987,9 @@ extern "C" int bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!t->collected) { ctx->err = "bgpu_rerun needs a collected ticket"; return BGPU_E_BUSY; }
   if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
-  if (t->dense) RC(enqueue_dense(ctx, t, false)); else RC(enqueue_guided(ctx, t, false));
-  RC(enqueue_emit(ctx, t));
+  if (t->dense) { RC(enqueue_dense(ctx, t, false)); RC(enqueue_emit(ctx, t)); }
+  else if (t->fast) RC(enqueue_guided_fast(ctx, t, false));   // emit included (the arena exists by now)
+  else { RC(enqueue_guided(ctx, t, false)); RC(enqueue_emit(ctx, t)); }
   CK(wait_stream(ctx));
   gather_timing(t);
   return BGPU_OK;
@@ -816,7 +998,7 @@ extern "C" int bgpu_rerun(bgpu_ctx *ctx, bgpu_ticket t) {
 extern "C" int bgpu_timing_of(bgpu_ctx *ctx, bgpu_ticket t, bgpu_timing *out) {
   if (!ctx || !t || !out) return BGPU_E_INVALID;
   *out = t->timing;
-  out->devAllocs = ctx->nDevAlloc; out->pinAllocs = ctx->nPinAlloc;
+  out->devAllocs = ctx->devPool.nAlloc; out->pinAllocs = ctx->pinPool.nAlloc;
   return BGPU_OK;
 }
 
@@ -825,8 +1007,7 @@ extern "C" int bgpu_release(bgpu_ctx *ctx, bgpu_ticket t) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (void *v : t->dev) dev_free(ctx, v);
-  for (void *v : t->pin) pin_free(ctx, v);
+  slab_release(ctx->devPool, t->dev); slab_release(ctx->pinPool, t->pin);
   for (auto &e : t->ev) cudaEventDestroy(e);
   for (auto &e : t->waveEv) cudaEventDestroy(e);
   if (ctx->lastSync == t) ctx->lastSync = nullptr;

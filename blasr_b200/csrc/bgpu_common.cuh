@@ -105,6 +105,24 @@ struct BatchDev {         // device pointers of one submitted batch
   unsigned long long *cellSlots;  // cell slots executed by the guided fill kernels (lane-steps x groups), or NULL
 };
 
+// Device-resident schedule of one wave of a guided ticket: written by the planner kernels (bgpu_plan.cu) on the asynchronous
+// path, uploaded by the host planner on the multi-wave path.  order[] holds, class after class, the warp groups (32 / LPJ
+// job slots each, NOJOB pads a partial group) in dispatch order, then the traceback list.
+struct PlanHead {
+  uint32_t nGroups[N_CLS];       // warp groups per job class
+  uint32_t orderBegin[N_CLS];    // first slot of the class in order[]
+  uint32_t traceBegin, traceCount;
+  uint32_t clsCount[N_CLS];      // jobs with status OK per class
+  uint32_t nOk, nGroupsTotal, nSlots;
+  uint32_t overflow;             // bit 0: the traceback pool is too small for this wave, bit 1: the result arena is
+  unsigned long long arrowBytes; // traceback bytes reserved
+  unsigned long long cells;      // sum of nCells (ComputeMatrixNElem) over the OK jobs
+  unsigned long long laneSteps;  // lower bound of the cell slots the fill warps execute
+  unsigned long long totals[3];  // blocks, gap lists, gaps of the whole ticket (scan_counts_kernel)
+  unsigned long long caps[3];    // capacities of the result arena the emit kernel may write into
+};
+enum { PLAN_OVF_ARROWS = 1, PLAN_OVF_ARENA = 2 };
+
 struct DenseArgs {
   int algo;            // BGPU_KBAND / BGPU_SW / BGPU_AFFINE_KBAND
   int defaultBand, bndIns, bndDel;

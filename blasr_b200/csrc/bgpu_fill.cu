@@ -312,7 +312,7 @@ struct RingDispatch<LPJ, KM, AFFINE, FN, KM + 1> {
 // lockstep from d-block 0, with k = the widest member's need per block.
 template <int LPJ, int KM, bool AFFINE, int FN>
 __global__ void __launch_bounds__(KM <= KRING ? 128 : 32, KM <= 4 ? (AFFINE ? 4 : 5) : (KM <= KRING ? (AFFINE ? 4 : 5) : 1))
-fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nGroups, uint32_t *counter) {
+fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const PlanHead *plan, int cls, uint32_t *counter) {
   typedef Fmt<AFFINE> F;
   typedef SubSmem<LPJ, KM, FN> Smem;
   constexpr int NJ = 32 / LPJ;
@@ -321,6 +321,10 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
   constexpr int UNITW = (64 / F::SPW) * LPJ;                // words per arrow unit
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ int Mtab[25];
+  // the schedule lives on the device (planner kernels or the host planner's upload): this class's warp groups
+  if (plan->overflow & PLAN_OVF_ARROWS) return;                // the traceback pool cannot hold this wave: the host re-plans
+  const uint32_t nGroups = plan->nGroups[cls];
+  const uint32_t *order = orderBase + plan->orderBegin[cls];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPJ, sl = lane % LPJ;
   Smem &sm = reinterpret_cast<Smem *>(smemRaw)[warp * NJ + sub];
@@ -491,7 +495,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *order, uint32_t nG
 }
 
 template <int LPJ, int KM, bool AFFINE, int FN>
-static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, uint32_t nGroups,
+static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *order, const PlanHead *plan, int cls, uint32_t nGroups,
                        uint32_t *counter, int nSM, cudaStream_t s) {
   constexpr int WPC = KM <= KRING ? 4 : 1;          // warps per CTA
   const size_t smem = sizeof(SubSmem<LPJ, KM, FN>) * (32 / LPJ) * WPC;
@@ -503,32 +507,33 @@ static void launch_one(const BatchDev &B, const ScoreParams &P, const uint32_t *
   unsigned grid = (unsigned)(nSM * perSM);
   const unsigned need = (nGroups + WPC - 1) / WPC;
   if (grid > need) grid = need;
-  if (grid) kern<<<grid, WPC * 32, smem, s>>>(B, P, order, nGroups, counter);
+  if (grid) kern<<<grid, WPC * 32, smem, s>>>(B, P, order, plan, cls, counter);
 }
 
 template <bool AFFINE, int FN>
-static void launch_cls(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, uint32_t nGroups,
+static void launch_cls(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, const PlanHead *plan, uint32_t nGroups,
                        uint32_t *counter, int nSM, cudaStream_t s) {
-  if (cls == CLS_L8N) launch_one<8, 4, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
-  else if (cls == CLS_L8) launch_one<8, KRING, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
-  else if (cls == CLS_L16) launch_one<16, KRING, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
-  else if (cls == CLS_L32) launch_one<32, KRING, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
-  else launch_one<32, KWIDE, AFFINE, FN>(B, P, order, nGroups, counter, nSM, s);
+  if (cls == CLS_L8N) launch_one<8, 4, AFFINE, FN>(B, P, order, plan, cls, nGroups, counter, nSM, s);
+  else if (cls == CLS_L8) launch_one<8, KRING, AFFINE, FN>(B, P, order, plan, cls, nGroups, counter, nSM, s);
+  else if (cls == CLS_L16) launch_one<16, KRING, AFFINE, FN>(B, P, order, plan, cls, nGroups, counter, nSM, s);
+  else if (cls == CLS_L32) launch_one<32, KRING, AFFINE, FN>(B, P, order, plan, cls, nGroups, counter, nSM, s);
+  else launch_one<32, KWIDE, AFFINE, FN>(B, P, order, plan, cls, nGroups, counter, nSM, s);
 }
 
-// cls: CLS_*; order: nGroups groups of 32 / cls_lpj(cls) job indices
-void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, uint32_t nGroups,
-                        uint32_t *counter, int nSM, cudaStream_t s) {
+// cls: CLS_*; the class's warp groups (32 / cls_lpj(cls) job slots each) are plan->nGroups[cls] groups from
+// order[plan->orderBegin[cls]]; nGroupsBound (an upper bound known to the host) only sizes the grid.
+void launch_fill_guided(const BatchDev &B, const ScoreParams &P, int cls, const uint32_t *order, const PlanHead *plan,
+                        uint32_t nGroupsBound, uint32_t *counter, int nSM, cudaStream_t s) {
   const bool aff = P.affine != 0;
   if (P.kind == BGPU_FN_IDS) {
-    if (aff) launch_cls<true, 2>(B, P, cls, order, nGroups, counter, nSM, s);
-    else launch_cls<false, 2>(B, P, cls, order, nGroups, counter, nSM, s);
+    if (aff) launch_cls<true, 2>(B, P, cls, order, plan, nGroupsBound, counter, nSM, s);
+    else launch_cls<false, 2>(B, P, cls, order, plan, nGroupsBound, counter, nSM, s);
   } else if (P.kind == BGPU_FN_QUALITY) {
-    if (aff) launch_cls<true, 1>(B, P, cls, order, nGroups, counter, nSM, s);
-    else launch_cls<false, 1>(B, P, cls, order, nGroups, counter, nSM, s);
+    if (aff) launch_cls<true, 1>(B, P, cls, order, plan, nGroupsBound, counter, nSM, s);
+    else launch_cls<false, 1>(B, P, cls, order, plan, nGroupsBound, counter, nSM, s);
   } else {
-    if (aff) launch_cls<true, 0>(B, P, cls, order, nGroups, counter, nSM, s);
-    else launch_cls<false, 0>(B, P, cls, order, nGroups, counter, nSM, s);
+    if (aff) launch_cls<true, 0>(B, P, cls, order, plan, nGroupsBound, counter, nSM, s);
+    else launch_cls<false, 0>(B, P, cls, order, plan, nGroupsBound, counter, nSM, s);
   }
 }
 

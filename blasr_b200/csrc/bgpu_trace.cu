@@ -36,12 +36,17 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool AFFINE>
-__global__ void __launch_bounds__(TR_THREADS) trace_guided_kernel(BatchDev B, const uint32_t *order, uint32_t nOrder) {
+__global__ void __launch_bounds__(TR_THREADS) trace_guided_kernel(BatchDev B, const uint32_t *orderBase, const PlanHead *plan, uint32_t spread) {
   constexpr int BITS = AFFINE ? 8 : 2, SPW = 32 / BITS, ROWS = 64 / SPW, CR = TrGeom<AFFINE>::CR, CPB = ROWS / CR, WP = TrGeom<AFFINE>::WP;
   // piece (buffer bi, row r, piece pc) of thread tid: interleaved over the CTA's threads, 16 B each
   __shared__ __align__(16) uint32_t win[2 * CR * WP * TR_THREADS * 4];
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nOrder) return;
+  // spread = 1 << k: only every spread-th thread walks (a small ticket has fewer walks than the chip has warps, and walks
+  // that share a warp serialise on each other's branches: 64 walks of 10 kb take 6.1 ms packed, 2.8 ms one per warp)
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid & (spread - 1)) return;
+  const uint32_t idx = gtid / spread;
+  if ((plan->overflow & PLAN_OVF_ARROWS) || idx >= plan->traceCount) return;
+  const uint32_t *order = orderBase + plan->traceBegin;
   const uint32_t job = order[idx];
   if (job == 0xffffffffu) return;
   JobGeom &G = B.geom[job];
@@ -226,11 +231,18 @@ __device__ __forceinline__ uint32_t warp_excl_u32(uint32_t v, int lane, uint32_t
 // warp compares 32 consecutive query bases per step whatever the run lengths are.
 constexpr int EMIT_WARPS = 4;
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, ScoreParams P, EmitOut O, int doStats, int statsAffine,
-                                                   int keepLeading) {
+                                                   int keepLeading, PlanHead *plan) {
   __shared__ uint8_t lut[256];
   __shared__ int sM[64];
   __shared__ uint32_t sQ[EMIT_WARPS][32];
   __shared__ int sDelta[EMIT_WARPS][32];
+  if (plan) {   // asynchronous path: the arena was sized before the counts were known; the host re-emits when it is too small
+    if (plan->overflow & PLAN_OVF_ARROWS) return;
+    if (plan->totals[0] > plan->caps[0] || plan->totals[1] > plan->caps[1] || plan->totals[2] > plan->caps[2]) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&plan->overflow, (uint32_t)PLAN_OVF_ARENA);
+      return;
+    }
+  }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = base_code((uint8_t)i);
   if (threadIdx.x < 64) { const int r = threadIdx.x >> 3, c = threadIdx.x & 7; sM[threadIdx.x] = (r < 5 && c < 5) ? P.M[r * 5 + c] : 0; }
   __syncthreads();
@@ -365,12 +377,18 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
   if (lane == 0) O.results[job] = R;
 }
 
-void launch_trace_guided(const BatchDev &B, bool affine, const uint32_t *order, uint32_t nOrder, cudaStream_t s) {
+// the traceback list is plan->traceCount jobs from order[plan->traceBegin]; nOrder (a host-side upper bound) sizes the grid
+void launch_trace_guided(const BatchDev &B, bool affine, const uint32_t *order, const PlanHead *plan, uint32_t nOrder, cudaStream_t s) {
   const unsigned block = TR_THREADS;   // small CTAs spread the (few, long) walks over all SMs
-  const unsigned grid = (nOrder + block - 1) / block;
-  if (!grid) return;
-  if (affine) trace_guided_kernel<true><<<grid, block, 0, s>>>(B, order, nOrder);
-  else trace_guided_kernel<false><<<grid, block, 0, s>>>(B, order, nOrder);
+  if (!nOrder) return;
+  // one walk per warp while the walks fit the chip that way (about 7 resident CTAs of 64 threads per SM), else 2, 4, ... 32 per warp
+  static int nSM = 0;
+  if (!nSM) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev); }
+  unsigned spread = 32;
+  while (spread > 1 && (unsigned long long)nOrder * spread > (unsigned long long)nSM * 7 * TR_THREADS) spread >>= 1;
+  const unsigned grid = (unsigned)(((unsigned long long)nOrder * spread + block - 1) / block);
+  if (affine) trace_guided_kernel<true><<<grid, block, 0, s>>>(B, order, plan, spread);
+  else trace_guided_kernel<false><<<grid, block, 0, s>>>(B, order, plan, spread);
 }
 
 void launch_scan_counts(const BatchDev &B, uint64_t *blockOff, uint64_t *listOff, uint64_t *gapOff, uint64_t *totals,
@@ -380,10 +398,10 @@ void launch_scan_counts(const BatchDev &B, uint64_t *blockOff, uint64_t *listOff
 
 void launch_emit(const BatchDev &B, const ScoreParams &P, bgpu_result *results, bgpu_block *blocks,
                  uint32_t *gapCounts, bgpu_gap *gaps, const uint64_t *blockOff, const uint64_t *listOff,
-                 const uint64_t *gapOff, int doStats, int statsAffine, int keepLeading, cudaStream_t s) {
+                 const uint64_t *gapOff, int doStats, int statsAffine, int keepLeading, PlanHead *plan, cudaStream_t s) {
   EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff};
   const unsigned grid = (B.nJobs + EMIT_WARPS - 1) / EMIT_WARPS;
-  if (grid) emit_kernel<<<grid, EMIT_WARPS * 32, 0, s>>>(B, P, O, doStats, statsAffine, keepLeading);
+  if (grid) emit_kernel<<<grid, EMIT_WARPS * 32, 0, s>>>(B, P, O, doStats, statsAffine, keepLeading, plan);
 }
 
 }  // namespace bgpu

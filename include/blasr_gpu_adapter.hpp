@@ -17,6 +17,8 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -177,12 +179,13 @@ class RefineBatch {
 // RefineService keeps that structure untouched: every pthread hands its RefineBatch to Run() and blocks; the first
 // waiter becomes the leader, gathers the batches of the other threads until every client that is not already being
 // served has arrived (or a short window closes), submits them as ONE ticket and hands each thread its slice of the
-// results.  Two or more contexts let the next merged ticket copy in while the previous one computes.
+// results.  Three contexts keep three merged tickets in flight (a ticket's latency is the serial sweep of its longest read).
 class RefineService {
  public:
-  RefineService(int device, int nClients, int maxWaitUs = 300, int nContexts = 2)
+  RefineService(int device, int nClients, int maxWaitUs = 300, int nContexts = 3)
       : nClients_(nClients < 1 ? 1 : nClients), maxWaitUs_(maxWaitUs) {
     for (int i = 0; i < (nContexts < 1 ? 1 : nContexts); i++) ctxs_.push_back(std::unique_ptr<Context>(new Context(device)));
+    busy_.assign(ctxs_.size(), false);
   }
 
   template <typename T_ScoreFn>
@@ -197,22 +200,37 @@ class RefineService {
     pending_.push_back(&r);
     cv_.notify_all();
     while (!r.done) {
-      if (leaderActive_) { cv_.wait(lk); continue; }
+      if (leaderActive_ || r.taken) { cv_.wait(lk); continue; }   // someone else gathers, or already carries this request
       leaderActive_ = true;
-      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(maxWaitUs_);
-      while ((int)pending_.size() + inflight_ < nClients_)
-        if (cv_.wait_until(lk, deadline) == std::cv_status::timeout) break;
+      // The leader holds its ticket back until a context is free: a ticket queued behind a busy context gains nothing,
+      // while the requests that arrive in the meantime make the next ticket larger (batching by back-pressure).
+      const auto t0 = std::chrono::steady_clock::now();
+      const auto deadline = t0 + std::chrono::microseconds(maxWaitUs_);
+      int c = -1;
+      for (;;) {
+        c = -1;
+        for (size_t i = 0; i < busy_.size(); i++) if (!busy_[i]) { c = (int)i; break; }
+        const bool full = (int)pending_.size() + inflight_ >= nClients_;
+        const bool late = std::chrono::steady_clock::now() >= deadline;
+        if (c >= 0 && (full || late)) break;
+        if (c < 0 || late) cv_.wait(lk); else cv_.wait_until(lk, deadline);
+      }
       std::vector<Request *> mine, rest;          // one ticket = one (score function, parameters) pair
       for (Request *x : pending_)
         (std::memcmp(&x->fn, &r.fn, sizeof r.fn) == 0 && std::memcmp(&x->p, &r.p, sizeof r.p) == 0 ? mine : rest).push_back(x);
       pending_.swap(rest);
+      for (Request *x : mine) x->taken = true;
       inflight_ += (int)mine.size();
-      Context &ctx = *ctxs_[next_++ % ctxs_.size()];
+      busy_[c] = true;
       leaderActive_ = false;
       cv_.notify_all();
       lk.unlock();
-      Execute(ctx, mine);
+      const auto e0 = std::chrono::steady_clock::now();
+      Execute(*ctxs_[c], mine);
+      const double ems = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - e0).count();
       lk.lock();
+      executeMs_ += ems; gatherMs_ += std::chrono::duration<double, std::milli>(e0 - t0).count();
+      busy_[c] = false;
       inflight_ -= (int)mine.size();
       for (Request *x : mine) x->done = true;
       cv_.notify_all();
@@ -223,9 +241,16 @@ class RefineService {
 
   uint64_t Tickets() const { return tickets_; }
   uint64_t Jobs() const { return jobs_; }
+  ~RefineService() {
+    if (getenv("BGPU_SERVICE_STATS"))
+      fprintf(stderr, "RefineService: %llu tickets, %llu jobs (%.1f per ticket); per ticket: gather %.2f ms, execute %.2f ms (bgpu_submit %.2f, bgpu_collect %.2f, kernels on the device %.2f)\n",
+              (unsigned long long)tickets_, (unsigned long long)jobs_, tickets_ ? (double)jobs_ / tickets_ : 0.0,
+              tickets_ ? gatherMs_ / tickets_ : 0.0, tickets_ ? executeMs_ / tickets_ : 0.0, tickets_ ? submitMs_ / tickets_ : 0.0,
+              tickets_ ? collectMs_ / tickets_ : 0.0, tickets_ ? deviceMs_ / tickets_ : 0.0);
+  }
 
  private:
-  struct Request { RefineBatch *batch; bgpu_scorefn fn; bgpu_params p; bool done = false; int rc = BGPU_OK; std::string err; };
+  struct Request { RefineBatch *batch; bgpu_scorefn fn; bgpu_params p; bool taken = false, done = false; int rc = BGPU_OK; std::string err; };
 
   void Execute(Context &ctx, std::vector<Request *> &reqs) {
     std::vector<uint8_t> q, t, qual; std::vector<bgpu_block> guide; std::vector<uint64_t> qOff(1, 0), tOff(1, 0), gOff(1, 0);
@@ -245,15 +270,24 @@ class RefineService {
     std::vector<bgpu_result> res(mb.nJobs);
     bgpu_arena arena; std::memset(&arena, 0, sizeof arena);
     bgpu_ticket tk = nullptr;
+    const auto s0 = std::chrono::steady_clock::now();
     int rc = mb.nJobs ? bgpu_submit(ctx.get(), &reqs[0]->fn, &reqs[0]->p, &mb, &tk) : BGPU_OK;
+    const auto s1 = std::chrono::steady_clock::now();
     if (rc == BGPU_OK && tk) rc = bgpu_collect(ctx.get(), tk, res.data(), &arena);
+    if (rc == BGPU_OK && tk) {
+      bgpu_timing tm; bgpu_timing_of(ctx.get(), tk, &tm);
+      std::lock_guard<std::mutex> lk(mu_);
+      submitMs_ += std::chrono::duration<double, std::milli>(s1 - s0).count();
+      collectMs_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s1).count();
+      deviceMs_ += tm.msTotal;
+    }
     if (rc != BGPU_OK) {
       const std::string e = bgpu_last_error(ctx.get());
       if (tk) bgpu_release(ctx.get(), tk);
       for (Request *x : reqs) { x->rc = rc; x->err = e; }
       return;
     }
-    tickets_++; jobs_ += mb.nJobs;
+    { std::lock_guard<std::mutex> lk(mu_); tickets_++; jobs_ += mb.nJobs; }
     SharedTicket *sh = tk ? new SharedTicket(ctx.get(), tk, (int)reqs.size()) : nullptr;
     uint32_t at = 0;
     for (Request *x : reqs) {
@@ -268,9 +302,11 @@ class RefineService {
   const int nClients_, maxWaitUs_;
   std::mutex mu_; std::condition_variable cv_;
   std::vector<Request *> pending_;
-  bool leaderActive_ = false; int inflight_ = 0; size_t next_ = 0;
+  bool leaderActive_ = false; int inflight_ = 0;
+  std::vector<bool> busy_;
   std::vector<std::unique_ptr<Context>> ctxs_;
   uint64_t tickets_ = 0, jobs_ = 0;
+  double executeMs_ = 0, gatherMs_ = 0, submitMs_ = 0, collectMs_ = 0, deviceMs_ = 0;
 };
 
 // The other per-candidate DP call sites: jobs without a guide.
