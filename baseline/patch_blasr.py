@@ -46,6 +46,13 @@ def dump(src: str) -> str:
     return src
 
 
+def replace_once(src: str, old: str, new: str) -> str:
+    n = src.count(old)
+    if n != 1:
+        raise SystemExit(f"patch_blasr: text {old!r} occurs {n} times (expected 1)")
+    return src.replace(old, new)
+
+
 def gpu(src: str) -> str:
     # gpu_refine.hpp needs T_AlignmentCandidate, MappingParameters, MappingBuffers, SortAlignmentPointersByScore: all are
     # defined above RefineAlignments (Blasr.cpp:2163)
@@ -54,6 +61,11 @@ def gpu(src: str) -> str:
     # first statement of RefineAlignments: the batched GPU path takes the whole candidate list of this read
     src = insert_after_line(src, "vector<T_AlignmentCandidate*> &alignmentPtrs, MappingParameters &params, MappingBuffers &mappingBuffers) {",
                             "  if (BgpuRefineAlignments(bothQueryStrands, genome, alignmentPtrs, params, mappingBuffers)) return;\n")
+    # thread driver, Blasr.cpp:4838-4841: the -nproc MapReads instances run as fibers on one pthread per core
+    src = replace_once(src, "pthread_create(&threads[procIndex], &threadAttr[procIndex], (void* (*)(void*))MapReads, &mapdb[procIndex]);",
+                       "BgpuSpawn(&threads[procIndex], &threadAttr[procIndex], (void* (*)(void*))MapReads, &mapdb[procIndex], procIndex, params.nProc);")
+    src = replace_once(src, "pthread_join(threads[procIndex], NULL);", "BgpuJoin(threads[procIndex], procIndex);")
+    src = replace_once(src, "pthread_exit(NULL);", "BgpuFiberExit();")                      # end of MapReads, Blasr.cpp:3915
     return src
 
 

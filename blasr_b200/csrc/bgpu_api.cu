@@ -194,6 +194,8 @@ struct bgpu_ticket_s {
   bool arenaReady = false, collected = false, dense = false;
   bool holdsH2D = false;      // the ticket is inside the H2D gate and its release has not been queued on the stream yet
   bool holdsCompute = false;  // ... inside the kernel gate and its release has not been queued on the stream yet
+  double msUpload = 0;            // host time spent staging + enqueueing the input copies
+  cudaEvent_t evDone = nullptr;   // recorded behind everything bgpu_submit enqueued (bgpu_query)
   cudaEvent_t ev[6] = {};     // start, prepEnd, fillTraceEnd(unused), scanEnd, emitEnd
   std::vector<cudaEvent_t> waveEv;   // per wave: fillStart, fillEnd, traceEnd
   bgpu_timing timing{};
@@ -226,6 +228,7 @@ static int talloc_pin(bgpu_ctx *ctx, bgpu_ticket t, T **p, size_t n) {
 // H2D of caller memory: through pinned staging unless the caller's buffer is already pinned.
 static int upload(bgpu_ctx *ctx, bgpu_ticket t, void *dst, const void *src, size_t bytes) {
   if (!bytes) return BGPU_OK;
+  struct Tm { bgpu_ticket t; std::chrono::steady_clock::time_point t0; ~Tm() { t->msUpload += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } } tm{t, std::chrono::steady_clock::now()};
   cudaPointerAttributes at{};
   const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
   cudaGetLastError();
@@ -821,9 +824,24 @@ extern "C" int bgpu_submit(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_par
     delete t;
     return rc;
   }
+  if (cudaEventCreateWithFlags(&t->evDone, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(t->evDone, ctx->stream);
   t->timing.msHostSubmit = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+  static const bool hostTrace = getenv("BGPU_HOST_TRACE") != nullptr;
+  if (hostTrace && t->timing.msHostSubmit > 5.0)
+    fprintf(stderr, "BGPU_HOST_TRACE submit %.2f ms: jobs %u, upload %.2f ms (%llu bytes), dev allocs %u pin allocs %u\n", t->timing.msHostSubmit,
+            t->nJobs, t->msUpload, (unsigned long long)t->timing.h2dBytes, ctx->devPool.nAlloc, ctx->pinPool.nAlloc);
   *out = t;
   return BGPU_OK;
+}
+
+extern "C" int bgpu_query(bgpu_ctx *ctx, bgpu_ticket t) {
+  if (!ctx || !t) return BGPU_E_INVALID;
+  if (t->collected || !t->evDone) return 1;
+  const cudaError_t e = cudaEventQuery(t->evDone);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  cudaGetLastError();
+  return BGPU_E_CUDA;
 }
 
 extern "C" int bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_job *jobs,
@@ -1010,6 +1028,7 @@ extern "C" int bgpu_release(bgpu_ctx *ctx, bgpu_ticket t) {
   slab_release(ctx->devPool, t->dev); slab_release(ctx->pinPool, t->pin);
   for (auto &e : t->ev) cudaEventDestroy(e);
   for (auto &e : t->waveEv) cudaEventDestroy(e);
+  if (t->evDone) cudaEventDestroy(t->evDone);
   if (ctx->lastSync == t) ctx->lastSync = nullptr;
   delete t;
   return BGPU_OK;

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BGPU_VERSION 102 /* 0.1.2: + bgpu_cigar */
+#define BGPU_VERSION 103 /* 0.1.3: + bgpu_query, bgpu_base_code; bgpu_submit never waits for the device */
 
 /* ---- return codes (API level) ---- */
 enum {
@@ -166,6 +166,9 @@ int  bgpu_submit_jobs(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *
                       uint32_t nJobs, bgpu_ticket *out);
 /* Blocks until the ticket's kernels are done, copies results to the host. results[nJobs]. */
 int  bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, bgpu_arena *arena);
+/* 1 when bgpu_collect(t) would not wait for the device any more, 0 while the ticket's work is still in flight (a host
+ * that multiplexes many readers over few threads polls this instead of blocking in bgpu_collect), < 0 on error. */
+int  bgpu_query(bgpu_ctx *ctx, bgpu_ticket t);
 int  bgpu_release(bgpu_ctx *ctx, bgpu_ticket t);
 /* Re-executes every kernel of an already submitted ticket on its device-resident inputs
  * (benchmarking: inputs stay in HBM); synchronous. */

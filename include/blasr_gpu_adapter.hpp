@@ -14,6 +14,8 @@
 //   KBandAlign / AffineKBandAlign / SWAlign                      Blasr.cpp:717-730,820-824,1067-1076; SDPAlign.h:440,503,563   (DenseBatch)
 #ifndef BLASR_GPU_ADAPTER_HPP_
 #define BLASR_GPU_ADAPTER_HPP_
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -24,6 +26,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #include "blasr_gpu.h"
 
@@ -174,89 +177,131 @@ class RefineBatch {
   const uint32_t *cigarOps_ = nullptr; const uint64_t *cigarOff_ = nullptr;
 };
 
-// Cross-thread batching for blasr's thread driver.  MapReads (Blasr.cpp:3193) runs one pthread per -nproc, and each
+// Cross-thread batching for blasr's thread driver.  MapReads (Blasr.cpp:3193) runs one instance per -nproc, and each
 // calls RefineAlignments synchronously with the handful of candidates of ONE read -- far too few jobs to fill a GPU.
-// RefineService keeps that structure untouched: every pthread hands its RefineBatch to Run() and blocks; the first
-// waiter becomes the leader, gathers the batches of the other threads until every client that is not already being
-// served has arrived (or a short window closes), submits them as ONE ticket and hands each thread its slice of the
-// results.  Three contexts keep three merged tickets in flight (a ticket's latency is the serial sweep of its longest read).
+// RefineService keeps that structure untouched: every caller hands its RefineBatch to Run() and waits.  There are no
+// service threads: whoever waits drives the service by calling Poll(), which (1) starts a ticket from ALL requests that are
+// pending whenever one of the contexts is free (bgpu_submit only enqueues, it never waits for the device) and (2) collects
+// every ticket whose kernels are done (bgpu_query) and hands each caller its slice of the results.  While the contexts are
+// busy the next requests pile up, so tickets grow with the load (batching by back-pressure); several contexts keep several
+// tickets in flight (a ticket's latency is the serial sweep of its longest read, whatever the number of reads in it).
+//
+// How a caller waits is pluggable (Waiter): the default polls and naps on the calling thread; a host that runs its
+// per-read loop on user-level fibers (baseline/gpu_refine.hpp does, to overlap the CPU stages of one read with the GPU
+// refinement of another without oversubscribing the cores) yields to its scheduler, which polls between fibers.
 class RefineService {
  public:
-  RefineService(int device, int nClients, int maxWaitUs = 300, int nContexts = 3)
-      : nClients_(nClients < 1 ? 1 : nClients), maxWaitUs_(maxWaitUs) {
+  struct Waiter {                       // Wait() returns once done is true
+    virtual void Wait(RefineService &svc, const std::atomic<bool> &done) = 0;
+    virtual ~Waiter() {}
+  };
+
+  RefineService(int device, int nContexts = 3) {
     for (int i = 0; i < (nContexts < 1 ? 1 : nContexts); i++) ctxs_.push_back(std::unique_ptr<Context>(new Context(device)));
-    busy_.assign(ctxs_.size(), false);
+    flights_.resize(ctxs_.size());
+  }
+  ~RefineService() {
+    if (getenv("BGPU_SERVICE_STATS"))
+      fprintf(stderr, "RefineService: %llu tickets, %llu jobs (%.1f per ticket); per ticket: bgpu_submit %.2f ms, submit -> collected %.2f ms, bgpu_collect %.2f ms, kernels on the device %.2f ms; cudaMalloc + cudaHostAlloc calls of the busiest context %llu; per request: queued %.2f ms before its ticket started, resumed %.2f ms after it was done\n",
+              (unsigned long long)tickets_, (unsigned long long)jobs_, tickets_ ? (double)jobs_ / tickets_ : 0.0,
+              tickets_ ? submitMs_ / tickets_ : 0.0, tickets_ ? flightMs_ / tickets_ : 0.0, tickets_ ? collectMs_ / tickets_ : 0.0,
+              tickets_ ? deviceMs_ / tickets_ : 0.0, (unsigned long long)allocs_, requests_ ? pendingMs_ / requests_ : 0.0,
+              requests_ ? resumeMs_ / requests_ : 0.0);
   }
 
   template <typename T_ScoreFn>
-  void Run(RefineBatch &batch, const T_ScoreFn &fn, int bandSize, bool affine, int alignType = BGPU_GLOBAL) {
+  void Run(RefineBatch &batch, const T_ScoreFn &fn, int bandSize, bool affine, int alignType = BGPU_GLOBAL, Waiter *waiter = nullptr) {
     Request r;
     r.batch = &batch; r.fn = MakeScoreFn(fn);
     std::memset(&r.p, 0, sizeof r.p);
     r.p.algo = affine ? BGPU_AFFINE_GUIDED : BGPU_GUIDED; r.p.alignType = alignType; r.p.band = bandSize;
     r.p.doStats = 1; r.p.statsAffine = affine ? 1 : 0;
     batch.Release();
-    std::unique_lock<std::mutex> lk(mu_);
-    pending_.push_back(&r);
-    cv_.notify_all();
-    while (!r.done) {
-      if (leaderActive_ || r.taken) { cv_.wait(lk); continue; }   // someone else gathers, or already carries this request
-      leaderActive_ = true;
-      // The leader holds its ticket back until a context is free: a ticket queued behind a busy context gains nothing,
-      // while the requests that arrive in the meantime make the next ticket larger (batching by back-pressure).
-      const auto t0 = std::chrono::steady_clock::now();
-      const auto deadline = t0 + std::chrono::microseconds(maxWaitUs_);
-      int c = -1;
-      for (;;) {
-        c = -1;
-        for (size_t i = 0; i < busy_.size(); i++) if (!busy_[i]) { c = (int)i; break; }
-        const bool full = (int)pending_.size() + inflight_ >= nClients_;
-        const bool late = std::chrono::steady_clock::now() >= deadline;
-        if (c >= 0 && (full || late)) break;
-        if (c < 0 || late) cv_.wait(lk); else cv_.wait_until(lk, deadline);
-      }
-      std::vector<Request *> mine, rest;          // one ticket = one (score function, parameters) pair
-      for (Request *x : pending_)
-        (std::memcmp(&x->fn, &r.fn, sizeof r.fn) == 0 && std::memcmp(&x->p, &r.p, sizeof r.p) == 0 ? mine : rest).push_back(x);
-      pending_.swap(rest);
-      for (Request *x : mine) x->taken = true;
-      inflight_ += (int)mine.size();
-      busy_[c] = true;
-      leaderActive_ = false;
-      cv_.notify_all();
-      lk.unlock();
-      const auto e0 = std::chrono::steady_clock::now();
-      Execute(*ctxs_[c], mine);
-      const double ems = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - e0).count();
-      lk.lock();
-      executeMs_ += ems; gatherMs_ += std::chrono::duration<double, std::milli>(e0 - t0).count();
-      busy_[c] = false;
-      inflight_ -= (int)mine.size();
-      for (Request *x : mine) x->done = true;
-      cv_.notify_all();
+    r.tEnqueue = std::chrono::steady_clock::now();
+    { std::lock_guard<std::mutex> lk(mu_); pending_.push_back(&r); }
+    NappingWaiter nw;
+    (waiter ? waiter : &nw)->Wait(*this, r.done);
+    {
+      std::lock_guard<std::mutex> lk(statMu_);
+      requests_++;
+      pendingMs_ += std::chrono::duration<double, std::milli>(r.tStart - r.tEnqueue).count();
+      resumeMs_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - r.tDone).count();
     }
-    lk.unlock();
     if (r.rc != BGPU_OK) throw Error(r.rc, "blasr_gpu: " + r.err);
+  }
+
+  // Drives the service from the calling thread; returns true when it started or finished a ticket.
+  bool Poll() {
+    bool did = false;
+    std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
+    if (!lk.owns_lock()) return false;              // someone else is driving right now
+    // completion queries go through the CUDA driver's lock: at most one every 20 us, whoever calls
+    const auto now = std::chrono::steady_clock::now();
+    const bool ask = now - lastQuery_ >= std::chrono::microseconds(20);
+    if (ask) lastQuery_ = now;
+    for (size_t c = 0; ask && c < flights_.size(); c++) {
+      Flight &f = flights_[c];
+      if (f.state == Flight::FLYING && bgpu_query(ctxs_[c]->get(), f.ticket) != 0) {
+        f.state = Flight::LANDING;
+        lk.unlock();
+        Finish(*ctxs_[c], f);
+        lk.lock();
+        f.state = Flight::IDLE;
+        did = true;
+      }
+    }
+    if (!pending_.empty())
+      for (size_t c = 0; c < flights_.size(); c++) {
+        Flight &f = flights_[c];
+        if (f.state != Flight::IDLE) continue;
+        Request *first = pending_.front();
+        std::vector<Request *> rest;                // one ticket = one (score function, parameters) pair
+        f.reqs.clear();
+        for (Request *x : pending_)
+          (std::memcmp(&x->fn, &first->fn, sizeof first->fn) == 0 && std::memcmp(&x->p, &first->p, sizeof first->p) == 0 ? f.reqs : rest).push_back(x);
+        pending_.swap(rest);
+        f.state = Flight::STARTING;
+        lk.unlock();
+        const bool ok = Start(*ctxs_[c], f);
+        lk.lock();
+        f.state = ok ? Flight::FLYING : Flight::IDLE;
+        did = true;
+        break;
+      }
+    return did;
   }
 
   uint64_t Tickets() const { return tickets_; }
   uint64_t Jobs() const { return jobs_; }
-  ~RefineService() {
-    if (getenv("BGPU_SERVICE_STATS"))
-      fprintf(stderr, "RefineService: %llu tickets, %llu jobs (%.1f per ticket); per ticket: gather %.2f ms, execute %.2f ms (bgpu_submit %.2f, bgpu_collect %.2f, kernels on the device %.2f)\n",
-              (unsigned long long)tickets_, (unsigned long long)jobs_, tickets_ ? (double)jobs_ / tickets_ : 0.0,
-              tickets_ ? gatherMs_ / tickets_ : 0.0, tickets_ ? executeMs_ / tickets_ : 0.0, tickets_ ? submitMs_ / tickets_ : 0.0,
-              tickets_ ? collectMs_ / tickets_ : 0.0, tickets_ ? deviceMs_ / tickets_ : 0.0);
-  }
 
  private:
-  struct Request { RefineBatch *batch; bgpu_scorefn fn; bgpu_params p; bool taken = false, done = false; int rc = BGPU_OK; std::string err; };
+  struct Request {
+    RefineBatch *batch; bgpu_scorefn fn; bgpu_params p; std::atomic<bool> done; int rc = BGPU_OK; std::string err;
+    std::chrono::steady_clock::time_point tEnqueue, tStart, tDone;
+    Request() : done(false) {}
+  };
+  struct Flight {
+    enum { IDLE, STARTING, FLYING, LANDING } state = IDLE;
+    std::vector<Request *> reqs; bgpu_ticket ticket = nullptr; uint32_t nJobs = 0;
+    std::chrono::steady_clock::time_point t0;
+  };
+  struct NappingWaiter : Waiter {
+    void Wait(RefineService &svc, const std::atomic<bool> &done) {
+      while (!done.load(std::memory_order_acquire))
+        if (!svc.Poll()) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  };
 
-  void Execute(Context &ctx, std::vector<Request *> &reqs) {
+  static void Fail(std::vector<Request *> &reqs, int rc, const std::string &e) {
+    for (Request *x : reqs) { x->rc = rc; x->err = e; x->tStart = x->tDone = std::chrono::steady_clock::now(); x->done.store(true, std::memory_order_release); }
+  }
+
+  // concatenates the requests' jobs and enqueues them as one ticket (inputs are staged by bgpu_submit before it returns)
+  bool Start(Context &ctx, Flight &f) {
     std::vector<uint8_t> q, t, qual; std::vector<bgpu_block> guide; std::vector<uint64_t> qOff(1, 0), tOff(1, 0), gOff(1, 0);
     bool anyQual = false;
-    for (Request *x : reqs) anyQual = anyQual || !x->batch->qual_.empty();
-    for (Request *x : reqs) {
+    for (Request *x : f.reqs) anyQual = anyQual || !x->batch->qual_.empty();
+    for (Request *x : f.reqs) {
       RefineBatch &b = *x->batch;
       const uint64_t q0 = q.size(), t0 = t.size(), g0 = guide.size();
       q.insert(q.end(), b.q_.begin(), b.q_.end()); t.insert(t.end(), b.t_.begin(), b.t_.end());
@@ -267,46 +312,52 @@ class RefineService {
     bgpu_batch mb; std::memset(&mb, 0, sizeof mb);
     mb.nJobs = (uint32_t)qOff.size() - 1; mb.qBases = q.data(); mb.qOff = qOff.data(); mb.tBases = t.data(); mb.tOff = tOff.data();
     mb.qual = anyQual ? qual.data() : nullptr; mb.guide = guide.data(); mb.guideOff = gOff.data();
-    std::vector<bgpu_result> res(mb.nJobs);
+    f.nJobs = mb.nJobs; f.ticket = nullptr; f.t0 = std::chrono::steady_clock::now();
+    for (Request *x : f.reqs) x->tStart = f.t0;
+    const int rc = bgpu_submit(ctx.get(), &f.reqs[0]->fn, &f.reqs[0]->p, &mb, &f.ticket);
+    if (rc != BGPU_OK) { Fail(f.reqs, rc, bgpu_last_error(ctx.get())); return false; }
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - f.t0).count();
+    std::lock_guard<std::mutex> lk(statMu_);
+    submitMs_ += ms;
+    return true;
+  }
+
+  void Finish(Context &ctx, Flight &f) {
+    std::vector<bgpu_result> res(f.nJobs);
     bgpu_arena arena; std::memset(&arena, 0, sizeof arena);
-    bgpu_ticket tk = nullptr;
-    const auto s0 = std::chrono::steady_clock::now();
-    int rc = mb.nJobs ? bgpu_submit(ctx.get(), &reqs[0]->fn, &reqs[0]->p, &mb, &tk) : BGPU_OK;
-    const auto s1 = std::chrono::steady_clock::now();
-    if (rc == BGPU_OK && tk) rc = bgpu_collect(ctx.get(), tk, res.data(), &arena);
-    if (rc == BGPU_OK && tk) {
-      bgpu_timing tm; bgpu_timing_of(ctx.get(), tk, &tm);
-      std::lock_guard<std::mutex> lk(mu_);
-      submitMs_ += std::chrono::duration<double, std::milli>(s1 - s0).count();
-      collectMs_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s1).count();
-      deviceMs_ += tm.msTotal;
+    const auto c0 = std::chrono::steady_clock::now();
+    const int rc = bgpu_collect(ctx.get(), f.ticket, res.data(), &arena);
+    if (rc != BGPU_OK) { const std::string e = bgpu_last_error(ctx.get()); bgpu_release(ctx.get(), f.ticket); Fail(f.reqs, rc, e); return; }
+    const auto c1 = std::chrono::steady_clock::now();
+    bgpu_timing tm; bgpu_timing_of(ctx.get(), f.ticket, &tm);
+    {
+      std::lock_guard<std::mutex> lk(statMu_);
+      collectMs_ += std::chrono::duration<double, std::milli>(c1 - c0).count();
+      flightMs_ += std::chrono::duration<double, std::milli>(c1 - f.t0).count();
+      deviceMs_ += tm.msTotal; tickets_++; jobs_ += f.nJobs;
+      allocs_ = std::max<uint64_t>(allocs_, tm.devAllocs + tm.pinAllocs);
     }
-    if (rc != BGPU_OK) {
-      const std::string e = bgpu_last_error(ctx.get());
-      if (tk) bgpu_release(ctx.get(), tk);
-      for (Request *x : reqs) { x->rc = rc; x->err = e; }
-      return;
-    }
-    { std::lock_guard<std::mutex> lk(mu_); tickets_++; jobs_ += mb.nJobs; }
-    SharedTicket *sh = tk ? new SharedTicket(ctx.get(), tk, (int)reqs.size()) : nullptr;
+    SharedTicket *sh = new SharedTicket(ctx.get(), f.ticket, (int)f.reqs.size());
     uint32_t at = 0;
-    for (Request *x : reqs) {
+    for (Request *x : f.reqs) {
       RefineBatch &b = *x->batch;
       b.results_.assign(res.begin() + at, res.begin() + at + b.size());
       b.base_ = at;
       at += b.size();
       b.arena_ = arena; b.owner_ = ctx.get(); b.ticket_ = nullptr; b.shared_ = sh; b.cigarOps_ = nullptr; b.cigarOff_ = nullptr;
+      x->tDone = std::chrono::steady_clock::now();
+      x->done.store(true, std::memory_order_release);          // x may be gone right after this
     }
   }
 
-  const int nClients_, maxWaitUs_;
-  std::mutex mu_; std::condition_variable cv_;
+  std::mutex mu_, statMu_;
+  std::chrono::steady_clock::time_point lastQuery_;
   std::vector<Request *> pending_;
-  bool leaderActive_ = false; int inflight_ = 0;
-  std::vector<bool> busy_;
   std::vector<std::unique_ptr<Context>> ctxs_;
-  uint64_t tickets_ = 0, jobs_ = 0;
-  double executeMs_ = 0, gatherMs_ = 0, submitMs_ = 0, collectMs_ = 0, deviceMs_ = 0;
+  std::vector<Flight> flights_;
+  uint64_t tickets_ = 0, jobs_ = 0, allocs_ = 0, requests_ = 0;
+  double pendingMs_ = 0, resumeMs_ = 0;
+  double submitMs_ = 0, flightMs_ = 0, collectMs_ = 0, deviceMs_ = 0;
 };
 
 // The other per-candidate DP call sites: jobs without a guide.

@@ -5,7 +5,8 @@ Generates configs[0] (4.6 Mb genome, 10 kb reads at 15 % error; --reads to scale
 reference's sawriter, then times
     baseline/_ref/blasrmc      reads.fa genome.fa -sa genome.sa -sam -nproc C          (the unmodified reference)
     ... -noRefineAlignments                                                               (how much of it is refinement)
-    baseline/_ref/blasrmc_gpu  ... -nproc T    for T in --gpu-threads                   (RefineAlignments on the GPU)
+    baseline/_ref/blasrmc_gpu  ... -nproc T    for T in --gpu-threads                   (RefineAlignments on the GPU; T MapReads
+                                                                                          fibers on one pthread per core)
 and prints one JSON object.  Wall times include the program's start-up (index load); `startup_s` is measured with an
 empty read set so that reads/s can be quoted net of it.  Sorted SAM of every GPU run is compared with the stock run.
 """
@@ -40,7 +41,7 @@ def measure(n_reads=1000, genome=4600000, length=10000, gpu_threads=None, workdi
     if not all(os.path.exists(p) for p in (STOCK, GPU, SAW)):
         return {"unavailable": "baseline/_ref binaries absent"}
     cores = len(os.sched_getaffinity(0))
-    gpu_threads = gpu_threads or [cores, 2 * cores, 4 * cores]
+    gpu_threads = gpu_threads or [2 * cores, 4 * cores]   # -nproc = MapReads fibers (reads in flight) on `cores` pthreads
     tmp = workdir or tempfile.mkdtemp(prefix="bgpu_pipe_")
     subprocess.check_call([sys.executable, os.path.join(BL, "make_data.py"), "c0", tmp, "--genome", str(genome), "--reads", str(n_reads),
                            "--len", str(length)], stdout=subprocess.DEVNULL)
