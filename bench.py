@@ -50,6 +50,12 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--e2e-threads", type=int, default=5, help="host threads (one context each) of the e2e measurement")
     ap.add_argument("--e2e-chunks", type=int, default=10, help="sub-batches the shard is cut into for the e2e measurement")
+    ap.add_argument("--no-subrecords", dest="subrecords", action="store_false", help="skip the affine / affine_production / quality / sdp_guides sub-records")
+    ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the parity samples against oracle/_ref")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false", help="skip the reads/s leg (stock blasr vs GPU-refined blasr)")
+    ap.add_argument("--prod-jobs", type=int, default=40000, help="pairs of the affine_production sub-record (10 kb, band 16)")
+    ap.add_argument("--sdp-jobs", type=int, default=2048, help="pairs of the sdp_guides sub-record (0 = skip)")
+    ap.add_argument("--pipeline-reads", type=int, default=2000, help="reads of the configs[0] pipeline run")
     return ap.parse_args()
 
 
@@ -78,26 +84,39 @@ def config_dict(args, n_jobs):
 
 
 # ---------------------------------------------------------------- CPU side (reference / port)
-def cpu_replay(batch, algo, n_threads, target_seconds, est_gcups_per_core=0.05, quality=False):
-    """Replays a bounded prefix of the batch through oracle/_ref (or the C port) on n_threads; returns dict."""
+def cpu_sample(batch, n_threads, target_seconds, algo, est_gcups_per_core=0.05, seed=7):
+    """A bounded, seeded RANDOM sample of the shard (not a prefix: job sizes follow the shard's own mix) worth about
+    target_seconds of CPU work on n_threads cores."""
+    target_cells = target_seconds * n_threads * est_gcups_per_core * 1e9 * (0.45 if algo else 1.0)
+    ql = np.diff(batch.qOff.astype(np.int64))
+    band = batch.band.astype(np.int64) if batch.band is not None else np.full(batch.n, 16, np.int64)
+    est = ql * (2 * band + 2)
+    order = np.random.default_rng(seed).permutation(batch.n)
+    cum = np.cumsum(est[order])
+    k = int(np.searchsorted(cum, target_cells)) + 1
+    return np.sort(order[:max(min(k, batch.n), min(n_threads, batch.n))])
+
+
+def cpu_replay(batch, algo, n_threads, target_seconds, quality=False, idx=None):
+    """Replays a bounded sample of the batch through oracle/_ref (the unmodified reference templates; the C port when that
+    build is absent) on n_threads threads, ComputeAlignmentStats included (the GPU path computes it too); returns dict."""
     from tests import cases, oracle as O
     which = "ref" if O.have_ref() else "orc"
     fn = O.score_fn(__import__("blasr_b200").SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0, kind=1 if quality else 0)
-    target_cells = target_seconds * n_threads * est_gcups_per_core * 1e9 * (0.5 if algo else 1.0)
-    jobs, keep, est = [], [], 0
-    for i in range(batch.n):
-        q, t, g, qv = cases.job_arrays(batch, i)
-        j, k = O.make_job(algo, 1, int(batch.band[i]), q, t, g, qv if quality else None, 0, 0, 0, 0)
+    if idx is None:
+        idx = cpu_sample(batch, n_threads, target_seconds, algo)
+    jobs, keep = [], []
+    for i in idx:
+        q, t, g, qv = cases.job_arrays(batch, int(i))
+        j, k = O.make_job(algo, 1, int(batch.band[i]) if batch.band is not None else 16, q, t, g, qv if quality else None, 0, 0, 1, algo)
         jobs.append(j); keep.append(k)
-        est += len(q) * (2 * int(batch.band[i]) + 2)
-        if est >= target_cells and len(jobs) >= n_threads:
-            break
     t0 = time.perf_counter()
     cells, _ = O.replay(which, fn, jobs, n_threads)
     dt = time.perf_counter() - t0
     return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": n_threads, "kind": "reference" if which == "ref" else "port",
-            "sample": f"first {len(jobs)} pairs of the rank-0 shard ({cells} cells) replayed once in {dt:.1f} s",
-            "_cells": cells, "_seconds": dt}
+            "sample": f"{len(jobs)} pairs drawn at random (seeded) from the rank-0 shard ({cells} cells), "
+                      f"{'AffineGuidedAlign' if algo else 'GuidedAlign'} + ComputeAlignmentStats, replayed once in {dt:.1f} s",
+            "_cells": cells, "_seconds": dt, "_idx": idx}
 
 
 def run_reference(args):
@@ -106,15 +125,17 @@ def run_reference(args):
         return
     n_threads = os.cpu_count() or 1
     algo = 1 if args.algo == "affine" else 0
-    # a shard prefix is enough: the sample is bounded by CPU time, not by the 100k pairs
     quality = args.scorefn == "quality"
-    batch = make_workload(min(args.jobs, max(256, n_threads * 32)), args.seed, with_qual=quality, **workload_args(args))
+    # the sample is drawn from a shard prefix large enough to hold the shard's mix of lengths and bands; it is bounded by
+    # CPU time, not by the 100k pairs
+    batch = make_workload(min(args.jobs, max(4096, n_threads * 128)), args.seed, with_qual=quality, **workload_args(args))
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    idx = cpu_sample(batch, n_threads, per_step, algo)
     for _ in range(args.warmup):
-        cpu_replay(batch, algo, n_threads, min(per_step, 2.0), quality=quality)
+        cpu_replay(batch, algo, n_threads, per_step, quality=quality, idx=idx[:max(n_threads, len(idx) // 4)])
     vals, ms = [], []
     for _ in range(args.steps):
-        r = cpu_replay(batch, algo, n_threads, per_step, quality=quality)
+        r = cpu_replay(batch, algo, n_threads, per_step, quality=quality, idx=idx)
         vals.append(r["value"]); ms.append(r["_seconds"] * 1e3)
     v = float(np.mean(vals))
     cb = {k: r[k] for k in ("unit", "cores", "kind", "sample")}
@@ -194,46 +215,25 @@ def range_view(batch, a, b):
                     batch.qual[q0:q1] if batch.qual is not None else None, batch.band[a:b] if batch.band is not None else None)
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from blasr_b200 import Aligner, DistanceMatrixScoreFunction, QualityValueScoreFunction, capi
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    # the generator forks worker processes: run it before CUDA / NCCL are initialised in this process
-    batch = make_workload(args.jobs, args.seed + 1000 * rank, with_qual=args.scorefn == "quality", **workload_args(args))
-    torch.cuda.set_device(local)
-    all_cpus = os.sched_getaffinity(0)
-    numa = bind_to_gpu_cpus(local)     # before any pinned allocation: first touch then lands on the GPU's own NUMA node
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    algo = capi.AFFINE_GUIDED if args.algo == "affine" else capi.GUIDED
-    # inputs in pinned host memory (the library then DMA's straight from them)
-    keep = []
+def _pin_batch(batch, keep):
     for name in ("q", "qOff", "t", "tOff", "guide", "guideOff", "band") + (("qual",) if batch.qual is not None else ()):
+        if getattr(batch, name) is None:
+            continue
         v, t = pinned_copy(getattr(batch, name)); setattr(batch, name, v); keep.append(t)
-    fn_cls = QualityValueScoreFunction if args.scorefn == "quality" else DistanceMatrixScoreFunction
-    fn = fn_cls(ins=5, del_=5, affineOpen=50 if algo == capi.AFFINE_GUIDED else 0, affineExtend=0)
-    al = Aligner(local)
+    return batch
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    # ---- e2e: submit (H2D + kernels) + collect (D2H) through the C ABI, host buffers in, host results out.
-    # The way a multi-threaded host (blasr's MapReads pthreads) drives the library: a few host threads, each with its
-    # own context, push sub-batches of the shard; copies of one sub-batch overlap the kernels of another.
-    e2e_host = {}
-    n_chunks = max(1, min(args.e2e_chunks, batch.n))
+def e2e_measure(local, batch, fn, algo, n_threads, n_chunks, warm, steps, barrier):
+    """submit (H2D + kernels) + collect (D2H) through the C ABI, host buffers in, host results out.  The way a multi-threaded
+    host (blasr's MapReads pthreads) drives the library: a few host threads, each with its own context, push sub-batches of
+    the shard; copies of one sub-batch overlap the kernels of another."""
+    from blasr_b200 import Aligner
+    n_chunks = max(1, min(n_chunks, batch.n))
     bounds = np.linspace(0, batch.n, n_chunks + 1).astype(np.int64)
     chunks = [range_view(batch, int(bounds[i]), int(bounds[i + 1])) for i in range(n_chunks)]
-    workers = [Aligner(local) for _ in range(max(1, min(args.e2e_threads, n_chunks)))]
+    workers = [Aligner(local) for _ in range(max(1, min(n_threads, n_chunks)))]
 
-    def e2e_pass():
+    def one_pass():
         nxt = iter(range(n_chunks)); lock = threading.Lock()
         tot = {"cells": 0, "ok": 0, "h2d": 0, "d2h": 0}
         errs = []
@@ -261,49 +261,207 @@ def run_ours(args):
         if errs:
             raise errs[0]
         return tot
-    e2e_warm = max(1, min(args.warmup, 2))
-    for _ in range(e2e_warm):
-        e2e_pass()
+    for _ in range(warm):
+        one_pass()
     barrier()
-    e2e_steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        tot = e2e_pass()
+    for _ in range(steps):
+        tot = one_pass()
     barrier()
-    e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    sec = (time.perf_counter() - t0) / steps
     for a in workers:
         a.close()
-    e2e_cells, h2d, d2h = tot["cells"], tot["h2d"], tot["d2h"]
-    e2e_host.update(threads=len(workers), sub_batches=n_chunks)
+    return {"sec": sec, "cells": tot["cells"], "ok": tot["ok"], "h2d": tot["h2d"], "d2h": tot["d2h"], "threads": len(workers), "chunks": n_chunks}
 
-    # one ticket for the whole shard: the device-resident measurement below re-runs it; its own submit -> collect time
-    # is reported as e2e.single_ticket (no copy/compute overlap)
+
+def parity_sample(al, batch, fn, algo, quality, n=256, seed=11):
+    """Outside every timed region: a seeded sample of the very shard the bench times (at least n/8 of it band-64 jobs of
+    >= 15 kb when the shard has them), through the GPU and through oracle/_ref, every field compared."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tests import cases, oracle as O
+    which = "ref" if O.have_ref() else "orc"
+    rng = np.random.default_rng(seed)
+    ql = np.diff(batch.qOff.astype(np.int64))
+    band = batch.band if batch.band is not None else np.full(batch.n, 16)
+    big = np.flatnonzero((band == 64) & (ql >= 15000))
+    pick = set(rng.choice(big, min(len(big), n // 8), replace=False).tolist()) if len(big) else set()
+    rest = rng.permutation(batch.n)
+    for i in rest:
+        if len(pick) >= min(n, batch.n):
+            break
+        pick.add(int(i))
+    idx = sorted(pick)
+    sub = batch.slice(idx)
+    res = al.AffineGuidedAlign(sub, fn, 16) if algo else al.GuidedAlign(sub, fn, 16)
+    ofn = O.score_fn(fn.scoreMatrix, fn.ins, fn.del_, fn.affineOpen, fn.affineExtend, fn.kind)
+
+    def one(k):
+        q, t, g, qv = cases.job_arrays(sub, k)
+        j, keep = O.make_job(algo, 1, int(sub.band[k]) if sub.band is not None else 16, q, t, g, qv if quality else None, 0, 0, 1, algo)
+        return O.align(which, ofn, j)
+    with ThreadPoolExecutor(max_workers=len(os.sched_getaffinity(0))) as ex:
+        want = list(ex.map(one, range(sub.n)))
+    bad = [idx[k] for k in range(sub.n) if cases.compare(cases.gpu_to_dict(res, k), want[k], cases.GPU_FIELDS)]
+    return {"n": len(idx), "mismatches": len(bad), "band64_ge15kb": int(sum(1 for i in idx if band[i] == 64 and ql[i] >= 15000)),
+            "checker": "oracle/_ref (unmodified reference templates)" if which == "ref" else "oracle C port",
+            "fields": "status score qPos tPos nCells blocks gaps nMatch nMismatch nIns nDel pctSimilarity statsScore",
+            "first_bad": bad[:4]}
+
+
+def measure(al, local, batch, fn, algo, args, steps, warmup, barrier, do_e2e=True, do_parity=True, do_cpu=True, all_cpus=None,
+            quality=False, clocks=False):
+    """One (workload, aligner, score function) combination: device-resident GCUPS (bgpu_rerun), per-stage times, the fill
+    kernel against the int32 roofline, optionally e2e through the C ABI, the parity sample and the CPU baseline."""
+    from blasr_b200 import capi
+    rec = {}
+    al.trim()                          # the e2e contexts below share this GPU: hand them the memory of earlier measurements
+    e2e = e2e_measure(local, batch, fn, algo, args.e2e_threads, args.e2e_chunks, max(1, min(warmup, 2)), max(1, min(steps, 3)),
+                      barrier) if do_e2e else None
+    # one ticket for the whole shard: the device-resident measurement below re-runs it; its own submit -> collect time is
+    # reported as e2e.single_ticket (no copy/compute overlap; second ticket of the context, i.e. with its slabs cached)
+    tk = al.submit(batch, fn, algo, band=16, doStats=True)
+    al.collect(tk)
+    al.release(tk)
     h0 = time.perf_counter()
     tk = al.submit(batch, fn, algo, band=16, doStats=True)
     h1 = time.perf_counter()
     res = al.collect(tk)
     h2 = time.perf_counter()
-    e2e_host.update(single_submit_ms=(h1 - h0) * 1e3, single_collect_ms=(h2 - h1) * 1e3)
     tm = res.timing
     cells = int(tm.cells)
-    assert cells == e2e_cells, (cells, e2e_cells)
     ok = int((res.results["status"] == 0).sum())
-
-    # ---- device-resident: re-run every kernel of the ticket on inputs already in HBM
-    for _ in range(args.warmup):
+    if e2e:
+        assert cells == e2e["cells"], (cells, e2e["cells"])
+    for _ in range(warmup):
         al.rerun(tk)
     barrier()
-    sampler = ClockSampler(local); sampler.start()
-    ms_total, ms_fill, ms_trace, ms_prep, ms_emit, launches = [], [], [], [], [], 0
+    sampler = None
+    if clocks:
+        sampler = ClockSampler(local); sampler.start()
+    ms = {k: [] for k in ("total", "fill", "trace", "prep", "emit")}
+    launches = 0
     w0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         t = al.rerun(tk)
-        ms_total.append(t.msTotal); ms_fill.append(t.msFill); ms_trace.append(t.msTrace); ms_prep.append(t.msPrep); ms_emit.append(t.msEmit)
+        ms["total"].append(t.msTotal); ms["fill"].append(t.msFill); ms["trace"].append(t.msTrace); ms["prep"].append(t.msPrep); ms["emit"].append(t.msEmit)
         launches += int(t.kernelLaunches)
     barrier()
     wall = time.perf_counter() - w0
-    sampler.stop_flag = True; sampler.join(2)
-    dev_ms = float(np.sum(ms_total))
+    if sampler:
+        sampler.stop_flag = True; sampler.join(2)
+    lane_steps = float(al.timing(tk).fillCells)
+    al.release(tk)
+    a = 1 if algo == capi.AFFINE_GUIDED else 0
+    fill_s = float(np.mean(ms["fill"])) * 1e-3
+    fill_gcups = cells / fill_s / 1e9
+    rec.update(cells=cells, jobs_ok=ok, dev_ms=float(np.sum(ms["total"])), launches=launches, wall=wall, sampler=sampler,
+               stage_ms={"prep": float(np.mean(ms["prep"])), "fill": float(np.mean(ms["fill"])), "trace": float(np.mean(ms["trace"])),
+                         "emit": float(np.mean(ms["emit"])), "wall_per_step": wall / steps * 1e3},
+               fill_gcups=fill_gcups, fill_s=fill_s, lane_steps_per_cell=lane_steps / max(1, cells), algo=a,
+               single={"submit_ms": (h1 - h0) * 1e3, "collect_ms": (h2 - h1) * 1e3}, e2e=e2e)
+    if do_parity:
+        rec["parity_sample"] = parity_sample(al, batch, fn, a, quality)
+    if do_cpu:
+        try:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)            # the CPU baseline gets every host core back
+            cb = cpu_replay(batch, a, len(all_cpus or os.sched_getaffinity(0)), args.cpu_seconds, quality=quality)
+            rec["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # noqa: BLE001
+            rec["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    return rec
+
+
+def sub_record(rec, steps, int_peak, world=1):
+    """A sub-record of the JSON line (single rank's view)."""
+    v = rec["cells"] * steps / (rec["dev_ms"] * 1e-3) / 1e9
+    out = {"value": v, "unit": "GCUPS", "ms_per_step": rec["dev_ms"] / steps, "cells_per_step": rec["cells"], "jobs_ok": rec["jobs_ok"],
+           "aligned_pairs_per_s": rec["jobs_ok"] * steps / (rec["dev_ms"] * 1e-3), "stage_ms": rec["stage_ms"], "gpu_launches": rec["launches"],
+           "int_roofline": {"fill_gcups": rec["fill_gcups"], "ops_per_cell": OPS_PER_CELL[rec["algo"]],
+                            "achieved": rec["fill_gcups"] * OPS_PER_CELL[rec["algo"]] / 1e3, "peak": int_peak / 1e12, "unit": "Tops/s",
+                            "frac": rec["fill_gcups"] * 1e9 * OPS_PER_CELL[rec["algo"]] / int_peak if int_peak else None,
+                            "lane_steps_per_cell": rec["lane_steps_per_cell"]}}
+    if rec.get("e2e"):
+        e = rec["e2e"]
+        out["e2e"] = {"value": e["cells"] / e["sec"] / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
+                      "pairs_per_s": e["ok"] / e["sec"], "ms_per_step": e["sec"] * 1e3}
+    for k in ("parity_sample", "cpu_baseline"):
+        if k in rec:
+            out[k] = rec[k]
+    return out
+
+
+def sdp_guided_batch(n, seed, len_lo, len_hi, bands):
+    """configs[1] as SURVEY 8(d) words it: guides = the reference's own SDPAlign(k=11, sdpIns 5, sdpDel 10, indelRate 0.3 x 3) output
+    (oracle/_ref ref_sdp_guide, the argument pattern of Blasr.cpp:1716-1722), sliced the way RefineAlignment slices them
+    (Blasr.cpp:850-859).  Workload preparation, outside every timed region."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    from blasr_b200 import JobBatch, SMRTDistanceMatrix
+    from tests import cases, oracle as O
+    if not O.have_ref():
+        return None
+    L = O._load("ref")
+    base = make_workload(n, seed, len_lo=len_lo, len_hi=len_hi, bands=bands)
+    fn = O.score_fn(SMRTDistanceMatrix, 5, 5, 0, 0)
+
+    def one(i):
+        q, t, _, _ = cases.job_arrays(base, i)
+        q = np.ascontiguousarray(q); t = np.ascontiguousarray(t)
+        cap = len(q) + 16
+        blocks = np.zeros((cap, 3), np.uint32)
+        nb = L.ref_sdp_guide(q.ctypes.data, len(q), t.ctypes.data, len(t), C.byref(fn), 11, 5, 10, C.c_float(0.9), blocks.ctypes.data, cap)
+        if nb <= 0:
+            return None
+        g = blocks[:nb].astype(np.int64)
+        q0, t0 = int(g[0, 0]), int(g[0, 1]); q1, t1 = int(g[-1, 0] + g[-1, 2]), int(g[-1, 1] + g[-1, 2])
+        g[:, 0] -= q0; g[:, 1] -= t0
+        return q[q0:q1].tobytes(), t[t0:t1].tobytes(), g.astype(np.uint32), int(base.band[i])
+    with ThreadPoolExecutor(max_workers=len(os.sched_getaffinity(0))) as ex:
+        got = [x for x in ex.map(one, range(base.n)) if x is not None]
+    return JobBatch.from_lists([x[0] for x in got], [x[1] for x in got], [x[2] for x in got], None, [x[3] for x in got])
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from blasr_b200 import Aligner, DistanceMatrixScoreFunction, QualityValueScoreFunction, capi
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    # the generator forks worker processes: run it before CUDA / NCCL are initialised in this process
+    headline_quality = args.scorefn == "quality"
+    want_subs = args.subrecords and (args.algo, args.scorefn) == ("guided", "distance")
+    batch = make_workload(args.jobs, args.seed + 1000 * rank, with_qual=headline_quality or want_subs, **workload_args(args))
+    prod = make_workload(args.prod_jobs, args.seed + 1000 * rank + 500, len_lo=10000, len_hi=10000, bands=(16,)) if want_subs else None
+    torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    sdp = sdp_guided_batch(args.sdp_jobs, args.seed + 77, args.len_lo, args.len_hi, tuple(int(x) for x in args.bands.split(","))) \
+        if (want_subs and rank == 0 and args.sdp_jobs > 0) else None
+    numa = bind_to_gpu_cpus(local)     # before any pinned allocation: first touch then lands on the GPU's own NUMA node
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    algo = capi.AFFINE_GUIDED if args.algo == "affine" else capi.GUIDED
+    keep = []
+    _pin_batch(batch, keep)            # inputs in pinned host memory (the library then DMA's straight from them)
+    if prod is not None:
+        _pin_batch(prod, keep)
+
+    def mkfn(a, quality):
+        return (QualityValueScoreFunction if quality else DistanceMatrixScoreFunction)(ins=5, del_=5, affineOpen=50 if a == capi.AFFINE_GUIDED else 0, affineExtend=0)
+    al = Aligner(local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    solo = rank == 0 and world == 1
+    head = measure(al, local, batch, mkfn(algo, headline_quality), algo, args, args.steps, args.warmup, barrier, do_e2e=True,
+                   do_parity=solo and args.parity, do_cpu=solo, all_cpus=all_cpus, quality=headline_quality, clocks=True)
+    os.sched_setaffinity(0, all_cpus) if numa is None else bind_to_gpu_cpus(local)
 
     def allmax(x):
         if world == 1:
@@ -314,7 +472,8 @@ def run_ours(args):
         if world == 1:
             return x
         tt = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.SUM); return float(tt.item())
-    dev_ms_max = allmax(dev_ms); e2e_sec_max = allmax(e2e_sec); cells_all = allsum(float(cells)); jobs_all = allsum(float(ok))
+    cells = head["cells"]
+    dev_ms_max = allmax(head["dev_ms"]); e2e_sec_max = allmax(head["e2e"]["sec"]); cells_all = allsum(float(cells)); jobs_all = allsum(float(head["jobs_ok"]))
     value = cells_all * args.steps / (dev_ms_max * 1e-3) / 1e9
     e2e_val = cells_all / e2e_sec_max / 1e9
     int_peak, _ = al.int_peak()
@@ -324,7 +483,7 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    a = 1 if algo == capi.AFFINE_GUIDED else 0
+    a = head["algo"]
     # DRAM bytes of the fill kernels from the committed ncu --set full capture of this very workload (same pairs, same seed)
     traffic, traffic_src = None, None
     try:
@@ -334,22 +493,21 @@ def run_ours(args):
             traffic, traffic_src = tr["dram_bytes_per_step"], tr["source"]
     except Exception:  # noqa: BLE001
         pass
-    fill_s = float(np.mean(ms_fill)) * 1e-3
-    fill_gcups = cells / fill_s / 1e9
+    fill_s, fill_gcups = head["fill_s"], head["fill_gcups"]
+    single = head["single"]
     out = {
         "metric": "banded_dp_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": config_dict(args, args.jobs),
         "aligned_pairs_per_s": jobs_all * args.steps / (dev_ms_max * 1e-3),
-        "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": head["e2e"]["h2d"], "d2h_bytes_per_step": head["e2e"]["d2h"],
                 "pairs_per_s": jobs_all / e2e_sec_max, "ms_per_step": e2e_sec_max * 1e3,
-                "how": f"{e2e_host['threads']} host threads x own context, {e2e_host['sub_batches']} sub-batches of the shard, pinned host buffers "
+                "how": f"{head['e2e']['threads']} host threads x own context, {head['e2e']['chunks']} sub-batches of the shard, pinned host buffers "
                        "in, pinned result arena out, H2D + D2H inside the timed region",
-                "single_ticket": {"value": cells / ((e2e_host["single_submit_ms"] + e2e_host["single_collect_ms"]) * 1e-3) / 1e9,
-                                  "submit_ms": e2e_host["single_submit_ms"], "collect_ms": e2e_host["single_collect_ms"]}},
-        "gpu_launches": launches,
-        "stage_ms": {"prep": float(np.mean(ms_prep)), "fill": float(np.mean(ms_fill)), "trace": float(np.mean(ms_trace)),
-                     "emit": float(np.mean(ms_emit)), "wall_per_step": wall / args.steps * 1e3},
+                "single_ticket": {"value": cells / ((single["submit_ms"] + single["collect_ms"]) * 1e-3) / 1e9,
+                                  "submit_ms": single["submit_ms"], "collect_ms": single["collect_ms"]}},
+        "gpu_launches": head["launches"],
+        "stage_ms": head["stage_ms"],
         "roofline": {"bound": "hbm", "kernel": "fill_guided_kernel", "achieved": cells * BYTES_PER_CELL[a] / fill_s / 1e9, "peak": hbm_peak,
                      "unit": "GB/s", "frac": cells * BYTES_PER_CELL[a] / fill_s / 1e9 / hbm_peak, "traffic": traffic,
                      "algorithmic_bytes": cells * BYTES_PER_CELL[a], "traffic_source": traffic_src,
@@ -358,19 +516,46 @@ def run_ours(args):
         "int_roofline": {"bound": "int32 ALU issue", "fill_gcups": fill_gcups, "ops_per_cell": OPS_PER_CELL[a],
                          "achieved": fill_gcups * OPS_PER_CELL[a] / 1e3, "peak": int_peak / 1e12, "unit": "Tops/s",
                          "frac": fill_gcups * 1e9 * OPS_PER_CELL[a] / int_peak if int_peak else None,
-                         "lane_steps_per_cell": float(tm.fillCells) / max(1, cells),
+                         "lane_steps_per_cell": head["lane_steps_per_cell"],
                          "peak_by_mix_tops": {k: v / 1e12 for k, v in al.int_peak_modes.items()},
                          "peak_source": "bgpu_measure_int_peak: best of add / min / mad / add+mad chains on this device"},
-        "clocks": sampler.summary(), "jobs_ok": int(jobs_all), "host_cpus_bound_per_rank": numa,
+        "clocks": head["sampler"].summary(), "jobs_ok": int(jobs_all), "host_cpus_bound_per_rank": numa,
     }
-    if rank == 0 and world == 1:
+    for k in ("parity_sample", "cpu_baseline"):
+        if k in head:
+            out[k] = head[k]
+    if want_subs:
+        # the other aligners of the hot path, on this rank's GPU, so that the driver's record pins them too (single-rank views)
+        sub_steps, sub_warm = max(2, min(args.steps, 3)), 3
+        r = measure(al, local, batch, mkfn(capi.AFFINE_GUIDED, False), capi.AFFINE_GUIDED, args, sub_steps, sub_warm, barrier,
+                    do_e2e=solo, do_parity=solo and args.parity, do_cpu=solo, all_cpus=all_cpus)
+        out["affine"] = dict(sub_record(r, sub_steps, int_peak), workload="the configs[1] pairs above through AffineGuidedAlign (affineOpen 50, affineExtend 0)")
+        r = measure(al, local, prod, mkfn(capi.AFFINE_GUIDED, False), capi.AFFINE_GUIDED, args, sub_steps, sub_warm, barrier,
+                    do_e2e=solo, do_parity=solo and args.parity, do_cpu=solo, all_cpus=all_cpus)
+        out["affine_production"] = dict(sub_record(r, sub_steps, int_peak),
+                                        workload=f"blasr's refinement jobs (configs[0] shape): {args.prod_jobs} pairs of 10 kb, band 16, AffineGuidedAlign, "
+                                                 "ins 5 / del 5 / affineOpen 50 / affineExtend 0 (MappingParameters.h:338-342,395-397)")
+        r = measure(al, local, batch, mkfn(capi.GUIDED, True), capi.GUIDED, args, sub_steps, sub_warm, barrier,
+                    do_e2e=False, do_parity=solo and args.parity, do_cpu=solo, all_cpus=all_cpus, quality=True)
+        out["quality"] = dict(sub_record(r, sub_steps, int_peak),
+                              workload="configs[3]-style: the configs[1] pairs with a simulated QV track, GuidedAlign x QualityValueScoreFunction")
+        if sdp is not None and sdp.n:
+            _pin_batch(sdp, keep)
+            r = measure(al, local, sdp, mkfn(capi.GUIDED, False), capi.GUIDED, args, sub_steps, sub_warm, barrier, do_e2e=False,
+                        do_parity=args.parity, do_cpu=False)
+            out["sdp_guides"] = dict(sub_record(r, sub_steps, int_peak),
+                                     workload=f"{sdp.n} pairs of the configs[1] generator with guides = the reference's own SDPAlign(k=11, sdpIns 5, "
+                                              "sdpDel 10, indelRate 0.3 x 3) output sliced as RefineAlignment does (SURVEY 8d C2); a small ticket: "
+                                              "the fill kernel's tail is a visible share of it")
+    al.close()
+    if solo and args.pipeline:
         try:
-            os.sched_setaffinity(0, all_cpus)            # the CPU baseline gets every host core back
-            cb = cpu_replay(batch, a, len(all_cpus), args.cpu_seconds, quality=args.scorefn == "quality")
-            out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        except Exception as e:  # noqa: BLE001
-            out["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-    al.release(tk); al.close()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import pipeline_bench
+            os.sched_setaffinity(0, all_cpus)
+            out["pipeline"] = pipeline_bench.measure(n_reads=args.pipeline_reads, device=local)
+        except BaseException as e:  # noqa: BLE001
+            out["pipeline"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -286,6 +286,10 @@ class Aligner:
     def release(self, ticket):
         self._lib.bgpu_release(self._ctx, ticket[0])
 
+    def trim(self):
+        """Give the context's cached (idle) device / pinned slabs back to the driver."""
+        self._lib.bgpu_trim(self._ctx)
+
     def int_peak(self):
         ops, mhz = C.c_double(), C.c_double()
         rc = self._lib.bgpu_measure_int_peak(self._ctx, C.byref(ops), C.byref(mhz))

@@ -129,6 +129,16 @@ static cudaError_t raw_alloc(bool pinned, void **p, size_t bytes) {
 }
 static void raw_free(bool pinned, void *p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
 
+// every live context of the process: when an allocation fails, the idle slabs cached by the OTHER contexts of the same device
+// are given back to the driver before the retry (several host threads, one context each, share a GPU)
+static std::mutex g_ctxMu;
+static std::vector<bgpu_ctx *> g_ctxs;
+static void trim_pool(SlabPool &pool) {
+  for (auto &f : pool.free_) raw_free(pool.pinned, f.base);
+  pool.free_.clear();
+}
+static void trim_others(bgpu_ctx *self, bool pinned);
+
 static int slab_alloc(bgpu_ctx *ctx, SlabPool &pool, TicketMem &tm, void **p, size_t bytes) {
   bytes = (bytes + 255) & ~(size_t)255;
   if (!tm.owned.empty() && tm.used + bytes <= tm.owned.back().cap) {
@@ -153,11 +163,11 @@ static int slab_alloc(bgpu_ctx *ctx, SlabPool &pool, TicketMem &tm, void **p, si
     pool.nAlloc++;
     cudaError_t e = raw_alloc(pool.pinned, &v, cap);
     if (e != cudaSuccess && cap > bytes) { cudaGetLastError(); cap = (bytes + 0xfffff) & ~(size_t)0xfffff; e = raw_alloc(pool.pinned, &v, cap); }
-    if (e != cudaSuccess) {   // drop the cache and retry once
+    if (e != cudaSuccess) {   // drop this context's cache, then the other contexts' idle slabs, and retry
       cudaGetLastError();
-      for (auto &f : pool.free_) raw_free(pool.pinned, f.base);
-      pool.free_.clear();
+      trim_pool(pool);
       e = raw_alloc(pool.pinned, &v, cap);
+      if (e != cudaSuccess) { cudaGetLastError(); trim_others(ctx, pool.pinned); e = raw_alloc(pool.pinned, &v, cap); }
     }
     if (e != cudaSuccess) { ctx->err = std::string(pool.pinned ? "cudaHostAlloc: " : "cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); return BGPU_E_OOM; }
     sl.base = (char *)v; sl.cap = cap; pool.lastCap = cap;
@@ -170,6 +180,15 @@ static int slab_alloc(bgpu_ctx *ctx, SlabPool &pool, TicketMem &tm, void **p, si
 static void slab_release(SlabPool &pool, TicketMem &tm) {
   for (auto &sl : tm.owned) pool.free_.push_back(sl);
   tm.owned.clear(); tm.used = 0; tm.hint = 0;
+}
+
+static void trim_others(bgpu_ctx *self, bool pinned) {
+  std::lock_guard<std::mutex> lk(g_ctxMu);
+  for (bgpu_ctx *c : g_ctxs) {
+    if (c == self || c->device != self->device) continue;
+    std::unique_lock<std::mutex> cl(c->mu, std::try_to_lock);   // a context busy in a call keeps its slabs
+    if (cl.owns_lock()) trim_pool(pinned ? c->pinPool : c->devPool);
+  }
 }
 
 struct Wave { uint32_t begin[N_CLS], count[N_CLS]; uint32_t traceBegin, traceCount; };  // index by job class
@@ -276,12 +295,23 @@ extern "C" int bgpu_create(bgpu_ctx **out, int device) {
   const char *env = getenv("BGPU_ARROW_POOL_MB");
   if (env) ctx->arrowPoolCap = (size_t)atoll(env) << 20;
   trace_init(ctx->stream);
+  { std::lock_guard<std::mutex> lk(g_ctxMu); g_ctxs.push_back(ctx); }
   *out = ctx;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_trim(bgpu_ctx *ctx) {
+  if (!ctx) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  cudaStreamSynchronize(ctx->stream);
+  trim_pool(ctx->devPool); trim_pool(ctx->pinPool);
   return BGPU_OK;
 }
 
 extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
   if (!ctx) return;
+  { std::lock_guard<std::mutex> lk(g_ctxMu); g_ctxs.erase(std::remove(g_ctxs.begin(), g_ctxs.end(), ctx), g_ctxs.end()); }
   cudaSetDevice(ctx->device);
   if (ctx->lastSync) bgpu_release(ctx, ctx->lastSync);
   cudaStreamSynchronize(ctx->stream);
@@ -614,7 +644,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
     // traceback bytes this job is expected to reserve: d-blocks x rows per block x words per row (window of the band plus
     // drift and class quantisation) -- an estimate, the planner kernels check the real sum against the pool
     const int64_t bd = std::max<int64_t>(b->band ? b->band[i] : p->band, 0);
-    poolEst += ((((ql + tl + 1) / 64 + 2) * rowsPerBlock * (uint64_t)(bd + 49) * 4ull) + 255ull) & ~255ull;
+    poolEst += ((((ql + tl + 1) / 64 + 2) * rowsPerBlock * (uint64_t)(bd + 24 + (bd > 40 ? 16 : 0)) * 4ull) + 255ull) & ~255ull;
   }
   RC(talloc_dev(ctx, t, &t->d_rowOff, 3 * (size_t)n + 3));
   t->d_dblkOff = t->d_rowOff + n; t->d_runOff = t->d_rowOff + 2 * (size_t)n;

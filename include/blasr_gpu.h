@@ -153,6 +153,9 @@ typedef struct bgpu_ticket_s *bgpu_ticket;
 int  bgpu_create(bgpu_ctx **ctx, int device);       /* binds to one GPU; one ctx per host thread or shared (calls are serialised) */
 void bgpu_destroy(bgpu_ctx *ctx);
 const char *bgpu_last_error(const bgpu_ctx *ctx);
+/* A context caches the device / pinned slabs of released tickets for the next ones; bgpu_trim gives the idle ones back to the
+ * driver (a failing allocation also trims the idle slabs of the other contexts on the same device before it gives up). */
+int  bgpu_trim(bgpu_ctx *ctx);
 int  bgpu_version(void);
 /* The base -> code table every kernel uses: ThreeBit[] of common/NucConversion.h:48-84 (0..3 ACGT, 4 = N / IUPAC,
  * 5 = '$', 255 = not a base -> BGPU_JOB_BAD_INPUT).  Host-callable so that the table can be pinned without a GPU. */
