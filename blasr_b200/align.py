@@ -272,6 +272,34 @@ class Aligner:
         c = np.frombuffer((C.c_ubyte * (4 * tot)).from_address(ops.value), dtype="<u4").copy() if tot else np.zeros(0, "<u4")
         return c, o
 
+    def cigar_clipped(self, ticket, clips=None, tStrand=None):
+        """CreateCIGARString (SAMPrinter.h:345-400): clips (n, 4) uint32 = hard prefix, soft prefix, soft suffix, hard suffix per job
+        (None = -clipping none), tStrand (n,) uint8.  Returns (ops, off) like cigar()."""
+        tk, n = ticket
+        ops, off = C.c_void_p(), C.c_void_p()
+        cl = np.ascontiguousarray(clips, np.uint32).reshape(n, 4) if clips is not None else None
+        st = np.ascontiguousarray(tStrand, np.uint8) if tStrand is not None else None
+        rc = self._lib.bgpu_cigar_clipped(self._ctx, tk, _ptr(cl), _ptr(st), C.byref(ops), C.byref(off))
+        if rc != 0:
+            self._err(rc, "bgpu_cigar_clipped")
+        o = np.frombuffer((C.c_ubyte * (8 * (n + 1))).from_address(off.value), dtype="<u8").copy()
+        tot = int(o[-1])
+        c = np.frombuffer((C.c_ubyte * (4 * tot)).from_address(ops.value), dtype="<u4").copy() if tot else np.zeros(0, "<u4")
+        return c, o
+
+    def strings(self, ticket):
+        """CreateAlignmentStrings (AlignmentUtils.h:390-533) of every alignment of a collected guided ticket (bgpu_strings):
+        returns (text, align, query, off): three uint8 arrays and nJobs+1 offsets."""
+        tk, n = ticket
+        p = [C.c_void_p() for _ in range(4)]
+        rc = self._lib.bgpu_strings(self._ctx, tk, *[C.byref(x) for x in p])
+        if rc != 0:
+            self._err(rc, "bgpu_strings")
+        o = np.frombuffer((C.c_ubyte * (8 * (n + 1))).from_address(p[3].value), dtype="<u8").copy()
+        tot = int(o[-1])
+        arrs = [np.frombuffer((C.c_ubyte * tot).from_address(x.value), dtype=np.uint8).copy() if tot else np.zeros(0, np.uint8) for x in p[:3]]
+        return arrs[0], arrs[1], arrs[2], o
+
     def rerun(self, ticket):
         rc = self._lib.bgpu_rerun(self._ctx, ticket[0])
         if rc != 0:

@@ -26,7 +26,7 @@ E_NO_DEVICE, E_CUDA, E_INVALID, E_OOM, E_BUSY = -1, -2, -3, -4, -5
 EXPORTS = [
     "bgpu_create", "bgpu_destroy", "bgpu_last_error", "bgpu_version", "bgpu_submit", "bgpu_submit_jobs",
     "bgpu_collect", "bgpu_release", "bgpu_rerun", "bgpu_timing_of", "bgpu_align", "bgpu_device_count",
-    "bgpu_measure_int_peak", "bgpu_int_peak_modes", "bgpu_cigar", "bgpu_base_code", "bgpu_query", "bgpu_trim",
+    "bgpu_measure_int_peak", "bgpu_int_peak_modes", "bgpu_cigar", "bgpu_base_code", "bgpu_query", "bgpu_trim", "bgpu_cigar_clipped", "bgpu_strings",
 ]
 
 
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     L.bgpu_release.argtypes = [C.c_void_p, C.c_void_p]
     L.bgpu_query.argtypes = [C.c_void_p, C.c_void_p]
     L.bgpu_trim.argtypes = [C.c_void_p]
+    L.bgpu_cigar_clipped.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.bgpu_strings.argtypes = [C.c_void_p, C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
     L.bgpu_rerun.argtypes = [C.c_void_p, C.c_void_p]
     L.bgpu_cigar.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.bgpu_timing_of.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Timing)]

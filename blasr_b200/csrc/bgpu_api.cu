@@ -31,8 +31,11 @@ void launch_dense_prep(const BatchDev &, const ScoreParams &, const DenseArgs &,
 void launch_dense_fill(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, uint32_t *, int,
                        cudaStream_t);
 void launch_dense_trace(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, cudaStream_t);
-void launch_cigar_count(const BatchDev &, uint32_t *, cudaStream_t);
-void launch_cigar_write(const BatchDev &, const uint64_t *, uint32_t *, cudaStream_t);
+void launch_fmt_count(const BatchDev &, uint32_t *, uint32_t *, cudaStream_t);
+void launch_fmt_scan(uint32_t, const uint32_t *, const uint32_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
+void launch_fmt_cigar(const BatchDev &, const uint64_t *, const uint64_t *, uint32_t *, uint32_t *, uint32_t *, const uint32_t *,
+                      const uint8_t *, cudaStream_t);
+void launch_fmt_strings(const BatchDev &, const uint64_t *, char *, char *, char *, cudaStream_t);
 double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz);
 extern double g_peakByMode[4];
 }  // namespace bgpu
@@ -222,6 +225,8 @@ struct bgpu_ticket_s {
   std::vector<uint64_t> h_arrowBytes;   // dense: host-computed traceback bytes per job
   std::vector<uint64_t> h_cellsMetric;  // dense: SURVEY 8(d) cell count per job
   uint32_t *h_cigar = nullptr; uint64_t *h_cigarOff = nullptr;   // bgpu_cigar results (pinned), once built
+  uint32_t *d_fmtOps = nullptr, *d_fmtCols = nullptr;            // per-job CIGAR op / alignment column counts, once counted
+  char *h_str = nullptr; uint64_t *h_strOff = nullptr; size_t strTotal = 0;   // bgpu_strings results (pinned), once built
   // asynchronous guided path: the schedule is built on the device (bgpu_plan.cu), one wave, speculative sizes
   bool fast = false;            // submit enqueued everything without waiting for the device
   bool gated = false;           // large ticket: goes through the H2D / kernel / D2H phase gates
@@ -999,34 +1004,90 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
   return BGPU_OK;
 }
 
-extern "C" int bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, const uint64_t **cigarOff) {
-  if (!ctx || !t || !ops || !cigarOff) return BGPU_E_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+// per-job op / column counts of a collected guided ticket (one kernel, cached in the ticket)
+static int fmt_counts(bgpu_ctx *ctx, bgpu_ticket t) {
+  if (t->d_fmtOps) return BGPU_OK;
+  RC(talloc_dev(ctx, t, &t->d_fmtOps, (size_t)t->nJobs + 1)); RC(talloc_dev(ctx, t, &t->d_fmtCols, (size_t)t->nJobs + 1));
+  launch_fmt_count(t->B, t->d_fmtOps, t->d_fmtCols, ctx->stream);
+  return BGPU_OK;
+}
+
+static int cigar_impl(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t *clips, const uint8_t *tStrand, const uint32_t **ops,
+                      const uint64_t **cigarOff) {
   if (!t->collected) { ctx->err = "bgpu_cigar needs a collected ticket"; return BGPU_E_BUSY; }
   if (t->dense) { ctx->err = "bgpu_cigar: GuidedAlign / AffineGuidedAlign tickets only"; return BGPU_E_INVALID; }
   if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = t->nJobs;
+  RC(fmt_counts(ctx, t));
+  uint32_t *d_clips = nullptr; uint8_t *d_strand = nullptr;
+  if (clips && n) { RC(talloc_dev(ctx, t, &d_clips, 4 * (size_t)n)); RC(upload(ctx, t, d_clips, clips, sizeof(uint32_t) * 4 * n)); }
+  if (tStrand && n) { RC(talloc_dev(ctx, t, &d_strand, (size_t)n)); RC(upload(ctx, t, d_strand, tStrand, n)); }
+  uint64_t *d_off = nullptr, *d_core = nullptr, *d_tot = nullptr, *h_off = nullptr, *h_tot = nullptr;
+  RC(talloc_dev(ctx, t, &d_off, (size_t)n + 1)); RC(talloc_dev(ctx, t, &d_core, (size_t)n + 1)); RC(talloc_dev(ctx, t, &d_tot, 2));
+  RC(talloc_pin(ctx, t, &h_off, (size_t)n + 1)); RC(talloc_pin(ctx, t, &h_tot, 2));
+  launch_fmt_scan(n, t->d_fmtOps, d_clips, d_off, d_core, d_tot, s);      // offsets on the device: only the two totals come back
+  CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_off, d_off, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, s));
+  CK(wait_stream(ctx));
+  uint32_t *d_ops = nullptr, *h_ops = nullptr, *d_tc = nullptr, *d_tp = nullptr;
+  RC(talloc_dev(ctx, t, &d_ops, h_tot[0] + 1)); RC(talloc_pin(ctx, t, &h_ops, h_tot[0] + 1));
+  RC(talloc_dev(ctx, t, &d_tc, h_tot[1] + 1)); RC(talloc_dev(ctx, t, &d_tp, h_tot[1] + 1));
+  launch_fmt_cigar(t->B, d_off, d_core, d_tc, d_tp, d_ops, d_clips, d_strand, s);
+  CK(cudaMemcpyAsync(h_ops, d_ops, sizeof(uint32_t) * h_tot[0], cudaMemcpyDeviceToHost, s));
+  CK(wait_stream(ctx));
+  CK(cudaGetLastError());
+  *ops = h_ops; *cigarOff = h_off;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, const uint64_t **cigarOff) {
+  if (!ctx || !t || !ops || !cigarOff) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
   if (!t->h_cigarOff) {
-    cudaStream_t s = ctx->stream;
-    const uint32_t n = t->nJobs;
-    uint32_t *d_cnt = nullptr, *h_cnt = nullptr; uint64_t *d_off = nullptr, *h_off = nullptr;
-    RC(talloc_dev(ctx, t, &d_cnt, (size_t)n + 1)); RC(talloc_pin(ctx, t, &h_cnt, (size_t)n + 1));
-    RC(talloc_dev(ctx, t, &d_off, (size_t)n + 1)); RC(talloc_pin(ctx, t, &h_off, (size_t)n + 1));
-    launch_cigar_count(t->B, d_cnt, s);                                   // pass 1: ops per job
-    CK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
-    CK(wait_stream(ctx));
-    uint64_t tot = 0;
-    for (uint32_t i = 0; i < n; i++) { h_off[i] = tot; tot += h_cnt[i]; }
-    h_off[n] = tot;
-    uint32_t *d_ops = nullptr, *h_ops = nullptr;
-    RC(talloc_dev(ctx, t, &d_ops, tot + 1)); RC(talloc_pin(ctx, t, &h_ops, tot + 1));
-    CK(cudaMemcpyAsync(d_off, h_off, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, s));
-    launch_cigar_write(t->B, d_off, d_ops, s);                            // pass 2: the ops themselves
-    CK(cudaMemcpyAsync(h_ops, d_ops, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, s));
-    CK(wait_stream(ctx));
-    CK(cudaGetLastError());
-    t->h_cigar = h_ops; t->h_cigarOff = h_off;
+    const uint32_t *o = nullptr; const uint64_t *f = nullptr;
+    RC(cigar_impl(ctx, t, nullptr, nullptr, &o, &f));
+    t->h_cigar = const_cast<uint32_t *>(o); t->h_cigarOff = const_cast<uint64_t *>(f);
   }
   *ops = t->h_cigar; *cigarOff = t->h_cigarOff;
+  return BGPU_OK;
+}
+
+extern "C" int bgpu_cigar_clipped(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t *clips, const uint8_t *tStrand, const uint32_t **ops,
+                                  const uint64_t **cigarOff) {
+  if (!ctx || !t || !ops || !cigarOff) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return cigar_impl(ctx, t, clips, tStrand, ops, cigarOff);
+}
+
+extern "C" int bgpu_strings(bgpu_ctx *ctx, bgpu_ticket t, const char **text, const char **align, const char **query,
+                            const uint64_t **strOff) {
+  if (!ctx || !t || !text || !align || !query || !strOff) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!t->collected) { ctx->err = "bgpu_strings needs a collected ticket"; return BGPU_E_BUSY; }
+  if (t->dense) { ctx->err = "bgpu_strings: GuidedAlign / AffineGuidedAlign tickets only"; return BGPU_E_INVALID; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  if (!t->h_strOff) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = t->nJobs;
+    RC(fmt_counts(ctx, t));
+    uint64_t *d_off = nullptr, *d_tot = nullptr, *h_off = nullptr, *h_tot = nullptr;
+    RC(talloc_dev(ctx, t, &d_off, (size_t)n + 1)); RC(talloc_dev(ctx, t, &d_tot, 2));
+    RC(talloc_pin(ctx, t, &h_off, (size_t)n + 1)); RC(talloc_pin(ctx, t, &h_tot, 2));
+    launch_fmt_scan(n, t->d_fmtCols, nullptr, d_off, nullptr, d_tot, s);
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_off, d_off, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, s));
+    CK(wait_stream(ctx));
+    const size_t tot = h_tot[0];
+    char *d_str = nullptr, *h_str = nullptr;
+    RC(talloc_dev(ctx, t, &d_str, 3 * tot + 16)); RC(talloc_pin(ctx, t, &h_str, 3 * tot + 16));
+    launch_fmt_strings(t->B, d_off, d_str, d_str + tot, d_str + 2 * tot, s);
+    CK(cudaMemcpyAsync(h_str, d_str, 3 * tot, cudaMemcpyDeviceToHost, s));
+    CK(wait_stream(ctx));
+    CK(cudaGetLastError());
+    t->h_str = h_str; t->h_strOff = h_off; t->strTotal = tot;
+  }
+  *text = t->h_str; *align = t->h_str + t->strTotal; *query = t->h_str + 2 * t->strTotal; *strOff = t->h_strOff;
   return BGPU_OK;
 }
 

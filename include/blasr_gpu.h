@@ -186,6 +186,19 @@ int  bgpu_timing_of(bgpu_ctx *ctx, bgpu_ticket t, bgpu_timing *out);
  * 'D' 2); job i owns ops[cigarOff[i] .. cigarOff[i+1]) (empty for jobs without blocks).  Both arrays are pinned host
  * memory owned by the library until bgpu_release(). */
 int  bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, const uint64_t **cigarOff);
+/* The whole CreateCIGARString (SAMPrinter.h:345-400): the core above wrapped in the clipping ops and reversed for reverse-strand
+ * alignments.  clips[4 * i .. 4 * i + 3] = hard-clipped prefix, soft-clipped prefix, soft-clipped suffix, hard-clipped suffix
+ * of job i (the values SetHardClip :311-327 / SetSoftClip :295-309 compute from the read; 0 = no such op; NULL = no clipping,
+ * `-clipping none`), tStrand[i] = alignment.tStrand (NULL = all forward).  Ops: 'H' 5, 'S' 4 and the core's codes; the
+ * arrays are new pinned memory owned by the library until bgpu_release(). */
+int  bgpu_cigar_clipped(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t *clips, const uint8_t *tStrand, const uint32_t **ops,
+                        const uint64_t **cigarOff);
+/* The three strings of CreateAlignmentStrings (common/algorithms/alignment/AlignmentUtils.h:390-533, what
+ * PrintCompareSequencesAlignment, printers/CompareSequencesAlignmentPrinter.h:17-89, prints for -m 5 and what StoreMapQVs
+ * rescoring walks) for every alignment of a collected GuidedAlign / AffineGuidedAlign ticket, built on the device: text = target
+ * bases / '-', align = '|' (TwoBit-equal) / '*' / ' ' (gap), query = query bases / '-'.  Job i owns [strOff[i], strOff[i+1]) of
+ * each of the three arrays (no terminators); pinned host memory owned by the library until bgpu_release(). */
+int  bgpu_strings(bgpu_ctx *ctx, bgpu_ticket t, const char **text, const char **align, const char **query, const uint64_t **strOff);
 
 /* ---- synchronous one-shot: submit + collect; arena valid until the next call on ctx ---- */
 int  bgpu_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b,

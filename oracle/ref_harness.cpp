@@ -191,6 +191,31 @@ extern "C" int ref_cigar(const orc_scorefn *fn, const orc_job *job, uint32_t *op
   return (int)opSize.size();
 }
 
+/* The whole CreateCIGARString (SAMPrinter.h:345-400) on the job's alignment placed inside a longer read: the candidate's
+ * qAlignedSeqPos = qSeqPos, read.length = readLength, read.lowQualityPrefix / Suffix, tStrand.  clipping: 0 hard, 1 soft,
+ * 2 subread, 3 none.  Writes the CIGAR text and the four clip lengths (hard prefix, soft prefix, soft suffix, hard suffix). */
+extern "C" int ref_cigar_string(const orc_scorefn *fn, const orc_job *job, int clipping, int tStrand, uint32_t qSeqPos,
+                                uint32_t readLength, uint32_t lowQPrefix, uint32_t lowQSuffix, char *out, uint32_t capOut,
+                                uint32_t *clips) {
+  Scratch s; T_AlignmentCandidate cand; orc_result res;
+  RunOne(fn, job, &res, s, cand);
+  if (res.status != ORC_OK || cand.blocks.size() == 0) return 0;
+  DNASequence t; t.seq = (Nucleotide *)job->t; t.length = job->tLen;
+  FASTQSequence q; q.seq = (Nucleotide *)job->q; q.length = job->qLen;
+  cand.qAlignedSeq.ReferenceSubstring(q, 0, q.length); cand.tAlignedSeq.ReferenceSubstring(t, 0, t.length);
+  cand.qAlignedSeqPos = qSeqPos; cand.tStrand = tStrand;
+  SMRTSequence read;
+  read.length = readLength; read.lowQualityPrefix = lowQPrefix; read.lowQualitySuffix = lowQSuffix;
+  read.subreadStart = 0; read.subreadEnd = readLength;
+  std::string cigar;
+  DNALength pS = 0, sS = 0, pH = 0, sH = 0;
+  SAMOutput::CreateCIGARString(cand, read, cigar, (SAMOutput::Clipping)clipping, pS, sS, pH, sH);
+  clips[0] = pH; clips[1] = pS; clips[2] = sS; clips[3] = sH;
+  if (cigar.size() + 1 > capOut) return -1;
+  memcpy(out, cigar.data(), cigar.size()); out[cigar.size()] = 0;
+  return (int)cigar.size();
+}
+
 extern "C" int ref_alignment_strings(const orc_scorefn *fn, const orc_job *job, char *textStr, char *alignStr, char *queryStr,
                                      uint32_t capOut) {
   Scratch s; Alignment aln; orc_result res;

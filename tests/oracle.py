@@ -206,6 +206,22 @@ def ref_cigar(fn: OrcScoreFn, job: OrcJob) -> np.ndarray:
     return ops[:n].copy()
 
 
+def ref_cigar_string(fn: OrcScoreFn, job: OrcJob, clipping: int, tStrand: int, qSeqPos: int, readLength: int, lowQPrefix: int,
+                     lowQSuffix: int):
+    """The reference's whole CreateCIGARString on the job's alignment placed inside a longer read: (text, clips[4])."""
+    L = _load("ref")
+    cap = 16 * (int(job.qLen) + int(job.tLen)) + 64
+    buf = C.create_string_buffer(cap)
+    clips = np.zeros(4, np.uint32)
+    L.ref_cigar_string.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                   C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    n = L.ref_cigar_string(C.byref(fn), C.byref(job), clipping, tStrand, qSeqPos, readLength, lowQPrefix, lowQSuffix, buf, cap,
+                           clips.ctypes.data)
+    if n < 0:
+        raise RuntimeError("ref_cigar_string overflow")
+    return buf.raw[:n].decode(), clips
+
+
 def orc_cigar_from(q: np.ndarray, t: np.ndarray, aln: dict) -> np.ndarray:
     """C restatement of the printer, from an alignment dict as align() returns it."""
     L = _load("orc")

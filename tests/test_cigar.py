@@ -123,3 +123,64 @@ def test_m5_strings_of_block_only_alignments():
         assert got == want, (i, got[1][:60], want[1][:60])
         total += len(want[0])
     assert total > 5000
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", [0, 1])
+def test_gpu_clipped_cigar_matches_create_cigar_string(aligner, algo):
+    """bgpu_cigar_clipped against the reference's whole CreateCIGARString (SAMPrinter.h:345-400): alignments placed inside longer
+    reads, -clipping hard / soft / none, both strands (the op list of a reverse-strand alignment is reversed)."""
+    rng = np.random.default_rng(31 + algo)
+    b = _mixed_case_batch(390 + algo, 36, 50, 3000)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50 if algo else 0, affineExtend=0)
+    ofn = O.score_fn(SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0)
+    for at in (1, 0):
+        tk = aligner.submit(b, fn, algo, alignType=at, band=16)
+        aligner.collect(tk)
+        clips = np.zeros((b.n, 4), np.uint32); strand = np.zeros(b.n, np.uint8); want = []
+        for i in range(b.n):
+            q, t, g, _ = cases.job_arrays(b, i)
+            j, keep = O.make_job(algo, at, 16, q, t, g, None, 0, 0, 0, 0)
+            mode = int(rng.integers(0, 4)) if i % 4 else 3            # hard, soft, subread, none
+            lowp, lows = (int(rng.integers(0, 30)), int(rng.integers(0, 30))) if mode in (1, 2) else (0, 0)
+            qpos = lowp + int(rng.integers(0, 50)); rlen = qpos + len(q) + lows + int(rng.integers(0, 50))
+            strand[i] = int(rng.integers(0, 2))
+            text, cl = O.ref_cigar_string(ofn, j, mode, int(strand[i]), qpos, rlen, lowp, lows)
+            want.append(text); clips[i] = cl
+        ops, off = aligner.cigar_clipped(tk, clips, strand)
+        for i in range(b.n):
+            got = A.cigar_string(ops[int(off[i]):int(off[i + 1])])
+            assert got == want[i], (at, i, got[:80], want[i][:80])
+        # without clips / strands it is the core that bgpu_cigar returns
+        o2, f2 = aligner.cigar_clipped(tk, None, None)
+        o1, f1 = aligner.cigar(tk)
+        assert np.array_equal(o1, o2) and np.array_equal(f1, f2)
+        aligner.release(tk)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", [0, 1])
+def test_gpu_alignment_strings_match_reference(aligner, algo):
+    """bgpu_strings (the three columns -m 5 prints) against the reference's CreateAlignmentStrings run on the reference's own
+    alignment of the same job: mixed case, N's, per-job bands, Global and Local."""
+    b = _mixed_case_batch(490 + algo, 40, 50, 5000)
+    b.band = np.random.default_rng(5).choice([8, 16, 32, 64], size=b.n).astype(np.int32)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50 if algo else 0, affineExtend=0)
+    ofn = O.score_fn(SMRTDistanceMatrix, 5, 5, 50 if algo else 0, 0)
+    total = 0
+    for at in (1, 0):
+        tk = aligner.submit(b, fn, algo, alignType=at, band=16)
+        aligner.collect(tk)
+        text, aln, query, off = aligner.strings(tk)
+        for i in range(b.n):
+            q, t, g, _ = cases.job_arrays(b, i)
+            j, keep = O.make_job(algo, at, int(b.band[i]), q, t, g, None, 0, 0, 0, 0)
+            want = O.ref_alignment_strings(ofn, j)
+            lo, hi = int(off[i]), int(off[i + 1])
+            got = (text[lo:hi].tobytes(), aln[lo:hi].tobytes(), query[lo:hi].tobytes())
+            assert got == want, (at, i, got[1][:60], want[1][:60])
+            total += hi - lo
+        aligner.release(tk)
+    assert total > 100000
