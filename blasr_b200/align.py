@@ -159,15 +159,52 @@ class Alignment:
     statsScore: int = 0
 
 
+def pack_guide(guide: np.ndarray, guideOff: np.ndarray):
+    """bgpu_batch::guidePacked: per block (gap to the previous block's end in q, in t, length) as three bytes; blocks that do
+    not fit go to the side list {block, dq, dt, length}.  Returns (packed uint8 (3n,), wide uint32 (m, 4))."""
+    g = np.ascontiguousarray(guide, np.uint32).reshape(-1, 3).astype(np.int64)
+    n = len(g)
+    if n == 0:
+        return np.zeros(0, np.uint8), np.zeros((0, 4), np.uint32)
+    first = np.zeros(n, bool)
+    off = np.asarray(guideOff, np.int64)
+    first[off[:-1][off[:-1] < n]] = True
+    qe = np.zeros(n, np.int64); te = np.zeros(n, np.int64)
+    qe[1:] = g[:-1, 0] + g[:-1, 2]; te[1:] = g[:-1, 1] + g[:-1, 2]
+    qe[first] = 0; te[first] = 0
+    dq, dt, ln = g[:, 0] - qe, g[:, 1] - te, g[:, 2]
+    wide = (dq < 0) | (dq >= 255) | (dt < 0) | (dt >= 255) | (ln >= 255)
+    packed = np.stack([dq, dt, ln], axis=1)
+    packed[wide] = 255
+    w = np.stack([np.flatnonzero(wide), dq[wide], dt[wide], ln[wide]], axis=1).astype(np.int64)
+    return packed.astype(np.uint8).reshape(-1), (w & 0xffffffff).astype(np.uint32)
+
+
 class BatchResult:
-    def __init__(self, results: np.ndarray, blocks: np.ndarray, gapCounts: np.ndarray, gaps: np.ndarray, timing=None):
-        self.results, self.blocks, self.gapCounts, self.gaps, self.timing = results, blocks, gapCounts, gaps, timing
+    def __init__(self, results: np.ndarray, blocks: np.ndarray, gapCounts: np.ndarray, gaps: np.ndarray, timing=None, runs=None):
+        self.results, self.blocks, self.gapCounts, self.gaps, self.timing, self.runs = results, blocks, gapCounts, gaps, timing, runs
 
     def __len__(self):
         return len(self.results)
 
     def alignment(self, i: int) -> Alignment:
         r = self.results[i]
+        if self.runs is not None:
+            # compact results: the path as runs (type << 30 | length); expanded the way blasr_gpu::RefineBatch::Store does
+            lo = int(r["blockOff"]) + int(r["gapOff"])
+            run = self.runs[lo:lo + int(r["nBlocks"]) + int(r["nGaps"])].astype(np.int64)
+            ty, ln = run >> 30, run & 0x3fffffff
+            qa = np.cumsum(np.where(ty != 2, ln, 0)) - np.where(ty != 2, ln, 0)
+            ta = np.cumsum(np.where(ty != 1, ln, 0)) - np.where(ty != 1, ln, 0)
+            d = ty == 0
+            blocks = np.stack([qa[d], ta[d], ln[d]], axis=1).astype(np.uint32) if d.any() else np.zeros((0, 3), np.uint32)
+            gaps = [[] for _ in range(int(r["nGapLists"]))]
+            bidx = np.cumsum(d)
+            for k in np.flatnonzero(~d):
+                gaps[int(bidx[k])].append((1 if ty[k] == 1 else 0, int(ln[k])))
+            return Alignment(int(r["status"]), int(r["score"]), int(r["qPos"]), int(r["tPos"]), int(r["nCells"]), blocks, gaps,
+                             int(r["nMatch"]), int(r["nMismatch"]), int(r["nIns"]), int(r["nDel"]), float(r["pctSimilarity"]),
+                             int(r["statsScore"]))
         b = self.blocks[int(r["blockOff"]):int(r["blockOff"]) + int(r["nBlocks"])]
         blocks = np.stack([b["qPos"], b["tPos"], b["length"]], axis=1) if len(b) else np.zeros((0, 3), np.uint32)
         cnt = self.gapCounts[int(r["gapListOff"]):int(r["gapListOff"]) + int(r["nGapLists"])]
@@ -210,7 +247,9 @@ class Aligner:
     # ---- low level: ticket API ----
     def submit(self, batch: JobBatch, fn: DistanceMatrixScoreFunction, algo: int, alignType: int = GLOBAL, band: int = 16,
                bndIns: int = 0, bndDel: int = 0, doStats: bool = True, statsAffine: Optional[bool] = None,
-               affineKBand: Sequence[int] = (0, 0, 0, 0)):
+               affineKBand: Sequence[int] = (0, 0, 0, 0), compact: bool = False, packed: bool = False):
+        """compact: results come back as run-length paths (bgpu_params.compactResults); packed: the guide goes over as three
+        bytes per block (bgpu_batch.guidePacked; batch.guidePacked / guideWide are used when present, else packed here)."""
         keep = dict(q=np.ascontiguousarray(batch.q, np.uint8), qOff=np.ascontiguousarray(batch.qOff, np.uint64),
                     t=np.ascontiguousarray(batch.t, np.uint8), tOff=np.ascontiguousarray(batch.tOff, np.uint64))
         n = batch.n
@@ -219,6 +258,13 @@ class Aligner:
                 raise ValueError("guided aligners need batch.guide")
             keep["guide"] = np.ascontiguousarray(batch.guide, np.uint32)
             keep["guideOff"] = np.ascontiguousarray(batch.guideOff, np.uint64)
+            if packed:
+                gp = getattr(batch, "guidePacked", None)
+                gw = getattr(batch, "guideWide", None)
+                if gp is None:
+                    gp, gw = pack_guide(batch.guide, batch.guideOff)
+                keep["guidePacked"] = np.ascontiguousarray(gp, np.uint8)
+                keep["guideWide"] = np.ascontiguousarray(gw, np.uint32).reshape(-1, 4)
         if batch.qual is not None:
             keep["qual"] = np.ascontiguousarray(batch.qual, np.uint8)
         if batch.band is not None:
@@ -227,11 +273,12 @@ class Aligner:
             if getattr(batch, name, None) is not None:
                 keep[name] = np.ascontiguousarray(getattr(batch, name), np.uint8)
         b = capi.Batch(n, _ptr(keep["q"]), _ptr(keep["qOff"]), _ptr(keep["t"]), _ptr(keep["tOff"]), _ptr(keep.get("qual")),
-                       _ptr(keep.get("guide")), _ptr(keep.get("guideOff")), _ptr(keep.get("band")),
-                       *[_ptr(keep.get(name)) for name in JobBatch.TRACKS])
+                       _ptr(keep.get("guide")) if not packed else None, _ptr(keep.get("guideOff")), _ptr(keep.get("band")),
+                       *[_ptr(keep.get(name)) for name in JobBatch.TRACKS],
+                       _ptr(keep.get("guidePacked")), _ptr(keep.get("guideWide")), len(keep["guideWide"]) if "guideWide" in keep else 0)
         if statsAffine is None:
             statsAffine = algo == AFFINE_GUIDED
-        p = capi.Params(algo, alignType, band, bndIns, bndDel, int(doStats), int(statsAffine), *[int(x) for x in affineKBand])
+        p = capi.Params(algo, alignType, band, bndIns, bndDel, int(doStats), int(statsAffine), *[int(x) for x in affineKBand], int(compact))
         f = fn.c_struct()
         tk = C.c_void_p()
         rc = self._lib.bgpu_submit(self._ctx, C.byref(f), C.byref(p), C.byref(b), C.byref(tk))
@@ -255,6 +302,8 @@ class Aligner:
             buf = (C.c_ubyte * (int(count) * dt.itemsize)).from_address(ptr)
             a = np.frombuffer(buf, dtype=dt)
             return a.copy() if copy else a
+        if arena.runs:
+            return BatchResult(res, None, None, None, self.timing(ticket), runs=view(arena.runs, arena.nRuns, np.dtype("<u4")))
         return BatchResult(res, view(arena.blocks, arena.nBlocks, capi.BLOCK_DTYPE),
                            view(arena.gapCounts, arena.nGapLists, np.dtype("<u4")),
                            view(arena.gaps, arena.nGaps, capi.GAP_DTYPE), self.timing(ticket))

@@ -39,14 +39,14 @@ class ScoreFn(C.Structure):
 class Params(C.Structure):
     _fields_ = [("algo", C.c_int32), ("alignType", C.c_int32), ("band", C.c_int32), ("bndIns", C.c_int32),
                 ("bndDel", C.c_int32), ("doStats", C.c_int32), ("statsAffine", C.c_int32), ("hpInsOpen", C.c_int32),
-                ("hpInsExtend", C.c_int32), ("insOpen", C.c_int32), ("insExtend", C.c_int32)]
+                ("hpInsExtend", C.c_int32), ("insOpen", C.c_int32), ("insExtend", C.c_int32), ("compactResults", C.c_int32)]
 
 
 class Batch(C.Structure):
     _fields_ = [("nJobs", C.c_uint32), ("qBases", C.c_void_p), ("qOff", C.c_void_p), ("tBases", C.c_void_p),
                 ("tOff", C.c_void_p), ("qual", C.c_void_p), ("guide", C.c_void_p), ("guideOff", C.c_void_p),
                 ("band", C.c_void_p), ("insQV", C.c_void_p), ("delQV", C.c_void_p), ("subQV", C.c_void_p),
-                ("delTag", C.c_void_p), ("subTag", C.c_void_p)]
+                ("delTag", C.c_void_p), ("subTag", C.c_void_p), ("guidePacked", C.c_void_p), ("guideWide", C.c_void_p), ("nGuideWide", C.c_uint64)]
 
 
 class Job(C.Structure):
@@ -58,7 +58,7 @@ class Job(C.Structure):
 
 class Arena(C.Structure):
     _fields_ = [("blocks", C.c_void_p), ("nBlocks", C.c_uint64), ("gapCounts", C.c_void_p),
-                ("nGapLists", C.c_uint64), ("gaps", C.c_void_p), ("nGaps", C.c_uint64)]
+                ("nGapLists", C.c_uint64), ("gaps", C.c_void_p), ("nGaps", C.c_uint64), ("runs", C.c_void_p), ("nRuns", C.c_uint64)]
 
 
 class Timing(C.Structure):

@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "bgpu_common.cuh"
 
@@ -22,11 +23,12 @@ void launch_prep_guided(const BatchDev &, const ScoreParams &, int, const uint64
 void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32_t *, const PlanHead *, uint32_t, uint32_t *, int,
                         cudaStream_t);
 void launch_trace_guided(const BatchDev &, bool, const uint32_t *, const PlanHead *, uint32_t, cudaStream_t);
+void launch_unpack_guide(uint32_t, const uint64_t *, const uint8_t *, const uint32_t *, uint64_t, bgpu_block *, cudaStream_t);
 void launch_plan_guided(const BatchDev &, bool, PlanHead *, uint32_t *, uint32_t *, uint64_t *, unsigned long long, cudaStream_t);
 size_t plan_scratch_words(uint32_t);
 void launch_scan_counts(const BatchDev &, uint64_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
 void launch_emit(const BatchDev &, const ScoreParams &, bgpu_result *, bgpu_block *, uint32_t *, bgpu_gap *,
-                 const uint64_t *, const uint64_t *, const uint64_t *, int, int, int, PlanHead *, cudaStream_t);
+                 const uint64_t *, const uint64_t *, const uint64_t *, int, int, int, PlanHead *, uint32_t *, cudaStream_t);
 void launch_dense_prep(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint64_t *, const uint64_t *, cudaStream_t);
 void launch_dense_fill(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, uint32_t *, int,
                        cudaStream_t);
@@ -121,10 +123,22 @@ struct bgpu_ctx {
 // threads sleep on an event created with cudaEventBlockingSync instead: for hosts that run more waiting threads than
 // they have cores (blasr's one pthread per core, several GPUs per box).
 static bool blocking_sync() { static const bool on = [] { const char *e = getenv("BGPU_BLOCKING_SYNC"); return e && *e && *e != '0'; }(); return on; }
+static bool spin_sync() { static const bool on = [] { const char *e = getenv("BGPU_SPIN_SYNC"); return e && *e && *e != '0'; }(); return on; }
 static cudaError_t wait_stream(bgpu_ctx *ctx) {
-  if (!blocking_sync()) return cudaStreamSynchronize(ctx->stream);
+  if (spin_sync()) return cudaStreamSynchronize(ctx->stream);
   cudaError_t e = cudaEventRecord(ctx->evSync, ctx->stream);
-  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->evSync);
+  if (e != cudaSuccess) return e;
+  if (blocking_sync()) return cudaEventSynchronize(ctx->evSync);
+  // default: poll with short naps that grow to 200 us -- a waiting host thread costs (almost) no CPU, which matters as soon as
+  // a box drives several GPUs with several threads each, and wakes within the time a PCIe copy of the results takes anyway
+  unsigned nap = 5;
+  for (;;) {
+    e = cudaEventQuery(ctx->evSync);
+    if (e != cudaErrorNotReady) return e;
+    cudaGetLastError();
+    std::this_thread::sleep_for(std::chrono::microseconds(nap));
+    if (nap < 200) nap += nap;
+  }
 }
 
 static cudaError_t raw_alloc(bool pinned, void **p, size_t bytes) {
@@ -207,6 +221,7 @@ struct bgpu_ticket_s {
   uint64_t *d_blockOff = nullptr, *d_listOff = nullptr, *d_gapOff = nullptr, *d_totals = nullptr;
   bgpu_result *d_results = nullptr;
   bgpu_block *d_blocks = nullptr; uint32_t *d_gapCounts = nullptr; bgpu_gap *d_gaps = nullptr;
+  uint32_t *d_runsOut = nullptr, *h_runsOut = nullptr;          // params.compactResults: the run-length paths instead
   // pinned host
   JobGeom *h_geom = nullptr; uint64_t *h_totals = nullptr;
   bgpu_result *h_results = nullptr; bgpu_block *h_blocks = nullptr; uint32_t *h_gapCounts = nullptr; bgpu_gap *h_gaps = nullptr;
@@ -526,6 +541,30 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
 
 static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t);
 
+// result arena for nB blocks, nL gap lists, nG gaps (device + pinned host): Block / Gap arrays, or the run-length paths
+static int alloc_arena(bgpu_ctx *ctx, bgpu_ticket t, uint64_t nB, uint64_t nL, uint64_t nG) {
+  if (t->params.compactResults && !t->dense) {
+    RC(talloc_dev(ctx, t, &t->d_runsOut, nB + nG + 1)); RC(talloc_pin(ctx, t, &t->h_runsOut, nB + nG + 1));
+  } else {
+    RC(talloc_dev(ctx, t, &t->d_blocks, nB + 1)); RC(talloc_dev(ctx, t, &t->d_gapCounts, nL + 1)); RC(talloc_dev(ctx, t, &t->d_gaps, nG + 1));
+    RC(talloc_pin(ctx, t, &t->h_blocks, nB + 1)); RC(talloc_pin(ctx, t, &t->h_gapCounts, nL + 1)); RC(talloc_pin(ctx, t, &t->h_gaps, nG + 1));
+  }
+  t->arenaReady = true;
+  return BGPU_OK;
+}
+static uint64_t arena_bytes(bgpu_ticket t, uint64_t nB, uint64_t nL, uint64_t nG) {
+  if (t->params.compactResults && !t->dense) return sizeof(uint32_t) * (nB + nG);
+  return sizeof(bgpu_block) * nB + sizeof(uint32_t) * nL + sizeof(bgpu_gap) * nG;
+}
+static int copy_arena(bgpu_ctx *ctx, bgpu_ticket t, uint64_t nB, uint64_t nL, uint64_t nG) {
+  cudaStream_t s = ctx->stream;
+  if (t->d_runsOut) { CK(cudaMemcpyAsync(t->h_runsOut, t->d_runsOut, sizeof(uint32_t) * (nB + nG), cudaMemcpyDeviceToHost, s)); return BGPU_OK; }
+  CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * nB, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * nL, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * nG, cudaMemcpyDeviceToHost, s));
+  return BGPU_OK;
+}
+
 // ---- the asynchronous schedule of a guided ticket: nothing here waits for the device.  prep -> planner kernels (classes,
 // warp groups, dispatch order, traceback offsets: bgpu_plan.cu) -> the fill kernel of every class (each reads its share of
 // the schedule from the device-resident PlanHead; empty classes exit at once) -> traceback -> count scan -> emit into an
@@ -569,11 +608,7 @@ static int enqueue_guided_fast(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
     CK(cudaMemcpyAsync(t->h_plan, t->d_plan, sizeof(PlanHead), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(t->h_totals, t->d_totals, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, s));
     if (t->arenaReady) CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * n, cudaMemcpyDeviceToHost, s));
-    if (t->arenaInline) {
-      CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->arenaCap[0], cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->arenaCap[1], cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->arenaCap[2], cudaMemcpyDeviceToHost, s));
-    }
+    if (t->arenaInline) RC(copy_arena(ctx, t, t->arenaCap[0], t->arenaCap[1], t->arenaCap[2]));
   }
   CK(cudaGetLastError());
   return BGPU_OK;
@@ -582,7 +617,7 @@ static int enqueue_guided_fast(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
 static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t) {
   cudaStream_t s = ctx->stream;
   launch_emit(t->B, t->sp, t->d_results, t->d_blocks, t->d_gapCounts, t->d_gaps, t->d_blockOff, t->d_listOff,
-              t->d_gapOff, t->params.doStats, t->params.statsAffine, t->dense ? 1 : 0, t->fast ? t->d_plan : nullptr, s);
+              t->d_gapOff, t->params.doStats, t->params.statsAffine, t->dense ? 1 : 0, t->fast ? t->d_plan : nullptr, t->d_runsOut, s);
   t->timing.kernelLaunches++;
   CK(cudaEventRecord(t->ev[4], s));
   CK(cudaGetLastError());
@@ -626,13 +661,21 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   CK(cudaMemsetAsync(d_tc, 0, totT + 16, ctx->stream));
   // the phase gates keep LARGE tickets of concurrent contexts pipelined (copy in / compute / copy out); small tickets
   // (the candidates of a few reads) would only pay their host round trips
-  t->gated = totQ + totT + sizeof(bgpu_block) * totG > (32u << 20);
+  t->gated = totQ + totT + (b->guidePacked ? 3 : sizeof(bgpu_block)) * totG > (32u << 20);
   if (t->gated) { gate(ctx->device, GATE_H2D).acquire(); t->holdsH2D = true; }   // until the uploads below are done
   RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
   RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));
   RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
   RC(upload(ctx, t, d_gOff, b->guideOff, sizeof(uint64_t) * (n + 1)));
-  RC(upload(ctx, t, d_guide, b->guide, sizeof(bgpu_block) * totG));
+  if (b->guidePacked) {       // three bytes per block over PCIe, expanded into Block form on the device
+    uint8_t *d_packed = nullptr; uint32_t *d_wide = nullptr;
+    RC(talloc_dev(ctx, t, &d_packed, 3 * totG + 16)); RC(talloc_dev(ctx, t, &d_wide, 4 * b->nGuideWide + 4));
+    RC(upload(ctx, t, d_packed, b->guidePacked, 3 * totG));
+    if (b->nGuideWide) RC(upload(ctx, t, d_wide, b->guideWide, sizeof(uint32_t) * 4 * b->nGuideWide));
+    launch_unpack_guide(n, d_gOff, d_packed, d_wide, b->nGuideWide, d_guide, ctx->stream);
+  } else {
+    RC(upload(ctx, t, d_guide, b->guide, sizeof(bgpu_block) * totG));
+  }
   if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
   if (b->band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
   B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tc = d_tc; B.tOff = d_tOff; B.qual = d_qual; B.guide = d_guide; B.guideOff = d_gOff; B.band = d_band;
@@ -682,13 +725,9 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   // result arena sized from the batch (a block needs a matching base, gap runs sit between blocks): speculative when that
   // is small enough to keep around, else sized exactly by bgpu_collect once the counts are known
   t->arenaCap[0] = totQ / 4 + 2ull * n + 16; t->arenaCap[1] = t->arenaCap[0] + n; t->arenaCap[2] = 2 * t->arenaCap[0];
-  const uint64_t arenaBytes = sizeof(bgpu_block) * t->arenaCap[0] + sizeof(uint32_t) * t->arenaCap[1] + sizeof(bgpu_gap) * t->arenaCap[2];
+  const uint64_t arenaBytes = arena_bytes(t, t->arenaCap[0], t->arenaCap[1], t->arenaCap[2]);
   if (arenaBytes <= (64u << 20)) {
-    RC(talloc_dev(ctx, t, &t->d_blocks, t->arenaCap[0])); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->arenaCap[1]));
-    RC(talloc_dev(ctx, t, &t->d_gaps, t->arenaCap[2]));
-    RC(talloc_pin(ctx, t, &t->h_blocks, t->arenaCap[0])); RC(talloc_pin(ctx, t, &t->h_gapCounts, t->arenaCap[1]));
-    RC(talloc_pin(ctx, t, &t->h_gaps, t->arenaCap[2]));
-    t->arenaReady = true;
+    RC(alloc_arena(ctx, t, t->arenaCap[0], t->arenaCap[1], t->arenaCap[2]));
     t->arenaInline = arenaBytes <= (1u << 20);
     for (int k = 0; k < 3; k++) t->h_planInit->caps[k] = t->arenaCap[k];
   } else {
@@ -918,11 +957,7 @@ static int ensure_arena(bgpu_ctx *ctx, bgpu_ticket t) {
   CK(wait_stream(ctx));
   for (int i = 0; i < 3; i++) t->totals[i] = t->h_totals[i];
   if (!t->dense) t->timing.fillCells = t->h_totals[3];
-  RC(talloc_dev(ctx, t, &t->d_blocks, t->totals[0] + 1)); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->totals[1] + 1));
-  RC(talloc_dev(ctx, t, &t->d_gaps, t->totals[2] + 1));
-  RC(talloc_pin(ctx, t, &t->h_blocks, t->totals[0] + 1)); RC(talloc_pin(ctx, t, &t->h_gapCounts, t->totals[1] + 1));
-  RC(talloc_pin(ctx, t, &t->h_gaps, t->totals[2] + 1));
-  t->arenaReady = true;
+  RC(alloc_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2]));
   return BGPU_OK;
 }
 
@@ -941,7 +976,7 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
         t->fast = false; t->arenaReady = false; t->arenaInline = false;
         for (auto &e : t->waveEv) cudaEventDestroy(e);
         t->waveEv.clear(); t->waves.clear();
-        t->d_blocks = nullptr;
+        t->d_blocks = nullptr; t->d_runsOut = nullptr; t->h_runsOut = nullptr;
         RC(enqueue_guided(ctx, t, true));
       } else {
         for (int i = 0; i < 3; i++) t->totals[i] = t->h_plan->totals[i];
@@ -949,11 +984,8 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
         const bool emitted = t->arenaReady && !(t->h_plan->overflow & PLAN_OVF_ARENA);
         if (!emitted) {                                  // no speculative arena, or it was too small: exact sizes now
           t->fast = false;                               // (emit without the capacity check)
-          RC(talloc_dev(ctx, t, &t->d_blocks, t->totals[0] + 1)); RC(talloc_dev(ctx, t, &t->d_gapCounts, t->totals[1] + 1));
-          RC(talloc_dev(ctx, t, &t->d_gaps, t->totals[2] + 1));
-          RC(talloc_pin(ctx, t, &t->h_blocks, t->totals[0] + 1)); RC(talloc_pin(ctx, t, &t->h_gapCounts, t->totals[1] + 1));
-          RC(talloc_pin(ctx, t, &t->h_gaps, t->totals[2] + 1));
-          t->arenaReady = true; t->arenaInline = false;
+          RC(alloc_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2]));
+          t->arenaInline = false;
           for (int k = 0; k < 3; k++) t->h_planInit->caps[k] = ~0ull;   // a later bgpu_rerun emits into this exact-size arena
           RC(enqueue_emit(ctx, t));
           t->fast = true;
@@ -961,9 +993,7 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
         if (!t->arenaInline) {
           struct Hold { Gate *g; Hold(Gate *x) : g(x) { if (g) g->acquire(); } ~Hold() { if (g) g->release(); } } hold(t->gated ? &gate(ctx->device, GATE_D2H) : nullptr);
           if (!emitted) CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
-          CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
-          CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
-          CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
+          RC(copy_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2]));
           CK(cudaEventRecord(t->ev[5], s));
           CK(wait_stream(ctx));
         }
@@ -975,14 +1005,11 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
       RC(enqueue_emit(ctx, t));                          // a kernel: outside the D2H gate, which only covers the copies
       struct Hold { Gate *g; Hold(Gate *x) : g(x) { if (g) g->acquire(); } ~Hold() { if (g) g->release(); } } hold(t->gated || t->dense ? &gate(ctx->device, GATE_D2H) : nullptr);
       CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * t->totals[0], cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * t->totals[1], cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(t->h_gaps, t->d_gaps, sizeof(bgpu_gap) * t->totals[2], cudaMemcpyDeviceToHost, s));
+      RC(copy_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2]));
       CK(cudaEventRecord(t->ev[5], s));
       CK(wait_stream(ctx));
     }
-    t->timing.d2hBytes = sizeof(bgpu_result) * (uint64_t)t->nJobs + sizeof(bgpu_block) * t->totals[0] +
-                         sizeof(uint32_t) * t->totals[1] + sizeof(bgpu_gap) * t->totals[2];
+    t->timing.d2hBytes = sizeof(bgpu_result) * (uint64_t)t->nJobs + arena_bytes(t, t->totals[0], t->totals[1], t->totals[2]);
     gather_timing(t);
     if (g_trace) {
       auto at = [&](cudaEvent_t e) { float ms = -1; if (e) cudaEventElapsedTime(&ms, g_refEvent, e); return ms; };
@@ -1000,6 +1027,7 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
     arena->blocks = t->h_blocks; arena->nBlocks = t->totals[0];
     arena->gapCounts = t->h_gapCounts; arena->nGapLists = t->totals[1];
     arena->gaps = t->h_gaps; arena->nGaps = t->totals[2];
+    arena->runs = t->h_runsOut; arena->nRuns = t->h_runsOut ? t->totals[0] + t->totals[2] : 0;
   }
   return BGPU_OK;
 }

@@ -269,6 +269,46 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   }
 }
 
+// Packed guides (bgpu_batch::guidePacked): three bytes per block (gap before the block in q, in t, length), a side list
+// for the rare block that does not fit a byte.  One warp per job turns them back into the {qPos, tPos, length} blocks
+// prep reads: the positions are prefix sums of the advances.
+__global__ void __launch_bounds__(128) unpack_guide_kernel(uint32_t nJobs, const uint64_t *guideOff, const uint8_t *packed,
+                                                           const uint32_t *wide, uint64_t nWide, bgpu_block *guide) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (job >= nJobs) return;
+  const uint64_t g0 = guideOff[job], nb = guideOff[job + 1] - g0;
+  uint32_t carryQ = 0, carryT = 0;
+  for (uint64_t base = 0; base < nb; base += 32) {
+    const uint64_t g = g0 + base + lane;
+    const bool act = base + lane < nb;
+    uint32_t dq = 0, dt = 0, len = 0;
+    if (act) {
+      dq = packed[3 * g]; dt = packed[3 * g + 1]; len = packed[3 * g + 2];
+      if (dq == 255 && dt == 255 && len == 255) {          // escaped: binary search of the side list
+        uint64_t lo = 0, hi = nWide;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (wide[4 * mid] < (uint32_t)g) lo = mid + 1; else hi = mid; }
+        if (lo < nWide && wide[4 * lo] == (uint32_t)g) { dq = wide[4 * lo + 1]; dt = wide[4 * lo + 2]; len = wide[4 * lo + 3]; }
+        else { dq = dt = 0; len = 0; }                      // malformed: a zero-length block makes prep reject the job
+      }
+    }
+    uint32_t aq = dq + len, at = dt + len, xq = aq, xt = at;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t uq = __shfl_up_sync(0xffffffffu, xq, o), ut = __shfl_up_sync(0xffffffffu, xt, o);
+      if (lane >= o) { xq += uq; xt += ut; }
+    }
+    if (act) { bgpu_block b; b.qPos = carryQ + xq - len; b.tPos = carryT + xt - len; b.length = len; guide[g] = b; }
+    carryQ += __shfl_sync(0xffffffffu, xq, 31); carryT += __shfl_sync(0xffffffffu, xt, 31);
+  }
+}
+
+void launch_unpack_guide(uint32_t nJobs, const uint64_t *guideOff, const uint8_t *packed, const uint32_t *wide, uint64_t nWide,
+                         bgpu_block *guide, cudaStream_t s) {
+  const unsigned grid = (nJobs + 3) / 4;
+  if (grid) unpack_guide_kernel<<<grid, 128, 0, s>>>(nJobs, guideOff, packed, wide, nWide, guide);
+}
+
 void launch_prep_guided(const BatchDev &B, const ScoreParams &P, int defaultBand, const uint64_t *rowOff,
                         const uint64_t *dblkOff, const uint64_t *runOff, cudaStream_t s) {
   const int warpsPerBlock = PREP_WARPS;

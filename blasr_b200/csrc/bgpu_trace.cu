@@ -214,6 +214,7 @@ struct EmitOut {
   bgpu_result *results;
   bgpu_block *blocks; uint32_t *gapCounts; bgpu_gap *gaps;
   const uint64_t *blockOff, *listOff, *gapOff;
+  uint32_t *runsOut;     // compact results: the kept runs in path order, job i from runsOut[blockOff[i] + gapOff[i]]; else NULL
 };
 
 __device__ __forceinline__ uint32_t warp_excl_u32(uint32_t v, int lane, uint32_t &total) {
@@ -265,9 +266,11 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
   const uint8_t *tb = B.t + B.tOff[job] + G.tStart;  // raw bytes, mapped through the same table as the query's
   int oob = 0;
   const uint32_t qPrefix = G.qPos - (uint32_t)G.qStart, tPrefix = G.tPos - (uint32_t)G.tStart;
-  bgpu_block *blocks = O.blocks + R.blockOff;
-  uint32_t *gapCounts = O.gapCounts + R.gapListOff;
-  bgpu_gap *gaps = O.gaps + R.gapOff;
+  const bool compact = O.runsOut != nullptr;
+  bgpu_block *blocks = compact ? nullptr : O.blocks + R.blockOff;
+  uint32_t *gapCounts = compact ? nullptr : O.gapCounts + R.gapListOff;
+  bgpu_gap *gaps = compact ? nullptr : O.gaps + R.gapOff;
+  uint32_t *runsOut = compact ? O.runsOut + R.blockOff + R.gapOff : nullptr;
 
   uint32_t cq = 0, ct = 0, cD = 0, cG = 0;            // carries: q/t consumed, D runs seen, kept gap runs seen
   uint32_t gAtPrevD = 0;                              // kept gap runs before the latest block seen so far
@@ -294,9 +297,12 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
     const uint32_t gPrevLane = __shfl_sync(0xffffffffu, gBefore, below ? 31 - __clz((int)below) : lane);
     bool cmp = false;                                 // this lane's block takes part in the per-base pass
     if (isD) {
-      bgpu_block bl; bl.qPos = pq - qPrefix; bl.tPos = pt - tPrefix; bl.length = len;
-      blocks[dBefore] = bl;
-      gapCounts[dBefore] = gBefore - (below ? gPrevLane : gAtPrevD);
+      if (compact) runsOut[dBefore + gBefore] = len;                      // RUN_D << 30 | len
+      else {
+        bgpu_block bl; bl.qPos = pq - qPrefix; bl.tPos = pt - tPrefix; bl.length = len;
+        blocks[dBefore] = bl;
+        gapCounts[dBefore] = gBefore - (below ? gPrevLane : gAtPrevD);
+      }
       if (doStats) {
         const long long q0 = (long long)G.qStart + pq, t0 = (long long)G.tStart + pt;
         // KBandAlign can leave qPos/tPos pointing outside the sequences (KBandAlign.h:394-399); the reference then reads
@@ -305,8 +311,8 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
         cols += len;
       }
     } else if (kept) {
-      bgpu_gap g; g.seq = (type == RUN_L) ? 0 : 1; g.length = (int32_t)len;
-      gaps[gBefore] = g;
+      if (compact) runsOut[dBefore + gBefore] = (type << 30) | len;       // 1 = Gap::Target (insertion), 2 = Gap::Query (deletion)
+      else { bgpu_gap g; g.seq = (type == RUN_L) ? 0 : 1; g.length = (int32_t)len; gaps[gBefore] = g; }
       if (doStats) {
         if (type == RUN_L) nDel += (int)len; else nIns += (int)len;
         cols += len;
@@ -361,7 +367,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
     }
     cq += totQ; ct += totT; cD += totD; cG += totG;
   }
-  if (lane == 0 && R.nGapLists) gapCounts[nBlocks] = 0;   // the list after the last block: its gap runs are dropped
+  if (lane == 0 && R.nGapLists && !compact) gapCounts[nBlocks] = 0;   // the list after the last block: its gap runs are dropped
   if (doStats) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -398,8 +404,9 @@ void launch_scan_counts(const BatchDev &B, uint64_t *blockOff, uint64_t *listOff
 
 void launch_emit(const BatchDev &B, const ScoreParams &P, bgpu_result *results, bgpu_block *blocks,
                  uint32_t *gapCounts, bgpu_gap *gaps, const uint64_t *blockOff, const uint64_t *listOff,
-                 const uint64_t *gapOff, int doStats, int statsAffine, int keepLeading, PlanHead *plan, cudaStream_t s) {
-  EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff};
+                 const uint64_t *gapOff, int doStats, int statsAffine, int keepLeading, PlanHead *plan, uint32_t *runsOut,
+                 cudaStream_t s) {
+  EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff, runsOut};
   const unsigned grid = (B.nJobs + EMIT_WARPS - 1) / EMIT_WARPS;
   if (grid) emit_kernel<<<grid, EMIT_WARPS * 32, 0, s>>>(B, P, O, doStats, statsAffine, keepLeading, plan);
 }

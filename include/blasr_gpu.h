@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BGPU_VERSION 103 /* 0.1.3: + bgpu_query, bgpu_base_code; bgpu_submit never waits for the device */
+#define BGPU_VERSION 104 /* 0.1.4: + compact results (arena.runs), packed guides, bgpu_cigar_clipped, bgpu_strings, bgpu_trim */
 
 /* ---- return codes (API level) ---- */
 enum {
@@ -87,6 +87,12 @@ typedef struct {
    * band columns, :322-330, and its traceback then spins on NoArrow cells).  It returns blocks / gaps / score only:
    * qPos, tPos and nCells are never set by the reference and come back 0. */
   int32_t hpInsOpen, hpInsExtend, insOpen, insExtend;
+  /* Guided aligners: return every alignment as its run-length path instead of Block / Gap arrays (a third of the bytes over
+   * PCIe).  arena.runs then holds, for job i, nBlocks + nGaps words from runs[blockOff + gapOff]: type << 30 | length in
+   * path order from the first block to the last, type 0 = a block (advance q and t), 1 = Gap::Target (an insertion: advance
+   * q), 2 = Gap::Query (a deletion: advance t); arena.blocks / gapCounts / gaps are NULL.  blasr_gpu::RefineBatch::Store
+   * expands them into Alignment::blocks / gaps (block positions relative to qPos / tPos, gaps[0] and the last list empty). */
+  int32_t compactResults;
 } bgpu_params;
 
 /* A batch in structure-of-arrays form.  Sequences are ASCII exactly as DNASequence::seq holds
@@ -104,6 +110,12 @@ typedef struct {
    * insertionQV, substitutionQV, substitutionTag are required there, deletionQV + deletionTag are optional as a pair
    * (without them Deletion() is the constant del, IDSScoreFunction.h:85-101).  mergeQV is never read (`if (false)`, :82). */
   const uint8_t  *insQV, *delQV, *subQV, *delTag, *subTag;
+  /* Optional packed form of the guides (a quarter of the bytes over PCIe); when guidePacked != NULL, `guide` is ignored
+   * (guideOff, the per-job block offsets, is still required).  Block g of the batch is the three bytes guidePacked[3g..3g+2]:
+   * qPos - (end of the previous block of the job in q), tPos - (end of the previous block in t) -- both absolute for a job's
+   * first block -- and length.  A block with a value >= 255 stores 255,255,255 there and its three numbers in guideWide:
+   * nGuideWide entries {g, dq, dt, length} sorted by g.  (blasr_gpu::RefineBatch::Add writes this form.) */
+  const uint8_t  *guidePacked; const uint32_t *guideWide; uint64_t nGuideWide;
 } bgpu_batch;
 
 /* One job in pointer form (what a per-candidate call site has in hand). */
@@ -133,6 +145,7 @@ typedef struct {
   const bgpu_block *blocks;    uint64_t nBlocks;
   const uint32_t   *gapCounts; uint64_t nGapLists;
   const bgpu_gap   *gaps;      uint64_t nGaps;
+  const uint32_t   *runs;      uint64_t nRuns;   /* params.compactResults: the run-length paths, else NULL */
 } bgpu_arena;   /* pinned host memory owned by the library until bgpu_release() */
 
 typedef struct {

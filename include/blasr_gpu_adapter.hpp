@@ -77,12 +77,25 @@ class RefineBatch {
   template <typename T_BlockVector>
   void Add(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen, const T_BlockVector &blocks,
            const uint8_t *qual = nullptr) {
-    const size_t g0 = guide_.size();
-    guide_.resize(g0 + blocks.size());
-    for (size_t i = 0; i < blocks.size(); i++) { guide_[g0 + i].qPos = blocks[i].qPos; guide_[g0 + i].tPos = blocks[i].tPos; guide_[g0 + i].length = blocks[i].length; }
+    // the guide travels packed (bgpu_batch::guidePacked): per block the gap to the previous block's end in q and in t and the
+    // length, one byte each; the rare block that does not fit goes to the side list
+    const size_t g0 = nGuide_;
+    guideP_.resize(3 * (g0 + blocks.size()));
+    uint64_t qe = 0, te = 0;
+    for (size_t i = 0; i < blocks.size(); i++) {
+      const uint64_t dq = (uint64_t)blocks[i].qPos - qe, dt = (uint64_t)blocks[i].tPos - te, len = blocks[i].length;
+      uint8_t *p = &guideP_[3 * (g0 + i)];
+      if (dq < 255 && dt < 255 && len < 255 && blocks[i].qPos >= qe && blocks[i].tPos >= te) { p[0] = (uint8_t)dq; p[1] = (uint8_t)dt; p[2] = (uint8_t)len; }
+      else {
+        p[0] = p[1] = p[2] = 255;
+        guideW_.push_back((uint32_t)(g0 + i)); guideW_.push_back((uint32_t)dq); guideW_.push_back((uint32_t)dt); guideW_.push_back((uint32_t)len);
+      }
+      qe = (uint64_t)blocks[i].qPos + len; te = (uint64_t)blocks[i].tPos + len;
+    }
+    nGuide_ = g0 + blocks.size();
     q_.insert(q_.end(), q, q + qLen); t_.insert(t_.end(), t, t + tLen);
     if (qual) { qual_.resize(q_.size() - qLen, 0); qual_.insert(qual_.end(), qual, qual + qLen); }
-    qOff_.push_back(q_.size()); tOff_.push_back(t_.size()); gOff_.push_back(guide_.size());
+    qOff_.push_back(q_.size()); tOff_.push_back(t_.size()); gOff_.push_back(nGuide_);
   }
   uint32_t size() const { return (uint32_t)qOff_.size() - 1; }
 
@@ -92,13 +105,16 @@ class RefineBatch {
   void Run(Context &ctx, const T_ScoreFn &fn, int bandSize, bool affine, int alignType = BGPU_GLOBAL) {
     bgpu_scorefn s = MakeScoreFn(fn);
     bgpu_params p;
+    std::memset(&p, 0, sizeof p);
     p.algo = affine ? BGPU_AFFINE_GUIDED : BGPU_GUIDED; p.alignType = alignType; p.band = bandSize;
-    p.bndIns = p.bndDel = 0; p.doStats = 1; p.statsAffine = affine ? 1 : 0;
+    p.doStats = 1; p.statsAffine = affine ? 1 : 0;
+    p.compactResults = 1;                                              // run-length paths back, expanded by Store()
     if (!qual_.empty()) qual_.resize(q_.size(), 0);
     bgpu_batch b;
     std::memset(&b, 0, sizeof b);   // no rich QV tracks on this path (DistanceMatrixScoreFunction)
     b.nJobs = size(); b.qBases = q_.data(); b.qOff = qOff_.data(); b.tBases = t_.data(); b.tOff = tOff_.data();
-    b.qual = qual_.empty() ? nullptr : qual_.data(); b.guide = guide_.data(); b.guideOff = gOff_.data(); b.band = nullptr;
+    b.qual = qual_.empty() ? nullptr : qual_.data(); b.guideOff = gOff_.data(); b.band = nullptr;
+    b.guidePacked = guideP_.data(); b.guideWide = guideW_.data(); b.nGuideWide = guideW_.size() / 4;
     results_.resize(b.nJobs);
     Release();
     int rc = bgpu_submit(ctx.get(), &s, &p, &b, &ticket_);
@@ -135,18 +151,35 @@ class RefineBatch {
       throw Error(r.status, "ERROR, this path has gone awry");
     if (r.status != BGPU_JOB_OK && r.status != BGPU_JOB_EMPTY_GUIDE) throw Error(r.status, "blasr_gpu: job rejected");
     out.blocks.resize(r.nBlocks);
-    for (uint32_t k = 0; k < r.nBlocks; k++) {
-      const bgpu_block &bk = arena_.blocks[r.blockOff + k];
-      out.blocks[k].qPos = bk.qPos; out.blocks[k].tPos = bk.tPos; out.blocks[k].length = bk.length;
-    }
     out.gaps.clear(); out.gaps.resize(r.nGapLists);
-    uint64_t g = r.gapOff;
-    for (uint32_t k = 0; k < r.nGapLists; k++) {
-      const uint32_t c = arena_.gapCounts[r.gapListOff + k];
-      out.gaps[k].resize(c);
-      for (uint32_t x = 0; x < c; x++, g++) {
-        typedef decltype(out.gaps[k][x].seq) seq_t;
-        out.gaps[k][x].seq = (seq_t)arena_.gaps[g].seq; out.gaps[k][x].length = arena_.gaps[g].length;
+    if (arena_.runs) {
+      // compact results: the path as runs (type << 30 | length) from the first block to the last; block positions are relative
+      // to qPos / tPos, gaps[b + 1] holds the gap runs after block b (gaps[0] and the last list stay empty)
+      const uint32_t *run = arena_.runs + r.blockOff + r.gapOff;
+      uint32_t q = 0, t = 0, b = 0;
+      for (uint32_t k = 0; k < r.nBlocks + r.nGaps; k++) {
+        const uint32_t type = run[k] >> 30, len = run[k] & 0x3fffffffu;
+        if (type == 0) { out.blocks[b].qPos = q; out.blocks[b].tPos = t; out.blocks[b].length = len; b++; q += len; t += len; }
+        else {
+          out.gaps[b].resize(out.gaps[b].size() + 1);
+          typedef decltype(out.gaps[b][0].seq) seq_t;
+          out.gaps[b].back().seq = (seq_t)(type == 1 ? 1 : 0); out.gaps[b].back().length = (int)len;   // Gap::Target = 1, Gap::Query = 0
+          if (type == 1) q += len; else t += len;
+        }
+      }
+    } else {
+      for (uint32_t k = 0; k < r.nBlocks; k++) {
+        const bgpu_block &bk = arena_.blocks[r.blockOff + k];
+        out.blocks[k].qPos = bk.qPos; out.blocks[k].tPos = bk.tPos; out.blocks[k].length = bk.length;
+      }
+      uint64_t g = r.gapOff;
+      for (uint32_t k = 0; k < r.nGapLists; k++) {
+        const uint32_t c = arena_.gapCounts[r.gapListOff + k];
+        out.gaps[k].resize(c);
+        for (uint32_t x = 0; x < c; x++, g++) {
+          typedef decltype(out.gaps[k][x].seq) seq_t;
+          out.gaps[k][x].seq = (seq_t)arena_.gaps[g].seq; out.gaps[k][x].length = arena_.gaps[g].length;
+        }
       }
     }
     out.qPos = r.qPos; out.tPos = r.tPos; out.nCells = r.nCells;
@@ -163,13 +196,15 @@ class RefineBatch {
     }
     if (ticket_) { bgpu_release(owner_, ticket_); ticket_ = nullptr; }
   }
-  void Clear() { Release(); q_.clear(); t_.clear(); qual_.clear(); guide_.clear(); qOff_.assign(1, 0); tOff_.assign(1, 0); gOff_.assign(1, 0); results_.clear(); }
+  void Clear() { Release(); q_.clear(); t_.clear(); qual_.clear(); guideP_.clear(); guideW_.clear(); nGuide_ = 0; qOff_.assign(1, 0); tOff_.assign(1, 0); gOff_.assign(1, 0); results_.clear(); }
 
  private:
   SharedTicket *shared_ = nullptr;                                 // set when the jobs ran inside a merged submission
   uint32_t base_ = 0;                                              // ... and the index of this batch's first job in it
   std::vector<uint8_t> q_, t_, qual_;
-  std::vector<bgpu_block> guide_;
+  std::vector<uint8_t> guideP_;                                    // packed guide: 3 bytes per block
+  std::vector<uint32_t> guideW_;                                   // ... and the side list {block, dq, dt, length}
+  uint64_t nGuide_ = 0;
   std::vector<uint64_t> qOff_{0}, tOff_{0}, gOff_{0};
   std::vector<bgpu_result> results_;
   bgpu_arena arena_{};
@@ -215,7 +250,7 @@ class RefineService {
     r.batch = &batch; r.fn = MakeScoreFn(fn);
     std::memset(&r.p, 0, sizeof r.p);
     r.p.algo = affine ? BGPU_AFFINE_GUIDED : BGPU_GUIDED; r.p.alignType = alignType; r.p.band = bandSize;
-    r.p.doStats = 1; r.p.statsAffine = affine ? 1 : 0;
+    r.p.doStats = 1; r.p.statsAffine = affine ? 1 : 0; r.p.compactResults = 1;
     batch.Release();
     r.tEnqueue = std::chrono::steady_clock::now();
     { std::lock_guard<std::mutex> lk(mu_); pending_.push_back(&r); }
@@ -298,20 +333,24 @@ class RefineService {
 
   // concatenates the requests' jobs and enqueues them as one ticket (inputs are staged by bgpu_submit before it returns)
   bool Start(Context &ctx, Flight &f) {
-    std::vector<uint8_t> q, t, qual; std::vector<bgpu_block> guide; std::vector<uint64_t> qOff(1, 0), tOff(1, 0), gOff(1, 0);
+    std::vector<uint8_t> q, t, qual, guideP; std::vector<uint32_t> guideW; std::vector<uint64_t> qOff(1, 0), tOff(1, 0), gOff(1, 0);
     bool anyQual = false;
     for (Request *x : f.reqs) anyQual = anyQual || !x->batch->qual_.empty();
     for (Request *x : f.reqs) {
       RefineBatch &b = *x->batch;
-      const uint64_t q0 = q.size(), t0 = t.size(), g0 = guide.size();
+      const uint64_t q0 = q.size(), t0 = t.size(), g0 = guideP.size() / 3;
       q.insert(q.end(), b.q_.begin(), b.q_.end()); t.insert(t.end(), b.t_.begin(), b.t_.end());
-      guide.insert(guide.end(), b.guide_.begin(), b.guide_.end());
+      guideP.insert(guideP.end(), b.guideP_.begin(), b.guideP_.end());
+      for (size_t k = 0; k < b.guideW_.size(); k += 4) {
+        guideW.push_back((uint32_t)(b.guideW_[k] + g0)); guideW.push_back(b.guideW_[k + 1]); guideW.push_back(b.guideW_[k + 2]); guideW.push_back(b.guideW_[k + 3]);
+      }
       if (anyQual) { qual.resize(q0, 0); qual.insert(qual.end(), b.qual_.begin(), b.qual_.end()); qual.resize(q.size(), 0); }
       for (uint32_t i = 1; i <= b.size(); i++) { qOff.push_back(q0 + b.qOff_[i]); tOff.push_back(t0 + b.tOff_[i]); gOff.push_back(g0 + b.gOff_[i]); }
     }
     bgpu_batch mb; std::memset(&mb, 0, sizeof mb);
     mb.nJobs = (uint32_t)qOff.size() - 1; mb.qBases = q.data(); mb.qOff = qOff.data(); mb.tBases = t.data(); mb.tOff = tOff.data();
-    mb.qual = anyQual ? qual.data() : nullptr; mb.guide = guide.data(); mb.guideOff = gOff.data();
+    mb.qual = anyQual ? qual.data() : nullptr; mb.guideOff = gOff.data();
+    mb.guidePacked = guideP.data(); mb.guideWide = guideW.data(); mb.nGuideWide = guideW.size() / 4;
     f.nJobs = mb.nJobs; f.ticket = nullptr; f.t0 = std::chrono::steady_clock::now();
     for (Request *x : f.reqs) x->tStart = f.t0;
     const int rc = bgpu_submit(ctx.get(), &f.reqs[0]->fn, &f.reqs[0]->p, &mb, &f.ticket);

@@ -244,3 +244,32 @@ def test_traceback_pool_waves(monkeypatch):
                 assert not bad, (algo, i, bad)
     finally:
         big.close(); small.close()
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_packed_guides_and_compact_results(aligner, algo, monkeypatch):
+    """The PCIe-lean forms -- guides as three bytes per block (+ a side list for blocks that do not fit a byte), results as
+    run-length paths -- give exactly the alignments of the plain forms; wide guide gaps exercise the side list."""
+    from blasr_b200 import capi
+    from blasr_b200.align import pack_guide
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    b = cases.guided_batch(seed=640 + algo, n=48, lo=100, hi=5000, n_rate=0.01, adversarial=0.4, run=300, min_block=1)
+    b = _embed(b, seed=3, pad_lo=1, pad_hi=600)                        # first blocks at offsets > 255 as well
+    gp, gw = pack_guide(b.guide, b.guideOff)
+    assert len(gw) > 0 and len(gp) == 3 * len(b.guide)
+    a = capi.AFFINE_GUIDED if algo else capi.GUIDED
+    tk0 = aligner.submit(b, fn, a, band=16)
+    want = aligner.collect(tk0, copy=True)
+    aligner.release(tk0)
+    for compact, packed in ((True, False), (False, True), (True, True)):
+        tk = aligner.submit(b, fn, a, band=16, compact=compact, packed=packed)
+        got = aligner.collect(tk, copy=True)
+        assert (got.runs is not None) == compact
+        for i in range(b.n):
+            bad = cases.compare(cases.gpu_to_dict(got, i), cases.gpu_to_dict(want, i), cases.GPU_FIELDS)
+            assert not bad, (compact, packed, i, bad)
+        if compact:                                                    # the formatting kernels read the device-side path either way
+            ops, off = aligner.cigar(tk)
+            assert int(off[-1]) == len(ops) > 0
+        aligner.release(tk)
+    assert got.timing.d2hBytes < want.timing.d2hBytes and got.timing.h2dBytes < want.timing.h2dBytes
