@@ -48,8 +48,8 @@ def parse():
     ap.add_argument("--bands", default=",".join(str(b) for b in BANDS), help="band sizes drawn per job (configs[1]: 16,32,64; blasr's default -bandSize: 16)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
-    ap.add_argument("--e2e-threads", type=int, default=5, help="host threads (one context each) of the e2e measurement")
-    ap.add_argument("--e2e-chunks", type=int, default=10, help="sub-batches the shard is cut into for the e2e measurement")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) of the e2e measurement")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches the shard is cut into for the e2e measurement")
     ap.add_argument("--no-subrecords", dest="subrecords", action="store_false", help="skip the affine / affine_production / quality / sdp_guides sub-records")
     ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the parity samples against oracle/_ref")
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false", help="skip the reads/s leg (stock blasr vs GPU-refined blasr)")
@@ -244,19 +244,29 @@ def e2e_measure(local, batch, fn, algo, n_threads, n_chunks, warm, steps, barrie
         tot = {"cells": 0, "ok": 0, "h2d": 0, "d2h": 0}
         errs = []
 
+        def finish(a, tk):
+            res = a.collect(tk)
+            with lock:
+                tot["cells"] += int(res.timing.cells); tot["ok"] += int((res.results["status"] == 0).sum())
+                tot["h2d"] += int(res.timing.h2dBytes); tot["d2h"] += int(res.timing.d2hBytes)
+            a.release(tk)
+
         def work(a):
+            # bgpu_submit only enqueues: a host thread hands over its next sub-batch before it collects the previous one, so
+            # the device always has a ticket to copy in behind the ones that compute (two tickets in flight per thread)
             try:
+                prev = None
                 while True:
                     with lock:
                         i = next(nxt, None)
                     if i is None:
-                        return
+                        break
                     tk = a.submit(chunks[i], fn, algo, band=16, doStats=True, compact=True, packed=True)
-                    res = a.collect(tk)
-                    with lock:
-                        tot["cells"] += int(res.timing.cells); tot["ok"] += int((res.results["status"] == 0).sum())
-                        tot["h2d"] += int(res.timing.h2dBytes); tot["d2h"] += int(res.timing.d2hBytes)
-                    a.release(tk)
+                    if prev is not None:
+                        finish(a, prev)
+                    prev = tk
+                if prev is not None:
+                    finish(a, prev)
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         th = [threading.Thread(target=work, args=(a,)) for a in workers]

@@ -265,7 +265,7 @@ class Aligner:
                     gp, gw = pack_guide(batch.guide, batch.guideOff)
                 keep["guidePacked"] = np.ascontiguousarray(gp, np.uint8)
                 keep["guideWide"] = np.ascontiguousarray(gw, np.uint32).reshape(-1, 4)
-        if batch.qual is not None:
+        if batch.qual is not None and fn.kind == FN_QUALITY:      # only QualityValueScoreFunction reads the QV track
             keep["qual"] = np.ascontiguousarray(batch.qual, np.uint8)
         if batch.band is not None:
             keep["band"] = np.ascontiguousarray(batch.band, np.int32)

@@ -100,6 +100,7 @@ struct bgpu_ctx {
   cudaStream_t aux[N_CLS] = {};                  // one per job class: the class kernels of a wave run concurrently
   cudaEvent_t evFork = nullptr, evJoin[N_CLS] = {};
   cudaEvent_t evSync = nullptr;                  // blocking-sync event: waiting host threads sleep instead of spinning
+  cudaStream_t copyStream = nullptr;             // bgpu_collect's copies (and late emit): not behind the next ticket's kernels
   std::string err;
   std::mutex mu;
   size_t arrowPoolCap = 0;                       // max bytes of traceback pool per wave
@@ -124,16 +125,23 @@ struct bgpu_ctx {
 // they have cores (blasr's one pthread per core, several GPUs per box).
 static bool blocking_sync() { static const bool on = [] { const char *e = getenv("BGPU_BLOCKING_SYNC"); return e && *e && *e != '0'; }(); return on; }
 static bool spin_sync() { static const bool on = [] { const char *e = getenv("BGPU_SPIN_SYNC"); return e && *e && *e != '0'; }(); return on; }
-static cudaError_t wait_stream(bgpu_ctx *ctx) {
-  if (spin_sync()) return cudaStreamSynchronize(ctx->stream);
-  cudaError_t e = cudaEventRecord(ctx->evSync, ctx->stream);
+static cudaError_t wait_event(cudaEvent_t ev);
+static cudaError_t wait_stream(bgpu_ctx *ctx, cudaStream_t st = nullptr) {
+  if (!st) st = ctx->stream;
+  if (spin_sync()) return cudaStreamSynchronize(st);
+  cudaError_t e = cudaEventRecord(ctx->evSync, st);
   if (e != cudaSuccess) return e;
   if (blocking_sync()) return cudaEventSynchronize(ctx->evSync);
+  return wait_event(ctx->evSync);
+}
+static cudaError_t wait_event(cudaEvent_t ev) {
+  if (spin_sync() || blocking_sync()) return cudaEventSynchronize(ev);
+  cudaError_t e;
   // default: poll with short naps that grow to 200 us -- a waiting host thread costs (almost) no CPU, which matters as soon as
   // a box drives several GPUs with several threads each, and wakes within the time a PCIe copy of the results takes anyway
   unsigned nap = 5;
   for (;;) {
-    e = cudaEventQuery(ctx->evSync);
+    e = cudaEventQuery(ev);
     if (e != cudaErrorNotReady) return e;
     cudaGetLastError();
     std::this_thread::sleep_for(std::chrono::microseconds(nap));
@@ -303,6 +311,7 @@ extern "C" int bgpu_create(bgpu_ctx **out, int device) {
   cudaGetDeviceProperties(&pr, device);
   ctx->nSM = pr.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
   for (int c = 0; c < N_CLS; c++) {
     if (cudaStreamCreateWithFlags(&ctx->aux[c], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evJoin[c], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BGPU_E_CUDA; }
@@ -339,6 +348,7 @@ extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
   for (auto &sl : ctx->pinPool.free_) cudaFreeHost(sl.base);
   for (int c = 0; c < N_CLS; c++) { cudaStreamDestroy(ctx->aux[c]); cudaEventDestroy(ctx->evJoin[c]); }
   cudaEventDestroy(ctx->evFork); cudaEventDestroy(ctx->evSync);
+  cudaStreamDestroy(ctx->copyStream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -539,7 +549,7 @@ static int enqueue_guided(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   return BGPU_OK;
 }
 
-static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t);
+static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t, cudaStream_t st = nullptr);
 
 // result arena for nB blocks, nL gap lists, nG gaps (device + pinned host): Block / Gap arrays, or the run-length paths
 static int alloc_arena(bgpu_ctx *ctx, bgpu_ticket t, uint64_t nB, uint64_t nL, uint64_t nG) {
@@ -556,8 +566,8 @@ static uint64_t arena_bytes(bgpu_ticket t, uint64_t nB, uint64_t nL, uint64_t nG
   if (t->params.compactResults && !t->dense) return sizeof(uint32_t) * (nB + nG);
   return sizeof(bgpu_block) * nB + sizeof(uint32_t) * nL + sizeof(bgpu_gap) * nG;
 }
-static int copy_arena(bgpu_ctx *ctx, bgpu_ticket t, uint64_t nB, uint64_t nL, uint64_t nG) {
-  cudaStream_t s = ctx->stream;
+static int copy_arena(bgpu_ctx *ctx, bgpu_ticket t, uint64_t nB, uint64_t nL, uint64_t nG, cudaStream_t s = nullptr) {
+  if (!s) s = ctx->stream;
   if (t->d_runsOut) { CK(cudaMemcpyAsync(t->h_runsOut, t->d_runsOut, sizeof(uint32_t) * (nB + nG), cudaMemcpyDeviceToHost, s)); return BGPU_OK; }
   CK(cudaMemcpyAsync(t->h_blocks, t->d_blocks, sizeof(bgpu_block) * nB, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(t->h_gapCounts, t->d_gapCounts, sizeof(uint32_t) * nL, cudaMemcpyDeviceToHost, s));
@@ -614,8 +624,8 @@ static int enqueue_guided_fast(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   return BGPU_OK;
 }
 
-static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t) {
-  cudaStream_t s = ctx->stream;
+static int enqueue_emit(bgpu_ctx *ctx, bgpu_ticket t, cudaStream_t st) {
+  cudaStream_t s = st ? st : ctx->stream;
   launch_emit(t->B, t->sp, t->d_results, t->d_blocks, t->d_gapCounts, t->d_gaps, t->d_blockOff, t->d_listOff,
               t->d_gapOff, t->params.doStats, t->params.statsAffine, t->dense ? 1 : 0, t->fast ? t->d_plan : nullptr, t->d_runsOut, s);
   t->timing.kernelLaunches++;
@@ -970,7 +980,10 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
   if (!t->collected) {
     bool copied = false;
     if (t->fast) {
-      CK(wait_stream(ctx));                              // everything bgpu_submit enqueued
+      // everything bgpu_submit enqueued for THIS ticket (the context's stream may already hold the next ticket: a host
+      // thread submits sub-batch i+1 before it collects sub-batch i); what follows runs on the copy stream for the same reason
+      CK(t->evDone ? wait_event(t->evDone) : wait_stream(ctx));
+      cudaStream_t cs = ctx->copyStream;
       if (t->h_plan->overflow & PLAN_OVF_ARROWS) {
         // the traceback pool was under-estimated (adversarial guides): plan this ticket on the host, in waves
         t->fast = false; t->arenaReady = false; t->arenaInline = false;
@@ -987,15 +1000,15 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
           RC(alloc_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2]));
           t->arenaInline = false;
           for (int k = 0; k < 3; k++) t->h_planInit->caps[k] = ~0ull;   // a later bgpu_rerun emits into this exact-size arena
-          RC(enqueue_emit(ctx, t));
+          RC(enqueue_emit(ctx, t, cs));
           t->fast = true;
         }
         if (!t->arenaInline) {
           struct Hold { Gate *g; Hold(Gate *x) : g(x) { if (g) g->acquire(); } ~Hold() { if (g) g->release(); } } hold(t->gated ? &gate(ctx->device, GATE_D2H) : nullptr);
-          if (!emitted) CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, s));
-          RC(copy_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2]));
-          CK(cudaEventRecord(t->ev[5], s));
-          CK(wait_stream(ctx));
+          if (!emitted) CK(cudaMemcpyAsync(t->h_results, t->d_results, sizeof(bgpu_result) * t->nJobs, cudaMemcpyDeviceToHost, cs));
+          RC(copy_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2], cs));
+          CK(cudaEventRecord(t->ev[5], cs));
+          CK(wait_stream(ctx, cs));
         }
         copied = true;
       }
@@ -1143,7 +1156,8 @@ extern "C" int bgpu_release(bgpu_ctx *ctx, bgpu_ticket t) {
   if (!ctx || !t) return BGPU_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  // a collected ticket has nothing in flight (the context's stream may hold LATER tickets: do not wait for those)
+  if (!t->collected || !t->fast || !t->evDone) cudaStreamSynchronize(ctx->stream);
   slab_release(ctx->devPool, t->dev); slab_release(ctx->pinPool, t->pin);
   for (auto &e : t->ev) cudaEventDestroy(e);
   for (auto &e : t->waveEv) cudaEventDestroy(e);
