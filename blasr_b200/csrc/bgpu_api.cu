@@ -656,12 +656,13 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   const uint64_t totQ = b->qOff[n], totT = b->tOff[n], totG = b->guideOff[n];
   fill_score_params(t->sp, fn, p);
   // what this ticket is going to ask for besides the traceback pool (sequences, band table, runs, job tables, results)
-  t->dev.hint = 17 * totQ + 7 * totT + 12 * totG + 512ull * n + (1u << 16);
+  t->dev.hint = 18 * totQ + 7 * totT + 12 * totG + 512ull * n + (1u << 16);
   t->pin.hint = 4 * totQ + totT + 12 * totG + 320ull * n + (1u << 16);
   BatchDev &B = t->B;
   B.nJobs = n;
-  uint64_t *d_qOff, *d_tOff, *d_gOff; uint8_t *d_q, *d_t, *d_tc, *d_qual = nullptr; bgpu_block *d_guide; int32_t *d_band = nullptr;
+  uint64_t *d_qOff, *d_tOff, *d_gOff; uint8_t *d_q, *d_t, *d_tc, *d_qc, *d_qual = nullptr; bgpu_block *d_guide; int32_t *d_band = nullptr;
   RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16)); RC(talloc_dev(ctx, t, &d_tc, totT + 16));
+  RC(talloc_dev(ctx, t, &d_qc, totQ + 16));
   RC(talloc_dev(ctx, t, &d_qOff, n + 1)); RC(talloc_dev(ctx, t, &d_tOff, n + 1)); RC(talloc_dev(ctx, t, &d_gOff, n + 1));
   RC(talloc_dev(ctx, t, &d_guide, totG + 1));
   if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
@@ -669,6 +670,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   // prep writes tc only inside [tStart, tEnd) of each job, the fill kernels also stage the boundary column t' = 0 and the
   // columns past the guide's end: those bytes must be valid codes (0), not whatever the cached allocation last held
   CK(cudaMemsetAsync(d_tc, 0, totT + 16, ctx->stream));
+  CK(cudaMemsetAsync(d_qc, 0, totQ + 16, ctx->stream));      // likewise the coded query outside [qStart, qEnd)
   // the phase gates keep LARGE tickets of concurrent contexts pipelined (copy in / compute / copy out); small tickets
   // (the candidates of a few reads) would only pay their host round trips
   t->gated = totQ + totT + (b->guidePacked ? 3 : sizeof(bgpu_block)) * totG > (32u << 20);
@@ -688,7 +690,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   }
   if (b->qual) RC(upload(ctx, t, d_qual, b->qual, totQ));
   if (b->band) RC(upload(ctx, t, d_band, b->band, sizeof(int32_t) * n));
-  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tc = d_tc; B.tOff = d_tOff; B.qual = d_qual; B.guide = d_guide; B.guideOff = d_gOff; B.band = d_band;
+  B.q = d_q; B.qOff = d_qOff; B.t = d_t; B.tc = d_tc; B.qc = d_qc; B.tOff = d_tOff; B.qual = d_qual; B.guide = d_guide; B.guideOff = d_gOff; B.band = d_band;
   RC(upload_ids_tracks(ctx, t, fn, b, totQ));
   // capacities from sequence lengths (upper bounds of the guide extents)
   uint64_t *h_off = nullptr;

@@ -21,7 +21,6 @@ constexpr int DBLK = 64;               // anti-diagonals per d-block
 constexpr int KRING = 6;               // most diagonal groups per lane in the register-ring kernels (6: the ring state still
                                        // fits 5 linear / 4 affine resident CTAs per SM; 8 and 5 measured slower)
 constexpr int KWIDE = 128;             // groups per lane of the wide fallback kernel (32 lanes x 2 x 128 = 8192 diagonals)
-constexpr int ROW_W_BITS = 20;
 
 // Job classes: how many lanes of a warp sweep one job.  A lane owns 2k consecutive diagonals ("lane-major"
 // slots), k = groups active in the current d-block, so a class covers windows of up to 2 * LPJ * KRING diagonals.
@@ -40,10 +39,11 @@ enum { TB_DIAG = 0, TB_LEFT = 1, TB_UP = 2, TB_ICLOSE = 3, TB_DCLOSE = 4, TB_NON
 enum { TL_DIAG = 0, TL_LEFT = 1, TL_UP = 2, TL_NONE = 3 };
 
 struct alignas(8) RowInfo {  // 8 B per guide row in HBM, consumed as is by the fill kernels
-  int32_t cd8;            // (diagonal of the row's first in-band cell) << 8, diagonal = t' - q' + C0;
-                          // low byte: the row's QV for BGPU_FN_QUALITY, else 0
-  uint32_t packed;        // bits 8-27: hi'-lo' (cells in the row - 1), bits 0-7: query base code * 20
+  int32_t lo8;            // 8 * (diagonal of the row's first in-band cell), diagonal = t' - q' + C0
+  int32_t nhi8;           // -8 * (diagonal of the row's last in-band cell)
+  // (x 8: a lane turns the two into the byte offset of its row of the in-band mask table, see bgpu_fill.cu)
 };
+constexpr int DEAD_LO8 = 1 << 29;      // {DEAD_LO8, -DEAD_LO8}: a row no slot can be inside of
 
 struct DBlock {           // 16 B per d-block
   int32_t wbase;          // even: diagonal held by slot 0 of the job's window in this block
@@ -65,6 +65,7 @@ struct JobGeom {          // per job, written by prep, extended by fill / trace
   int32_t score;          // fill result: S[qEnd-1][tEnd-1]
   int32_t cls;            // CLS_*
   int32_t ksum;           // sum of k over the d-blocks
+  int32_t minW;           // cells of the job's narrowest band row (the ring kernels need rows >= a lane's 2k slots)
   uint64_t rowOff;        // RowInfo index of row 0
   uint64_t dblkOff;       // DBlock index of d-block 0
   uint64_t arrowBytes;    // unused by the guided path (the host bounds it per warp group)
@@ -88,6 +89,8 @@ struct BatchDev {         // device pointers of one submitted batch
   const uint8_t *t; const uint64_t *tOff; // raw bytes as the caller passed them (emit / cigar compare these)
   uint8_t *tc;                            // the target as the fill kernels read it, written by prep: base codes 0..4
                                           // (raw bytes for BGPU_FN_IDS), indexed like t
+  uint8_t *qc;                            // the query as the fill kernels read it, written by prep: base code * 20 (the
+                                          // byte offset of the base's row in the 5x5 score table), indexed like q
   const uint8_t *qual;
   const uint8_t *insQV, *delQV, *subQV, *delTag, *subTag;   // IDSScoreFunction tracks (parallel to q), else NULL
   const bgpu_block *guide; const uint64_t *guideOff;

@@ -21,18 +21,26 @@
 // DP loop never waits on HBM.
 //
 // Inner loop (run_block_ring): the k rows and k columns a lane touches slide by one per two steps, so they are kept
-// in register rings (the loop is unrolled by k, every ring index is static) and refilled with one shared-memory
-// load per row / column; per cell that leaves one LDS (the substitution score), two VIADDMNMX, the in-band test
-// and the tag split; one funnel shift appends the arrow to the lane's traceback word.  Words are
-// stored [d-block][16-step row][slot pair], 2 bits per cell for the linear aligner (8 for the affine one).
+// in register rings refilled with one shared-memory load per row / column.  The loop body is a chunk of 8 (linear) / 4
+// (affine) step pairs unrolled with every ring index static; between chunks the rings are rotated by (chunk mod k)
+// registers, so traceback words complete at fixed places of the code for every k.
+// Instruction budget.  The integer ALU pipe issues a warp instruction every second clock (VIADDMNMX, LOP3, ISETP, SEL,
+// SHF all live there), the FMA pipe (IMAD) is otherwise idle and shared memory delivers one 32-lane load per clock and
+// SM -- so the loop keeps on the ALU pipe only what has no other home: per cell the two VIADDMNMX of the min chain, one
+// ISETP for the in-band test ((unsigned)(lane's diagonal - row's first diagonal) <= row width), the tag split and the
+// funnel shift that appends the arrow to the lane's traceback word.  The diagonal offset of the test and the
+// out-of-band overwrite are written as IMADs with a run-time 1 (FillConsts::one) so that they issue on the FMA pipe
+// (the overwrite predicated on the test), S + m likewise; the substitution score is ONE LDS per cell (an in-band mask
+// table in shared memory was measured: 2.4 shared-memory wavefronts per cell make the kernel LSU-bound and slower).
+// Words are stored [d-block][16-step row][slot pair], 2 bits per cell for the linear aligner (8 for the affine one).
 // Blocks that touch the boundary row, a job's last block, the IDS score function and very wide windows take the
 // generic path (run_block_gen), which reads its rows and columns from shared memory per cell.
+#include <type_traits>
 #include "bgpu_common.cuh"
 
 namespace bgpu {
 
 constexpr uint32_t NOJOB = 0xffffffffu;
-constexpr int DEAD_CD8 = 1 << 30;   // a row no slot can be inside of
 
 struct FillConsts {
   int delT, insT;        // (del<<SH)|LEFT, (ins<<SH)|UP
@@ -40,21 +48,21 @@ struct FillConsts {
   int ext, openI, openD; // ext<<SH, (open<<SH)|TB_IOPEN, (open<<SH)|TB_DOPEN
   int open;              // open<<SH
   int del0;              // row-0 step: (Global ? del : 0) << SH
-  int k256, kacc;        // 256 and 1 << BITS held in registers the compiler cannot fold: keeps these
-                         // multiply-adds on the FMA pipe (IMAD) instead of the busier ALU pipe
+  int one, zero;         // 1 and 0 held in registers the compiler cannot fold (see "Instruction budget")
   int subPrior, delPrior, del;   // IDSScoreFunction: unshifted substitutionPrior / globalDeletionPrior / del
 };
 
 template <int LPJ, int KM, int FN>
 struct SubSmem {          // staging of one job: two d-blocks (current, next)
-  int2 rows[2][KM * LPJ + 32];           // RowInfo as prep wrote it: {cd8, (width << 8) | qcode * 20}
-  uint32_t colw[2][(KM * LPJ + 44) / 4]; // target codes (bytes), 4-byte chunks from an aligned-down address
-  int shift[2 * KM * LPJ];               // window re-mapping scratch
-  // per-row score data of the current block (QualityValueScoreFunction needs none: the QV rides in RowInfo::cd8);
-  // IDSScoreFunction: two words per row,
+  static constexpr int NR = KM * LPJ + 32;            // rows a d-block can touch
+  int2 rows[2][NR];                                   // RowInfo as prep wrote it: {lo8, nhi8}
+  uint32_t colw[2][(KM * LPJ + 44) / 4];              // target codes (bytes), 4-byte chunks from an aligned-down address
+  uint32_t qcw[2][(NR + 11) / 4];                     // query row offsets (code * 20, bytes), staged the same way
+  uint32_t qvw[FN == 1 ? 2 : 1][FN == 1 ? (NR + 11) / 4 : 1];   // QualityValueScoreFunction: the rows' QVs
+  int shift[2 * KM * LPJ];                            // window re-mapping scratch
+  // IDSScoreFunction: two words per row of the current block,
   //   [r]      query byte | substitutionTag << 8 | substitutionQV << 16 | insertionQV << 24
   //   [NR + r] deletionTag | deletionQV << 8 | (deletion tracks present) << 16
-  static constexpr int NR = KM * LPJ + 32;
   int rowq[FN == 2 ? 2 * NR : 2];
 };
 
@@ -80,10 +88,31 @@ __device__ __forceinline__ void cp_async4(void *dst, const void *src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// The min chain of one DP cell.
+// In-band test and out-of-band overwrite of the ring kernels.  x = rX + IMM is the cell's diagonal minus the row's first
+// diagonal (x 8), rY the row's width: outside <=> (unsigned)x > rY.  The add and the overwrites are IMADs by a run-time 1,
+// i.e. FMA-pipe instructions; only the compare issues on the ALU pipe.
+template <int IMM>
+__device__ __forceinline__ void mask_lin(int &cnd, const int rX, const int rY, const FillConsts &c) {
+  // the overwrite is x * 0 + (BIG | NoArrow) with a run-time 0: depending on x keeps it a predicated IMAD of its own
+  asm("{\n\t.reg .pred p;\n\t.reg .s32 x;\n\tmad.lo.s32 x, %1, %3, %5;\n\tsetp.gt.u32 p, x, %2;\n\t@p mad.lo.s32 %0, x, %4, %6;\n\t}"
+      : "+r"(cnd) : "r"(rX), "r"(rY), "r"(c.one), "r"(c.zero), "n"(IMM), "n"(BIG | TL_NONE));
+}
+// (three different stand-ins for "invalid" -- BIG, BIG + 32, BIG + 64, any value >= BIG with clear tag bits does -- so
+// that the three overwrites stay three predicated IMADs instead of being merged into one IMAD and SELs)
+template <int IMM>
+__device__ __forceinline__ void mask_aff(int &cnd, int &s0, int &ai, int &ad, const int rX, const int rY, const FillConsts &c) {
+  asm("{\n\t.reg .pred p;\n\t.reg .s32 x;\n\tmad.lo.s32 x, %4, %6, %8;\n\tsetp.gt.u32 p, x, %5;\n\t"
+      "@p mad.lo.s32 %0, x, %7, %9;\n\t@p mad.lo.s32 %1, x, %7, %10;\n\t@p mad.lo.s32 %2, x, %7, %11;\n\t@p mad.lo.s32 %3, x, %7, %12;\n\t}"
+      : "+r"(cnd), "+r"(s0), "+r"(ai), "+r"(ad) : "r"(rX), "r"(rY), "r"(c.one), "r"(c.zero), "n"(IMM),
+        "n"(BIG | TB_NONE), "n"(BIG), "n"(BIG + 32), "n"(BIG + 64));
+}
+
+// The min chain of one DP cell.  Returns the arrow word (tag | affine flags in its low bits); s0 / ai / ad = the
+// scores with the tag bits cleared.  The caller masks out-of-band cells.
 template <bool AFFINE>
 __device__ __forceinline__ int dp_core(const int S, const int leftS, const int leftAD, const int upS, const int upAI,
-                                       const int m, const int delT, const int insT, const FillConsts &c, int &ai, int &ad) {
+                                       const int m, const int delT, const int insT, const FillConsts &c,
+                                       int &s0, int &ai, int &ad) {
   int cnd = S + m;                                         // Diagonal (tag 0)
   cnd = __viaddmin_s32(leftS, delT, cnd);                  // Left
   cnd = __viaddmin_s32(upS, insT, cnd);                    // Up
@@ -92,10 +121,14 @@ __device__ __forceinline__ int dp_core(const int S, const int leftS, const int l
     cnd = __viaddmin_s32(leftAD, c.extT4, cnd);            // AffineDelClose
     // strict '<' in the reference: a tie extends (AffineGuidedAlign.h:357-373) -> the open candidate carries a
     // flag bit, so it loses ties.
-    const int s0 = cnd & ~31;
+    s0 = cnd & ~31;
     ai = __viaddmin_s32(s0, c.openI, upAI + c.ext);
     ad = __viaddmin_s32(s0, c.openD, leftAD + c.ext);
-    cnd |= (ai | ad) & 24;                                  // tag | affine flags, still below bit 5
+    cnd = cnd | ai | ad;                                    // tag | the two open flags (ai: 0 / 8, ad: 0 / 16 below bit 5);
+                                                            // the traceback reads bits 0-4 of the byte only
+    ai &= ~31; ad &= ~31;
+  } else {
+    s0 = cnd & ~3;
   }
   return cnd;
 }
@@ -109,9 +142,29 @@ __device__ __forceinline__ int sub_dn(int v) { return __shfl_down_sync(0xfffffff
 struct BlockView {
   const int2 *rows;       // staged RowInfo
   const uint8_t *cols;    // staged target codes, cols[c]
-  int wbase8;             // window base diagonal << 8
+  const uint8_t *qrows;   // staged query row offsets (code * 20), qrows[r]
+  const uint8_t *qvs;     // staged QVs (QualityValueScoreFunction), qvs[r]
+  int wbase;              // window base diagonal
   int qlo, tlo;
 };
+
+// compile-time loop: f(integral_constant<int, I>) for I = 0 .. N-1 (the asm immediates of the ring kernels need constant
+// expressions, which a #pragma-unrolled loop variable is not)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
+template <int KA, int ROT, typename T>
+__device__ __forceinline__ void ring_rotate(T (&a)[KA]) {   // a[s] <- a[(s + ROT) % KA]
+  if (ROT != 0) {
+    T tmp[KA];
+#pragma unroll
+    for (int s = 0; s < KA; s++) tmp[s] = a[(s + ROT) % KA];
+#pragma unroll
+    for (int s = 0; s < KA; s++) a[s] = tmp[s];
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fast path: KA groups per lane (compile time), rows / columns in register rings, no boundary row, full 64 steps.
@@ -121,81 +174,96 @@ __device__ __forceinline__ void run_block_ring(int (&Se)[KM], int (&So)[KM], int
                                                const int mtabAddr, const FillConsts &c, const int sl,
                                                uint32_t *aw, const bool live) {
   typedef Fmt<AFFINE> F;
+  constexpr int PPW = F::SPW / 2;                            // step pairs per traceback word
+  // step pairs per unrolled chunk: the chunk is the loop body, and five warps per scheduler at different places of a
+  // body that outgrows the instruction caches (L0 ~6 KB, L1.5 32 KB, ~190 B of code per linear cell) stall on fetches
+  constexpr int CH = (AFFINE ? 2 : 4) * (KA <= 2 ? 2 : 1);
+  constexpr int ROT = CH % KA;
   const int kL = KA * sl;
-  const int2 *rp = bv.rows + KA * (LPJ - 1 - sl);           // rp[i + m]: row of group KA-1-m at step pair i
+  const int rbase = KA * (LPJ - 1 - sl);
+  const int2 *rp = bv.rows + rbase;                          // rp[i + m]: row of group KA-1-m at step pair i
+  const uint8_t *qp = bv.qrows + rbase;
+  const uint8_t *vp = bv.qvs + rbase;
   const uint8_t *cp = bv.cols + kL;                          // cp[i + g]: column of group g on the even step of pair i
-  const int s08 = bv.wbase8 + ((2 * kL) << 8);
-  int rX[KA], rY[KA], rQ[KA], cT[KA];
+  const int lb8 = (bv.wbase + 2 * kL) << 3;                 // 8 * (diagonal of the lane's slot 0)
+  int rQ[KA], rX[KA], rY[KA], cT[KA];
   int rV[FN == 1 ? KA : 1];                                  // QualityValueScoreFunction: the rows' QVs
   uint32_t acc[KA];
+  auto load_row = [&](const int slot, const int ridx) {
+    const int2 v = rp[ridx];
+    rX[slot] = lb8 - v.x;                                    // 8 * (slot 0's diagonal - the row's first diagonal)
+    rY[slot] = -v.y - v.x;                                   // 8 * (cells in the row - 1)
+    rQ[slot] = qp[ridx];
+    if (FN == 1) rV[slot] = vp[ridx];
+  };
 #pragma unroll
   for (int m = 0; m < KA; m++) {
-    const int2 v = rp[m];
-    if (FN == 1) { rV[m] = v.x & 0xff; rX[m] = s08 - v.x + rV[m]; } else rX[m] = s08 - v.x;
-    rY[m] = v.y; rQ[m] = v.y & 0xff;
+    load_row(m, m);
     cT[m] = (int)cp[m] * 4 + mtabAddr;
     acc[m] = 0;
   }
   aw += kL;
 #pragma unroll 1
-  for (int i0 = 0; i0 < 32; i0 += KA) {
-#pragma unroll
-    for (int j = 0; j < KA; j++) {
-      if ((32 % KA) != 0 && i0 + j >= 32) break;
+  for (int i0 = 0; i0 < 32; i0 += CH) {
+    static_for<0, CH>([&](auto JJ) {
+      constexpr int jj = decltype(JJ)::value, j = jj % KA;
       // ---- even step: cells on slots 2g
       {
         const int left0 = sub_up<LPJ>(So[KA - 1]);
         const int leftA0 = AFFINE ? sub_up<LPJ>(ADo[KA - 1]) : 0;
-#pragma unroll
-        for (int g = 0; g < KA; g++) {
-          const int p = (j + KA - 1 - g) % KA, cs = (j + g) % KA;
-          const int leftS = g == 0 ? left0 : So[g - 1];
-          const int leftAD = AFFINE ? (g == 0 ? leftA0 : ADo[g - 1]) : 0;
+        static_for<0, KA>([&](auto GG) {
+          constexpr int g = decltype(GG)::value, p = (jj + KA - 1 - g) % KA, cs = (jj + g) % KA;
+          const int leftS = g == 0 ? left0 : So[g == 0 ? 0 : g - 1];
+          const int leftAD = AFFINE ? (g == 0 ? leftA0 : ADo[g == 0 ? 0 : g - 1]) : 0;
           int m = lds32((uint32_t)(rQ[p] + cT[cs]));
-          if (FN == 1) m *= rV[p];                            // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
-          int ai = 0, ad = 0;
-          int cnd = dp_core<AFFINE>(Se[g], leftS, leftAD, So[g], AFFINE ? AIo[g] : 0, m, c.delT, c.insT, c, ai, ad);
-          const bool inb = (unsigned)(c.k256 * (2 * g) + rX[p]) <= (unsigned)rY[p];
-          cnd = inb ? cnd : (BIG | F::NONE);
-          Se[g] = cnd & ~F::TAGMASK;
-          if (AFFINE) { AIe[g] = inb ? (ai & ~31) : BIG; ADe[g] = inb ? (ad & ~31) : BIG; }
+          if (FN == 1) m *= rV[FN == 1 ? p : 0];            // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+          int s0, ai = 0, ad = 0;
+          int cnd = dp_core<AFFINE>(Se[g], leftS, leftAD, So[g], AFFINE ? AIo[g] : 0, m, c.delT, c.insT, c, s0, ai, ad);
+          if (AFFINE) mask_aff<16 * g>(cnd, s0, ai, ad, rX[p], rY[p], c);
+          else { mask_lin<16 * g>(cnd, rX[p], rY[p], c); s0 = cnd & ~3; }
+          Se[g] = s0;
+          if (AFFINE) { AIe[g] = ai; ADe[g] = ad; }
           acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);   // first step of a word ends up in its lowest field
-        }
+        });
       }
-      cT[j] = (int)cp[i0 + j + KA] * 4 + mtabAddr;          // column kL + i + KA replaces kL + i
+      cT[j] = (int)cp[i0 + jj + KA] * 4 + mtabAddr;         // column kL + i + KA replaces kL + i
       // ---- odd step: cells on slots 2g+1
       {
         const int up0 = sub_dn<LPJ>(Se[0]);
         const int upA0 = AFFINE ? sub_dn<LPJ>(AIe[0]) : 0;
-#pragma unroll
-        for (int g = 0; g < KA; g++) {
-          const int p = (j + KA - 1 - g) % KA, cs = (j + 1 + g) % KA;
-          const int upS = g == KA - 1 ? up0 : Se[g + 1];
-          const int upAI = AFFINE ? (g == KA - 1 ? upA0 : AIe[g + 1]) : 0;
+        static_for<0, KA>([&](auto GG) {
+          constexpr int g = decltype(GG)::value, p = (jj + KA - 1 - g) % KA, cs = (jj + 1 + g) % KA;
+          const int upS = g == KA - 1 ? up0 : Se[g == KA - 1 ? 0 : g + 1];
+          const int upAI = AFFINE ? (g == KA - 1 ? upA0 : AIe[g == KA - 1 ? 0 : g + 1]) : 0;
           int m = lds32((uint32_t)(rQ[p] + cT[cs]));
-          if (FN == 1) m *= rV[p];
-          int ai = 0, ad = 0;
-          int cnd = dp_core<AFFINE>(So[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, m, c.delT, c.insT, c, ai, ad);
-          const bool inb = (unsigned)(c.k256 * (2 * g + 1) + rX[p]) <= (unsigned)rY[p];
-          cnd = inb ? cnd : (BIG | F::NONE);
-          So[g] = cnd & ~F::TAGMASK;
-          if (AFFINE) { AIo[g] = inb ? (ai & ~31) : BIG; ADo[g] = inb ? (ad & ~31) : BIG; }
-          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);   // first step of a word ends up in its lowest field
-        }
+          if (FN == 1) m *= rV[FN == 1 ? p : 0];
+          int s0, ai = 0, ad = 0;
+          int cnd = dp_core<AFFINE>(So[g], Se[g], AFFINE ? ADe[g] : 0, upS, upAI, m, c.delT, c.insT, c, s0, ai, ad);
+          if (AFFINE) mask_aff<16 * g + 8>(cnd, s0, ai, ad, rX[p], rY[p], c);
+          else { mask_lin<16 * g + 8>(cnd, rX[p], rY[p], c); s0 = cnd & ~3; }
+          So[g] = s0;
+          if (AFFINE) { AIo[g] = ai; ADo[g] = ad; }
+          acc[g] = __funnelshift_r(acc[g], (uint32_t)cnd, F::BITS);
+        });
       }
-      {                                                       // row baseR + i + KA replaces row baseR + i
-        const int2 v = rp[i0 + j + KA];
-        if (FN == 1) { rV[j] = v.x & 0xff; rX[j] = s08 - v.x + rV[j]; } else rX[j] = s08 - v.x;
-        rY[j] = v.y; rQ[j] = v.y & 0xff;
-      }
-      if (((i0 + j) & (F::SPW / 2 - 1)) == F::SPW / 2 - 1) {  // a traceback word is complete
+      load_row(j, i0 + jj + KA);                              // row baseR + i + KA replaces row baseR + i
+      if (CH >= PPW && (jj % PPW) == PPW - 1) {               // a traceback word is complete
         if (live) {
 #pragma unroll
           for (int g = 0; g < KA; g++) aw[g] = acc[g];
         }
         aw += KA * LPJ;
       }
+    });
+    if (CH < PPW && ((i0 + CH) & (PPW - 1)) == 0) {           // (linear, k >= 3: a word is two chunks)
+      if (live) {
+#pragma unroll
+        for (int g = 0; g < KA; g++) aw[g] = acc[g];
+      }
+      aw += KA * LPJ;
     }
+    ring_rotate<KA, ROT>(rQ); ring_rotate<KA, ROT>(rX); ring_rotate<KA, ROT>(rY); ring_rotate<KA, ROT>(cT);
+    if (FN == 1) ring_rotate<(FN == 1 ? KA : 1), (FN == 1 ? ROT : 0)>(rV);
   }
 }
 
@@ -228,20 +296,21 @@ __device__ __forceinline__ void run_block_gen(int (&Se)[KM], int (&So)[KM], int 
       const int dc = (rb >> 16) ? ((dtag != 'N' && dtag == tb) ? ((rb >> 8) & 0xff) : c.delPrior) : c.del;
       delT = (dc << F::SHv) | TB_LEFT;
     } else {
-      m = lds32((uint32_t)(mtabAddr + (rv.y & 0xff) + (int)bv.cols[cidx] * 4));
-      if (FN == 1) m *= rv.x & 0xff;                        // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
+      m = lds32((uint32_t)(mtabAddr + (int)bv.qrows[ridx] + (int)bv.cols[cidx] * 4));
+      if (FN == 1) m *= (int)bv.qvs[ridx];                  // +-(1<<SH) * QV  (QualityValueScoreFunction.h:78-83)
     }
-    int ai = 0, ad = 0;
-    int cnd = dp_core<AFFINE>(S, leftS, leftAD, upS, upAI, m, delT, insT, c, ai, ad);
+    int s0, ai = 0, ad = 0;
+    int cnd = dp_core<AFFINE>(S, leftS, leftAD, upS, upAI, m, delT, insT, c, s0, ai, ad);
     if (first && bv.qlo + ridx == 0) {                      // boundary row (GuidedAlign.h:415-442)
       cnd = ((bv.tlo + cidx) * c.del0) | (AFFINE ? (TB_LEFT | TB_IOPEN | TB_DOPEN) : TL_LEFT);
-      ai = c.open; ad = c.open;
+      s0 = cnd & ~F::TAGMASK; ai = c.open; ad = c.open;
     }
-    const bool inb = (unsigned)(bv.wbase8 + (slot << 8) - (FN == 1 ? (rv.x & ~0xff) : rv.x)) <= (unsigned)rv.y;
+    const int d8 = (bv.wbase + slot) << 3;
+    const bool inb = d8 >= rv.x && -d8 >= rv.y;
     cnd = inb ? cnd : (BIG | F::NONE);
     if (e <= eLast) {
-      S = cnd & ~F::TAGMASK;
-      if (AFFINE) { AI = inb ? (ai & ~31) : BIG; AD = inb ? (ad & ~31) : BIG; }
+      S = inb ? s0 : BIG;
+      if (AFFINE) { AI = inb ? ai : BIG; AD = inb ? ad : BIG; }
     } else cnd = F::NONE;
     a = __funnelshift_r(a, (uint32_t)cnd, F::BITS);
   };
@@ -340,7 +409,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
   c.ext = P.ext << F::SHv; c.open = P.open << F::SHv;
   c.openI = (P.open << F::SHv) | TB_IOPEN; c.openD = (P.open << F::SHv) | TB_DOPEN;
   c.del0 = (P.alignType == BGPU_GLOBAL ? P.del : 0) << F::SHv;
-  c.k256 = 256 + P.pad; c.kacc = (1 << F::BITS) + P.pad;    // P.pad is always 0
+  c.one = 1 + P.pad; c.zero = P.pad;   // P.pad is always 0
   c.subPrior = P.subPrior; c.delPrior = P.delPrior; c.del = P.del;
 
   for (;;) {
@@ -353,45 +422,55 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
     JobGeom *G = have ? &B.geom[job] : nullptr;
     if (have && G->status != BGPU_JOB_OK) have = false;
     int Qn = 0, Tn = 0, C0 = 0, nDB = 0, hi0 = 0;
-    const RowInfo *rows = nullptr; DBlock *dblk = nullptr; const uint8_t *tcodes = nullptr, *tJobLo = nullptr, *tJobHi = nullptr;
+    const RowInfo *rows = nullptr; DBlock *dblk = nullptr;
+    const uint8_t *tcodes = nullptr, *qcodes = nullptr, *qvals = nullptr;
+    int tLoOff = 0, tHiOff = 0, qLoOff = 0, qHiOff = 0;      // the job's own bytes: [tcodes + tLoOff, tcodes + tHiOff) etc.
     size_t trackOff = 0;                                     // IDS: track index of row q' is trackOff + q'
     uint32_t *arrowsJob = nullptr;
     if (have) {
       Qn = G->Qn; Tn = G->Tn; C0 = G->C0; nDB = G->nDB; hi0 = G->hi0;
       rows = B.rows + G->rowOff; dblk = B.dblk + G->dblkOff;
-      tJobLo = B.tc + B.tOff[job]; tJobHi = B.tc + B.tOff[job + 1];
-      tcodes = tJobLo + G->tStart - 1;                       // tcodes[t'] for t' in [1,Tn]
+      const uint64_t t0 = B.tOff[job], q0 = B.qOff[job];
+      tcodes = B.tc + t0 + G->tStart - 1;                    // tcodes[t'] for t' in [1,Tn]
+      tLoOff = 1 - G->tStart; tHiOff = tLoOff + (int)(B.tOff[job + 1] - t0);
+      qcodes = B.qc + q0 + G->qStart - 1;                    // qcodes[q'] for q' in [1,Qn]
+      qLoOff = 1 - G->qStart; qHiOff = qLoOff + (int)(B.qOff[job + 1] - q0);
+      if (FN == 1) qvals = B.qual + q0 + G->qStart - 1;
       if (FN == 2) trackOff = (size_t)B.qOff[job] + (size_t)G->qStart - 1;
       arrowsJob = reinterpret_cast<uint32_t *>(B.arrows + B.arrowOff[job]);
     }
     const int nDBw = __reduce_max_sync(0xffffffffu, nDB);
     const int nD = Qn + Tn + 1;
 
+    // bytes [p0, p0 + n) of a per-base array, copied as aligned 4-byte chunks clamped to the job's own bytes [lo, hi);
+    // returns the offset of p0 inside the first chunk
+    auto stage_bytes = [&](uint32_t *dstw, const uint8_t *base, const int off, const int lo, const int hi, const int n, const bool liveB) {
+      const int a = liveB ? (int)((uintptr_t)(base + off) & 3u) : 0;
+      const int nch = (n + a + 3) >> 2;
+      if (liveB) {
+        // chunk ch covers bytes [off - a + 4 ch, + 4): whole aligned words that overlap [lo, hi) (the arrays are padded)
+        for (int ch = sl; ch < nch; ch += LPJ) {
+          const int o = off - a + 4 * ch;
+          if (o + 3 >= lo && o < hi) cp_async4(&dstw[ch], base + o);
+          else dstw[ch] = 0;
+        }
+      } else {
+        for (int ch = sl; ch < nch; ch += LPJ) dstw[ch] = 0;
+      }
+      return a;
+    };
     // issue the cp.async copies of one block's rows and columns into buffer `buf`
-    auto stage = [&](const int buf, const int b, const int wbase, const int k, const bool liveB, int &colShift) {
+    auto stage = [&](const int buf, const int b, const int wbase, const int k, const bool liveB, int &colShift, int &qShift) {
       const int cq = (C0 - wbase) >> 1;
       const int qlo = 32 * b + cq - (k * LPJ - 1), tlo = 32 * b - cq;
       for (int r = sl; r < k * LPJ + 32; r += LPJ) {
         const int qp = qlo + r;
         if (liveB && qp >= 0 && qp <= Qn) cp_async8(&sm.rows[buf][r], rows + qp);
-        else sm.rows[buf][r] = make_int2(DEAD_CD8, 0);
+        else sm.rows[buf][r] = make_int2(DEAD_LO8, -DEAD_LO8);
       }
-      // columns: bytes [tcodes + tlo, + k*LPJ + 33), copied as aligned 4-byte chunks clamped to the job's own bytes
-      const uint8_t *p0 = tcodes + tlo;
-      const int a = liveB ? (int)((uintptr_t)p0 & 3u) : 0;
-      colShift = a;
-      if (liveB) {
-        const uint8_t *lo4 = (const uint8_t *)((uintptr_t)tJobLo & ~(uintptr_t)3);
-        const uint8_t *hi4 = (const uint8_t *)(((uintptr_t)tJobHi + 3) & ~(uintptr_t)3);
-        const int nch = (k * LPJ + 33 + a + 3) >> 2;
-        for (int ch = sl; ch < nch; ch += LPJ) {
-          const uint8_t *src = p0 - a + 4 * ch;
-          if (src >= lo4 && src < hi4) cp_async4(&sm.colw[buf][ch], src);
-          else sm.colw[buf][ch] = 0;
-        }
-      } else {
-        for (int ch = sl; ch < (k * LPJ + 36) >> 2; ch += LPJ) sm.colw[buf][ch] = 0;
-      }
+      colShift = stage_bytes(sm.colw[buf], tcodes, tlo, tLoOff, tHiOff, k * LPJ + 33, liveB);
+      if (FN != 2) qShift = stage_bytes(sm.qcw[buf], qcodes, qlo, qLoOff, qHiOff, k * LPJ + 32, liveB);
+      if (FN == 1) stage_bytes(sm.qvw[buf], qvals, qlo, qLoOff, qHiOff, k * LPJ + 32, liveB);
       cp_async_commit();
     };
 
@@ -405,9 +484,9 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
     int wbase = 0, kown = 1;
     if (have && nDB > 0) { const DBlock db = dblk[0]; wbase = db.wbase; kown = db.k; }
     int k = __reduce_max_sync(0xffffffffu, kown);
-    int colShift0 = 0, colShift1 = 0;
+    int colShift0 = 0, colShift1 = 0, qShift0 = 0, qShift1 = 0;
     __syncwarp();
-    stage(0, 0, wbase, k, have && nDB > 0, colShift0);
+    stage(0, 0, wbase, k, have && nDB > 0, colShift0, qShift0);
     int wnext = wbase, knextOwn = 1;
     if (have && 1 < nDB) { const DBlock db = dblk[1]; wnext = db.wbase; knextOwn = db.k; }
 
@@ -417,7 +496,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
       // ---- next block: its window is known, start its copies, fetch the DBlock after it
       const int knext = __reduce_max_sync(0xffffffffu, knextOwn);
       const bool liveN = have && b + 1 < nDB;
-      if (b + 1 < nDBw) { if (buf) stage(0, b + 1, wnext, knext, liveN, colShift0); else stage(1, b + 1, wnext, knext, liveN, colShift1); }
+      if (b + 1 < nDBw) { if (buf) stage(0, b + 1, wnext, knext, liveN, colShift0, qShift0); else stage(1, b + 1, wnext, knext, liveN, colShift1, qShift1); }
       int wnext2 = wnext, knext2 = 1;
       if (have && b + 2 < nDB) { const DBlock db = dblk[b + 2]; wnext2 = db.wbase; knext2 = db.k; }
       // ---- this block's data has landed
@@ -450,7 +529,9 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
       BlockView bv;
       bv.rows = sm.rows[buf];
       bv.cols = reinterpret_cast<const uint8_t *>(sm.colw[buf]) + (buf ? colShift1 : colShift0);
-      bv.wbase8 = wbase << 8;
+      bv.qrows = reinterpret_cast<const uint8_t *>(sm.qcw[buf]) + (buf ? qShift1 : qShift0);
+      bv.qvs = reinterpret_cast<const uint8_t *>(sm.qvw[FN == 1 ? buf : 0]) + (buf ? qShift1 : qShift0);   // q and qual share their offsets
+      bv.wbase = wbase;
       bv.qlo = 32 * b + cq - (k * LPJ - 1); bv.tlo = 32 * b - cq;
       if (FN == 2) {
         for (int r = sl; r < k * LPJ + 32; r += LPJ) {
@@ -469,10 +550,13 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
       const bool first = live && (b << 6) <= hi0;          // row 0 holds cells on d <= hi0
       const bool last = live && (b == nDB - 1);
       const int eLast = last ? ((nD - 1) & 63) : 63;
-      if (RING && !__any_sync(0xffffffffu, first || last))
-        RingDispatch<LPJ, KM, AFFINE, FN, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
-      else
-        run_block_gen<LPJ, KM, AFFINE, FN>(Se, So, AIe, AIo, ADe, ADo, bv, sm.rowq, mtabAddr, c, k, sl, first, eLast, aw, live);
+      const bool slow = first || last;
+      bool ring = false;
+      if constexpr (RING) {
+        ring = !__any_sync(0xffffffffu, slow);
+        if (ring) RingDispatch<LPJ, KM, AFFINE, FN, 1>::run(k, Se, So, AIe, AIo, ADe, ADo, bv, mtabAddr, c, sl, aw, live);
+      }
+      if (!ring) run_block_gen<LPJ, KM, AFFINE, FN>(Se, So, AIe, AIo, ADe, ADo, bv, sm.rowq, mtabAddr, c, k, sl, first, eLast, aw, live);
       if (live && sl == 0) { dblk[b].k = k; dblk[b].arrowUnit = unit; }
       unit += (uint32_t)k;
       // ---- the end cell (Qn, Tn) sits on diagonal Tn-Qn+C0 and is the last cell written to its slot

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
     G.rowOff = rowOffIn[job]; G.dblkOff = dblkOffIn[job]; G.runOff = runOffIn[job];
     G.arrowBytes = 0; G.nRuns = G.nBlocks = G.nGaps = G.nGapLists = 0;
     G.qPos = G.tPos = 0; G.score = 0; G.nCells = 0; G.kmax = 0; G.nDB = 0; G.band = band;
-    G.Qn = G.Tn = 0; G.qStart = G.tStart = 0; G.C0 = 0; G.hi0 = 0; G.cls = 0; G.ksum = 0;
+    G.Qn = G.Tn = 0; G.qStart = G.tStart = 0; G.C0 = 0; G.hi0 = 0; G.cls = 0; G.ksum = 0; G.minW = 0;
   }
   if (nB == 0) { if (lane == 0) G.status = BGPU_JOB_EMPTY_GUIDE; return; }   // GuidedAlign.h:388-392
   if (band < 0) { if (lane == 0) G.status = BGPU_JOB_BAD_INPUT; return; }
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   const int Qn = qEnd - qStart, Tn = tEnd - tStart;
   const int C0 = Qn + (Qn & 1);
   const int nD = Qn + Tn + 1, nDB = (nD + DBLK - 1) / DBLK;
-  if (nD >= (1 << 21)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }   // diagonals are carried << 8
+  if (nD >= (1 << 21)) { if (lane == 0) G.status = BGPU_JOB_RANGE; return; }   // diagonals are carried * 8
   // score range the shifted-domain kernels can carry.  Every in-band cell is reachable by Diagonal / Left / Up moves
   // alone (they stay candidates of the affine 5-way min), so |S| <= steps * max(|M|, |ins|, |del|, |ext|); the affine
   // matrices sit at most one open above S.  QualityValueScoreFunction: |Match| <= the largest QV of this job's rows
@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   // row 0: boundary row, t' in [0, min(tPost0, Tn)]
   const int hi0 = min(tPost0, Tn);
   if (lane == 0) {
-    rows[0].cd8 = C0 << 8; rows[0].packed = (uint32_t)hi0 << 8;   // boundary row: columns [0, hi0], no base
+    rows[0].lo8 = C0 * 8; rows[0].nhi8 = -(C0 + hi0) * 8;          // boundary row: columns [0, hi0], no base
     cells += (long long)tPost0 + 1;                    // tPre=0
-    if (hi0 >= (1 << ROW_W_BITS)) wide = 1;
   }
+  int minW = hi0 + 1;
   add_rows(0, lane == 0 ? 0 : 1, lane == 0 ? hi0 : 0);
 
   int carryL = tStart - 1;                              // L_0
@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   bgpu_block *win = sWin[threadIdx.x >> 5];
   int wb = 0, we = 0;                                   // window = blocks [wb, we)
   uint8_t qchNext = Qn >= 1 + lane ? qb[qStart + lane] : 0;
-  // QualityValueScoreFunction: the row's QV rides in the low byte of RowInfo::cd8 (the fill kernels multiply by it)
+  // QualityValueScoreFunction: the fill kernels read the rows' QVs from B.qual themselves; only their maximum is needed here
+  uint8_t *qcb = B.qc + qo;
   const uint8_t *qvb = (P.kind == BGPU_FN_QUALITY && B.qual) ? B.qual + qo : nullptr;
   uint8_t qvNext = (qvb && Qn >= 1 + lane) ? qvb[qStart + lane] : 0;
   int maxQV = 0;
@@ -214,12 +215,12 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
       const int hi = min(t + tPost, tEnd - 1);
       lop = L - tStart + 1; hip = hi - tStart + 1;
       if (tPre < 0 || hip < lop) bad = 1;
-      const int w = hip - lop;
-      if (w >= (1 << ROW_W_BITS)) wide = 1;
+      minW = min(minW, hip - lop + 1);
       const uint32_t qc = lut[qch];
       if (qc > 4) bad = 1;
-      RowInfo r; r.cd8 = ((lop - i + C0) << 8) | (int)qv; r.packed = (((uint32_t)w & ((1u << ROW_W_BITS) - 1)) << 8) | ((qc & 7u) * 20u);
+      RowInfo r; r.lo8 = (lop - i + C0) * 8; r.nhi8 = -(hip - i + C0) * 8;
       rows[i] = r;
+      qcb[qStart + i - 1] = (uint8_t)((qc & 7u) * 20u);
       if (bad || wide) { lop = 1; hip = 0; }
     }
     add_rows(i, lop, hip);
@@ -262,9 +263,10 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   }
   kmax = __reduce_max_sync(0xffffffffu, kmax);
   ksum = __reduce_add_sync(0xffffffffu, ksum);
+  minW = __reduce_min_sync(0xffffffffu, minW);
   if (lane == 0) {
     G.status = status; G.qStart = qStart; G.tStart = tStart; G.Qn = Qn; G.Tn = Tn; G.C0 = C0;
-    G.nDB = nDB; G.kmax = kmax; G.nCells = (int)cells; G.hi0 = hi0; G.cls = cls; G.ksum = ksum;
+    G.nDB = nDB; G.kmax = kmax; G.nCells = (int)cells; G.hi0 = hi0; G.cls = cls; G.ksum = ksum; G.minW = minW;
     G.arrowBytes = 0;
   }
 }
