@@ -656,21 +656,24 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   const uint64_t totQ = b->qOff[n], totT = b->tOff[n], totG = b->guideOff[n];
   fill_score_params(t->sp, fn, p);
   // what this ticket is going to ask for besides the traceback pool (sequences, band table, runs, job tables, results)
-  t->dev.hint = 18 * totQ + 7 * totT + 12 * totG + 512ull * n + (1u << 16);
+  t->dev.hint = 18 * totQ + 7 * totT + 12 * totG + (512ull + 16 * ROW_PAD) * n + (1u << 16);
   t->pin.hint = 4 * totQ + totT + 12 * totG + 320ull * n + (1u << 16);
   BatchDev &B = t->B;
   B.nJobs = n;
   uint64_t *d_qOff, *d_tOff, *d_gOff; uint8_t *d_q, *d_t, *d_tc, *d_qc, *d_qual = nullptr; bgpu_block *d_guide; int32_t *d_band = nullptr;
-  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16)); RC(talloc_dev(ctx, t, &d_tc, totT + 16));
-  RC(talloc_dev(ctx, t, &d_qc, totQ + 16));
+  // tc / qc / qual are read by unchecked 16-byte-aligned bulk copies that start up to a window before and end up to a
+  // window behind a job's bytes: BYTE_PAD bytes on either side
+  RC(talloc_dev(ctx, t, &d_q, totQ + 16)); RC(talloc_dev(ctx, t, &d_t, totT + 16)); RC(talloc_dev(ctx, t, &d_tc, totT + 2 * BYTE_PAD));
+  RC(talloc_dev(ctx, t, &d_qc, totQ + 2 * BYTE_PAD));
   RC(talloc_dev(ctx, t, &d_qOff, n + 1)); RC(talloc_dev(ctx, t, &d_tOff, n + 1)); RC(talloc_dev(ctx, t, &d_gOff, n + 1));
   RC(talloc_dev(ctx, t, &d_guide, totG + 1));
-  if (b->qual) RC(talloc_dev(ctx, t, &d_qual, totQ + 16));
+  if (b->qual) { RC(talloc_dev(ctx, t, &d_qual, totQ + 2 * BYTE_PAD)); d_qual += BYTE_PAD; }
   if (b->band) RC(talloc_dev(ctx, t, &d_band, n));
   // prep writes tc only inside [tStart, tEnd) of each job, the fill kernels also stage the boundary column t' = 0 and the
   // columns past the guide's end: those bytes must be valid codes (0), not whatever the cached allocation last held
-  CK(cudaMemsetAsync(d_tc, 0, totT + 16, ctx->stream));
-  CK(cudaMemsetAsync(d_qc, 0, totQ + 16, ctx->stream));      // likewise the coded query outside [qStart, qEnd)
+  CK(cudaMemsetAsync(d_tc, 0, totT + 2 * BYTE_PAD, ctx->stream));
+  CK(cudaMemsetAsync(d_qc, 0, totQ + 2 * BYTE_PAD, ctx->stream));      // likewise the coded query outside [qStart, qEnd)
+  d_tc += BYTE_PAD; d_qc += BYTE_PAD;
   // the phase gates keep LARGE tickets of concurrent contexts pipelined (copy in / compute / copy out); small tickets
   // (the candidates of a few reads) would only pay their host round trips
   t->gated = totQ + totT + (b->guidePacked ? 3 : sizeof(bgpu_block)) * totG > (32u << 20);
@@ -700,7 +703,7 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   for (uint32_t i = 0; i < n; i++) {
     const uint64_t ql = b->qOff[i + 1] - b->qOff[i], tl = b->tOff[i + 1] - b->tOff[i];
     h_off[i] = rowTot; h_off[n + i] = dbTot; h_off[2 * (size_t)n + i] = runTot;
-    rowTot += ql + 1; dbTot += (ql + tl + 1) / 64 + 2; runTot += ql + tl + 2;
+    rowTot += ql + 1 + 2 * ROW_PAD; dbTot += (ql + tl + 1) / 64 + 2; runTot += ql + tl + 2;
     // traceback bytes this job is expected to reserve: d-blocks x rows per block x words per row (window of the band plus
     // drift and class quantisation) -- an estimate, the planner kernels check the real sum against the pool
     const int64_t bd = std::max<int64_t>(b->band ? b->band[i] : p->band, 0);

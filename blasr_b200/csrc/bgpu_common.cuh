@@ -44,6 +44,12 @@ struct alignas(8) RowInfo {  // 8 B per guide row in HBM, consumed as is by the 
   // (x 8: a lane turns the two into the byte offset of its row of the in-band mask table, see bgpu_fill.cu)
 };
 constexpr int DEAD_LO8 = 1 << 29;      // {DEAD_LO8, -DEAD_LO8}: a row no slot can be inside of
+// The ring kernels stage a d-block's rows / target codes / query codes with ONE bulk copy (TMA) each, 16-byte aligned and
+// without bounds checks: every job's band table carries ROW_PAD dead rows in front of row 0 and behind row Qn (a window
+// reaches at most 6 * 32 rows past the live ones, plus the 32 of a block), and the per-base arrays (tc, qc, qual) sit
+// BYTE_PAD bytes inside their allocations.
+constexpr int ROW_PAD = 256;
+constexpr int BYTE_PAD = 512;
 
 struct DBlock {           // 16 B per d-block
   int32_t wbase;          // even: diagonal held by slot 0 of the job's window in this block

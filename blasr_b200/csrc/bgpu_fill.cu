@@ -53,12 +53,15 @@ struct FillConsts {
 };
 
 template <int LPJ, int KM, int FN>
-struct SubSmem {          // staging of one job: two d-blocks (current, next)
+struct alignas(16) SubSmem {   // staging of one job: two d-blocks (current, next)
   static constexpr int NR = KM * LPJ + 32;            // rows a d-block can touch
-  int2 rows[2][NR];                                   // RowInfo as prep wrote it: {lo8, nhi8}
-  uint32_t colw[2][(KM * LPJ + 44) / 4];              // target codes (bytes), 4-byte chunks from an aligned-down address
-  uint32_t qcw[2][(NR + 11) / 4];                     // query row offsets (code * 20, bytes), staged the same way
-  uint32_t qvw[FN == 1 ? 2 : 1][FN == 1 ? (NR + 11) / 4 : 1];   // QualityValueScoreFunction: the rows' QVs
+  static constexpr int NRS = (NR + 3) & ~1;           // ... staged from an even (16-byte aligned) row index
+  static constexpr int NBW = (NR + 1 + 15 + 15) / 16 * 4;   // words of a byte window staged from a 16-byte aligned address
+  int2 rows[2][NRS];                                  // RowInfo as prep wrote it: {lo8, nhi8}
+  uint32_t colw[2][NBW];                              // target codes (bytes)
+  uint32_t qcw[2][NBW];                               // query row offsets (code * 20, bytes)
+  uint32_t qvw[FN == 1 ? 2 : 1][FN == 1 ? NBW : 4];   // QualityValueScoreFunction: the rows' QVs
+  unsigned long long mbar[2];                         // one mbarrier per buffer: the bulk copies of a block complete on it
   int shift[2 * KM * LPJ];                            // window re-mapping scratch
   // IDSScoreFunction: two words per row of the current block,
   //   [r]      query byte | substitutionTag << 8 | substitutionQV << 16 | insertionQV << 24
@@ -84,6 +87,21 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async4(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+// TMA (bulk copy) + mbarrier: one lane arms the barrier with the byte count and issues the copies, everyone waits on the phase
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+               ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -401,6 +419,8 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
     if (FN == 1) { const int r = threadIdx.x / 5, cc = threadIdx.x % 5; Mtab[threadIdx.x] = ((r == cc && r < 4) ? -1 : 1) << F::SHv; }  // ScoreMatrices.h:4-10
     else Mtab[threadIdx.x] = P.M[threadIdx.x] << F::SHv;
   }
+  if (RING && sl == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); }
+  if (RING) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   const int mtabAddr = (int)__cvta_generic_to_shared(Mtab);
   FillConsts c;
@@ -412,6 +432,7 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
   c.one = 1 + P.pad; c.zero = P.pad;   // P.pad is always 0
   c.subPrior = P.subPrior; c.delPrior = P.delPrior; c.del = P.del;
 
+  uint32_t mbarPhase = 0;                                    // bit b: parity the next wait on this job slot's mbar[b] looks for
   for (;;) {
     uint32_t grp = 0;
     if (lane == 0) grp = atomicAdd(counter, 1u);
@@ -459,18 +480,53 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
       }
       return a;
     };
-    // issue the cp.async copies of one block's rows and columns into buffer `buf`
-    auto stage = [&](const int buf, const int b, const int wbase, const int k, const bool liveB, int &colShift, int &qShift) {
+    // Stage one block's rows, target codes and query codes into buffer `buf`.  Ring kernels: lane 0 of the job arms the
+    // buffer's mbarrier and issues one bulk copy (TMA) per array, from 16-byte aligned addresses, no bounds checks (the
+    // arrays are padded, see ROW_PAD / BYTE_PAD); desc = row offset | column offset << 4 | query offset << 8 of the block's first
+    // element inside the staged data | (the block has to be waited for on the mbarrier) << 12 | (blanked) << 13.  Otherwise (wide kernel, IDS, a window that
+    // would leave the pads): per-lane cp.async copies with the out-of-range elements filled in.
+    auto stage = [&](const int buf, const int b, const int wbase, const int k, const bool liveB, int &desc) {
       const int cq = (C0 - wbase) >> 1;
       const int qlo = 32 * b + cq - (k * LPJ - 1), tlo = 32 * b - cq;
-      for (int r = sl; r < k * LPJ + 32; r += LPJ) {
+      const int nr = k * LPJ + 32;
+      if (RING) {
+        // a finished / absent job keeps computing (nothing is stored): its buffers only have to hold aligned table offsets,
+        // so they are blanked once (bit 13) and then left alone
+        if (!liveB) {
+          if (desc & (1 << 13)) return;
+          for (int r = sl; r < Smem::NRS; r += LPJ) sm.rows[buf][r] = make_int2(DEAD_LO8, -DEAD_LO8);   // the whole buffer: k may grow
+          for (int w = sl; w < Smem::NBW; w += LPJ) { sm.colw[buf][w] = 0; sm.qcw[buf][w] = 0; if (FN == 1) sm.qvw[FN == 1 ? buf : 0][w] = 0; }
+          desc = 1 << 13;
+          return;
+        }                                  // a finished / absent job computes on stale data, nothing is stored
+        const bool inPads = qlo >= -ROW_PAD + 1 && qlo + nr + 2 <= Qn + ROW_PAD &&
+                            tlo - 16 >= tLoOff - BYTE_PAD && tlo + nr + 1 + 32 <= tHiOff + BYTE_PAD &&
+                            qlo - 16 >= qLoOff - BYTE_PAD && qlo + nr + 32 <= qHiOff + BYTE_PAD;
+        if (liveB && inPads) {
+          const RowInfo *rsrc = rows + qlo;
+          const int ra = (int)(((uintptr_t)rsrc >> 3) & 1u);  // rows: 8 B each, the copy starts at an even one
+          const uint8_t *csrc = tcodes + tlo, *qsrc = qcodes + qlo;
+          const int ca = (int)((uintptr_t)csrc & 15u), qa = (int)((uintptr_t)qsrc & 15u);
+          desc = ra | (ca << 4) | (qa << 8) | (1 << 12);
+          if (sl == 0) {
+            const uint32_t rb = (uint32_t)((nr + ra + 1) & ~1) * 8u, cb = (uint32_t)(nr + 1 + ca + 15) & ~15u, qb = (uint32_t)(nr + qa + 15) & ~15u;
+            mbar_expect_tx(&sm.mbar[buf], rb + cb + qb + (FN == 1 ? qb : 0u));
+            bulk_g2s(sm.rows[buf], rsrc - ra, rb, &sm.mbar[buf]);
+            bulk_g2s(sm.colw[buf], csrc - ca, cb, &sm.mbar[buf]);
+            bulk_g2s(sm.qcw[buf], qsrc - qa, qb, &sm.mbar[buf]);
+            if (FN == 1) bulk_g2s(sm.qvw[buf], qvals + qlo - qa, qb, &sm.mbar[buf]);   // q and qual share their offsets
+          }
+          return;
+        }
+      }
+      for (int r = sl; r < nr; r += LPJ) {
         const int qp = qlo + r;
         if (liveB && qp >= 0 && qp <= Qn) cp_async8(&sm.rows[buf][r], rows + qp);
         else sm.rows[buf][r] = make_int2(DEAD_LO8, -DEAD_LO8);
       }
-      colShift = stage_bytes(sm.colw[buf], tcodes, tlo, tLoOff, tHiOff, k * LPJ + 33, liveB);
-      if (FN != 2) qShift = stage_bytes(sm.qcw[buf], qcodes, qlo, qLoOff, qHiOff, k * LPJ + 32, liveB);
-      if (FN == 1) stage_bytes(sm.qvw[buf], qvals, qlo, qLoOff, qHiOff, k * LPJ + 32, liveB);
+      desc = (stage_bytes(sm.colw[buf], tcodes, tlo, tLoOff, tHiOff, nr + 1, liveB) << 4) | (liveB ? 0 : 1 << 13);
+      if (FN != 2) desc |= stage_bytes(sm.qcw[buf], qcodes, qlo, qLoOff, qHiOff, nr, liveB) << 8;
+      if (FN == 1) stage_bytes(sm.qvw[buf], qvals, qlo, qLoOff, qHiOff, nr, liveB);
       cp_async_commit();
     };
 
@@ -484,9 +540,9 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
     int wbase = 0, kown = 1;
     if (have && nDB > 0) { const DBlock db = dblk[0]; wbase = db.wbase; kown = db.k; }
     int k = __reduce_max_sync(0xffffffffu, kown);
-    int colShift0 = 0, colShift1 = 0, qShift0 = 0, qShift1 = 0;
+    int desc0 = 0, desc1 = 0;
     __syncwarp();
-    stage(0, 0, wbase, k, have && nDB > 0, colShift0, qShift0);
+    stage(0, 0, wbase, k, have && nDB > 0, desc0);
     int wnext = wbase, knextOwn = 1;
     if (have && 1 < nDB) { const DBlock db = dblk[1]; wnext = db.wbase; knextOwn = db.k; }
 
@@ -496,11 +552,13 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
       // ---- next block: its window is known, start its copies, fetch the DBlock after it
       const int knext = __reduce_max_sync(0xffffffffu, knextOwn);
       const bool liveN = have && b + 1 < nDB;
-      if (b + 1 < nDBw) { if (buf) stage(0, b + 1, wnext, knext, liveN, colShift0, qShift0); else stage(1, b + 1, wnext, knext, liveN, colShift1, qShift1); }
+      if (b + 1 < nDBw) { if (buf) stage(0, b + 1, wnext, knext, liveN, desc0); else stage(1, b + 1, wnext, knext, liveN, desc1); }
       int wnext2 = wnext, knext2 = 1;
       if (have && b + 2 < nDB) { const DBlock db = dblk[b + 2]; wnext2 = db.wbase; knext2 = db.k; }
       // ---- this block's data has landed
       if (b + 1 < nDBw) cp_async_wait<1>(); else cp_async_wait<0>();
+      const int desc = buf ? desc1 : desc0;
+      if (RING && (desc & (1 << 12))) { mbar_wait(&sm.mbar[buf], (mbarPhase >> buf) & 1u); mbarPhase ^= 1u << buf; }
       __syncwarp();
       // ---- re-map the register window (old: kprev groups from diagonal wprev; new: k groups from wbase)
       if (b > 0 && __any_sync(0xffffffffu, wbase != wprev || k != kprev)) {
@@ -527,10 +585,10 @@ fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const P
       wprev = wbase; kprev = k;
       const int cq = (C0 - wbase) >> 1;
       BlockView bv;
-      bv.rows = sm.rows[buf];
-      bv.cols = reinterpret_cast<const uint8_t *>(sm.colw[buf]) + (buf ? colShift1 : colShift0);
-      bv.qrows = reinterpret_cast<const uint8_t *>(sm.qcw[buf]) + (buf ? qShift1 : qShift0);
-      bv.qvs = reinterpret_cast<const uint8_t *>(sm.qvw[FN == 1 ? buf : 0]) + (buf ? qShift1 : qShift0);   // q and qual share their offsets
+      bv.rows = sm.rows[buf] + (desc & 1);
+      bv.cols = reinterpret_cast<const uint8_t *>(sm.colw[buf]) + ((desc >> 4) & 15);
+      bv.qrows = reinterpret_cast<const uint8_t *>(sm.qcw[buf]) + ((desc >> 8) & 15);
+      bv.qvs = reinterpret_cast<const uint8_t *>(sm.qvw[FN == 1 ? buf : 0]) + ((desc >> 8) & 15);   // q and qual share their offsets
       bv.wbase = wbase;
       bv.qlo = 32 * b + cq - (k * LPJ - 1); bv.tlo = 32 * b - cq;
       if (FN == 2) {

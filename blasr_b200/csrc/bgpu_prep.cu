@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
 
   int status = BGPU_JOB_OK;
   if (lane == 0) {
-    G.rowOff = rowOffIn[job]; G.dblkOff = dblkOffIn[job]; G.runOff = runOffIn[job];
+    G.rowOff = rowOffIn[job] + ROW_PAD; G.dblkOff = dblkOffIn[job]; G.runOff = runOffIn[job];
     G.arrowBytes = 0; G.nRuns = G.nBlocks = G.nGaps = G.nGapLists = 0;
     G.qPos = G.tPos = 0; G.score = 0; G.nCells = 0; G.kmax = 0; G.nDB = 0; G.band = band;
     G.Qn = G.Tn = 0; G.qStart = G.tStart = 0; G.C0 = 0; G.hi0 = 0; G.cls = 0; G.ksum = 0; G.minW = 0;
@@ -117,7 +117,11 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prep_guided_kernel(BatchDev B
   for (int b = lane; b < nDB; b += 32) { dmin[b] = INT_MAX; dmax[b] = INT_MIN; }
   __syncwarp();
 
-  RowInfo *rows = B.rows + rowOffIn[job];
+  RowInfo *rows = B.rows + rowOffIn[job] + ROW_PAD;      // row 0; ROW_PAD dead rows lie on either side of rows [0, Qn]
+  for (int r = lane; r < ROW_PAD; r += 32) {
+    RowInfo dead; dead.lo8 = DEAD_LO8; dead.nhi8 = -DEAD_LO8;
+    rows[r - ROW_PAD] = dead; rows[Qn + 1 + r] = dead;
+  }
   const int drift0 = abs(tStart - qStart);                       // GuidedAlign.h:128
   const int tPost0 = drift0 > band ? drift0 : band;              // :129-134
   long long cells = 0;
