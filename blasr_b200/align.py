@@ -412,6 +412,30 @@ class Aligner:
         return self._run(batch, fn, AFFINE_KBAND, alignType=alignType, band=k, bndDel=del_, doStats=computeStats,
                          statsAffine=False, affineKBand=(hpInsOpen, hpInsExtend, insOpen, insExtend))
 
+    def SDPAlign(self, batch: JobBatch, scoreFn, wordSize: int = 11, sdpIns: int = 5, sdpDel: int = 10, indelRate: float = 0.30,
+                 alignType: int = capi.LOCAL, detailedAlignment: bool = True, extendFrontByLocalAlignment: bool = False,
+                 sdpPrefixLength: int = 50, recurse: int = 2, noRecurseUnder: int = 1000, maxMatchesPerPosition: int = 0):
+        """SDPAlign.h:95-107 with MappingParameters' defaults (the call of Blasr.cpp:1716-1722): the guide the refinement
+        receives.  Returns (results, blocks): results[i] holds status / qPos / tPos / nBlocks / blockOff, blocks is the
+        concatenated Block array (positions relative to qPos / tPos, as Alignment::blocks)."""
+        keep = {"q": np.ascontiguousarray(batch.q, np.uint8), "qOff": np.ascontiguousarray(batch.qOff, np.uint64),
+                "t": np.ascontiguousarray(batch.t, np.uint8), "tOff": np.ascontiguousarray(batch.tOff, np.uint64)}
+        b = capi.Batch(batch.n, _ptr(keep["q"]), _ptr(keep["qOff"]), _ptr(keep["t"]), _ptr(keep["tOff"]))
+        p = capi.SdpParams(wordSize, sdpIns, sdpDel, float(indelRate), alignType, int(detailedAlignment), int(extendFrontByLocalAlignment),
+                           sdpPrefixLength, recurse, noRecurseUnder, maxMatchesPerPosition)
+        f = scoreFn.c_struct()
+        res = np.zeros(batch.n, dtype=capi.RESULT_DTYPE)
+        arena = capi.Arena()
+        rc = self._lib.bgpu_sdp_align(self._ctx, C.byref(f), C.byref(p), C.byref(b), res.ctypes.data_as(C.c_void_p), C.byref(arena))
+        if rc != 0:
+            self._err(rc, "bgpu_sdp_align")
+        if arena.nBlocks:
+            buf = (C.c_ubyte * (int(arena.nBlocks) * capi.BLOCK_DTYPE.itemsize)).from_address(arena.blocks)
+            blocks = np.frombuffer(buf, dtype=capi.BLOCK_DTYPE).copy()
+        else:
+            blocks = np.zeros(0, dtype=capi.BLOCK_DTYPE)
+        return res, blocks
+
     def SWAlign(self, batch: JobBatch, scoreFn, alignType: int = capi.LOCAL, computeStats: bool = False) -> BatchResult:
         """SWAlign.h:18."""
         return self._run(batch, scoreFn, SW, alignType=alignType, band=0, doStats=computeStats, statsAffine=False)

@@ -27,6 +27,7 @@ EXPORTS = [
     "bgpu_create", "bgpu_destroy", "bgpu_last_error", "bgpu_version", "bgpu_submit", "bgpu_submit_jobs",
     "bgpu_collect", "bgpu_release", "bgpu_rerun", "bgpu_timing_of", "bgpu_align", "bgpu_device_count",
     "bgpu_measure_int_peak", "bgpu_int_peak_modes", "bgpu_cigar", "bgpu_base_code", "bgpu_query", "bgpu_trim", "bgpu_cigar_clipped", "bgpu_strings",
+    "bgpu_sdp_align",
 ]
 
 
@@ -59,6 +60,12 @@ class Job(C.Structure):
 class Arena(C.Structure):
     _fields_ = [("blocks", C.c_void_p), ("nBlocks", C.c_uint64), ("gapCounts", C.c_void_p),
                 ("nGapLists", C.c_uint64), ("gaps", C.c_void_p), ("nGaps", C.c_uint64), ("runs", C.c_void_p), ("nRuns", C.c_uint64)]
+
+
+class SdpParams(C.Structure):   # bgpu_sdp_params: SDPAlign's parameter list (SDPAlign.h:95-107)
+    _fields_ = [("wordSize", C.c_int32), ("sdpIns", C.c_int32), ("sdpDel", C.c_int32), ("indelRate", C.c_float),
+                ("alignType", C.c_int32), ("detailed", C.c_int32), ("extendFront", C.c_int32), ("sdpPrefix", C.c_int32),
+                ("recurse", C.c_int32), ("noRecurseUnder", C.c_int32), ("maxMatches", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -123,6 +130,7 @@ def lib() -> C.CDLL:
     L.bgpu_timing_of.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Timing)]
     L.bgpu_align.argtypes = [C.c_void_p, C.POINTER(ScoreFn), C.POINTER(Params), C.POINTER(Batch), C.c_void_p,
                              C.POINTER(Arena)]
+    L.bgpu_sdp_align.argtypes = [C.c_void_p, C.POINTER(ScoreFn), C.POINTER(SdpParams), C.POINTER(Batch), C.c_void_p, C.POINTER(Arena)]
     L.bgpu_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.bgpu_int_peak_modes.argtypes = [C.POINTER(C.c_double * 4)]
     _lib = L

@@ -18,6 +18,8 @@
 #include "bgpu_common.cuh"
 
 namespace bgpu {
+int run_sdp(const bgpu_scorefn *, const int *, float, int, int, uint32_t, const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *,
+            uint8_t *, size_t, unsigned, uint32_t *, bgpu_result *, bgpu_block *, const uint64_t *, cudaStream_t);
 void launch_prep_guided(const BatchDev &, const ScoreParams &, int, const uint64_t *, const uint64_t *,
                         const uint64_t *, cudaStream_t);
 void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32_t *, const PlanHead *, uint32_t, uint32_t *, int,
@@ -106,6 +108,8 @@ struct bgpu_ctx {
   size_t arrowPoolCap = 0;                       // max bytes of traceback pool per wave
   SlabPool devPool{false}, pinPool{true};        // cached device / pinned slabs, handed to tickets whole
   bgpu_ticket lastSync = nullptr;                // ticket owned by bgpu_align
+  void *sdpPinned = nullptr; size_t sdpPinnedBytes = 0;   // result arena of the last bgpu_sdp_align
+  bool sdpStackSet = false;
 };
 
 #define CK(call)                                                                                  \
@@ -348,6 +352,7 @@ extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
   for (auto &sl : ctx->pinPool.free_) cudaFreeHost(sl.base);
   for (int c = 0; c < N_CLS; c++) { cudaStreamDestroy(ctx->aux[c]); cudaEventDestroy(ctx->evJoin[c]); }
   cudaEventDestroy(ctx->evFork); cudaEventDestroy(ctx->evSync);
+  if (ctx->sdpPinned) cudaFreeHost(ctx->sdpPinned);
   cudaStreamDestroy(ctx->copyStream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1182,6 +1187,74 @@ extern "C" int bgpu_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_para
   rc = bgpu_collect(ctx, t, results, arena);
   if (rc) { bgpu_release(ctx, t); return rc; }
   ctx->lastSync = t;
+  return BGPU_OK;
+}
+
+
+// ---- SDPAlign: synchronous, one thread per job (bgpu_sdp.cu) ----
+extern "C" int bgpu_sdp_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_sdp_params *p, const bgpu_batch *b,
+                              bgpu_result *results, bgpu_arena *arena) {
+  if (!ctx || !fn || !p || !b || (!results && b->nJobs) || !arena) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  memset(arena, 0, sizeof *arena);
+  const uint32_t n = b->nJobs;
+  if (n == 0) return BGPU_OK;
+  if (!b->qOff || !b->tOff || !b->qBases || !b->tBases) { ctx->err = "null batch arrays"; return BGPU_E_INVALID; }
+  if (fn->kind != BGPU_FN_DISTANCE) { ctx->err = "bgpu_sdp_align takes a DistanceMatrixScoreFunction (what blasr passes, Blasr.cpp:1716)"; return BGPU_E_INVALID; }
+  if (p->wordSize < 1 || p->wordSize > 15 || (p->alignType != BGPU_LOCAL && p->alignType != BGPU_GLOBAL) || p->recurse < 0 || p->recurse > 8) {
+    ctx->err = "bgpu_sdp_align: wordSize 1..15, alignType Local / Global, recurse 0..8"; return BGPU_E_INVALID;
+  }
+  if (!ctx->sdpStackSet) {       // sdp_align recurses (recurse + 1 frames) and sorts with an explicit 1.7 KB stack
+    size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitStackSize);
+    if (cur < 16384) CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+    ctx->sdpStackSet = true;
+  }
+  const uint64_t totQ = b->qOff[n], totT = b->tOff[n];
+  std::vector<uint64_t> blockOff(n + 1, 0);
+  uint64_t qMax = 0, tMax = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t ql = b->qOff[i + 1] - b->qOff[i], tl = b->tOff[i + 1] - b->tOff[i];
+    qMax = std::max(qMax, ql); tMax = std::max(tMax, tl);
+    blockOff[i + 1] = blockOff[i] + std::min(ql, tl) + 2;      // blocks are disjoint in both sequences
+  }
+  // scratch slice per thread: the k-mer table of the target (40 B / base) + 80 B per fragment, room for 2 (|q| + |t|) + 4096
+  // fragments (a 10 kb pair at 15 % error has ~2,000); a job that needs more comes back BGPU_JOB_RANGE
+  const size_t slice = (40 * tMax + 80 * (2 * (qMax + tMax) + 4096) + 65536 + 255) & ~(size_t)255;
+  size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+  const size_t budget = std::min<size_t>(freeB / 4, (size_t)24 << 30);
+  unsigned slices = (unsigned)std::min<size_t>(std::min<size_t>(budget / slice, (size_t)ctx->nSM * 128), ((size_t)n + 63) / 64 * 64);
+  slices = slices / 64 * 64;
+  if (slices < 64) { ctx->err = "bgpu_sdp_align: not enough device memory for the scratch arena"; return BGPU_E_OOM; }
+  uint8_t *d_q = nullptr, *d_t = nullptr, *d_arena = nullptr; uint64_t *d_off = nullptr; uint32_t *d_counter = nullptr;
+  bgpu_result *d_res = nullptr; bgpu_block *d_blocks = nullptr;
+  auto freeAll = [&]() { cudaFree(d_q); cudaFree(d_t); cudaFree(d_arena); cudaFree(d_off); cudaFree(d_counter); cudaFree(d_res); cudaFree(d_blocks); };
+#define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char buf_[256]; snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); ctx->err = buf_; freeAll(); return e_ == cudaErrorMemoryAllocation ? BGPU_E_OOM : BGPU_E_CUDA; } } while (0)
+  SCK(cudaMalloc(&d_q, totQ + 16)); SCK(cudaMalloc(&d_t, totT + 16));
+  SCK(cudaMalloc(&d_off, sizeof(uint64_t) * 3 * ((size_t)n + 1))); SCK(cudaMalloc(&d_counter, 64));
+  SCK(cudaMalloc(&d_res, sizeof(bgpu_result) * n)); SCK(cudaMalloc(&d_blocks, sizeof(bgpu_block) * (blockOff[n] + 1)));
+  SCK(cudaMalloc(&d_arena, slice * slices));
+  cudaStream_t s = ctx->stream;
+  SCK(cudaMemcpyAsync(d_q, b->qBases, totQ, cudaMemcpyHostToDevice, s)); SCK(cudaMemcpyAsync(d_t, b->tBases, totT, cudaMemcpyHostToDevice, s));
+  SCK(cudaMemcpyAsync(d_off, b->qOff, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+  SCK(cudaMemcpyAsync(d_off + (n + 1), b->tOff, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+  SCK(cudaMemcpyAsync(d_off + 2 * ((size_t)n + 1), blockOff.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+  const int prm[8] = {p->wordSize, p->alignType, p->detailed, p->extendFront, p->sdpPrefix, p->recurse, p->noRecurseUnder, p->maxMatches};
+  SCK((cudaError_t)run_sdp(fn, prm, p->indelRate, p->sdpIns, p->sdpDel, n, d_q, d_off, d_t, d_off + (n + 1), d_arena, slice, slices, d_counter,
+                           d_res, d_blocks, d_off + 2 * ((size_t)n + 1), s));
+  const size_t needPin = sizeof(bgpu_block) * (blockOff[n] + 1);
+  if (ctx->sdpPinnedBytes < needPin) {
+    if (ctx->sdpPinned) cudaFreeHost(ctx->sdpPinned);
+    ctx->sdpPinned = nullptr; ctx->sdpPinnedBytes = 0;
+    SCK(cudaHostAlloc(&ctx->sdpPinned, needPin, cudaHostAllocDefault));
+    ctx->sdpPinnedBytes = needPin;
+  }
+  SCK(cudaMemcpyAsync(results, d_res, sizeof(bgpu_result) * n, cudaMemcpyDeviceToHost, s));
+  SCK(cudaMemcpyAsync(ctx->sdpPinned, d_blocks, needPin, cudaMemcpyDeviceToHost, s));
+  SCK(cudaStreamSynchronize(s));
+#undef SCK
+  freeAll();
+  arena->blocks = (const bgpu_block *)ctx->sdpPinned; arena->nBlocks = blockOff[n];
   return BGPU_OK;
 }
 

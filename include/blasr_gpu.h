@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BGPU_VERSION 104 /* 0.1.4: + compact results (arena.runs), packed guides, bgpu_cigar_clipped, bgpu_strings, bgpu_trim */
+#define BGPU_VERSION 105 /* 0.1.5: + bgpu_sdp_align (0.1.4: compact results, packed guides, bgpu_cigar_clipped, bgpu_strings, bgpu_trim) */
 
 /* ---- return codes (API level) ---- */
 enum {
@@ -212,6 +212,28 @@ int  bgpu_cigar_clipped(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t *clips, con
  * bases / '-', align = '|' (TwoBit-equal) / '*' / ' ' (gap), query = query bases / '-'.  Job i owns [strOff[i], strOff[i+1]) of
  * each of the three arrays (no terminators); pinned host memory owned by the library until bgpu_release(). */
 int  bgpu_strings(bgpu_ctx *ctx, bgpu_ticket t, const char **text, const char **align, const char **query, const uint64_t **strOff);
+
+/* ---- SDPAlign (common/algorithms/alignment/SDPAlign.h:95-637), the step that produces the guide the refinement consumes
+ * (called at alignment/Blasr.cpp:1716-1722 and :1080-1090): fragment set (k-mer matches of prefix / whole /
+ * suffix), sparse-DP chain, chain -> blocks, and -- when `detailed` -- the SWAlign / recursive SDPAlign fills of the boxes
+ * between chained blocks.  Field names are the reference's parameter names (SDPAlign.h:95-107).  Jobs are (query, target)
+ * pairs of `b` (guide / band / qual ignored); results[i] carries status, qPos, tPos and the blocks (arena->blocks[blockOff ..
+ * +nBlocks), positions relative to qPos / tPos as Alignment::blocks holds them; the other result fields are 0).  Synchronous;
+ * arena is pinned memory owned by the library until the next bgpu_sdp_align on ctx or bgpu_destroy.  A job whose fragment
+ * set outgrows its scratch slice (room for 2 (|q| + |t|) + 4096 fragments) comes back BGPU_JOB_RANGE. */
+typedef struct {
+  int32_t wordSize;                 /* blasr: params.sdpTupleSize (11) */
+  int32_t sdpIns, sdpDel;           /* 5, 10 */
+  float   indelRate;                /* params.indelRate * 3 */
+  int32_t alignType;                /* BGPU_LOCAL (Blasr.cpp:1719) or BGPU_GLOBAL (AlignSubstring, :1075) */
+  int32_t detailed;                 /* params.detailedSDPAlignment (true) */
+  int32_t extendFront;              /* params.extendFrontAlignment (false) */
+  int32_t sdpPrefix;                /* params.sdpPrefix (50) */
+  int32_t recurse, noRecurseUnder;  /* params.recurse (2), params.recurseOver (1000) */
+  int32_t maxMatches;               /* params.sdpMaxAnchorsPerPosition (0 = any number) */
+} bgpu_sdp_params;
+int  bgpu_sdp_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_sdp_params *p, const bgpu_batch *b,
+                    bgpu_result *results, bgpu_arena *arena);
 
 /* ---- synchronous one-shot: submit + collect; arena valid until the next call on ctx ---- */
 int  bgpu_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b,
