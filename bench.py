@@ -432,10 +432,49 @@ def sdp_guided_batch(n, seed, len_lo, len_hi, bands):
         g = blocks[:nb].astype(np.int64)
         q0, t0 = int(g[0, 0]), int(g[0, 1]); q1, t1 = int(g[-1, 0] + g[-1, 2]), int(g[-1, 1] + g[-1, 2])
         g[:, 0] -= q0; g[:, 1] -= t0
-        return q[q0:q1].tobytes(), t[t0:t1].tobytes(), g.astype(np.uint32), int(base.band[i])
-    with ThreadPoolExecutor(max_workers=len(os.sched_getaffinity(0))) as ex:
-        got = [x for x in ex.map(one, range(base.n)) if x is not None]
-    return JobBatch.from_lists([x[0] for x in got], [x[1] for x in got], [x[2] for x in got], None, [x[3] for x in got])
+        return q[q0:q1].tobytes(), t[t0:t1].tobytes(), g.astype(np.uint32), int(base.band[i]), blocks[:nb].copy()
+    nthr = len(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=nthr) as ex:
+        raw = list(ex.map(one, range(base.n)))
+    cpu_s = time.perf_counter() - t0
+    got = [x for x in raw if x is not None]
+    out = JobBatch.from_lists([x[0] for x in got], [x[1] for x in got], [x[2] for x in got], None, [x[3] for x in got])
+    # what the device SDPAlign is checked against / timed beside: the raw pairs, the reference's absolute blocks per pair
+    # and the wall time the reference's SDPAlign took on the host cores (ctypes releases the GIL)
+    out.sdp_pairs = base
+    out.sdp_ref = raw
+    out.sdp_cpu = dict(seconds=cpu_s, threads=nthr)
+    return out
+
+
+def sdp_device_record(al, sdp, fn):
+    """SDPAlign itself on the device (bgpu_sdp_align) on the pairs of the sdp_guides workload: wall time of the
+    synchronous call from host buffers (H2D + kernel + D2H), every pair's blocks compared with the reference's own SDPAlign,
+    and the reference's time for the same pairs on the host cores beside it."""
+    base, ref = sdp.sdp_pairs, sdp.sdp_ref
+    res = blocks = None
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res, blocks = al.SDPAlign(base, fn, wordSize=11, sdpIns=5, sdpDel=10, indelRate=0.9)
+        times.append(time.perf_counter() - t0)
+    bad = refused = 0
+    for i in range(base.n):
+        if int(res["status"][i]) != 0:
+            refused += 1
+            continue
+        b = blocks[int(res["blockOff"][i]):int(res["blockOff"][i]) + int(res["nBlocks"][i])]
+        got = np.stack([b["qPos"] + res["qPos"][i], b["tPos"] + res["tPos"][i], b["length"]], axis=1).astype(np.uint32).reshape(-1, 3)
+        want = ref[i][4] if ref[i] is not None else np.zeros((0, 3), np.uint32)
+        bad += int(not np.array_equal(got, want.reshape(-1, 3)))
+    best = min(times)
+    return dict(metric="sdp_pairs_per_s", value=base.n / best, unit="pairs/s", ms_per_call=1e3 * best, pairs=base.n,
+                bases=int(len(base.q) + len(base.t)), parity=dict(n=base.n, mismatches=bad, refused=refused, checker="oracle/_ref SDPAlign (unmodified reference)"),
+                cpu_baseline=dict(value=base.n / sdp.sdp_cpu["seconds"], unit="pairs/s", cores=sdp.sdp_cpu["threads"], kind="reference",
+                                  sample=f"the same {base.n} pairs through the reference's SDPAlign, {sdp.sdp_cpu['seconds']:.2f} s"),
+                how="bgpu_sdp_align: one warp per pair, walked by lane 0 (first device version: every phase after the k-mer matching is an order-dependent sequential algorithm), synchronous call from host buffers, best of 3",
+                workload="SDPAlign(k=11, sdpIns 5, sdpDel 10, indelRate 0.9, Local, detailed, sdpPrefix 50, recurse 2, recurseOver 1000) -- Blasr.cpp:1716-1722")
 
 
 def run_ours(args):
@@ -564,6 +603,7 @@ def run_ours(args):
                                      workload=f"{sdp.n} pairs of the configs[1] generator with guides = the reference's own SDPAlign(k=11, sdpIns 5, "
                                               "sdpDel 10, indelRate 0.3 x 3) output sliced as RefineAlignment does (SURVEY 8d C2); a small ticket: "
                                               "the fill kernel's tail is a visible share of it")
+            out["sdp_device"] = sdp_device_record(al, sdp, mkfn(capi.GUIDED, False))
     al.close()
     if solo and args.pipeline:
         try:

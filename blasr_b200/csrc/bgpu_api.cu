@@ -1223,9 +1223,9 @@ extern "C" int bgpu_sdp_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_
   const size_t slice = (40 * tMax + 80 * (2 * (qMax + tMax) + 4096) + 65536 + 255) & ~(size_t)255;
   size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
   const size_t budget = std::min<size_t>(freeB / 4, (size_t)24 << 30);
-  unsigned slices = (unsigned)std::min<size_t>(std::min<size_t>(budget / slice, (size_t)ctx->nSM * 128), ((size_t)n + 63) / 64 * 64);
-  slices = slices / 64 * 64;
-  if (slices < 64) { ctx->err = "bgpu_sdp_align: not enough device memory for the scratch arena"; return BGPU_E_OOM; }
+  unsigned slices = (unsigned)std::min<size_t>(std::min<size_t>(budget / slice, (size_t)ctx->nSM * 48), ((size_t)n + 1) / 2 * 2);   // warps
+  slices = slices / 2 * 2;
+  if (slices < 2) { ctx->err = "bgpu_sdp_align: not enough device memory for the scratch arena"; return BGPU_E_OOM; }
   uint8_t *d_q = nullptr, *d_t = nullptr, *d_arena = nullptr; uint64_t *d_off = nullptr; uint32_t *d_counter = nullptr;
   bgpu_result *d_res = nullptr; bgpu_block *d_blocks = nullptr;
   auto freeAll = [&]() { cudaFree(d_q); cudaFree(d_t); cudaFree(d_arena); cudaFree(d_off); cudaFree(d_counter); cudaFree(d_res); cudaFree(d_blocks); };
