@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false", help="skip the reads/s leg (stock blasr vs GPU-refined blasr)")
     ap.add_argument("--prod-jobs", type=int, default=40000, help="pairs of the affine_production sub-record (10 kb, band 16)")
     ap.add_argument("--sdp-jobs", type=int, default=2048, help="pairs of the sdp_guides sub-record (0 = skip)")
+    ap.add_argument("--gap-jobs", type=int, default=328000, help="AffineKBandAlign jobs of the gap_fills sub-record (configs[4]-style; 0 = skip)")
     ap.add_argument("--pipeline-reads", type=int, default=2000, help="reads of the configs[0] pipeline run")
     return ap.parse_args()
 
@@ -477,6 +478,58 @@ def sdp_device_record(al, sdp, fn):
                 workload="SDPAlign(k=11, sdpIns 5, sdpDel 10, indelRate 0.9, Local, detailed, sdpPrefix 50, recurse 2, recurseOver 1000) -- Blasr.cpp:1716-1722")
 
 
+def gap_fill_record(al, n):
+    """configs[4]-style dense aligner leg: the gap fills of -alignContigs (~41 k AffineKBandAlign jobs of ~80 cells per 1 Mb
+    contig, the parameter pattern of Blasr.cpp:1064-1076) through bgpu_submit / bgpu_collect from host buffers, a seeded
+    sample compared field by field with the reference's own AffineKBandAlign, and the reference replaying the same jobs on
+    the host cores beside it."""
+    from blasr_b200 import JobBatch, SMRTDistanceMatrix
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    lens = rng.integers(2, 14, n)                                       # (|q|+1) * (2k+1) ~ 80 cells at k = 4..5
+    tl = np.maximum(1, lens + rng.integers(-2, 3, n))
+    q = acgt[rng.integers(0, 4, int(lens.sum()))]; t = acgt[rng.integers(0, 4, int(tl.sum()))]
+    qOff = np.zeros(n + 1, np.uint64); qOff[1:] = np.cumsum(lens); tOff = np.zeros(n + 1, np.uint64); tOff[1:] = np.cumsum(tl)
+    band = np.maximum(np.abs(lens - tl) + 3, 4).astype(np.int32)       # bandSize of AlignSubstring grows with the length difference
+    b = JobBatch(q, qOff, t, tOff, np.zeros((0, 3), np.uint32), np.zeros(n + 1, np.uint64), None, band)
+    indel = 5
+    pr = (indel + 2, indel - 3, indel + 2, indel - 1)                   # Blasr.cpp:1067-1076
+    res = al.AffineKBandAlign(b, SMRTDistanceMatrix, pr[0], pr[1], pr[2], pr[3], indel, 0, computeStats=True)   # warm-up (allocations)
+    best = 1e9
+    for _ in range(5):
+        t0 = time.perf_counter(); res = al.AffineKBandAlign(b, SMRTDistanceMatrix, pr[0], pr[1], pr[2], pr[3], indel, 0, computeStats=True)
+        best = min(best, time.perf_counter() - t0)
+    tm = res.timing
+    cells = int(((lens + 1) * (2 * band + 1)).sum())
+    out = dict(metric="gap_fill_jobs_per_s", value=n / best, unit="jobs/s", ms_per_call=1e3 * best, jobs=n, jobs_ok=int((res.results["status"] == 0).sum()),
+               cells=cells, gcups=cells / best * 1e-9,
+               device_ms=dict(prep=tm.msPrep, fill=tm.msFill, trace=tm.msTrace, emit=tm.msEmit, total=tm.msTotal),
+               how="bgpu_submit + bgpu_collect from host buffers, best of 5",
+               workload=f"{n} AffineKBandAlign jobs, |q| 2-13, k = |dq-dt|+3, mean {cells / n:.0f} cells, hpInsOpen/hpInsExtend/insOpen/insExtend/del = "
+                        f"{pr[0]}/{pr[1]}/{pr[2]}/{pr[3]}/{indel} (Blasr.cpp:1067-1076)")
+    try:
+        from tests import cases, oracle as O
+        if O.have_ref():
+            ofn = O.score_fn(SMRTDistanceMatrix, 5, 5)
+            pick = np.random.default_rng(9).choice(n, size=min(n, 512), replace=False)
+            bad = 0
+            for i in pick:
+                qq, tt, _, _ = cases.job_arrays(b, int(i))
+                j, keep = O.make_job(4, 1, int(band[i]), qq, tt, None, None, 0, indel, 1, 0, affineKBand=pr)
+                bad += bool(cases.compare(cases.gpu_to_dict(res, int(i)), O.align("ref", ofn, j), cases.GPU_FIELDS))
+            out["parity_sample"] = dict(n=len(pick), mismatches=int(bad), checker="oracle/_ref AffineKBandAlign (unmodified reference template)")
+            m = min(n, 200000); jobs, keeps = [], []
+            for i in range(m):
+                qq, tt, _, _ = cases.job_arrays(b, i)
+                j, k = O.make_job(4, 1, int(band[i]), qq, tt, None, None, 0, indel, 0, 0, affineKBand=pr); jobs.append(j); keeps.append(k)
+            nthr = len(os.sched_getaffinity(0))
+            t0 = time.perf_counter(); O.replay("ref", ofn, jobs, nthr); dt = time.perf_counter() - t0
+            out["cpu_baseline"] = dict(value=m / dt, unit="jobs/s", cores=nthr, kind="reference", sample=f"the first {m} jobs replayed once in {dt:.2f} s")
+    except Exception as e:  # noqa: BLE001
+        out["cpu_baseline"] = {"unavailable": str(e)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -604,6 +657,8 @@ def run_ours(args):
                                               "sdpDel 10, indelRate 0.3 x 3) output sliced as RefineAlignment does (SURVEY 8d C2); a small ticket: "
                                               "the fill kernel's tail is a visible share of it")
             out["sdp_device"] = sdp_device_record(al, sdp, mkfn(capi.GUIDED, False))
+        if solo and args.gap_jobs > 0:
+            out["gap_fills"] = gap_fill_record(al, args.gap_jobs)
     al.close()
     if solo and args.pipeline:
         try:
