@@ -61,3 +61,39 @@ def gather_records(local: np.ndarray, n_jobs: int, device=None):
     for r, a in enumerate(parts):
         merged[shard_indices(n_jobs, r, world)] = a
     return merged
+
+
+def run_on_devices(batch, run, devices: Sequence[int], threads_per_device: int = 1):
+    """One process, many devices -- how a pthread blasr drives a multi-GPU box: worker thread w of W = len(devices) *
+    threads_per_device owns a context on device devices[w % len(devices)], takes jobs w, w+W, ... (the reference's
+    -start / -stride, Blasr.cpp:4057-4058) and calls run(aligner, sub_batch) -> per-job records (a structured / 2-D
+    numpy array, one row per job).  Returns the records merged back into read order.  No collective is involved."""
+    import threading
+    from .align import Aligner
+    W = len(devices) * threads_per_device
+    parts: List = [None] * W
+    errs: List = []
+
+    def work(w):
+        try:
+            idx = shard_indices(batch.n, w, W)
+            al = Aligner(devices[w % len(devices)])
+            try:
+                parts[w] = run(al, batch.slice(idx)) if len(idx) else None
+            finally:
+                al.close()
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(w,)) for w in range(W)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    if errs:
+        raise errs[0]
+    first = next(p for p in parts if p is not None)
+    out = np.zeros((batch.n,) + first.shape[1:], dtype=first.dtype)
+    for w, p in enumerate(parts):
+        if p is not None:
+            out[shard_indices(batch.n, w, W)] = p
+    return out

@@ -273,3 +273,28 @@ def test_packed_guides_and_compact_results(aligner, algo, monkeypatch):
             assert int(off[-1]) == len(ops) > 0
         aligner.release(tk)
     assert got.timing.d2hBytes < want.timing.d2hBytes and got.timing.h2dBytes < want.timing.h2dBytes
+
+
+def test_one_process_drives_every_device():
+    """One process, threads x contexts x devices (how a pthread blasr would drive a multi-GPU box): jobs are dealt out by
+    -start / -stride over 2 worker threads per visible device, every worker owns a context on its device, and the per-job
+    records merged back into read order equal the single-context run and the oracle."""
+    from blasr_b200 import Aligner, capi, shard
+    ndev = capi.lib().bgpu_device_count()
+    b = cases.guided_batch(seed=812, n=61, lo=200, hi=5000)
+    b.band = np.random.default_rng(4).choice([8, 16, 32, 64], size=b.n).astype(np.int32)
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+
+    def run(al, sub):
+        return al.AffineGuidedAlign(sub, fn, 16).results.copy()
+    merged = shard.run_on_devices(b, run, devices=list(range(ndev)), threads_per_device=2)
+    al = Aligner(0)
+    try:
+        whole = al.AffineGuidedAlign(b, fn, 16).results
+        for f in ("status", "score", "qPos", "tPos", "nCells", "nMatch", "nMismatch", "nIns", "nDel", "statsScore", "nBlocks", "nGaps"):
+            assert np.array_equal(merged[f], whole[f]), f
+    finally:
+        al.close()
+    ofn = O.score_fn(fn.scoreMatrix, 5, 5, 50, 0)
+    want = cases.oracle_batch(WHICH, b, ofn, 1, 1, b.band, statsAffine=1)
+    assert [int(x) for x in merged["score"]] == [w["score"] for w in want]
