@@ -398,7 +398,7 @@ struct RingDispatch<LPJ, KM, AFFINE, FN, KM + 1> {
 // order[] holds warp groups: 32 / LPJ job indices each (NOJOB pads the last group); a warp sweeps its jobs in
 // lockstep from d-block 0, with k = the widest member's need per block.
 template <int LPJ, int KM, bool AFFINE, int FN>
-__global__ void __launch_bounds__(KM <= KRING ? 128 : 32, KM <= 4 ? (AFFINE ? 4 : 5) : (KM <= KRING ? (AFFINE ? 4 : 5) : 1))
+__global__ void __launch_bounds__(KM <= KRING ? 128 : 32, KM <= KRING ? ((AFFINE || FN == 1) ? 4 : 5) : 1)
 fill_guided_kernel(BatchDev B, ScoreParams P, const uint32_t *orderBase, const PlanHead *plan, int cls, uint32_t *counter) {
   typedef Fmt<AFFINE> F;
   typedef SubSmem<LPJ, KM, FN> Smem;
