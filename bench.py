@@ -219,6 +219,8 @@ def range_view(batch, a, b):
     gp, gw = pack_guide(v.guide, v.guideOff)
     v.guidePacked, _k1 = pinned_copy(gp); v.guideWide, _k2 = pinned_copy(gw.reshape(-1, 4) if len(gw) else np.zeros((0, 4), np.uint32))
     v._keep = (_k1, _k2)
+    v.tRefOffAbs, _k3 = pinned_copy(np.ascontiguousarray(batch.tOff[a:b], np.uint64))    # where the targets sit in the whole shard's t
+    v._keep = (_k1, _k2, _k3)
     return v
 
 
@@ -230,7 +232,7 @@ def _pin_batch(batch, keep):
     return batch
 
 
-def e2e_measure(local, batch, fn, algo, n_threads, n_chunks, warm, steps, barrier):
+def e2e_measure(local, batch, fn, algo, n_threads, n_chunks, warm, steps, barrier, resident_reference=False):
     """submit (H2D + kernels) + collect (D2H) through the C ABI, host buffers in, host results out.  The way a multi-threaded
     host (blasr's MapReads pthreads) drives the library: a few host threads, each with its own context, push sub-batches of
     the shard; copies of one sub-batch overlap the kernels of another."""
@@ -239,6 +241,12 @@ def e2e_measure(local, batch, fn, algo, n_threads, n_chunks, warm, steps, barrie
     bounds = np.linspace(0, batch.n, n_chunks + 1).astype(np.int64)
     chunks = [range_view(batch, int(bounds[i]), int(bounds[i + 1])) for i in range(n_chunks)]
     workers = [Aligner(local) for _ in range(max(1, min(n_threads, n_chunks)))]
+    if resident_reference:
+        # the targets become windows of a reference resident on the device (blasr's genome: loaded once, outside the timed
+        # region, like the reference program loads it into RAM); per step only 8 bytes per job describe them
+        workers[0].set_reference(batch.t)
+        for c in chunks:
+            c.tRefOff = c.tRefOffAbs
 
     def one_pass():
         nxt = iter(range(n_chunks)); lock = threading.Lock()
@@ -286,6 +294,8 @@ def e2e_measure(local, batch, fn, algo, n_threads, n_chunks, warm, steps, barrie
         tot = one_pass()
     barrier()
     sec = (time.perf_counter() - t0) / steps
+    if resident_reference:
+        workers[0].set_reference(None)
     for a in workers:
         a.close()
     return {"sec": sec, "cells": tot["cells"], "ok": tot["ok"], "h2d": tot["h2d"], "d2h": tot["d2h"], "threads": len(workers), "chunks": n_chunks}
@@ -334,6 +344,10 @@ def measure(al, local, batch, fn, algo, args, steps, warmup, barrier, do_e2e=Tru
     al.trim()                          # the e2e contexts below share this GPU: hand them the memory of earlier measurements
     e2e = e2e_measure(local, batch, fn, algo, args.e2e_threads, args.e2e_chunks, max(1, min(warmup, 2)), max(1, min(steps, 3)),
                       barrier) if do_e2e else None
+    if e2e and clocks:       # headline record only: the same passes with the targets taken from a device-resident reference
+        al.trim()
+        e2e["resident_reference"] = e2e_measure(local, batch, fn, algo, args.e2e_threads, args.e2e_chunks, 1, max(1, min(steps, 3)), barrier,
+                                                resident_reference=True)
     # one ticket for the whole shard: the device-resident measurement below re-runs it; its own submit -> collect time is
     # reported as e2e.single_ticket (no copy/compute overlap; second ticket of the context, i.e. with its slabs cached)
     tk = al.submit(batch, fn, algo, band=16, doStats=True)
@@ -584,6 +598,15 @@ def run_ours(args):
     dev_ms_max = allmax(head["dev_ms"]); e2e_sec_max = allmax(head["e2e"]["sec"]); cells_all = allsum(float(cells)); jobs_all = allsum(float(head["jobs_ok"]))
     value = cells_all * args.steps / (dev_ms_max * 1e-3) / 1e9
     e2e_val = cells_all / e2e_sec_max / 1e9
+    resident_ref = None
+    if head["e2e"].get("resident_reference"):
+        rr = head["e2e"]["resident_reference"]
+        rr_sec = allmax(rr["sec"])
+        resident_ref = {"value": cells_all / rr_sec / 1e9, "unit": "GCUPS", "ms_per_step": rr_sec * 1e3, "h2d_bytes_per_step": rr["h2d"],
+                        "d2h_bytes_per_step": rr["d2h"], "jobs_ok": rr["ok"],
+                        "how": "the same passes with the targets given as 8-byte offsets into a reference resident on the device "
+                               "(bgpu_set_reference, uploaded once outside the timed region the way blasr loads its genome; here the shard's "
+                               "own target array) and gathered there: reads, guides and results still cross PCIe every step"}
     int_peak, _ = al.int_peak()
     peaks = {}
     try:
@@ -614,7 +637,8 @@ def run_ours(args):
                        "in (guides packed 3 B / block, the form the C++ adapter writes), pinned result arena out (run-length paths, "
                        "expanded by the adapter's Store), H2D + D2H inside the timed region",
                 "single_ticket": {"value": cells / ((single["submit_ms"] + single["collect_ms"]) * 1e-3) / 1e9,
-                                  "submit_ms": single["submit_ms"], "collect_ms": single["collect_ms"]}},
+                                  "submit_ms": single["submit_ms"], "collect_ms": single["collect_ms"]},
+                "resident_reference": resident_ref},
         "gpu_launches": head["launches"],
         "stage_ms": head["stage_ms"],
         "roofline": {"bound": "hbm", "kernel": "fill_guided_kernel", "achieved": cells * BYTES_PER_CELL[a] / fill_s / 1e9, "peak": hbm_peak,

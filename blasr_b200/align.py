@@ -272,10 +272,16 @@ class Aligner:
         for name in JobBatch.TRACKS:
             if getattr(batch, name, None) is not None:
                 keep[name] = np.ascontiguousarray(getattr(batch, name), np.uint8)
-        b = capi.Batch(n, _ptr(keep["q"]), _ptr(keep["qOff"]), _ptr(keep["t"]), _ptr(keep["tOff"]), _ptr(keep.get("qual")),
+        t_ref = getattr(batch, "tRefOff", None)                    # targets = windows of the reference set with set_reference()
+        if t_ref is not None:
+            keep["tRefOff"] = np.ascontiguousarray(t_ref, np.uint64)
+            if getattr(batch, "tRefRc", None) is not None:
+                keep["tRefRc"] = np.ascontiguousarray(batch.tRefRc, np.uint8)
+        b = capi.Batch(n, _ptr(keep["q"]), _ptr(keep["qOff"]), None if t_ref is not None else _ptr(keep["t"]), _ptr(keep["tOff"]), _ptr(keep.get("qual")),
                        _ptr(keep.get("guide")) if not packed else None, _ptr(keep.get("guideOff")), _ptr(keep.get("band")),
                        *[_ptr(keep.get(name)) for name in JobBatch.TRACKS],
-                       _ptr(keep.get("guidePacked")), _ptr(keep.get("guideWide")), len(keep["guideWide"]) if "guideWide" in keep else 0)
+                       _ptr(keep.get("guidePacked")), _ptr(keep.get("guideWide")), len(keep["guideWide"]) if "guideWide" in keep else 0,
+                       _ptr(keep.get("tRefOff")), _ptr(keep.get("tRefRc")))
         if statsAffine is None:
             statsAffine = algo == AFFINE_GUIDED
         p = capi.Params(algo, alignType, band, bndIns, bndDel, int(doStats), int(statsAffine), *[int(x) for x in affineKBand], int(compact))
@@ -411,6 +417,14 @@ class Aligner:
         fn = DistanceMatrixScoreFunction(np.asarray(matchMat, np.int32).copy(), fn.ins, fn.del_, fn.affineOpen, fn.affineExtend)
         return self._run(batch, fn, AFFINE_KBAND, alignType=alignType, band=k, bndDel=del_, doStats=computeStats,
                          statsAffine=False, affineKBand=(hpInsOpen, hpInsExtend, insOpen, insExtend))
+
+    def set_reference(self, bases) -> None:
+        """bgpu_set_reference: the genome later batches take their targets from (JobBatch.tRefOff / tRefRc), resident on
+        this aligner's device and shared by every context on it.  None / empty frees it."""
+        a = np.ascontiguousarray(bases if bases is not None else np.zeros(0, np.uint8), np.uint8)
+        rc = self._lib.bgpu_set_reference(self._ctx, a.ctypes.data_as(C.c_void_p) if len(a) else None, len(a))
+        if rc != 0:
+            self._err(rc, "bgpu_set_reference")
 
     def SDPAlign(self, batch: JobBatch, scoreFn, wordSize: int = 11, sdpIns: int = 5, sdpDel: int = 10, indelRate: float = 0.30,
                  alignType: int = capi.LOCAL, detailedAlignment: bool = True, extendFrontByLocalAlignment: bool = False,

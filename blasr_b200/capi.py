@@ -27,7 +27,7 @@ EXPORTS = [
     "bgpu_create", "bgpu_destroy", "bgpu_last_error", "bgpu_version", "bgpu_submit", "bgpu_submit_jobs",
     "bgpu_collect", "bgpu_release", "bgpu_rerun", "bgpu_timing_of", "bgpu_align", "bgpu_device_count",
     "bgpu_measure_int_peak", "bgpu_int_peak_modes", "bgpu_cigar", "bgpu_base_code", "bgpu_query", "bgpu_trim", "bgpu_cigar_clipped", "bgpu_strings",
-    "bgpu_sdp_align",
+    "bgpu_sdp_align", "bgpu_set_reference",
 ]
 
 
@@ -47,7 +47,8 @@ class Batch(C.Structure):
     _fields_ = [("nJobs", C.c_uint32), ("qBases", C.c_void_p), ("qOff", C.c_void_p), ("tBases", C.c_void_p),
                 ("tOff", C.c_void_p), ("qual", C.c_void_p), ("guide", C.c_void_p), ("guideOff", C.c_void_p),
                 ("band", C.c_void_p), ("insQV", C.c_void_p), ("delQV", C.c_void_p), ("subQV", C.c_void_p),
-                ("delTag", C.c_void_p), ("subTag", C.c_void_p), ("guidePacked", C.c_void_p), ("guideWide", C.c_void_p), ("nGuideWide", C.c_uint64)]
+                ("delTag", C.c_void_p), ("subTag", C.c_void_p), ("guidePacked", C.c_void_p), ("guideWide", C.c_void_p), ("nGuideWide", C.c_uint64),
+                ("tRefOff", C.c_void_p), ("tRefRc", C.c_void_p)]
 
 
 class Job(C.Structure):
@@ -131,6 +132,7 @@ def lib() -> C.CDLL:
     L.bgpu_align.argtypes = [C.c_void_p, C.POINTER(ScoreFn), C.POINTER(Params), C.POINTER(Batch), C.c_void_p,
                              C.POINTER(Arena)]
     L.bgpu_sdp_align.argtypes = [C.c_void_p, C.POINTER(ScoreFn), C.POINTER(SdpParams), C.POINTER(Batch), C.c_void_p, C.POINTER(Arena)]
+    L.bgpu_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.bgpu_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.bgpu_int_peak_modes.argtypes = [C.POINTER(C.c_double * 4)]
     _lib = L

@@ -20,6 +20,7 @@
 namespace bgpu {
 int run_sdp(const bgpu_scorefn *, const int *, float, int, int, uint32_t, const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *,
             uint8_t *, size_t, unsigned, uint32_t *, bgpu_result *, bgpu_block *, const uint64_t *, cudaStream_t);
+void launch_gather_reference(uint32_t, const uint8_t *, uint64_t, const uint64_t *, const uint8_t *, const uint64_t *, uint8_t *, cudaStream_t);
 void launch_prep_guided(const BatchDev &, const ScoreParams &, int, const uint64_t *, const uint64_t *,
                         const uint64_t *, cudaStream_t);
 void launch_fill_guided(const BatchDev &, const ScoreParams &, int, const uint32_t *, const PlanHead *, uint32_t, uint32_t *, int,
@@ -291,6 +292,26 @@ static int upload(bgpu_ctx *ctx, bgpu_ticket t, void *dst, const void *src, size
   }
   CK(cudaMemcpyAsync(dst, from, bytes, cudaMemcpyHostToDevice, ctx->stream));
   t->timing.h2dBytes += bytes;
+  return BGPU_OK;
+}
+
+// the reference (genome) resident per device: shared by every context on it
+struct DeviceRef { uint8_t *d = nullptr; uint64_t n = 0; };
+static std::mutex g_refMu;
+static DeviceRef g_ref[64];
+
+extern "C" int bgpu_set_reference(bgpu_ctx *ctx, const uint8_t *bases, uint64_t n) {
+  if (!ctx || (n && !bases) || ctx->device >= 64) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::mutex> lr(g_refMu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  DeviceRef &r = g_ref[ctx->device];
+  CK(cudaDeviceSynchronize());                       // tickets in flight may still be gathering from the old one
+  if (r.d) { cudaFree(r.d); r.d = nullptr; r.n = 0; }
+  if (!n) return BGPU_OK;
+  CK(cudaMalloc(&r.d, n + 16));
+  CK(cudaMemcpy(r.d, bases, n, cudaMemcpyHostToDevice));
+  r.n = n;
   return BGPU_OK;
 }
 
@@ -655,7 +676,7 @@ static void gather_timing(bgpu_ticket t) {
 
 static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b, bgpu_ticket t) {
   const uint32_t n = b->nJobs;
-  if (!b->qOff || !b->tOff || !b->guideOff || (n && (!b->qBases || !b->tBases))) { ctx->err = "null batch arrays"; return BGPU_E_INVALID; }
+  if (!b->qOff || !b->tOff || !b->guideOff || (n && (!b->qBases || (!b->tBases && !b->tRefOff)))) { ctx->err = "null batch arrays"; return BGPU_E_INVALID; }
   if (fn->kind == BGPU_FN_QUALITY && !b->qual) { ctx->err = "BGPU_FN_QUALITY needs batch.qual"; return BGPU_E_INVALID; }
   RC(check_ids_tracks(ctx, fn, p, b));
   const uint64_t totQ = b->qOff[n], totT = b->tOff[n], totG = b->guideOff[n];
@@ -681,11 +702,22 @@ static int submit_guided(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_param
   d_tc += BYTE_PAD; d_qc += BYTE_PAD;
   // the phase gates keep LARGE tickets of concurrent contexts pipelined (copy in / compute / copy out); small tickets
   // (the candidates of a few reads) would only pay their host round trips
-  t->gated = totQ + totT + (b->guidePacked ? 3 : sizeof(bgpu_block)) * totG > (32u << 20);
+  t->gated = totQ + (b->tRefOff ? 0 : totT) + (b->guidePacked ? 3 : sizeof(bgpu_block)) * totG > (32u << 20);
   if (t->gated) { gate(ctx->device, GATE_H2D).acquire(); t->holdsH2D = true; }   // until the uploads below are done
-  RC(upload(ctx, t, d_q, b->qBases, totQ)); RC(upload(ctx, t, d_t, b->tBases, totT));
+  RC(upload(ctx, t, d_q, b->qBases, totQ));
   RC(upload(ctx, t, d_qOff, b->qOff, sizeof(uint64_t) * (n + 1)));
   RC(upload(ctx, t, d_tOff, b->tOff, sizeof(uint64_t) * (n + 1)));
+  if (b->tRefOff) {           // targets are windows of the reference resident on this device: 8 bytes per job over PCIe
+    const uint8_t *refD; uint64_t refN;
+    { std::lock_guard<std::mutex> lr(g_refMu); refD = ctx->device < 64 ? g_ref[ctx->device].d : nullptr; refN = ctx->device < 64 ? g_ref[ctx->device].n : 0; }
+    if (!refD) { ctx->err = "batch.tRefOff without bgpu_set_reference on this device"; return BGPU_E_INVALID; }
+    uint64_t *d_refOff = nullptr; uint8_t *d_rc = nullptr;
+    RC(talloc_dev(ctx, t, &d_refOff, std::max<uint32_t>(n, 1))); RC(upload(ctx, t, d_refOff, b->tRefOff, sizeof(uint64_t) * n));
+    if (b->tRefRc) { RC(talloc_dev(ctx, t, &d_rc, (size_t)n + 16)); RC(upload(ctx, t, d_rc, b->tRefRc, n)); }
+    launch_gather_reference(n, refD, refN, d_refOff, d_rc, d_tOff, d_t, ctx->stream);
+  } else {
+    RC(upload(ctx, t, d_t, b->tBases, totT));
+  }
   RC(upload(ctx, t, d_gOff, b->guideOff, sizeof(uint64_t) * (n + 1)));
   if (b->guidePacked) {       // three bytes per block over PCIe, expanded into Block form on the device
     uint8_t *d_packed = nullptr; uint32_t *d_wide = nullptr;

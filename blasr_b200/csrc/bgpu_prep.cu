@@ -309,6 +309,33 @@ __global__ void __launch_bounds__(128) unpack_guide_kernel(uint32_t nJobs, const
   }
 }
 
+// Targets as windows of the reference resident on the device (bgpu_batch.tRefOff): one CTA per job copies its window into
+// the ticket's contiguous target array, reverse-complemented on request (ReverseComplementNuc, NucConversion.h:337-352: ACGT <->
+// TGCA in either case, N kept; every other byte is kept too, where the reference's table would produce 127).
+__global__ void __launch_bounds__(256) gather_reference_kernel(uint32_t nJobs, const uint8_t *ref, uint64_t refLen, const uint64_t *refOff,
+                                                               const uint8_t *rc, const uint64_t *tOff, uint8_t *t) {
+  const uint32_t job = blockIdx.x;
+  if (job >= nJobs) return;
+  const uint64_t o = tOff[job], len = tOff[job + 1] - o, r0 = refOff[job];
+  const bool rev = rc && rc[job];
+  for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) {
+    const uint64_t src = rev ? r0 + len - 1 - i : r0 + i;
+    uint8_t c = src < refLen ? ref[src] : (uint8_t)'N';        // a window past the end of the reference reads as N
+    if (rev) {
+      switch (c) {
+        case 'A': c = 'T'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break; case 'T': c = 'A'; break;
+        case 'a': c = 't'; break; case 'c': c = 'g'; break; case 'g': c = 'c'; break; case 't': c = 'a'; break;
+        default: break;
+      }
+    }
+    t[o + i] = c;
+  }
+}
+void launch_gather_reference(uint32_t nJobs, const uint8_t *ref, uint64_t refLen, const uint64_t *refOff, const uint8_t *rc,
+                             const uint64_t *tOff, uint8_t *t, cudaStream_t s) {
+  if (nJobs) gather_reference_kernel<<<nJobs, 256, 0, s>>>(nJobs, ref, refLen, refOff, rc, tOff, t);
+}
+
 void launch_unpack_guide(uint32_t nJobs, const uint64_t *guideOff, const uint8_t *packed, const uint32_t *wide, uint64_t nWide,
                          bgpu_block *guide, cudaStream_t s) {
   const unsigned grid = (nJobs + 3) / 4;

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BGPU_VERSION 105 /* 0.1.5: + bgpu_sdp_align (0.1.4: compact results, packed guides, bgpu_cigar_clipped, bgpu_strings, bgpu_trim) */
+#define BGPU_VERSION 106 /* 0.1.6: + bgpu_set_reference / bgpu_batch.tRefOff (0.1.5: bgpu_sdp_align; 0.1.4: compact results, packed guides, ...) */
 
 /* ---- return codes (API level) ---- */
 enum {
@@ -116,6 +116,14 @@ typedef struct {
    * first block -- and length.  A block with a value >= 255 stores 255,255,255 there and its three numbers in guideWide:
    * nGuideWide entries {g, dq, dt, length} sorted by g.  (blasr_gpu::RefineBatch::Add writes this form.) */
   const uint8_t  *guidePacked; const uint32_t *guideWide; uint64_t nGuideWide;
+  /* Targets taken from the reference resident on the device (bgpu_set_reference) instead of tBases: when tRefOff != NULL,
+   * job i's target is reference[tRefOff[i] .. tRefOff[i] + (tOff[i+1] - tOff[i])), reverse-complemented when tRefRc != NULL
+   * and tRefRc[i] != 0 (the window is then read backwards from tRefOff[i] + length - 1; ACGT / acgt are complemented as
+   * ReverseComplementNuc does, NucConversion.h:337-352, N / n and every other byte are kept -- the reference's table turns
+   * the latter into 127, an invalid base); tBases is ignored (tOff still gives the lengths).  Guided aligners only.
+   * blasr's targets are windows of the genome it holds in RAM for the whole run (Blasr.cpp:850-853 copies them out per
+   * candidate): with the genome on the device only 8 bytes per job cross PCIe instead of the window. */
+  const uint64_t *tRefOff; const uint8_t *tRefRc;
 } bgpu_batch;
 
 /* One job in pointer form (what a per-candidate call site has in hand). */
@@ -173,6 +181,10 @@ int  bgpu_version(void);
 /* The base -> code table every kernel uses: ThreeBit[] of common/NucConversion.h:48-84 (0..3 ACGT, 4 = N / IUPAC,
  * 5 = '$', 255 = not a base -> BGPU_JOB_BAD_INPUT).  Host-callable so that the table can be pinned without a GPU. */
 int  bgpu_base_code(int asciiByte);
+
+/* The reference (genome) the targets of later batches may be windows of (bgpu_batch.tRefOff): copied to the device once,
+ * shared by every context on that device, replaced by the next call, freed with n == 0.  Synchronous. */
+int  bgpu_set_reference(bgpu_ctx *ctx, const uint8_t *bases, uint64_t n);
 
 /* ---- asynchronous batch API ---- */
 /* Copies the batch into pinned staging, enqueues H2D + all kernels on the ctx stream, returns at once. */

@@ -298,3 +298,36 @@ def test_one_process_drives_every_device():
     ofn = O.score_fn(fn.scoreMatrix, 5, 5, 50, 0)
     want = cases.oracle_batch(WHICH, b, ofn, 1, 1, b.band, statsAffine=1)
     assert [int(x) for x in merged["score"]] == [w["score"] for w in want]
+
+
+def test_targets_from_the_resident_reference(aligner):
+    """bgpu_set_reference + bgpu_batch.tRefOff / tRefRc: targets gathered on the device from the resident genome (forward and
+    reverse-complemented windows) give exactly the results of the same targets uploaded as bytes."""
+    rng = np.random.default_rng(31)
+    genome = cases.ACGT[rng.integers(0, 4, 24 * 4600 + 100)].copy()
+    genome[rng.random(len(genome)) < 0.002] = ord("N")
+    genome[rng.random(len(genome)) < 0.1] |= 0x20                 # soft-masked stretches
+    comp = np.arange(256, dtype=np.uint8)
+    for a, c in zip(b"ACGTacgt", b"TGCAtgca"):
+        comp[a] = c
+    b = cases.guided_batch(seed=77, n=24, lo=200, hi=3000)
+    # re-seat every target as a window of the genome: plant the job's target (or its reverse complement) there
+    assert np.diff(b.tOff.astype(np.int64)).max() < 4000
+    starts = (np.arange(b.n) * 4600 + rng.integers(0, 500, b.n)).astype(np.uint64)      # disjoint windows (targets < 4,000 b)
+    rc = (rng.random(b.n) < 0.5).astype(np.uint8)
+    for i in range(b.n):
+        t = b.t[int(b.tOff[i]):int(b.tOff[i + 1])]
+        genome[int(starts[i]):int(starts[i]) + len(t)] = comp[t][::-1] if rc[i] else t
+    fn = DistanceMatrixScoreFunction(ins=5, del_=5, affineOpen=50, affineExtend=0)
+    want = aligner.AffineGuidedAlign(b, fn, 16)
+    aligner.set_reference(genome)
+    try:
+        b.tRefOff = starts; b.tRefRc = rc
+        got = aligner.AffineGuidedAlign(b, fn, 16)
+    finally:
+        b.tRefOff = None
+        aligner.set_reference(None)
+    for i in range(b.n):
+        bad = cases.compare(cases.gpu_to_dict(got, i), cases.gpu_to_dict(want, i), cases.GPU_FIELDS)
+        assert not bad, (i, int(rc[i]), bad)
+    assert (got.results["status"] == 0).all() and rc.sum() > 3 and (1 - rc).sum() > 3
