@@ -493,5 +493,55 @@ class DenseBatch {
   int algo_ = BGPU_KBAND;
 };
 
+// SDPAlign (common/algorithms/alignment/SDPAlign.h:95-107) for the (query, target) pairs of a read's intervals: the call of
+// Blasr.cpp:1716-1722 (Local) / :1080-1090 (Global).  Add() the pairs, Run() with the reference's own parameter list, Store(i,
+// alignment) writes alignment.qPos / tPos / blocks exactly as SDPAlign leaves them (gaps stay empty, as there).
+class SdpBatch {
+ public:
+  void Add(const uint8_t *q, uint32_t qLen, const uint8_t *t, uint32_t tLen) {
+    q_.insert(q_.end(), q, q + qLen); t_.insert(t_.end(), t, t + tLen);
+    qOff_.push_back(q_.size()); tOff_.push_back(t_.size());
+  }
+  uint32_t size() const { return (uint32_t)qOff_.size() - 1; }
+  // the parameters in SDPAlign's own order: scoreFn, wordSize, sdpIns, sdpDel, indelRate, alignType, detailedAlignment,
+  // extendFrontByLocalAlignment, sdpPrefixLength, recurse, noRecurseUnder, maxMatchesPerPosition
+  template <typename T_ScoreFn>
+  void Run(Context &ctx, const T_ScoreFn &fn, int wordSize, int sdpIns, int sdpDel, float indelRate, int alignType = BGPU_GLOBAL,
+           bool detailedAlignment = true, bool extendFrontByLocalAlignment = true, int sdpPrefixLength = 50, int recurse = 0,
+           int noRecurseUnder = 10000, int maxMatchesPerPosition = 0) {
+    const bgpu_scorefn s = MakeScoreFn(fn, BGPU_FN_DISTANCE);
+    bgpu_sdp_params p; std::memset(&p, 0, sizeof p);
+    p.wordSize = wordSize; p.sdpIns = sdpIns; p.sdpDel = sdpDel; p.indelRate = indelRate; p.alignType = alignType;
+    p.detailed = detailedAlignment; p.extendFront = extendFrontByLocalAlignment; p.sdpPrefix = sdpPrefixLength;
+    p.recurse = recurse; p.noRecurseUnder = noRecurseUnder; p.maxMatches = maxMatchesPerPosition;
+    bgpu_batch b; std::memset(&b, 0, sizeof b);
+    b.nJobs = size(); b.qBases = q_.data(); b.qOff = qOff_.data(); b.tBases = t_.data(); b.tOff = tOff_.data();
+    results_.resize(b.nJobs);
+    const int rc = bgpu_sdp_align(ctx.get(), &s, &p, &b, results_.data(), &arena_);
+    if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
+    // the arena belongs to the library until the next bgpu_sdp_align on ctx: keep the blocks
+    blocks_.assign(arena_.blocks, arena_.blocks + arena_.nBlocks);
+  }
+  template <typename T_Alignment>
+  void Store(uint32_t i, T_Alignment &out) const {
+    const bgpu_result &r = results_[i];
+    if (r.status != BGPU_JOB_OK) throw Error(r.status, "blasr_gpu: SDPAlign job rejected");
+    out.qPos = r.qPos; out.tPos = r.tPos;
+    out.blocks.resize(r.nBlocks);
+    for (uint32_t k = 0; k < r.nBlocks; k++) {
+      const bgpu_block &bk = blocks_[r.blockOff + k];
+      out.blocks[k].qPos = bk.qPos; out.blocks[k].tPos = bk.tPos; out.blocks[k].length = bk.length;
+    }
+  }
+  void Clear() { q_.clear(); t_.clear(); qOff_.assign(1, 0); tOff_.assign(1, 0); results_.clear(); blocks_.clear(); }
+
+ private:
+  std::vector<uint8_t> q_, t_;
+  std::vector<uint64_t> qOff_{0}, tOff_{0};
+  std::vector<bgpu_result> results_;
+  std::vector<bgpu_block> blocks_;
+  bgpu_arena arena_{};
+};
+
 }  // namespace blasr_gpu
 #endif

@@ -172,6 +172,47 @@ int main(int argc, char **argv) {
   }
 
   if (argc > 3 && std::string(argv[3]) == "dense") return CheckDense(pairs, fn) ? 1 : 0;   /* the guide-less call sites */
+  if (argc > 3 && std::string(argv[3]) == "sdp") {     /* the candidate-producing call itself: SDPAlign on the device */
+    int badS = 0;
+    blasr_gpu::Context ctx(0);
+    blasr_gpu::SdpBatch batch;
+    for (int i = 0; i < nJobs; i++) batch.Add((const uint8_t *)pairs[i].q.data(), pairs[i].q.size(), (const uint8_t *)pairs[i].t.data(), pairs[i].t.size());
+    /* the argument list of Blasr.cpp:1716-1722 with MappingParameters' defaults, as above */
+    batch.Run(ctx, fn, 11, 5, 10, 0.30f, Local, true, false, 50, 2, 1000, 0);
+    size_t nBlocks = 0;
+    for (int i = 0; i < nJobs; i++) {
+      T_AlignmentCandidate g;
+      batch.Store(i, g);
+      const T_AlignmentCandidate &r = cands[i];
+      bool same = g.qPos == r.qPos && g.tPos == r.tPos && g.blocks.size() == r.blocks.size();
+      for (size_t k = 0; same && k < r.blocks.size(); k++)
+        same = g.blocks[k].qPos == r.blocks[k].qPos && g.blocks[k].tPos == r.blocks[k].tPos && g.blocks[k].length == r.blocks[k].length;
+      if (!same) { printf("pair %d: device SDPAlign differs from the reference's (blocks %zu vs %zu)\n", i, g.blocks.size(), r.blocks.size()); badS++; }
+      nBlocks += r.blocks.size();
+    }
+    /* the Global pattern of AlignSubstring (Blasr.cpp:1080-1090): front / tail extension on, no recursion over 10000 cells */
+    std::vector<T_AlignmentCandidate> glob(nJobs);
+    for (int i = 0; i < nJobs; i++) {
+      FASTQSequence q; DNASequence t;
+      q.seq = (Nucleotide *)pairs[i].q.data(); q.length = pairs[i].q.size();
+      t.seq = (Nucleotide *)pairs[i].t.data(); t.length = pairs[i].t.size();
+      SDPAlign(q, t, fn, 11, 5, 10, 0.25f, glob[i], Global, true, true, 50, 2, 1000, 0);
+    }
+    batch.Run(ctx, fn, 11, 5, 10, 0.25f, Global, true, true, 50, 2, 1000, 0);
+    for (int i = 0; i < nJobs; i++) {
+      T_AlignmentCandidate g;
+      batch.Store(i, g);
+      const T_AlignmentCandidate &r = glob[i];
+      bool same = g.qPos == r.qPos && g.tPos == r.tPos && g.blocks.size() == r.blocks.size();
+      for (size_t k = 0; same && k < r.blocks.size(); k++)
+        same = g.blocks[k].qPos == r.blocks[k].qPos && g.blocks[k].tPos == r.blocks[k].tPos && g.blocks[k].length == r.blocks[k].length;
+      if (!same) { printf("pair %d: device SDPAlign (Global) differs from the reference's (blocks %zu vs %zu)\n", i, g.blocks.size(), r.blocks.size()); badS++; }
+      nBlocks += r.blocks.size();
+    }
+    printf("adapter_check: SDPAlign x%d pairs (Local and Global patterns, %zu blocks) through blasr_gpu::SdpBatch: %s\n", nJobs, nBlocks,
+           badS ? "MISMATCH" : "identical to the reference call site");
+    return badS ? 1 : 0;
+  }
 
   int bad = 0;
   size_t printedBytes = 0;

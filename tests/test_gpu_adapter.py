@@ -33,6 +33,16 @@ def test_dense_adapter_matches_reference_call_sites():
 
 
 @needs_bin
+@pytest.mark.gpu
+def test_sdp_adapter_matches_reference_call_site():
+    """SDPAlign through blasr_gpu::SdpBatch into the reference's real T_AlignmentCandidate, against the reference's own
+    SDPAlign called with blasr's argument lists (Blasr.cpp:1716-1722 Local, :1080-1090 Global)."""
+    r = subprocess.run([BIN, "48", "6000", "sdp"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "through blasr_gpu::SdpBatch: identical to the reference call site" in r.stdout, r.stdout
+
+
+@needs_bin
 def test_adapter_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
