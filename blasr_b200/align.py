@@ -426,6 +426,55 @@ class Aligner:
         if rc != 0:
             self._err(rc, "bgpu_set_reference")
 
+    def set_suffix_array(self, index, startPosTable=None, endPosTable=None, lookupPrefixLength: int = 0) -> None:
+        """bgpu_set_suffix_array: the members of the reference's SuffixArray the anchoring reads (index, startPosTable,
+        endPosTable, lookupPrefixLength), resident on this aligner's device next to the genome of set_reference()."""
+        ix = np.ascontiguousarray(index if index is not None else np.zeros(0, np.uint32), np.uint32)
+        st = None if startPosTable is None else np.ascontiguousarray(startPosTable, np.uint32)
+        en = None if endPosTable is None else np.ascontiguousarray(endPosTable, np.uint32)
+        rc = self._lib.bgpu_set_suffix_array(self._ctx, _ptr(ix) if len(ix) else None, len(ix), _ptr(st), _ptr(en), lookupPrefixLength)
+        if rc != 0:
+            self._err(rc, "bgpu_set_suffix_array")
+
+    def MapReadToGenome(self, reads, readOff, minPrefixMatchLength: int = 8, minMatchLength: int = 12, expand: int = 0,
+                        useLookupTable: bool = True, maxAnchorsPerPosition: int = 1000, advanceExactMatches: int = 0,
+                        maxLCPLength: int = 0, stopMappingOnceUnique: bool = True, removeEncompassedMatches: bool = False,
+                        subreadStart=None, subreadEnd=None):
+        """MapReadToGenome (MapBySuffixArray.h:209-309) for every read of the batch, blasr's defaults (MappingParameters.h):
+        returns (matchOff[n + 1], matches) with matches a MATCH_DTYPE array (t, q, l), read i owning
+        matches[matchOff[i]:matchOff[i + 1]] in the reference's matchPosList order.  Pass reverse complements as reads."""
+        reads = np.ascontiguousarray(reads, np.uint8)
+        readOff = np.ascontiguousarray(readOff, np.uint64)
+        n = len(readOff) - 1
+        ss = None if subreadStart is None else np.ascontiguousarray(subreadStart, np.uint32)
+        se = None if subreadEnd is None else np.ascontiguousarray(subreadEnd, np.uint32)
+        p = capi.AnchorParams(minPrefixMatchLength, minMatchLength, expand, int(useLookupTable), maxAnchorsPerPosition, advanceExactMatches,
+                              maxLCPLength, int(stopMappingOnceUnique), int(removeEncompassedMatches))
+        off = np.zeros(n + 1, np.uint64)
+        out = C.c_void_p()
+        rc = self._lib.bgpu_map_reads(self._ctx, C.byref(p), _ptr(reads), _ptr(readOff), n, _ptr(ss), _ptr(se), _ptr(off), C.byref(out))
+        if rc != 0:
+            self._err(rc, "bgpu_map_reads")
+        total = int(off[-1])
+        if total == 0:
+            return off, np.zeros(0, capi.MATCH_DTYPE)
+        buf = (C.c_uint8 * (12 * total)).from_address(out.value)
+        return off, np.frombuffer(buf, dtype=capi.MATCH_DTYPE).copy()
+
+    def map_timing(self):
+        """(ms of the search kernel, ms of count + scan + emit, positions searched, H2D bytes, D2H bytes) of the last MapReadToGenome."""
+        ms = (C.c_double * 2)()
+        pos, h, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        rc = self._lib.bgpu_map_timing(self._ctx, C.byref(ms), C.byref(pos), C.byref(h), C.byref(d))
+        if rc != 0:
+            self._err(rc, "bgpu_map_timing")
+        return ms[0], ms[1], pos.value, h.value, d.value
+
+    def map_rerun(self):
+        rc = self._lib.bgpu_map_rerun(self._ctx)
+        if rc != 0:
+            self._err(rc, "bgpu_map_rerun")
+
     def SDPAlign(self, batch: JobBatch, scoreFn, wordSize: int = 11, sdpIns: int = 5, sdpDel: int = 10, indelRate: float = 0.30,
                  alignType: int = capi.LOCAL, detailedAlignment: bool = True, extendFrontByLocalAlignment: bool = False,
                  sdpPrefixLength: int = 50, recurse: int = 2, noRecurseUnder: int = 1000, maxMatchesPerPosition: int = 0):

@@ -27,7 +27,7 @@ EXPORTS = [
     "bgpu_create", "bgpu_destroy", "bgpu_last_error", "bgpu_version", "bgpu_submit", "bgpu_submit_jobs",
     "bgpu_collect", "bgpu_release", "bgpu_rerun", "bgpu_timing_of", "bgpu_align", "bgpu_device_count",
     "bgpu_measure_int_peak", "bgpu_int_peak_modes", "bgpu_cigar", "bgpu_base_code", "bgpu_query", "bgpu_trim", "bgpu_cigar_clipped", "bgpu_strings",
-    "bgpu_sdp_align", "bgpu_set_reference",
+    "bgpu_sdp_align", "bgpu_set_reference", "bgpu_set_suffix_array", "bgpu_map_reads", "bgpu_map_timing", "bgpu_map_rerun",
 ]
 
 
@@ -67,6 +67,15 @@ class SdpParams(C.Structure):   # bgpu_sdp_params: SDPAlign's parameter list (SD
     _fields_ = [("wordSize", C.c_int32), ("sdpIns", C.c_int32), ("sdpDel", C.c_int32), ("indelRate", C.c_float),
                 ("alignType", C.c_int32), ("detailed", C.c_int32), ("extendFront", C.c_int32), ("sdpPrefix", C.c_int32),
                 ("recurse", C.c_int32), ("noRecurseUnder", C.c_int32), ("maxMatches", C.c_int32)]
+
+
+class AnchorParams(C.Structure):   # bgpu_anchor_params: MapReadToGenome's scalar arguments (AnchorParameters.h:10-27)
+    _fields_ = [("minPrefixMatchLength", C.c_uint32), ("minMatchLength", C.c_uint32), ("expand", C.c_int32), ("useLookupTable", C.c_int32),
+                ("maxAnchorsPerPosition", C.c_int32), ("advanceExactMatches", C.c_int32), ("maxLCPLength", C.c_int32),
+                ("stopMappingOnceUnique", C.c_int32), ("removeEncompassedMatches", C.c_int32)]
+
+
+MATCH_DTYPE = np.dtype([("t", "<u4"), ("q", "<u4"), ("l", "<u4")])
 
 
 class Timing(C.Structure):
@@ -133,6 +142,11 @@ def lib() -> C.CDLL:
                              C.POINTER(Arena)]
     L.bgpu_sdp_align.argtypes = [C.c_void_p, C.POINTER(ScoreFn), C.POINTER(SdpParams), C.POINTER(Batch), C.c_void_p, C.POINTER(Arena)]
     L.bgpu_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.bgpu_set_suffix_array.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.bgpu_map_reads.argtypes = [C.c_void_p, C.POINTER(AnchorParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_void_p)]
+    L.bgpu_map_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double * 2), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.bgpu_map_rerun.argtypes = [C.c_void_p]
     L.bgpu_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.bgpu_int_peak_modes.argtypes = [C.POINTER(C.c_double * 4)]
     _lib = L

@@ -42,6 +42,13 @@ void launch_fmt_cigar(const BatchDev &, const uint64_t *, const uint64_t *, uint
                       const uint8_t *, cudaStream_t);
 void launch_fmt_strings(const BatchDev &, const uint64_t *, char *, char *, char *, cudaStream_t);
 double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz);
+struct AnchorState;
+int anchor_set_index(int, const uint32_t *, uint64_t, const uint32_t *, const uint32_t *, uint32_t, std::string &);
+int anchor_map(int, const uint8_t *, uint64_t, cudaStream_t, AnchorState **, const bgpu_anchor_params *, const uint8_t *, const uint64_t *, uint32_t,
+               const uint32_t *, const uint32_t *, uint64_t *, const bgpu_match **, std::string &);
+int anchor_rerun(AnchorState *, cudaStream_t, std::string &);
+int anchor_timing(const AnchorState *, double *, uint64_t *, uint64_t *, uint64_t *);
+void anchor_free_state(AnchorState *);
 extern double g_peakByMode[4];
 }  // namespace bgpu
 
@@ -111,6 +118,7 @@ struct bgpu_ctx {
   bgpu_ticket lastSync = nullptr;                // ticket owned by bgpu_align
   void *sdpPinned = nullptr; size_t sdpPinnedBytes = 0;   // result arena of the last bgpu_sdp_align
   bool sdpStackSet = false;
+  bgpu::AnchorState *anchor = nullptr;                    // buffers of the last bgpu_map_reads (bgpu_anchor.cu)
 };
 
 #define CK(call)                                                                                  \
@@ -374,6 +382,7 @@ extern "C" void bgpu_destroy(bgpu_ctx *ctx) {
   for (int c = 0; c < N_CLS; c++) { cudaStreamDestroy(ctx->aux[c]); cudaEventDestroy(ctx->evJoin[c]); }
   cudaEventDestroy(ctx->evFork); cudaEventDestroy(ctx->evSync);
   if (ctx->sdpPinned) cudaFreeHost(ctx->sdpPinned);
+  anchor_free_state(ctx->anchor);
   cudaStreamDestroy(ctx->copyStream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1288,6 +1297,39 @@ extern "C" int bgpu_sdp_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_
   freeAll();
   arena->blocks = (const bgpu_block *)ctx->sdpPinned; arena->nBlocks = blockOff[n];
   return BGPU_OK;
+}
+
+// ---- suffix-array anchoring: kernels and buffers in bgpu_anchor.cu ----
+extern "C" int bgpu_set_suffix_array(bgpu_ctx *ctx, const uint32_t *index, uint64_t n, const uint32_t *startPosTable,
+                                     const uint32_t *endPosTable, uint32_t lookupPrefixLength) {
+  if (!ctx) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::mutex> lr(g_refMu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  return anchor_set_index(ctx->device, index, n, startPosTable, endPosTable, lookupPrefixLength, ctx->err);
+}
+
+extern "C" int bgpu_map_reads(bgpu_ctx *ctx, const bgpu_anchor_params *p, const uint8_t *reads, const uint64_t *readOff, uint32_t nReads,
+                              const uint32_t *subreadStart, const uint32_t *subreadEnd, uint64_t *matchOff, const bgpu_match **matches) {
+  if (!ctx || !p || !matchOff || !matches || (nReads && (!reads || !readOff))) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  const uint8_t *refD; uint64_t refN;
+  { std::lock_guard<std::mutex> lr(g_refMu); refD = ctx->device < 64 ? g_ref[ctx->device].d : nullptr; refN = ctx->device < 64 ? g_ref[ctx->device].n : 0; }
+  return anchor_map(ctx->device, refD, refN, ctx->stream, &ctx->anchor, p, reads, readOff, nReads, subreadStart, subreadEnd, matchOff, matches, ctx->err);
+}
+
+extern "C" int bgpu_map_rerun(bgpu_ctx *ctx) {
+  if (!ctx) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  return anchor_rerun(ctx->anchor, ctx->stream, ctx->err);
+}
+
+extern "C" int bgpu_map_timing(bgpu_ctx *ctx, double ms[2], uint64_t *positions, uint64_t *h2dBytes, uint64_t *d2hBytes) {
+  if (!ctx) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return anchor_timing(ctx->anchor, ms, positions, h2dBytes, d2hBytes);
 }
 
 extern "C" int bgpu_measure_int_peak(bgpu_ctx *ctx, double *opsPerSec, double *smClockMHz) {

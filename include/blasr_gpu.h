@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BGPU_VERSION 106 /* 0.1.6: + bgpu_set_reference / bgpu_batch.tRefOff (0.1.5: bgpu_sdp_align; 0.1.4: compact results, packed guides, ...) */
+#define BGPU_VERSION 107 /* 0.1.7: + bgpu_set_suffix_array / bgpu_map_reads (0.1.6: bgpu_set_reference / bgpu_batch.tRefOff; 0.1.5: bgpu_sdp_align; 0.1.4: compact results, packed guides, ...) */
 
 /* ---- return codes (API level) ---- */
 enum {
@@ -246,6 +246,43 @@ typedef struct {
 } bgpu_sdp_params;
 int  bgpu_sdp_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_sdp_params *p, const bgpu_batch *b,
                     bgpu_result *results, bgpu_arena *arena);
+
+/* ---- Suffix-array anchoring: MapReadToGenome (common/algorithms/anchoring/MapBySuffixArray.h:209-309, called
+ * for the read and its reverse complement at alignment/Blasr.cpp:2282-2296) with LocateAnchorBoundsInSuffixArray (:24-207) and
+ * SuffixArray::StoreLCPBounds / SearchLeftBound / SearchRightBound (common/datastructures/suffixarray/SuffixArray.h:928-1067,
+ * 736-822) on the device, over an index that stays resident in HBM (4 B per base: 12.4 GB for a human genome).
+ *
+ * bgpu_set_suffix_array copies the members of the reference's SuffixArray object the search reads -- index[n], and
+ * startPosTable / endPosTable[4^lookupPrefixLength] with lookupPrefixLength (NULL / 0: no table, like a SuffixArray whose
+ * startPosTable is NULL) -- to the device of ctx; the genome is the one bgpu_set_reference gave (same n; set it first).
+ * Shared by every context on that device, replaced by the next call, freed with n == 0.  Synchronous. */
+int  bgpu_set_suffix_array(bgpu_ctx *ctx, const uint32_t *index, uint64_t n, const uint32_t *startPosTable,
+                           const uint32_t *endPosTable, uint32_t lookupPrefixLength);
+typedef struct {                      /* MapReadToGenome's scalar arguments; AnchorParameters.h:10-27 member names */
+  uint32_t minPrefixMatchLength;      /* 4th argument; blasr passes params.lookupTableLength (8) */
+  uint32_t minMatchLength;            /* anchorParameters.minMatchLength (12) */
+  int32_t  expand;                    /* 0 .. 14 */
+  int32_t  useLookupTable;            /* 1 */
+  int32_t  maxAnchorsPerPosition;     /* 1000 */
+  int32_t  advanceExactMatches;       /* 0 */
+  int32_t  maxLCPLength;              /* 0 = no limit */
+  int32_t  stopMappingOnceUnique;     /* 1 (MappingParameters.h:309) */
+  int32_t  removeEncompassedMatches;  /* must be 0: the reference reads its vectors out of bounds there (:247-251) */
+} bgpu_anchor_params;
+typedef struct { uint32_t t, q, l; } bgpu_match;   /* MatchPos::t, q, l (datastructures/anchoring/MatchPos.h:10-21) */
+/* Read i = reads[readOff[i] .. readOff[i + 1]) (ASCII as DNASequence::seq; pass the reverse complement as a read of its own,
+ * as blasr does); subreadStart / subreadEnd per read, or NULL = whole reads.  matchOff[nReads + 1] (caller's) receives the
+ * CSR offsets; *matches = every read's matchPosList in the reference's order (position ascending, then suffix-array order),
+ * pinned memory owned by the library until the next bgpu_map_reads on ctx or bgpu_destroy.  Synchronous.  Bytes of the genome
+ * at and beyond n read as 'N'.  BGPU_E_INVALID where the reference itself asserts or reads out of bounds (lookupPrefixLength >
+ * minPrefixMatchLength with the table in use; minPrefixMatchLength > max(minMatchLength, lookupPrefixLength) + 2, :279). */
+int  bgpu_map_reads(bgpu_ctx *ctx, const bgpu_anchor_params *p, const uint8_t *reads, const uint64_t *readOff, uint32_t nReads,
+                    const uint32_t *subreadStart, const uint32_t *subreadEnd, uint64_t *matchOff, const bgpu_match **matches);
+/* Device time of the kernels of the last bgpu_map_reads on ctx (CUDA events), ms: [0] locate, [1] count + scan + emit;
+ * positions searched and H2D / D2H bytes. */
+int  bgpu_map_timing(bgpu_ctx *ctx, double ms[2], uint64_t *positions, uint64_t *h2dBytes, uint64_t *d2hBytes);
+/* Re-executes the kernels of the last bgpu_map_reads on its device-resident reads (benchmarking); synchronous. */
+int  bgpu_map_rerun(bgpu_ctx *ctx);
 
 /* ---- synchronous one-shot: submit + collect; arena valid until the next call on ctx ---- */
 int  bgpu_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params *p, const bgpu_batch *b,

@@ -20,7 +20,7 @@ def test_abi_exports_match_header():
     lib = capi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bgpu_version() == 106
+    assert lib.bgpu_version() == 107
 
 
 def test_struct_layouts_match_header(tmp_path):
