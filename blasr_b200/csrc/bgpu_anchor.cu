@@ -296,6 +296,46 @@ int anchor_set_index(int device, const uint32_t *index, uint64_t n, const uint32
   return BGPU_OK;
 }
 
+// SuffixArray::BuildLookupTable (SuffixArray.h:193-250), what blasr runs when the .sa file carries no table (Blasr.cpp:4419)
+// and sawriter before it writes one (SAWriter.cpp:225): for every lookupPrefixLength-mer the run of suffix-array entries that
+// start with it.  Host code, one sequential pass in suffix-array order, with the reference's own edge behaviour: the last
+// prefixLength - 1 ENTRIES of the array are never looked at, a suffix whose k-mer ends exactly at the end of the text closes the
+// current run, and a k-mer that cannot be coded (N, or the text ending inside it: bytes at and beyond n read as 'N') leaves
+// the start of the tuple seen before it rewritten.  tests/test_anchor_oracle.py pins it against the reference's own tables.
+int build_lookup_table(const uint8_t *g, uint64_t n, const uint32_t *index, uint32_t L, uint32_t *startT, uint32_t *endT) {
+  if (!g || !index || !startT || !endT || L < 1 || L > 14 || n >= 0xFFFFFFFFull) return BGPU_E_INVALID;
+  const uint64_t tableLen = (uint64_t)1 << (2 * L);
+  for (uint64_t i = 0; i < tableLen; i++) startT[i] = endT[i] = 0;
+  if (n < L) return BGPU_OK;
+  auto tupleAt = [&](uint64_t at, uint64_t &tuple) -> bool {           // DNATuple::FromStringLR, DNATuple.h:24-53
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < L; i++) {
+      const int c = at + i < n ? base_code(g[at + i]) : 4;
+      if (c > 3) return false;
+      v = (v << 2) + (uint64_t)c;
+    }
+    tuple = v;
+    return true;
+  };
+  const uint64_t lim = n - L + 1;
+  uint64_t pos = 0, cur = 0;
+  do {
+    while (pos < lim && (uint64_t)index[pos] + L > n) pos++;
+    if (pos >= lim) break;
+    while (pos < lim && !tupleAt(index[pos], cur)) ++pos;
+    startT[cur] = (uint32_t)pos;
+    pos++;
+    while (pos < lim && (uint64_t)index[pos] + L < n) {
+      uint64_t next = 0;
+      tupleAt(index[pos], next);                                        // a k-mer that cannot be coded compares as tuple 0
+      if (next != cur) break;
+      pos++;
+    }
+    endT[cur] = (uint32_t)pos;
+  } while (pos < lim && cur + 1 < tableLen);
+  return BGPU_OK;
+}
+
 void anchor_free_state(AnchorState *st) {
   if (!st) return;
   cudaFree(st->dev); cudaFree(st->dMatches); if (st->pin) cudaFreeHost(st->pin);

@@ -49,6 +49,7 @@ int anchor_map(int, const uint8_t *, uint64_t, cudaStream_t, AnchorState **, con
 int anchor_rerun(AnchorState *, cudaStream_t, std::string &);
 int anchor_timing(const AnchorState *, double *, uint64_t *, uint64_t *, uint64_t *);
 void anchor_free_state(AnchorState *);
+int build_lookup_table(const uint8_t *, uint64_t, const uint32_t *, uint32_t, uint32_t *, uint32_t *);
 extern double g_peakByMode[4];
 }  // namespace bgpu
 
@@ -1317,6 +1318,11 @@ extern "C" int bgpu_map_reads(bgpu_ctx *ctx, const bgpu_anchor_params *p, const 
   const uint8_t *refD; uint64_t refN;
   { std::lock_guard<std::mutex> lr(g_refMu); refD = ctx->device < 64 ? g_ref[ctx->device].d : nullptr; refN = ctx->device < 64 ? g_ref[ctx->device].n : 0; }
   return anchor_map(ctx->device, refD, refN, ctx->stream, &ctx->anchor, p, reads, readOff, nReads, subreadStart, subreadEnd, matchOff, matches, ctx->err);
+}
+
+extern "C" int bgpu_build_lookup_table(const uint8_t *genome, uint64_t n, const uint32_t *index, uint32_t lookupPrefixLength,
+                                       uint32_t *startPosTable, uint32_t *endPosTable) {
+  return build_lookup_table(genome, n, index, lookupPrefixLength, startPosTable, endPosTable);
 }
 
 extern "C" int bgpu_map_rerun(bgpu_ctx *ctx) {

@@ -127,3 +127,62 @@ def _simulate_chunk(rng, lens, err, split, with_qual, anchor, min_block, n_rate)
 def batch_cells_estimate(batch: JobBatch, band: int) -> int:
     """Rough nCells (rows x (2*band+1)), for sizing only; the exact count comes back from the library."""
     return int((batch.qOff[-1] - batch.qOff[0])) * (2 * band + 1)
+
+
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTacgt", b"TGCAtgca"):
+    _COMP[_a] = _b
+
+
+def simulate_genome(n: int, seed: int = 1, repeat_families: int = 8, unit_lo: int = 3000, unit_hi: int = 6000, copies: int = 3,
+                    divergence: float = 0.03) -> np.ndarray:
+    """Uniform ACGT with embedded repeat families (units copied `copies` times at `divergence`, SURVEY 8d C3 in miniature: a
+    uniform-random genome gives every k-mer one candidate) and the trailing 'N' blasr's FASTA reader appends (FASTAReader.h:130)."""
+    rng = np.random.default_rng(seed)
+    g = _ACGT[rng.integers(0, 4, n, dtype=np.uint8)]
+    for _ in range(repeat_families):
+        ln = int(rng.integers(unit_lo, unit_hi + 1))
+        if 2 * ln >= n:
+            continue
+        unit = g[int(rng.integers(0, n - ln)):][:ln].copy()
+        for _ in range(copies):
+            u = unit.copy()
+            mut = rng.random(ln) < divergence
+            u[mut] = _ACGT[rng.integers(0, 4, int(mut.sum()), dtype=np.uint8)]
+            at = int(rng.integers(0, n - ln))
+            g[at:at + ln] = u
+    g[-1] = ord("N")
+    return g
+
+
+def simulate_reads(genome: np.ndarray, n_reads: int, length: int, err: float = 0.15, split=(0.55, 0.35, 0.10), seed: int = 1,
+                   both_strands: bool = True):
+    """Reads drawn from the genome with PacBio-like errors, odd reads reverse-complemented: (bases, readOff).
+    With both_strands every read is followed by its reverse complement, the two MapReadToGenome calls of Blasr.cpp:2282-2296."""
+    rng = np.random.default_rng(seed)
+    n = len(genome)
+    length = min(length, n - 1)
+    starts = rng.integers(0, n - length, n_reads)
+    base = genome[(starts[:, None] + np.arange(length)[None, :]).ravel()]
+    T = len(base)
+    r = rng.random(T)
+    is_sub = r < err * split[2]
+    is_del = (r >= err * split[2]) & (r < err * (split[2] + split[1]))
+    is_ins = rng.random(T) < err * split[0]
+    qb = np.where(is_sub, _ACGT[rng.integers(0, 4, T, dtype=np.uint8)], base)
+    vals = np.empty(2 * T, np.uint8); vals[0::2] = _ACGT[rng.integers(0, 4, T, dtype=np.uint8)]; vals[1::2] = qb
+    mask = np.empty(2 * T, bool); mask[0::2] = is_ins; mask[1::2] = ~is_del
+    q = vals[mask]
+    per = (is_ins.astype(np.int64) + (~is_del).astype(np.int64)).reshape(n_reads, length).sum(axis=1)
+    off = np.zeros(n_reads + 1, np.int64); off[1:] = np.cumsum(per)
+    reads = []
+    for i in range(n_reads):
+        rd = q[off[i]:off[i + 1]]
+        if i & 1:
+            rd = _COMP[rd[::-1]]
+        reads.append(rd)
+        if both_strands:
+            reads.append(_COMP[rd[::-1]])
+    ro = np.zeros(len(reads) + 1, np.uint64)
+    ro[1:] = np.cumsum([len(x) for x in reads])
+    return np.concatenate(reads), ro

@@ -258,6 +258,11 @@ int  bgpu_sdp_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_sdp_params
  * Shared by every context on that device, replaced by the next call, freed with n == 0.  Synchronous. */
 int  bgpu_set_suffix_array(bgpu_ctx *ctx, const uint32_t *index, uint64_t n, const uint32_t *startPosTable,
                            const uint32_t *endPosTable, uint32_t lookupPrefixLength);
+/* SuffixArray::BuildLookupTable (SuffixArray.h:193-250; blasr builds the table at start-up when the .sa file has none,
+ * alignment/Blasr.cpp:4415-4419): startPosTable / endPosTable[4^lookupPrefixLength] from the genome and its suffix array, with
+ * the reference's own edge behaviour (see bgpu_anchor.cu).  Index preparation, host code: needs no device. */
+int  bgpu_build_lookup_table(const uint8_t *genome, uint64_t n, const uint32_t *index, uint32_t lookupPrefixLength,
+                             uint32_t *startPosTable, uint32_t *endPosTable);
 typedef struct {                      /* MapReadToGenome's scalar arguments; AnchorParameters.h:10-27 member names */
   uint32_t minPrefixMatchLength;      /* 4th argument; blasr passes params.lookupTableLength (8) */
   uint32_t minMatchLength;            /* anchorParameters.minMatchLength (12) */

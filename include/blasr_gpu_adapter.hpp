@@ -543,5 +543,53 @@ class SdpBatch {
   bgpu_arena arena_{};
 };
 
+// MapReadToGenome (common/algorithms/anchoring/MapBySuffixArray.h:209-309) for the reads a MapReads instance holds: the two
+// calls of alignment/Blasr.cpp:2282-2296 (read and readRC) become two Add()s, Run() takes the reference's AnchorParameters
+// object as it is, Store(i, matchPosList) fills the vector the call would have filled (ChainedMatchPos or MatchPos: anything
+// constructible from (t, q, l)).  The index is loaded once per device with LoadIndex() from the reference's own
+// DNASuffixArray / DNASequence objects (what Blasr.cpp:4425-4470 reads from the .sa file).
+class AnchorBatch {
+ public:
+  template <typename T_SuffixArray, typename T_RefSequence>
+  static void LoadIndex(Context &ctx, const T_SuffixArray &sa, const T_RefSequence &genome) {
+    int rc = bgpu_set_reference(ctx.get(), (const uint8_t *)genome.seq, genome.length);
+    if (rc == BGPU_OK)
+      rc = bgpu_set_suffix_array(ctx.get(), sa.index, genome.length, sa.startPosTable, sa.endPosTable, sa.startPosTable ? sa.lookupPrefixLength : 0);
+    if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
+  }
+  template <typename T_Sequence>
+  void Add(const T_Sequence &read) {              // SMRTSequence: seq, length, subreadStart, subreadEnd
+    bases_.insert(bases_.end(), (const uint8_t *)read.seq, (const uint8_t *)read.seq + read.length);
+    off_.push_back(bases_.size()); subS_.push_back(read.subreadStart); subE_.push_back(read.subreadEnd);
+  }
+  uint32_t size() const { return (uint32_t)off_.size() - 1; }
+  template <typename T_AnchorParameters>
+  void Run(Context &ctx, unsigned int minPrefixMatchLength, const T_AnchorParameters &ap) {
+    bgpu_anchor_params p; std::memset(&p, 0, sizeof p);
+    p.minPrefixMatchLength = minPrefixMatchLength; p.minMatchLength = ap.minMatchLength; p.expand = ap.expand;
+    p.useLookupTable = ap.useLookupTable; p.maxAnchorsPerPosition = ap.maxAnchorsPerPosition;
+    p.advanceExactMatches = ap.advanceExactMatches; p.maxLCPLength = ap.maxLCPLength;
+    p.stopMappingOnceUnique = ap.stopMappingOnceUnique; p.removeEncompassedMatches = ap.removeEncompassedMatches;
+    matchOff_.assign(off_.size(), 0);
+    const bgpu_match *m = nullptr;
+    const int rc = bgpu_map_reads(ctx.get(), &p, bases_.data(), off_.data(), size(), subS_.data(), subE_.data(), matchOff_.data(), &m);
+    if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
+    matches_.assign(m, m + matchOff_.back());      // the library's buffer lives until the next bgpu_map_reads on ctx
+  }
+  // the return value of MapReadToGenome: matchPosList.size()
+  template <typename T_MatchPos>
+  int Store(uint32_t i, std::vector<T_MatchPos> &matchPosList) const {
+    for (uint64_t k = matchOff_[i]; k < matchOff_[i + 1]; k++) matchPosList.push_back(T_MatchPos(matches_[k].t, matches_[k].q, matches_[k].l));
+    return (int)matchPosList.size();
+  }
+  void Clear() { bases_.clear(); off_.assign(1, 0); subS_.clear(); subE_.clear(); matchOff_.clear(); matches_.clear(); }
+
+ private:
+  std::vector<uint8_t> bases_;
+  std::vector<uint64_t> off_{0}, matchOff_;
+  std::vector<uint32_t> subS_, subE_;
+  std::vector<bgpu_match> matches_;
+};
+
 }  // namespace blasr_gpu
 #endif

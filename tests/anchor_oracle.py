@@ -66,11 +66,13 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+PAD = 16   # BuildLookupTable reads up to lookupPrefixLength - 1 bytes past the text for the shortest suffixes (SuffixArray.h:227-228)
+
+
 def padded(genome: np.ndarray) -> np.ndarray:
     """The genome with one readable byte behind it (the convention of bgpu_map_reads / orc_anchor.c)."""
-    g = np.empty(len(genome) + 1, dtype=np.uint8)
-    g[:-1] = genome
-    g[-1] = ord("N")
+    g = np.full(len(genome) + PAD, ord("N"), dtype=np.uint8)
+    g[:len(genome)] = genome
     return g
 
 
@@ -91,7 +93,7 @@ class Index:
 
     @property
     def genome(self):
-        return self.gpad[:-1]
+        return self.gpad[:self.n]
 
 
 def map_read(which: str, ix, read: np.ndarray, prm: np.ndarray, subStart: int = 0, subEnd: int | None = None) -> np.ndarray:

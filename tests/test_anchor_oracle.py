@@ -97,3 +97,24 @@ def test_bulk_entry_matches_single_calls():
     mo, m = ao.map_reads_ref(ix, flat, off, ao.params(), nThreads=3)
     for i, r in enumerate(reads):
         assert np.array_equal(m[int(mo[i]):int(mo[i + 1])], ao.map_read("orc", ix, r, ao.params())), i
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_index_preparation_matches_sawriter(seed):
+    """blasr_b200/saindex.py (suffix array) and bgpu_build_lookup_table (SuffixArray::BuildLookupTable) against the
+    reference's own construction: Larsson-Sadakane on the ThreeBit text, then BuildLookupTable."""
+    from blasr_b200 import saindex
+    rng = np.random.default_rng(900 + seed)
+    n = [5000, 70000, 300, 12, 20000][seed]
+    g = ao.make_genome(rng, n, lower=(seed == 1), nRuns=[2, 5, 1, 0, 0][seed])
+    if seed in (0, 1):
+        g[-1] = ord("N")                               # blasr's genomes end with the separator FASTAReader.h:130 appends
+    if seed == 4:
+        g[-9:] = np.frombuffer(b"TTTTTTTTT", np.uint8)  # the text ends in the last tuple of the table
+    sa = saindex.suffix_array(g)
+    ix = ao.Index(g, table=False)
+    assert np.array_equal(sa, ix.sa)
+    for pl in (2, 5, 8):
+        want = ao.Index(g, prefixLength=pl)
+        start, end = saindex.lookup_table(g, sa, pl)
+        assert np.array_equal(start, want.start) and np.array_equal(end, want.end), pl

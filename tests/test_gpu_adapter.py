@@ -42,6 +42,17 @@ def test_sdp_adapter_matches_reference_call_site():
     assert "through blasr_gpu::SdpBatch: identical to the reference call site" in r.stdout, r.stdout
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "anchor_check")), reason="oracle/_ref/anchor_check not built")
+@pytest.mark.gpu
+def test_anchor_adapter_matches_reference_call_site():
+    """MapReadToGenome through blasr_gpu::AnchorBatch, loaded from the reference's real DNASuffixArray / DNASequence and fed
+    its SMRTSequence reads (forward and MakeRC, whole reads and subreads), against the reference's own calls
+    (Blasr.cpp:2282-2296) into vector<ChainedMatchPos>."""
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "anchor_check"), "24", "400000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "through blasr_gpu::AnchorBatch: identical to the reference call site" in r.stdout, r.stdout
+
+
 @needs_bin
 def test_adapter_fails_loudly_without_gpu():
     import torch
