@@ -21,6 +21,7 @@
 #include <ucontext.h>
 #include <sys/mman.h>
 #include <unistd.h>
+#include <mutex>
 #include "blasr_gpu_adapter.hpp"
 
 struct BgpuFiber;
@@ -177,5 +178,45 @@ bool BgpuRefineAlignments(vector<T_Sequence*> &bothQueryStrands, T_RefSequence &
   if (params.sortRefinedAlignments)
     std::sort(alignmentPtrs.begin(), alignmentPtrs.end(), SortAlignmentPointersByScore());
   return true;
+}
+// ---- anchoring.  The two MapReadToGenome calls of MapRead (Blasr.cpp:2282-2296: the read, then its reverse
+// complement) become ONE bgpu_map_reads call of two reads on the calling pthread's own context (stream + buffers; the index
+// and the genome are loaded to the device once, from the program's own DNASuffixArray / genome objects).  The call is
+// synchronous: a 10 kb read pair is ~20,000 independent searches, a fraction of a millisecond of device time against ~6 ms of
+// this thread's CPU time in the reference.  Parameter sets the library refuses (it refuses exactly where the reference
+// asserts or reads out of bounds) and the -lcpBounds debug output go to the reference's own function.
+static __thread blasr_gpu::Context *bgpuAnchorCtx = NULL;
+static __thread int bgpuRcCount = -1;                         // >= 0: the forward call has filled rcMatchPosList already
+
+template<typename T_RefSequence, typename T_SuffixArray, typename T_Sequence, typename T_MatchPos>
+int BgpuMapReadToGenome(T_Sequence *readRC, vector<T_MatchPos> *rcMatchPosList, bool forwardOnly,
+                        T_RefSequence &genome, T_SuffixArray &sa, T_Sequence &read, unsigned int minPrefixMatchLength,
+                        vector<T_MatchPos> &matchPosList, AnchorParameters &ap) {
+  static const bool off = getenv("BGPU_NO_ANCHOR") != NULL;
+  bgpuRcCount = -1;
+  if (off || ap.lcpBoundsOutPtr != NULL || ap.removeEncompassedMatches || ap.expand > 14)
+    return MapReadToGenome(genome, sa, read, minPrefixMatchLength, matchPosList, ap);
+  static std::once_flag loaded;
+  if (!bgpuAnchorCtx) bgpuAnchorCtx = new blasr_gpu::Context(getenv("BGPU_DEVICE") ? atoi(getenv("BGPU_DEVICE")) : 0);
+  std::call_once(loaded, [&] { blasr_gpu::AnchorBatch::LoadIndex(*bgpuAnchorCtx, sa, genome); });
+  blasr_gpu::AnchorBatch batch;
+  batch.Add(read);
+  if (!forwardOnly) batch.Add(*readRC);
+  try {
+    batch.Run(*bgpuAnchorCtx, minPrefixMatchLength, ap);
+  } catch (const blasr_gpu::Error &e) {
+    if (e.code != BGPU_E_INVALID) throw;
+    return MapReadToGenome(genome, sa, read, minPrefixMatchLength, matchPosList, ap);
+  }
+  // MapReadToGenome clears the list only on its early return (MapBySuffixArray.h:219-222); MapRead clears both before the calls
+  if (!forwardOnly) bgpuRcCount = batch.Store(1, *rcMatchPosList);
+  return batch.Store(0, matchPosList);
+}
+
+template<typename T_RefSequence, typename T_SuffixArray, typename T_Sequence, typename T_MatchPos>
+int BgpuMapReadToGenomeRC(T_RefSequence &genome, T_SuffixArray &sa, T_Sequence &readRC, unsigned int minPrefixMatchLength,
+                          vector<T_MatchPos> &rcMatchPosList, AnchorParameters &ap) {
+  if (bgpuRcCount >= 0) { const int n = bgpuRcCount; bgpuRcCount = -1; return n; }
+  return MapReadToGenome(genome, sa, readRC, minPrefixMatchLength, rcMatchPosList, ap);
 }
 #endif

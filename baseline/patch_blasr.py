@@ -66,6 +66,11 @@ def gpu(src: str) -> str:
                        "BgpuSpawn(&threads[procIndex], &threadAttr[procIndex], (void* (*)(void*))MapReads, &mapdb[procIndex], procIndex, params.nProc);")
     src = replace_once(src, "pthread_join(threads[procIndex], NULL);", "BgpuJoin(threads[procIndex], procIndex);")
     src = replace_once(src, "pthread_exit(NULL);", "BgpuFiberExit();")                      # end of MapReads, Blasr.cpp:3915
+    # anchoring, Blasr.cpp:2282-2296: both strands in one device call (the second call site takes the list the first one filled)
+    src = replace_once(src, "MapReadToGenome(genome, sarray, read, ",
+                       "BgpuMapReadToGenome(&readRC, &mappingBuffers.rcMatchPosList, params.forwardOnly, genome, sarray, read, ")
+    src = replace_once(src, "MapReadToGenome(genome, sarray, readRC, params.lookupTableLength, mappingBuffers.rcMatchPosList,",
+                       "BgpuMapReadToGenomeRC(genome, sarray, readRC, params.lookupTableLength, mappingBuffers.rcMatchPosList,")
     return src
 
 

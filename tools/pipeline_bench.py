@@ -5,7 +5,7 @@ Generates configs[0] (4.6 Mb genome, 10 kb reads at 15 % error; --reads to scale
 reference's sawriter, then times
     baseline/_ref/blasrmc      reads.fa genome.fa -sa genome.sa -sam -nproc C          (the unmodified reference)
     ... -noRefineAlignments                                                               (how much of it is refinement)
-    baseline/_ref/blasrmc_gpu  ... -nproc T    for T in --gpu-threads                   (RefineAlignments on the GPU; T MapReads
+    baseline/_ref/blasrmc_gpu  ... -nproc T    for T in --gpu-threads                   (anchoring + RefineAlignments on the GPU; T MapReads
                                                                                           fibers on one pthread per core)
 and prints one JSON object.  Wall times include the program's start-up (index load); `startup_s` is measured with an
 empty read set so that reads/s can be quoted net of it.  Sorted SAM of every GPU run is compared with the stock run.
@@ -66,6 +66,11 @@ def measure(n_reads=1000, genome=4600000, length=10000, gpu_threads=None, workdi
         out["gpu"].append({"nproc": t, "wall_s": dt, "reads_per_s": n_reads / dt,
                            "reads_per_s_net": n_reads / max(dt - out["gpu_startup_s"], 1e-9), "sam_identical_to_stock": same})
     best = max(out["gpu"], key=lambda r: r["reads_per_s_net"])
+    # the same program with anchoring left to the reference's CPU code (BGPU_NO_ANCHOR): what the device anchoring adds
+    dt = run(GPU, tmp, "gpu_noanchor.sam", best["nproc"], extra, env=dict(env, BGPU_NO_ANCHOR="1"))
+    out["gpu_refinement_only"] = {"nproc": best["nproc"], "wall_s": dt, "reads_per_s_net": n_reads / max(dt - out["gpu_startup_s"], 1e-9),
+                                  "sam_identical_to_stock": sam_lines(os.path.join(tmp, "gpu_noanchor.sam")) == want}
+    out["on_device"] = "MapReadToGenome (both strands, bgpu_map_reads) and RefineAlignments (bgpu_submit / bgpu_collect); SDPAlign, clustering, mapQV, printing = the reference's CPU code"
     out["reads_per_s"] = best["reads_per_s_net"]; out["reads_per_s_stock"] = out["stock"]["reads_per_s_net"]
     out["speedup_net"] = best["reads_per_s_net"] / out["stock"]["reads_per_s_net"]
     out["sam_identical_to_stock"] = all(r["sam_identical_to_stock"] for r in out["gpu"])
