@@ -355,6 +355,17 @@ class Aligner:
         arrs = [np.frombuffer((C.c_ubyte * tot).from_address(x.value), dtype=np.uint8).copy() if tot else np.zeros(0, np.uint8) for x in p[:3]]
         return arrs[0], arrs[1], arrs[2], o
 
+    def rescore(self, ticket, fn, useAffinePenalty: bool = False) -> np.ndarray:
+        """bgpu_rescore: ComputeAlignmentScore(alignment, q, t, fn, useAffinePenalty) (AlignmentUtils.h:127-169) of every alignment of
+        a collected guided ticket under another score function -- the rescoring StoreMapQVs does with SMRTLogProbMatrix."""
+        tk, n = ticket
+        out = np.zeros(n, np.int32)
+        f = fn.c_struct()
+        rc = self._lib.bgpu_rescore(self._ctx, tk, C.byref(f), int(useAffinePenalty), _ptr(out))
+        if rc != 0:
+            self._err(rc, "bgpu_rescore")
+        return out
+
     def rerun(self, ticket):
         rc = self._lib.bgpu_rerun(self._ctx, ticket[0])
         if rc != 0:
@@ -439,10 +450,11 @@ class Aligner:
     def MapReadToGenome(self, reads, readOff, minPrefixMatchLength: int = 8, minMatchLength: int = 12, expand: int = 0,
                         useLookupTable: bool = True, maxAnchorsPerPosition: int = 1000, advanceExactMatches: int = 0,
                         maxLCPLength: int = 0, stopMappingOnceUnique: bool = True, removeEncompassedMatches: bool = False,
-                        subreadStart=None, subreadEnd=None):
+                        subreadStart=None, subreadEnd=None, copy: bool = True):
         """MapReadToGenome (MapBySuffixArray.h:209-309) for every read of the batch, blasr's defaults (MappingParameters.h):
         returns (matchOff[n + 1], matches) with matches a MATCH_DTYPE array (t, q, l), read i owning
-        matches[matchOff[i]:matchOff[i + 1]] in the reference's matchPosList order.  Pass reverse complements as reads."""
+        matches[matchOff[i]:matchOff[i + 1]] in the reference's matchPosList order.  Pass reverse complements as reads.
+        copy=False returns a view of the library's pinned result buffer (valid until the next call on this aligner)."""
         reads = np.ascontiguousarray(reads, np.uint8)
         readOff = np.ascontiguousarray(readOff, np.uint64)
         n = len(readOff) - 1
@@ -459,7 +471,8 @@ class Aligner:
         if total == 0:
             return off, np.zeros(0, capi.MATCH_DTYPE)
         buf = (C.c_uint8 * (12 * total)).from_address(out.value)
-        return off, np.frombuffer(buf, dtype=capi.MATCH_DTYPE).copy()
+        m = np.frombuffer(buf, dtype=capi.MATCH_DTYPE)          # the library's pinned buffer: valid until the next call on this aligner
+        return off, (m.copy() if copy else m)
 
     def map_timing(self):
         """(ms of the search kernel, ms of count + scan + emit, positions searched, H2D bytes, D2H bytes) of the last MapReadToGenome."""

@@ -27,7 +27,7 @@ EXPORTS = [
     "bgpu_create", "bgpu_destroy", "bgpu_last_error", "bgpu_version", "bgpu_submit", "bgpu_submit_jobs",
     "bgpu_collect", "bgpu_release", "bgpu_rerun", "bgpu_timing_of", "bgpu_align", "bgpu_device_count",
     "bgpu_measure_int_peak", "bgpu_int_peak_modes", "bgpu_cigar", "bgpu_base_code", "bgpu_query", "bgpu_trim", "bgpu_cigar_clipped", "bgpu_strings",
-    "bgpu_sdp_align", "bgpu_set_reference", "bgpu_set_suffix_array", "bgpu_map_reads", "bgpu_map_timing", "bgpu_map_rerun", "bgpu_build_lookup_table",
+    "bgpu_sdp_align", "bgpu_set_reference", "bgpu_set_suffix_array", "bgpu_map_reads", "bgpu_map_timing", "bgpu_map_rerun", "bgpu_build_lookup_table", "bgpu_rescore",
 ]
 
 
@@ -147,6 +147,7 @@ def lib() -> C.CDLL:
                                  C.POINTER(C.c_void_p)]
     L.bgpu_map_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double * 2), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.bgpu_map_rerun.argtypes = [C.c_void_p]
+    L.bgpu_rescore.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ScoreFn), C.c_int, C.c_void_p]
     L.bgpu_build_lookup_table.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.bgpu_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.bgpu_int_peak_modes.argtypes = [C.POINTER(C.c_double * 4)]

@@ -25,11 +25,17 @@
 
 namespace bgpu {
 
-struct AnchorIndex { uint32_t *sa = nullptr, *startT = nullptr, *endT = nullptr; uint64_t n = 0; uint32_t prefixLen = 0; };
+// An index entry on the device: the suffix's position and, packed 3 bits each, the ThreeBit codes of the CTX_BASES genome bases
+// that follow the table's key (depths prefixLen .. prefixLen + 9 of the suffix; 6 = a byte outside the alphabet, 7 = past the
+// end of the genome).  The binary searches of the depths right behind the key -- nearly all of them: a bacterial genome is
+// unique after ~12 bases, a human one after ~17 -- then cost ONE 8-byte load per probe instead of the reference's dependent
+// pair (index entry, then genome byte).  Built on the device by bgpu_set_suffix_array; 8 B per base.
+constexpr uint32_t CTX_BASES = 10;
+struct AnchorIndex { uint2 *ent = nullptr; uint32_t *startT = nullptr, *endT = nullptr; uint64_t n = 0, refGen = 0; uint32_t prefixLen = 0; };
 
 struct MapArgs {
   const uint8_t *g; uint64_t n;
-  const uint32_t *sa, *startT, *endT; uint32_t prefixLen;      // startT == nullptr: no table
+  const uint2 *ent; const uint32_t *startT, *endT; uint32_t prefixLen;      // startT == nullptr: no table (entries' context starts at depth 0)
   const uint8_t *reads; const uint64_t *readOff; const uint32_t *subS, *subE;
   const uint64_t *posOff; uint32_t nReads; uint64_t totalPos;
   bgpu_anchor_params p;
@@ -38,36 +44,44 @@ struct MapArgs {
   bgpu_match *matches;
 };
 
-__device__ __forceinline__ int gcode(const MapArgs &a, uint64_t pos) {       // ThreeBit of the genome; 'N' at and beyond n
-  return pos >= a.n ? 4 : (int)base_code(__ldg(a.g + pos));
+__device__ __forceinline__ int code7(int c) { return c == 255 ? 6 : c; }     // ThreeBit order kept, the outsider next to the alphabet
+
+// What the searches compare at depth `off` of the suffix behind index entry m: its ThreeBit code (code7), -1 when the suffix
+// ends exactly there, -2 when it is shorter still.  *at = the suffix's position.
+__device__ __forceinline__ int probe(const MapArgs &a, int64_t m, uint32_t off, uint64_t *at) {
+  const uint2 e = __ldg(a.ent + m);
+  *at = e.x;
+  const uint32_t rel = off - a.prefixLen;
+  if (rel < CTX_BASES) {
+    const int c = (int)(e.y >> (3 * rel)) & 7;
+    if (c != 7) return c;
+    return (a.n - (uint64_t)e.x == (uint64_t)off) ? -1 : -2;
+  }
+  const int64_t sufLen = (int64_t)a.n - (int64_t)e.x;
+  if (sufLen == (int64_t)off) return -1;
+  if (sufLen < (int64_t)off) return -2;
+  return code7(base_code(__ldg(a.g + (uint64_t)e.x + off)));
 }
 
-// SuffixArray::SearchLeftBound, SuffixArray.h:736-776
-__device__ __forceinline__ int64_t left_bound(const MapArgs &a, uint32_t off, int qc, int64_t l, int64_t r) {
+// SuffixArray::SearchLeftBound, SuffixArray.h:736-776 (a suffix that has ended sorts before every base)
+__device__ __forceinline__ int64_t left_bound(const MapArgs &a, uint32_t off, int qc7, int64_t l, int64_t r) {
   int64_t ll = l, lr = r;
+  uint64_t at;
   while (ll < lr) {
     const int64_t m = (ll + lr) / 2;
-    const uint64_t at = __ldg(a.sa + m);
-    const int64_t sufLen = (int64_t)a.n - (int64_t)at;
-    if (sufLen == (int64_t)off) { ll = m + 1; continue; }
-    const int comp = sufLen < (int64_t)off ? -1 : (int)base_code(__ldg(a.g + at + off)) - qc;
-    if (comp < 0) ll = m + 1; else lr = m;
+    if (probe(a, m, off, &at) < qc7) ll = m + 1; else lr = m;
   }
   return ll;
 }
-// SuffixArray::SearchRightBound, SuffixArray.h:778-816
-__device__ __forceinline__ int64_t right_bound(const MapArgs &a, uint32_t off, int qc, int64_t l, int64_t r) {
+// SuffixArray::SearchRightBound, SuffixArray.h:778-816 (meeting a suffix that ends exactly at this depth ends the search, :786-789)
+__device__ __forceinline__ int64_t right_bound(const MapArgs &a, uint32_t off, int qc7, int64_t l, int64_t r) {
   int64_t rl = l, rr = r;
+  uint64_t at;
   while (rl < rr) {
     const int64_t m = (rl + rr) / 2;
-    const uint64_t at = __ldg(a.sa + m);
-    const int64_t sufLen = (int64_t)a.n - (int64_t)at;
-    if (sufLen == (int64_t)off) { rr = m; break; }
-    if (sufLen < (int64_t)off) rr = m;
-    else {
-      const int comp = (int)base_code(__ldg(a.g + at + off)) - qc;
-      if (comp <= 0) rl = m + 1; else rr = m;
-    }
+    const int k = probe(a, m, off, &at);
+    if (k == -1) { rr = m; break; }
+    if (k != -2 && k <= qc7) rl = m + 1; else rr = m;
   }
   return rr;
 }
@@ -118,13 +132,15 @@ __global__ void __launch_bounds__(256) locate_kernel(const MapArgs a) {
     while (l < r && lcp < queryLength) {
       if (a.p.stopMappingOnceUnique && l == r - 1) break;
       if (maxLCP && lcp >= maxLCP) break;
-      if (gcode(a, (uint64_t)__ldg(a.sa + l) + lcp) >= 4) break;
-      const int qc = base_code(__ldg(query + lcp));
-      l = left_bound(a, lcp, qc, l, r);
-      r = right_bound(a, lcp, qc, l, r);
+      uint64_t at;
+      const int k0 = probe(a, l, lcp, &at);          // SuffixArray.h:1021: the genome at and beyond n reads as 'N'
+      if (k0 < 0 || k0 >= 4) break;
+      const int qc = base_code(__ldg(query + lcp)), qc7 = code7(qc);
+      l = left_bound(a, lcp, qc7, l, r);
+      r = right_bound(a, lcp, qc7, l, r);
       if (l == r) break;
-      const uint64_t at = (uint64_t)__ldg(a.sa + l) + lcp;
-      if (at >= a.n || qc >= 4 || (int)base_code(__ldg(a.g + at)) != qc) break;
+      const int k1 = probe(a, l, lcp, &at);
+      if (k1 < 0 || qc >= 4 || k1 != qc7) break;     // :1040-1047
       push((uint32_t)l, (uint32_t)r);
       lcp++;
     }
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(256) locate_kernel(const MapArgs a) {
     mLow = loC; mHigh = hiC; mLen = minPrefix + s - 1;
     if (mLow + 1 == mHigh) {                                        // unique: extend along the genome :134-174
       lcp = minPrefix + s - 1;
-      int64_t refPos = (int64_t)__ldg(a.sa + mLow) + lcp - 1, queryPos = (int64_t)p + lcp - 1;
+      int64_t refPos = (int64_t)__ldg(&a.ent[mLow].x) + lcp - 1, queryPos = (int64_t)p + lcp - 1;
       bool extended = false;
       while (refPos + 1 < (int64_t)a.n && queryPos + 1 < (int64_t)readLen) {
         const uint8_t gc = __ldg(a.g + refPos + 1);
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const MapArgs a) {
     uint64_t before = carry;
     for (int w = 0; w < wid; w++) before += warpSum[w];
     uint64_t at = before + inc - cnt;
-    for (uint32_t k = 0; k < cnt; k++) { bgpu_match mt; mt.t = __ldg(a.sa + lo + k); mt.q = pos; mt.l = L; a.matches[at + k] = mt; }
+    for (uint32_t k = 0; k < cnt; k++) { bgpu_match mt; mt.t = __ldg(&a.ent[lo + k].x); mt.q = pos; mt.l = L; a.matches[at + k] = mt; }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry = before + inc;
     __syncthreads();
@@ -269,30 +285,49 @@ struct AnchorState {                // per context: device / pinned buffers of t
 
 static AnchorIndex g_index[64];
 
+__global__ void __launch_bounds__(256) build_entries_kernel(const uint32_t *sa, const uint8_t *g, uint64_t n, uint32_t prefixLen, uint2 *ent) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t at = sa[i];
+  uint32_t w = 0;
+  for (uint32_t k = 0; k < CTX_BASES; k++) {
+    const uint64_t pos = at + prefixLen + k;
+    const uint32_t c = pos < n ? (uint32_t)code7(base_code(g[pos])) : 7u;
+    w |= c << (3 * k);
+  }
+  ent[i] = make_uint2((uint32_t)at, w);
+}
+
 #define ACK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[256]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); err = b_; return e_ == cudaErrorMemoryAllocation ? BGPU_E_OOM : BGPU_E_CUDA; } } while (0)
 
-int anchor_set_index(int device, const uint32_t *index, uint64_t n, const uint32_t *startT, const uint32_t *endT, uint32_t prefixLen,
-                     std::string &err) {
+int anchor_set_index(int device, const uint8_t *genome, uint64_t gN, uint64_t refGen, const uint32_t *index, uint64_t n, const uint32_t *startT,
+                     const uint32_t *endT, uint32_t prefixLen, std::string &err) {
   if (device < 0 || device >= 64) return BGPU_E_INVALID;
   AnchorIndex &ix = g_index[device];
   ACK(cudaDeviceSynchronize());
-  cudaFree(ix.sa); cudaFree(ix.startT); cudaFree(ix.endT);
+  cudaFree(ix.ent); cudaFree(ix.startT); cudaFree(ix.endT);
   ix = AnchorIndex();
   if (!n) return BGPU_OK;
   if (!index || n >= 0xFFFFFFFFull) { err = "bgpu_set_suffix_array: index is NULL or the genome does not fit SAIndex (uint32)"; return BGPU_E_INVALID; }
   if ((startT == nullptr) != (endT == nullptr) || (startT && (prefixLen < 1 || prefixLen > 14))) {
     err = "bgpu_set_suffix_array: startPosTable and endPosTable come together, lookupPrefixLength 1..14"; return BGPU_E_INVALID;
   }
-  ACK(cudaMalloc(&ix.sa, sizeof(uint32_t) * (n + 4)));
-  ACK(cudaMemcpy(ix.sa, index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+  if (!genome || gN != n) { err = "bgpu_set_suffix_array: call bgpu_set_reference first, with the genome this array indexes (same length)"; return BGPU_E_INVALID; }
+  if (startT) ix.prefixLen = prefixLen;
+  uint32_t *dSa = nullptr;
+  ACK(cudaMalloc(&dSa, sizeof(uint32_t) * (n + 4)));
+  cudaError_t e = cudaMemcpy(dSa, index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&ix.ent, sizeof(uint2) * (n + 4));
+  if (e == cudaSuccess) { build_entries_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dSa, genome, n, ix.prefixLen, ix.ent); e = cudaDeviceSynchronize(); }
+  cudaFree(dSa);
+  if (e != cudaSuccess) { cudaFree(ix.ent); ix = AnchorIndex(); ACK(e); }
   if (startT) {
     const size_t tl = (size_t)1 << (2 * prefixLen);
     ACK(cudaMalloc(&ix.startT, sizeof(uint32_t) * tl)); ACK(cudaMalloc(&ix.endT, sizeof(uint32_t) * tl));
     ACK(cudaMemcpy(ix.startT, startT, sizeof(uint32_t) * tl, cudaMemcpyHostToDevice));
     ACK(cudaMemcpy(ix.endT, endT, sizeof(uint32_t) * tl, cudaMemcpyHostToDevice));
-    ix.prefixLen = prefixLen;
   }
-  ix.n = n;
+  ix.n = n; ix.refGen = refGen;
   return BGPU_OK;
 }
 
@@ -359,12 +394,12 @@ static int run_kernels(AnchorState *st, cudaStream_t s, std::string &err, bool e
   return BGPU_OK;
 }
 
-int anchor_map(int device, const uint8_t *genome, uint64_t gN, cudaStream_t s, AnchorState **stp, const bgpu_anchor_params *p,
+int anchor_map(int device, const uint8_t *genome, uint64_t gN, uint64_t refGen, cudaStream_t s, AnchorState **stp, const bgpu_anchor_params *p,
                const uint8_t *reads, const uint64_t *readOff, uint32_t nReads, const uint32_t *subS, const uint32_t *subE,
                uint64_t *matchOff, const bgpu_match **matches, std::string &err) {
   const AnchorIndex &ix = g_index[device];
-  if (!ix.sa) { err = "bgpu_map_reads without bgpu_set_suffix_array on this device"; return BGPU_E_INVALID; }
-  if (!genome || gN != ix.n) { err = "bgpu_map_reads: bgpu_set_reference must hold the genome the suffix array indexes (same length)"; return BGPU_E_INVALID; }
+  if (!ix.ent) { err = "bgpu_map_reads without bgpu_set_suffix_array on this device"; return BGPU_E_INVALID; }
+  if (!genome || gN != ix.n || refGen != ix.refGen) { err = "bgpu_map_reads: the genome was replaced after bgpu_set_suffix_array (the index entries carry its bases): set the reference, then the suffix array"; return BGPU_E_INVALID; }
   if (p->removeEncompassedMatches) { err = "removeEncompassedMatches reads out of bounds in the reference (MapBySuffixArray.h:247-251)"; return BGPU_E_INVALID; }
   if (p->expand < 0 || p->expand > RING - 2 || p->maxLCPLength < 0 || p->advanceExactMatches < 0 || p->maxAnchorsPerPosition < 0) {
     err = "bgpu_map_reads: expand 0..14, maxLCPLength / advanceExactMatches / maxAnchorsPerPosition >= 0"; return BGPU_E_INVALID;
@@ -407,7 +442,7 @@ int anchor_map(int device, const uint8_t *genome, uint64_t gN, cudaStream_t s, A
   auto take = [&](size_t b) { uint8_t *q = d; d += b; return q; };
   MapArgs &a = st->args;
   a = MapArgs();
-  a.g = genome; a.n = ix.n; a.sa = ix.sa; a.startT = ix.startT; a.endT = ix.endT; a.prefixLen = ix.prefixLen;
+  a.g = genome; a.n = ix.n; a.ent = ix.ent; a.startT = ix.startT; a.endT = ix.endT; a.prefixLen = ix.prefixLen;
   a.nReads = nReads; a.totalPos = totalPos; a.p = *p;
   uint8_t *dReads = take(szReads); uint64_t *dReadOff = (uint64_t *)take(szOff), *dPosOff = (uint64_t *)take(szOff), *dMatchOff = (uint64_t *)take(szOff);
   uint32_t *dS = (uint32_t *)take(szSub), *dE = (uint32_t *)take(szSub);

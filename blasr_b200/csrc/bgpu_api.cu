@@ -32,6 +32,7 @@ size_t plan_scratch_words(uint32_t);
 void launch_scan_counts(const BatchDev &, uint64_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
 void launch_emit(const BatchDev &, const ScoreParams &, bgpu_result *, bgpu_block *, uint32_t *, bgpu_gap *,
                  const uint64_t *, const uint64_t *, const uint64_t *, int, int, int, PlanHead *, uint32_t *, cudaStream_t);
+void launch_rescore(const BatchDev &, const ScoreParams &, const uint64_t *, const uint64_t *, const uint64_t *, int, int32_t *, cudaStream_t);
 void launch_dense_prep(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint64_t *, const uint64_t *, cudaStream_t);
 void launch_dense_fill(const BatchDev &, const ScoreParams &, const DenseArgs &, const uint32_t *, uint32_t, uint32_t *, int,
                        cudaStream_t);
@@ -43,8 +44,8 @@ void launch_fmt_cigar(const BatchDev &, const uint64_t *, const uint64_t *, uint
 void launch_fmt_strings(const BatchDev &, const uint64_t *, char *, char *, char *, cudaStream_t);
 double measure_int_peak(int nSM, cudaStream_t s, double *clockMHz);
 struct AnchorState;
-int anchor_set_index(int, const uint32_t *, uint64_t, const uint32_t *, const uint32_t *, uint32_t, std::string &);
-int anchor_map(int, const uint8_t *, uint64_t, cudaStream_t, AnchorState **, const bgpu_anchor_params *, const uint8_t *, const uint64_t *, uint32_t,
+int anchor_set_index(int, const uint8_t *, uint64_t, uint64_t, const uint32_t *, uint64_t, const uint32_t *, const uint32_t *, uint32_t, std::string &);
+int anchor_map(int, const uint8_t *, uint64_t, uint64_t, cudaStream_t, AnchorState **, const bgpu_anchor_params *, const uint8_t *, const uint64_t *, uint32_t,
                const uint32_t *, const uint32_t *, uint64_t *, const bgpu_match **, std::string &);
 int anchor_rerun(AnchorState *, cudaStream_t, std::string &);
 int anchor_timing(const AnchorState *, double *, uint64_t *, uint64_t *, uint64_t *);
@@ -305,7 +306,7 @@ static int upload(bgpu_ctx *ctx, bgpu_ticket t, void *dst, const void *src, size
 }
 
 // the reference (genome) resident per device: shared by every context on it
-struct DeviceRef { uint8_t *d = nullptr; uint64_t n = 0; };
+struct DeviceRef { uint8_t *d = nullptr; uint64_t n = 0, gen = 0; };   // gen: bumped by every bgpu_set_reference
 static std::mutex g_refMu;
 static DeviceRef g_ref[64];
 
@@ -317,6 +318,7 @@ extern "C" int bgpu_set_reference(bgpu_ctx *ctx, const uint8_t *bases, uint64_t 
   DeviceRef &r = g_ref[ctx->device];
   CK(cudaDeviceSynchronize());                       // tickets in flight may still be gathering from the old one
   if (r.d) { cudaFree(r.d); r.d = nullptr; r.n = 0; }
+  r.gen++;
   if (!n) return BGPU_OK;
   CK(cudaMalloc(&r.d, n + 16));
   CK(cudaMemcpy(r.d, bases, n, cudaMemcpyHostToDevice));
@@ -1146,6 +1148,28 @@ extern "C" int bgpu_cigar(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t **ops, co
   return BGPU_OK;
 }
 
+// ComputeAlignmentScore of every alignment of a collected guided ticket under another score function (StoreMapQVs)
+extern "C" int bgpu_rescore(bgpu_ctx *ctx, bgpu_ticket t, const bgpu_scorefn *fn, int useAffinePenalty, int32_t *scores) {
+  if (!ctx || !t || !fn || (!scores && t->nJobs)) return BGPU_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!t->collected) { ctx->err = "bgpu_rescore needs a collected ticket"; return BGPU_E_BUSY; }
+  if (t->dense) { ctx->err = "bgpu_rescore: GuidedAlign / AffineGuidedAlign tickets only"; return BGPU_E_INVALID; }
+  if (fn->kind != BGPU_FN_DISTANCE) { ctx->err = "bgpu_rescore takes a DistanceMatrixScoreFunction (what StoreMapQVs builds, Blasr.cpp:2768-2771)"; return BGPU_E_INVALID; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
+  const uint32_t n = t->nJobs;
+  if (!n) return BGPU_OK;
+  ScoreParams sp; fill_score_params(sp, fn, &t->params);
+  int32_t *d_out = nullptr, *h_out = nullptr;
+  RC(talloc_dev(ctx, t, &d_out, n)); RC(talloc_pin(ctx, t, &h_out, n));
+  cudaStream_t s = ctx->stream;
+  launch_rescore(t->B, sp, t->d_blockOff, t->d_listOff, t->d_gapOff, useAffinePenalty ? 1 : 0, d_out, s);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_out, d_out, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  CK(wait_stream(ctx));
+  memcpy(scores, h_out, sizeof(int32_t) * n);
+  return BGPU_OK;
+}
+
 extern "C" int bgpu_cigar_clipped(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t *clips, const uint8_t *tStrand, const uint32_t **ops,
                                   const uint64_t **cigarOff) {
   if (!ctx || !t || !ops || !cigarOff) return BGPU_E_INVALID;
@@ -1307,7 +1331,8 @@ extern "C" int bgpu_set_suffix_array(bgpu_ctx *ctx, const uint32_t *index, uint6
   std::lock_guard<std::mutex> lk(ctx->mu);
   std::lock_guard<std::mutex> lr(g_refMu);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
-  return anchor_set_index(ctx->device, index, n, startPosTable, endPosTable, lookupPrefixLength, ctx->err);
+  const DeviceRef &r = g_ref[ctx->device < 64 ? ctx->device : 0];
+  return anchor_set_index(ctx->device, r.d, r.n, r.gen, index, n, startPosTable, endPosTable, lookupPrefixLength, ctx->err);
 }
 
 extern "C" int bgpu_map_reads(bgpu_ctx *ctx, const bgpu_anchor_params *p, const uint8_t *reads, const uint64_t *readOff, uint32_t nReads,
@@ -1315,9 +1340,9 @@ extern "C" int bgpu_map_reads(bgpu_ctx *ctx, const bgpu_anchor_params *p, const 
   if (!ctx || !p || !matchOff || !matches || (nReads && (!reads || !readOff))) return BGPU_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return BGPU_E_CUDA;
-  const uint8_t *refD; uint64_t refN;
-  { std::lock_guard<std::mutex> lr(g_refMu); refD = ctx->device < 64 ? g_ref[ctx->device].d : nullptr; refN = ctx->device < 64 ? g_ref[ctx->device].n : 0; }
-  return anchor_map(ctx->device, refD, refN, ctx->stream, &ctx->anchor, p, reads, readOff, nReads, subreadStart, subreadEnd, matchOff, matches, ctx->err);
+  const uint8_t *refD; uint64_t refN, refGen;
+  { std::lock_guard<std::mutex> lr(g_refMu); const DeviceRef &r = g_ref[ctx->device < 64 ? ctx->device : 0]; refD = r.d; refN = r.n; refGen = r.gen; }
+  return anchor_map(ctx->device, refD, refN, refGen, ctx->stream, &ctx->anchor, p, reads, readOff, nReads, subreadStart, subreadEnd, matchOff, matches, ctx->err);
 }
 
 extern "C" int bgpu_build_lookup_table(const uint8_t *genome, uint64_t n, const uint32_t *index, uint32_t lookupPrefixLength,

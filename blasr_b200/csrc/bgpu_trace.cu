@@ -215,6 +215,7 @@ struct EmitOut {
   bgpu_block *blocks; uint32_t *gapCounts; bgpu_gap *gaps;
   const uint64_t *blockOff, *listOff, *gapOff;
   uint32_t *runsOut;     // compact results: the kept runs in path order, job i from runsOut[blockOff[i] + gapOff[i]]; else NULL
+  int32_t *rescoreOut;   // bgpu_rescore: only ComputeAlignmentScore(alignment, query, text, fn, affine) per job goes out; else NULL
 };
 
 __device__ __forceinline__ uint32_t warp_excl_u32(uint32_t v, int lane, uint32_t &total) {
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
   R.nMatch = R.nMismatch = R.nIns = R.nDel = 0; R.pctSimilarity = 0.f; R.statsScore = 0;
   R.nBlocks = 0; R.nGapLists = 0; R.nGaps = 0;
   R.blockOff = O.blockOff[job]; R.gapListOff = O.listOff[job]; R.gapOff = O.gapOff[job];
-  if (G.status != BGPU_JOB_OK) { if (lane == 0) O.results[job] = R; return; }
+  const bool rescore = O.rescoreOut != nullptr;   // the Alignment overload of ComputeAlignmentScore (AlignmentUtils.h:127-169): blocks + one cost per Gap
+  if (G.status != BGPU_JOB_OK) { if (lane == 0) { if (rescore) O.rescoreOut[job] = 0; else O.results[job] = R; } return; }
   R.score = G.score; R.qPos = G.qPos; R.tPos = G.tPos; R.nCells = G.nCells;
   R.nBlocks = G.nBlocks; R.nGapLists = G.nGapLists; R.nGaps = G.nGaps;
   const uint32_t nRuns = G.nRuns, nBlocks = G.nBlocks;
@@ -267,10 +269,10 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
   int oob = 0;
   const uint32_t qPrefix = G.qPos - (uint32_t)G.qStart, tPrefix = G.tPos - (uint32_t)G.tStart;
   const bool compact = O.runsOut != nullptr;
-  bgpu_block *blocks = compact ? nullptr : O.blocks + R.blockOff;
-  uint32_t *gapCounts = compact ? nullptr : O.gapCounts + R.gapListOff;
-  bgpu_gap *gaps = compact ? nullptr : O.gaps + R.gapOff;
-  uint32_t *runsOut = compact ? O.runsOut + R.blockOff + R.gapOff : nullptr;
+  bgpu_block *blocks = (compact || rescore) ? nullptr : O.blocks + R.blockOff;
+  uint32_t *gapCounts = (compact || rescore) ? nullptr : O.gapCounts + R.gapListOff;
+  bgpu_gap *gaps = (compact || rescore) ? nullptr : O.gaps + R.gapOff;
+  uint32_t *runsOut = (compact && !rescore) ? O.runsOut + R.blockOff + R.gapOff : nullptr;
 
   uint32_t cq = 0, ct = 0, cD = 0, cG = 0;            // carries: q/t consumed, D runs seen, kept gap runs seen
   uint32_t gAtPrevD = 0;                              // kept gap runs before the latest block seen so far
@@ -297,7 +299,8 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
     const uint32_t gPrevLane = __shfl_sync(0xffffffffu, gBefore, below ? 31 - __clz((int)below) : lane);
     bool cmp = false;                                 // this lane's block takes part in the per-base pass
     if (isD) {
-      if (compact) runsOut[dBefore + gBefore] = len;                      // RUN_D << 30 | len
+      if (rescore) {}
+      else if (compact) runsOut[dBefore + gBefore] = len;                 // RUN_D << 30 | len
       else {
         bgpu_block bl; bl.qPos = pq - qPrefix; bl.tPos = pt - tPrefix; bl.length = len;
         blocks[dBefore] = bl;
@@ -309,6 +312,12 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
         // out of bounds, here the job is flagged instead
         if (q0 < 0 || t0 < 0 || q0 + len > qLenJ || t0 + len > tLenJ) oob = 1; else cmp = true;
         cols += len;
+      }
+    } else if (kept && rescore) {
+      // :141-160: every Gap of the lists between blocks on its own; the leading list (gaps[0]) is not scored
+      if (dBefore >= 1) {
+        const int lin = (int)len * (type == RUN_L ? P.del : P.ins), aff = P.open + (int)len * P.ext;
+        score += (statsAffine && aff < lin) ? aff : lin;
       }
     } else if (kept) {
       if (compact) runsOut[dBefore + gBefore] = (type << 30) | len;       // 1 = Gap::Target (insertion), 2 = Gap::Query (deletion)
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
     }
     cq += totQ; ct += totT; cD += totD; cG += totG;
   }
-  if (lane == 0 && R.nGapLists && !compact) gapCounts[nBlocks] = 0;   // the list after the last block: its gap runs are dropped
+  if (lane == 0 && R.nGapLists && !compact && !rescore) gapCounts[nBlocks] = 0;   // the list after the last block: its gap runs are dropped
   if (doStats) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -376,6 +385,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 8) emit_kernel(BatchDev B, Sc
       score += __shfl_xor_sync(0xffffffffu, score, o); cols += __shfl_xor_sync(0xffffffffu, cols, o);
     }
     oob = __reduce_or_sync(0xffffffffu, (unsigned)oob);
+    if (rescore) { if (lane == 0) O.rescoreOut[job] = oob ? 0 : score; return; }
     if (oob) { nMatch = nMismatch = nIns = nDel = score = 0; cols = 0; R.status = BGPU_JOB_REF_UNDEFINED; }
     R.nMatch = nMatch; R.nMismatch = nMismatch; R.nIns = nIns; R.nDel = nDel; R.statsScore = score;
     R.pctSimilarity = cols > 0 ? (float)((nMatch * 2.0) / (double)(2 * cols) * 100) : 0.f;   // :566-576
@@ -406,9 +416,17 @@ void launch_emit(const BatchDev &B, const ScoreParams &P, bgpu_result *results, 
                  uint32_t *gapCounts, bgpu_gap *gaps, const uint64_t *blockOff, const uint64_t *listOff,
                  const uint64_t *gapOff, int doStats, int statsAffine, int keepLeading, PlanHead *plan, uint32_t *runsOut,
                  cudaStream_t s) {
-  EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff, runsOut};
+  EmitOut O{results, blocks, gapCounts, gaps, blockOff, listOff, gapOff, runsOut, nullptr};
   const unsigned grid = (B.nJobs + EMIT_WARPS - 1) / EMIT_WARPS;
   if (grid) emit_kernel<<<grid, EMIT_WARPS * 32, 0, s>>>(B, P, O, doStats, statsAffine, keepLeading, plan);
+}
+
+// bgpu_rescore: the emit pass again, under another score function, with only the score going out
+void launch_rescore(const BatchDev &B, const ScoreParams &P, const uint64_t *blockOff, const uint64_t *listOff, const uint64_t *gapOff,
+                    int useAffine, int32_t *out, cudaStream_t s) {
+  EmitOut O{nullptr, nullptr, nullptr, nullptr, blockOff, listOff, gapOff, nullptr, out};
+  const unsigned grid = (B.nJobs + EMIT_WARPS - 1) / EMIT_WARPS;
+  if (grid) emit_kernel<<<grid, EMIT_WARPS * 32, 0, s>>>(B, P, O, 1, useAffine, 0, nullptr);
 }
 
 }  // namespace bgpu

@@ -225,6 +225,15 @@ int  bgpu_cigar_clipped(bgpu_ctx *ctx, bgpu_ticket t, const uint32_t *clips, con
  * each of the three arrays (no terminators); pinned host memory owned by the library until bgpu_release(). */
 int  bgpu_strings(bgpu_ctx *ctx, bgpu_ticket t, const char **text, const char **align, const char **query, const uint64_t **strOff);
 
+/* ---- The rescoring step of StoreMapQVs (alignment/Blasr.cpp:2768-2780): ComputeAlignmentScore(alignment, qAlignedSeq,
+ * tAlignedSeq, scoreFn, useAffinePenalty) -- the Alignment overload, common/algorithms/alignment/AlignmentUtils.h:127-169: Match()
+ * over every block plus one cost per Gap of the lists between blocks (affineOpen + length * affineExtend when that is smaller
+ * and useAffinePenalty) -- of every alignment of a collected GuidedAlign / AffineGuidedAlign ticket under ANOTHER score function
+ * (blasr: the caller's ins / del / affine costs with SMRTLogProbMatrix; probScore = -scores[i] / 10.0).  scores[nJobs] is the
+ * caller's; jobs without an alignment get 0.  The partitioning of overlapping alignments and the phred arithmetic on these
+ * scores (Blasr.cpp:2781-2920) stay with the caller: O(candidates^2) scalar work per read. */
+int  bgpu_rescore(bgpu_ctx *ctx, bgpu_ticket t, const bgpu_scorefn *fn, int useAffinePenalty, int32_t *scores);
+
 /* ---- SDPAlign (common/algorithms/alignment/SDPAlign.h:95-637), the step that produces the guide the refinement consumes
  * (called at alignment/Blasr.cpp:1716-1722 and :1080-1090): fragment set (k-mer matches of prefix / whole /
  * suffix), sparse-DP chain, chain -> blocks, and -- when `detailed` -- the SWAlign / recursive SDPAlign fills of the boxes

@@ -63,8 +63,8 @@ inline bgpu_scorefn MakeScoreFn(const T_ScoreFn &fn, int kind = BGPU_FN_DISTANCE
 // A ticket shared by the RefineBatch objects whose jobs RefineService merged into one submission: released when the
 // last of them lets go.
 struct SharedTicket {
-  bgpu_ctx *ctx; bgpu_ticket ticket; int refs; std::mutex mu;
-  SharedTicket(bgpu_ctx *c, bgpu_ticket t, int r) : ctx(c), ticket(t), refs(r) {}
+  bgpu_ctx *ctx; bgpu_ticket ticket; int refs; std::mutex mu; uint32_t nJobs;
+  SharedTicket(bgpu_ctx *c, bgpu_ticket t, int r, uint32_t n = 0) : ctx(c), ticket(t), refs(r), nJobs(n) {}
 };
 
 class RefineService;
@@ -120,7 +120,7 @@ class RefineBatch {
     int rc = bgpu_submit(ctx.get(), &s, &p, &b, &ticket_);
     if (rc == BGPU_OK) { owner_ = ctx.get(); rc = bgpu_collect(owner_, ticket_, results_.data(), &arena_); }
     if (rc != BGPU_OK) throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(ctx.get()));
-    cigarOps_ = nullptr; cigarOff_ = nullptr; base_ = 0;
+    cigarOps_ = nullptr; cigarOff_ = nullptr; base_ = 0; rescored_.clear();
   }
   ~RefineBatch() { Release(); }
 
@@ -136,6 +136,21 @@ class RefineBatch {
     i += base_;                                   // position of this batch's first job inside a merged ticket
     for (uint64_t k = cigarOff_[i]; k < cigarOff_[i + 1]; k++) { out += std::to_string(cigarOps_[k] >> 4); out += "MIDNSHP=X"[cigarOps_[k] & 15]; }
     return out;
+  }
+
+  // The rescoring step of StoreMapQVs (alignment/Blasr.cpp:2768-2780): ComputeAlignmentScore(alignment, qAlignedSeq,
+  // tAlignedSeq, fn, useAffinePenalty) -- the Alignment overload, AlignmentUtils.h:127-169 -- of job i under ANOTHER score
+  // function (blasr: the run's gap costs with SMRTLogProbMatrix; probScore = -Rescore(i, fn, affine) / 10.0).  Evaluated on the
+  // device for the whole ticket at the first call.
+  template <typename T_ScoreFn>
+  int Rescore(uint32_t i, const T_ScoreFn &fn, bool useAffinePenalty) {
+    if (rescored_.empty()) {
+      const bgpu_scorefn s = MakeScoreFn(fn);
+      rescored_.resize(shared_ ? shared_->nJobs : size());
+      const int rc = bgpu_rescore(owner_, shared_ ? shared_->ticket : ticket_, &s, useAffinePenalty ? 1 : 0, rescored_.data());
+      if (rc != BGPU_OK) { rescored_.clear(); throw Error(rc, std::string("blasr_gpu: ") + bgpu_last_error(owner_)); }
+    }
+    return rescored_[base_ + i];
   }
 
   const bgpu_result &Result(uint32_t i) const { return results_[i]; }
@@ -210,6 +225,7 @@ class RefineBatch {
   bgpu_arena arena_{};
   bgpu_ctx *owner_ = nullptr; bgpu_ticket ticket_ = nullptr;       // results and the arena live until Release()
   const uint32_t *cigarOps_ = nullptr; const uint64_t *cigarOff_ = nullptr;
+  std::vector<int32_t> rescored_;                                  // Rescore(): the whole ticket's scores
 };
 
 // Cross-thread batching for blasr's thread driver.  MapReads (Blasr.cpp:3193) runs one instance per -nproc, and each
@@ -376,14 +392,14 @@ class RefineService {
       deviceMs_ += tm.msTotal; tickets_++; jobs_ += f.nJobs;
       allocs_ = std::max<uint64_t>(allocs_, tm.devAllocs + tm.pinAllocs);
     }
-    SharedTicket *sh = new SharedTicket(ctx.get(), f.ticket, (int)f.reqs.size());
+    SharedTicket *sh = new SharedTicket(ctx.get(), f.ticket, (int)f.reqs.size(), f.nJobs);
     uint32_t at = 0;
     for (Request *x : f.reqs) {
       RefineBatch &b = *x->batch;
       b.results_.assign(res.begin() + at, res.begin() + at + b.size());
       b.base_ = at;
       at += b.size();
-      b.arena_ = arena; b.owner_ = ctx.get(); b.ticket_ = nullptr; b.shared_ = sh; b.cigarOps_ = nullptr; b.cigarOff_ = nullptr;
+      b.arena_ = arena; b.owner_ = ctx.get(); b.ticket_ = nullptr; b.shared_ = sh; b.cigarOps_ = nullptr; b.cigarOff_ = nullptr; b.rescored_.clear();
       x->tDone = std::chrono::steady_clock::now();
       x->done.store(true, std::memory_order_release);          // x may be gone right after this
     }

@@ -247,7 +247,15 @@ int main(int argc, char **argv) {
       /* the CIGAR built on the device (bgpu_cigar) against the reference printer's text */
       if (batch.Cigar(j) != pr.substr(0, pr.find('|'))) { printf("job %d: device CIGAR differs from the reference printer's\n", i); bad++; }
       printedBytes += pr.size();
+      /* StoreMapQVs' rescoring (Blasr.cpp:2768-2780): the run's gap costs with SMRTLogProbMatrix, the Alignment overload of
+       * ComputeAlignmentScore, on the refined candidate */
+      DistFn logProb;
+      logProb.InitializeScoreMatrix(SMRTLogProbMatrix);
+      logProb.ins = fn.ins; logProb.del = fn.del; logProb.affineOpen = fn.affineOpen; logProb.affineExtend = fn.affineExtend;
+      const int wantProb = ComputeAlignmentScore(refRefined, qs[i], ts[i], logProb, affine != 0);
+      if (batch.Rescore(j, logProb, affine != 0) != wantProb) { printf("job %d: device rescoring differs from ComputeAlignmentScore (%d vs %d)\n", i, batch.Rescore(j, logProb, affine != 0), wantProb); bad++; }
     }
+    printf("adapter_check: StoreMapQVs rescoring (SMRTLogProbMatrix) x%zu candidates on the device: %s\n", jobOf.size(), bad ? "MISMATCH" : "identical");
     printf("adapter_check: %zu bytes of SAM CIGAR + m5 alignment strings printed by the reference's printers: %s\n", printedBytes,
            bad ? "MISMATCH" : "identical");
     printf("adapter_check: %s x%zu candidates through blasr_gpu::RefineBatch: %s\n", affine ? "AffineGuidedAlign" : "GuidedAlign",

@@ -229,6 +229,22 @@ extern "C" int ref_alignment_strings(const orc_scorefn *fn, const orc_job *job, 
   return (int)ts.size();
 }
 
+/* StoreMapQVs' rescoring (alignment/Blasr.cpp:2768-2780): the job aligned under fn, then ComputeAlignmentScore(alignment, query,
+ * text, fn2, useAffinePenalty) -- the Alignment overload, AlignmentUtils.h:127-169 -- under a second distance-matrix function. */
+extern "C" int ref_rescore(const orc_scorefn *fn, const orc_job *job, const orc_scorefn *fn2, int useAffine, int32_t *score) {
+  Scratch s; Alignment aln; orc_result res;
+  RunOne(fn, job, &res, s, aln);
+  *score = 0;
+  if (res.status != ORC_OK) return 0;
+  FASTQSequence q; DNASequence t;
+  q.seq = (Nucleotide *)job->q; q.length = job->qLen;
+  t.seq = (Nucleotide *)job->t; t.length = job->tLen;
+  DistFn f2; FillDist(fn2, f2);
+  *score = ComputeAlignmentScore(aln, q, t, f2, useAffine != 0);
+  q.seq = NULL; t.seq = NULL;
+  return 1;
+}
+
 extern "C" int ref_block_strings(const uint8_t *qs, uint32_t qLen, const uint8_t *ts, uint32_t tLen, const uint32_t *blocks,
                                  uint32_t nBlocks, char *textStr, char *alignStr, char *queryStr, uint32_t capOut) {
   Alignment aln;                                   /* blocks only, no gap lists: the form SDPAlign returns */

@@ -73,6 +73,7 @@ def _load(which: str):
         L.ref_alignment_strings.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.ref_sdp_fragments.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]
+        L.ref_rescore.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.POINTER(OrcScoreFn), C.c_int, C.POINTER(C.c_int32)]
         L.ref_cigar.argtypes = [C.POINTER(OrcScoreFn), C.POINTER(OrcJob), C.c_void_p, C.c_uint32]
         L.ref_sdp_guide.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(OrcScoreFn), C.c_int, C.c_int,
                                     C.c_int, C.c_float, C.c_void_p, C.c_uint32]
@@ -321,3 +322,11 @@ def replay(which: str, fn: OrcScoreFn, jobs, nThreads: int):
     s = C.c_int64(0)
     cells = getattr(L, f"{which}_replay")(C.byref(fn), arr, len(jobs), nThreads, C.byref(s))
     return int(cells), int(s.value)
+
+
+def rescore(fn: OrcScoreFn, job: OrcJob, fn2: OrcScoreFn, useAffine: bool) -> int:
+    """The reference's ComputeAlignmentScore(alignment, q, t, fn2, useAffine) (AlignmentUtils.h:127-169) of the alignment the job
+    gets under fn: the rescoring step of StoreMapQVs."""
+    out = C.c_int32(0)
+    _load("ref").ref_rescore(C.byref(fn), C.byref(job), C.byref(fn2), int(useAffine), C.byref(out))
+    return int(out.value)
