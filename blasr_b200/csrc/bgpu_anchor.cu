@@ -336,7 +336,7 @@ int anchor_set_index(int device, const uint8_t *genome, uint64_t gN, uint64_t re
 // start with it.  Host code, one sequential pass in suffix-array order, with the reference's own edge behaviour: the last
 // prefixLength - 1 ENTRIES of the array are never looked at, a suffix whose k-mer ends exactly at the end of the text closes the
 // current run, and a k-mer that cannot be coded (N, or the text ending inside it: bytes at and beyond n read as 'N') leaves
-// the start of the tuple seen before it rewritten.  tests/test_anchor_oracle.py pins it against the reference's own tables.
+// the start of the tuple seen before it rewritten.  the CPU tests pin it against the reference's own tables.
 int build_lookup_table(const uint8_t *g, uint64_t n, const uint32_t *index, uint32_t L, uint32_t *startT, uint32_t *endT) {
   if (!g || !index || !startT || !endT || L < 1 || L > 14 || n >= 0xFFFFFFFFull) return BGPU_E_INVALID;
   const uint64_t tableLen = (uint64_t)1 << (2 * L);

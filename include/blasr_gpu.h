@@ -259,11 +259,13 @@ int  bgpu_sdp_align(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_sdp_params
 /* ---- Suffix-array anchoring: MapReadToGenome (common/algorithms/anchoring/MapBySuffixArray.h:209-309, called
  * for the read and its reverse complement at alignment/Blasr.cpp:2282-2296) with LocateAnchorBoundsInSuffixArray (:24-207) and
  * SuffixArray::StoreLCPBounds / SearchLeftBound / SearchRightBound (common/datastructures/suffixarray/SuffixArray.h:928-1067,
- * 736-822) on the device, over an index that stays resident in HBM (4 B per base: 12.4 GB for a human genome).
+ * 736-822) on the device, over an index that stays resident in HBM (8 B per base on the device -- position + the next ten bases, so that a probe of
+ * the binary searches is one load: 25 GB for a human genome).
  *
  * bgpu_set_suffix_array copies the members of the reference's SuffixArray object the search reads -- index[n], and
  * startPosTable / endPosTable[4^lookupPrefixLength] with lookupPrefixLength (NULL / 0: no table, like a SuffixArray whose
- * startPosTable is NULL) -- to the device of ctx; the genome is the one bgpu_set_reference gave (same n; set it first).
+ * startPosTable is NULL) -- to the device of ctx; the genome is the one bgpu_set_reference gave (same n; set it FIRST: the device index
+ * entries carry its bases, and a later bgpu_set_reference invalidates them).
  * Shared by every context on that device, replaced by the next call, freed with n == 0.  Synchronous. */
 int  bgpu_set_suffix_array(bgpu_ctx *ctx, const uint32_t *index, uint64_t n, const uint32_t *startPosTable,
                            const uint32_t *endPosTable, uint32_t lookupPrefixLength);
