@@ -579,7 +579,9 @@ def gap_fill_record(al, n):
     out = dict(metric="gap_fill_jobs_per_s", value=n / best, unit="jobs/s", ms_per_call=1e3 * best, jobs=n, jobs_ok=int((res.results["status"] == 0).sum()),
                cells=cells, gcups=cells / best * 1e-9,
                device_ms=dict(prep=tm.msPrep, fill=tm.msFill, trace=tm.msTrace, emit=tm.msEmit, total=tm.msTotal),
-               how="bgpu_submit + bgpu_collect from host buffers, best of 5",
+               host_ms=dict(bgpu_submit=tm.msHostSubmit, bgpu_collect=tm.msHostCollect),
+               how="bgpu_submit + bgpu_collect from host buffers, best of 5 (batches of small matrices take the planner-free path: "
+                   "submission order, traceback offsets laid out by bgpu_submit, nothing read back before the kernels run)",
                workload=f"{n} AffineKBandAlign jobs, |q| 2-13, k = |dq-dt|+3, mean {cells / n:.0f} cells, hpInsOpen/hpInsExtend/insOpen/insExtend/del = "
                         f"{pr[0]}/{pr[1]}/{pr[2]}/{pr[3]}/{indel} (Blasr.cpp:1067-1076)")
     try:

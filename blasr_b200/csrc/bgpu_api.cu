@@ -262,6 +262,8 @@ struct bgpu_ticket_s {
   DenseArgs dargs{};
   std::vector<uint64_t> h_arrowBytes;   // dense: host-computed traceback bytes per job
   std::vector<uint64_t> h_cellsMetric;  // dense: SURVEY 8(d) cell count per job
+  bool denseSmall = false;              // dense: every matrix is small and all of them fit one wave: no read-back, no host planning
+  uint64_t *h_aoffFast = nullptr; uint64_t denseWaveBytes = 0;   // ... traceback offsets laid out by bgpu_submit itself
   uint32_t *h_cigar = nullptr; uint64_t *h_cigarOff = nullptr;   // bgpu_cigar results (pinned), once built
   uint32_t *d_fmtOps = nullptr, *d_fmtCols = nullptr;            // per-job CIGAR op / alignment column counts, once counted
   char *h_str = nullptr; uint64_t *h_strOff = nullptr; size_t strTotal = 0;   // bgpu_strings results (pinned), once built
@@ -633,7 +635,10 @@ static int enqueue_guided_fast(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   CK(cudaEventRecord(t->waveEv[0], s));
   CK(cudaEventRecord(ctx->evFork, s));
   t->timing.kernelLaunches = 2;
+  // BGPU_SERIAL_CLASSES=1 (diagnostic): the class kernels one after the other on the ticket's stream instead of concurrently
+  static const bool serialClasses = [] { const char *e = getenv("BGPU_SERIAL_CLASSES"); return e && *e && *e != '0'; }();
   for (int c = N_CLS - 1; c >= 0; c--) {
+    if (serialClasses) { launch_fill_guided(t->B, t->sp, c, t->d_order, t->d_plan, n + N_CLS, t->d_counters + c, ctx->nSM, s); t->timing.kernelLaunches++; continue; }
     CK(cudaStreamWaitEvent(ctx->aux[c], ctx->evFork, 0));
     launch_fill_guided(t->B, t->sp, c, t->d_order, t->d_plan, n + N_CLS, t->d_counters + c, ctx->nSM, ctx->aux[c]);
     CK(cudaEventRecord(ctx->evJoin[c], ctx->aux[c]));
@@ -811,7 +816,32 @@ static int enqueue_dense(bgpu_ctx *ctx, bgpu_ticket t, bool firstRun) {
   launch_dense_prep(t->B, t->sp, t->dargs, t->d_dblkOff /* row-buffer offsets */, t->d_runOff, s);
   t->timing.kernelLaunches = 1;
   CK(cudaEventRecord(t->ev[1], s));
-  if (firstRun) {
+  if (firstRun && t->denseSmall) {
+    // batches of small matrices (the ~80-cell AffineKBandAlign gap fills of -alignContigs, the SWAlign fills of SDPAlign): every
+    // job is dispatched in submission order -- the kernels skip the ones prep flagged -- with the traceback offsets bgpu_submit
+    // laid out from the lengths alone: nothing is read back, the host does not wait for the device
+    const uint32_t n = t->nJobs;
+    Wave w{};
+    w.begin[0] = 0; w.count[0] = n; w.traceBegin = 0; w.traceCount = n;
+    t->waves.push_back(w);
+    RC(talloc_dev(ctx, t, &t->d_order, std::max<uint32_t>(n, 1)));
+    RC(talloc_dev(ctx, t, &t->d_arrowOff, std::max<uint32_t>(n, 1)));
+    t->nCounters = 16;
+    RC(talloc_dev(ctx, t, &t->d_counters, t->nCounters));
+    uint8_t *arrows = nullptr;
+    RC(talloc_dev(ctx, t, &arrows, std::max<size_t>(t->denseWaveBytes, 16)));
+    t->B.arrows = arrows; t->B.arrowOff = t->d_arrowOff; t->dargs.arrowOff = t->d_arrowOff;
+    uint32_t *h_order = nullptr;
+    RC(talloc_pin(ctx, t, &h_order, std::max<uint32_t>(n, 1)));
+    for (uint32_t i = 0; i < n; i++) h_order[i] = i;
+    CK(cudaMemcpyAsync(t->d_order, h_order, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t->d_arrowOff, t->h_aoffFast, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    t->waveEv.resize(3);
+    for (auto &e : t->waveEv) CK(cudaEventCreate(&e));
+    uint64_t cells = 0;
+    for (uint32_t i = 0; i < n; i++) cells += t->h_cellsMetric[i];     // refused jobs are taken out again by bgpu_collect
+    t->timing.cells = cells; t->timing.fillCells = cells;
+  } else if (firstRun) {
     CK(cudaMemcpyAsync(t->h_geom, t->B.geom, sizeof(JobGeom) * t->nJobs, cudaMemcpyDeviceToHost, s));
     CK(wait_stream(ctx));
     const uint32_t n = t->nJobs;
@@ -912,7 +942,8 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
   uint64_t *h_off = nullptr;
   RC(talloc_pin(ctx, t, &h_off, 2 * (size_t)n + 2));
   t->h_arrowBytes.assign(n, 0); t->h_cellsMetric.assign(n, 0);
-  uint64_t rbTot = 0, runTot = 0;
+  RC(talloc_pin(ctx, t, &t->h_aoffFast, std::max<uint32_t>(n, 1)));
+  uint64_t rbTot = 0, runTot = 0, maxBytes = 0, waveBytes = 0;
   for (uint32_t i = 0; i < n; i++) {
     const uint64_t ql = b->qOff[i + 1] - b->qOff[i], tl = b->tOff[i + 1] - b->tOff[i];
     uint32_t qb = (uint32_t)ql, tb = (uint32_t)tl;
@@ -924,9 +955,13 @@ static int submit_dense(bgpu_ctx *ctx, const bgpu_scorefn *fn, const bgpu_params
     } else { bytes = (ql + 1) * (tl + 1); cells = bytes; }
     if (bytes > (1ull << 31)) bytes = 16;          // rejected by the prep kernel (matrix size is an int in the reference)
     t->h_arrowBytes[i] = bytes; t->h_cellsMetric[i] = cells;
+    t->h_aoffFast[i] = waveBytes; waveBytes += (bytes + 15) & ~15ull; maxBytes = std::max(maxBytes, bytes);
     h_off[i] = rbTot; h_off[n + i] = runTot;
     rbTot += (p->algo == BGPU_AFFINE_KBAND ? 6 : 2) * ((uint64_t)tb + 2); runTot += ql + tl + 2;   // ping-pong rows (x3 matrices)
   }
+  static const bool noFastDense = [] { const char *e = getenv("BGPU_DENSE_PLANNED"); return e && *e && *e != '0'; }();   // diagnostic: always plan on the host
+  t->denseSmall = !noFastDense && maxBytes <= (64u << 10) && waveBytes <= ctx->arrowPoolCap;
+  t->denseWaveBytes = waveBytes;
   RC(talloc_dev(ctx, t, &t->d_dblkOff, 2 * (size_t)n + 2));
   t->d_runOff = t->d_dblkOff + n;
   CK(cudaMemcpyAsync(t->d_dblkOff, h_off, sizeof(uint64_t) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -1075,6 +1110,11 @@ extern "C" int bgpu_collect(bgpu_ctx *ctx, bgpu_ticket t, bgpu_result *results, 
       RC(copy_arena(ctx, t, t->totals[0], t->totals[1], t->totals[2]));
       CK(cudaEventRecord(t->ev[5], s));
       CK(wait_stream(ctx));
+      if (t->dense && t->denseSmall) {                   // the cell metric counted every submitted job: take the refused ones out
+        uint64_t cells = t->timing.cells;
+        for (uint32_t i = 0; i < t->nJobs; i++) if (t->h_results[i].status != BGPU_JOB_OK) cells -= std::min(cells, t->h_cellsMetric[i]);
+        t->timing.cells = cells; t->timing.fillCells = cells;
+      }
     }
     t->timing.d2hBytes = sizeof(bgpu_result) * (uint64_t)t->nJobs + arena_bytes(t, t->totals[0], t->totals[1], t->totals[2]);
     gather_timing(t);
