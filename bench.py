@@ -420,7 +420,7 @@ def measure(al, local, batch, fn, algo, args, steps, warmup, barrier, do_e2e=Tru
             print(f"bench: resident_reference leg skipped: {type(e).__name__}: {e}", file=sys.stderr)
             torch_sync()
     pipelined = None
-    if e2e and clocks:
+    if e2e and clocks and int(os.environ.get("WORLD_SIZE", "1")) == 1:      # an explanatory leg of the single-GPU line only
         al.trim()
         try:
             pipelined = resident_pipelined(local, batch, fn, algo, args.e2e_threads, 2 * args.e2e_threads, max(1, min(warmup, 3)), steps, barrier)
@@ -690,7 +690,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     # the generator forks worker processes: run it before CUDA / NCCL are initialised in this process
     headline_quality = args.scorefn == "quality"
-    want_subs = args.subrecords and (args.algo, args.scorefn) == ("guided", "distance")
+    # the sub-records are single-rank views (one of them, sdp_guides, exists on rank 0 only): they belong to the N = 1 run; with
+    # more ranks every rank runs exactly the headline measurement, so that the ranks meet at the same barriers
+    want_subs = args.subrecords and world == 1 and (args.algo, args.scorefn) == ("guided", "distance")
     batch = make_workload(args.jobs, args.seed + 1000 * rank, with_qual=headline_quality or want_subs, **workload_args(args))
     prod = make_workload(args.prod_jobs, args.seed + 1000 * rank + 500, len_lo=10000, len_hi=10000, bands=(16,)) if want_subs else None
     torch.cuda.set_device(local)
