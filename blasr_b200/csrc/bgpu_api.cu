@@ -197,9 +197,7 @@ static int slab_alloc(bgpu_ctx *ctx, SlabPool &pool, TicketMem &tm, void **p, si
   Slab sl{};
   if (best >= 0) { sl = pool.free_[best]; pool.free_.erase(pool.free_.begin() + best); }
   else {
-    // an eighth of headroom: the next ticket of about the same size (a few per cent more bases) still fits this slab instead of
-    // paying a cudaMalloc / cudaHostAlloc of its own
-    size_t cap = std::max(want + want / 8, std::min(2 * pool.lastCap, (size_t)1 << 30));
+    size_t cap = std::max(want, std::min(2 * pool.lastCap, (size_t)1 << 30));
     cap = (cap + 0xfffff) & ~(size_t)0xfffff;
     void *v = nullptr;
     pool.nAlloc++;
