@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--bands", default=",".join(str(b) for b in BANDS), help="band sizes drawn per job (configs[1]: 16,32,64; blasr's default -bandSize: 16)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--ref-seconds", type=float, default=None,
+                    help="--impl reference: CPU time of one step's sample (default: 2-20 s so that steps + warmup end within ~2 min)")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) of the e2e measurement")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches the shard is cut into for the e2e measurement")
     ap.add_argument("--no-subrecords", dest="subrecords", action="store_false", help="skip the affine / affine_production / quality / sdp_guides sub-records")
@@ -131,7 +133,7 @@ def run_reference(args):
     # the sample is drawn from a shard prefix large enough to hold the shard's mix of lengths and bands; it is bounded by
     # CPU time, not by the 100k pairs
     batch = make_workload(min(args.jobs, max(4096, n_threads * 128)), args.seed, with_qual=quality, **workload_args(args))
-    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = args.ref_seconds if args.ref_seconds else max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     idx = cpu_sample(batch, n_threads, per_step, algo)
     for _ in range(args.warmup):
         cpu_replay(batch, algo, n_threads, per_step, quality=quality, idx=idx[:max(n_threads, len(idx) // 4)])
@@ -750,7 +752,9 @@ def run_ours(args):
         resident["pipelined"] = pl
     e2e_val = cells_all / e2e_sec_max / 1e9
     resident_ref = None
-    if head["e2e"].get("resident_reference"):
+    # the leg may have been skipped on ONE rank (out of memory): every rank takes the same branch, or the all-reduce below hangs
+    have_rr = allsum(1.0 if head["e2e"].get("resident_reference") else 0.0) == float(world)
+    if have_rr:
         rr = head["e2e"]["resident_reference"]
         rr_sec = allmax(rr["sec"])
         resident_ref = {"value": cells_all / rr_sec / 1e9, "unit": "GCUPS", "ms_per_step": rr_sec * 1e3, "h2d_bytes_per_step": rr["h2d"],

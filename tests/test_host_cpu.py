@@ -137,3 +137,20 @@ def test_base_code_table():
     if O.have_ref():
         L = O._load("ref")
         assert [L.ref_three_bit(c) for c in range(256)] == want.tolist()
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the reference's own templates on the host cores, no GPU): rank 0 prints one JSON line with
+    the contract's keys; the other ranks of a torchrun launch exit 0 without work."""
+    import json
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-seconds", "0.5"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0"))
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "banded_dp_gcups" and line["unit"] == "GCUPS" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and "pairs" in cb["sample"]
+    assert line["config"]["workload"].startswith("configs[1]") and line["config"]["pairs_per_gpu"] == 100000
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1"))
+    assert out.returncode == 0 and out.stdout.strip() == ""
