@@ -1,9 +1,11 @@
 // bgpu_api.cu -- host side of the C ABI declared in include/blasr_gpu.h.
 //
-// Owns device memory, pinned staging, the stream and the kernel schedule of one batch:
-//   H2D -> prep (guide rows, d-block windows) -> [host: classify by window width, order longest-first,
-//   cut into waves that fit the traceback pool] -> per wave { fill kernels, traceback kernel } ->
+// Owns device memory, pinned staging, the streams and the kernel schedule of one batch:
+//   H2D -> prep (guide rows, d-block windows) -> planner kernels (bgpu_plan.cu: classify by window width, order
+//   longest-first, lay out the traceback pool) -> fill kernels (one per job class, concurrently) -> traceback ->
 //   count scan -> emit (blocks, gaps, stats) -> D2H.
+// bgpu_submit enqueues all of it and returns (enqueue_guided_fast); a ticket whose traceback does not fit the pool in one
+// wave -- or BGPU_HOST_PLAN=1 -- takes the round-1 path instead (enqueue_guided: geometry read back, waves cut on the host).
 // No CPU implementation of any aligner exists here: without a CUDA device every entry point fails.
 #include <algorithm>
 #include <chrono>
