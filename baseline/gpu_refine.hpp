@@ -158,6 +158,15 @@ bool BgpuRefineAlignments(vector<T_Sequence*> &bothQueryStrands, T_RefSequence &
   for (UInt i = 0; i < alignmentPtrs.size(); i++) {
     T_AlignmentCandidate &c = *alignmentPtrs[i];
     if (c.blocks.size() == 0) continue;
+    // a candidate the device refuses (a window wider than the widest kernel, scores beyond the kernels' number format: see
+    // INTEGRATION.md section 6) stays with the reference's own RefineAlignment -- c is still untouched at this point
+    const int st = batch.Result(j).status;
+    if (st == BGPU_JOB_TOO_WIDE || st == BGPU_JOB_RANGE) {
+      j++;
+      tSeqs[i].Free();
+      RefineAlignment(query, genome, c, params, mappingBuffers);
+      continue;
+    }
     T_AlignmentCandidate refinedAlignment;
     batch.Store(j++, refinedAlignment);
     c.blocks.clear();
