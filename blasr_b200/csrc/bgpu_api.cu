@@ -136,10 +136,10 @@ struct bgpu_ctx {
     }                                                                                             \
   } while (0)
 
-// Waits for everything queued on the context's stream.  By default the wait spins (lowest latency: 5 host threads x 10
-// sub-batches of 100k pairs pass in 131-140 ms against 140-150 ms with sleeping waits).  BGPU_BLOCKING_SYNC=1 makes waiting
-// threads sleep on an event created with cudaEventBlockingSync instead: for hosts that run more waiting threads than
-// they have cores (blasr's one pthread per core, several GPUs per box).
+// Waits for everything queued on the context's stream.  By default the waiting thread polls an event with short naps (5 us
+// growing to 200 us, wait_event below): close to the latency of a spinning wait without its CPU cost.  BGPU_SPIN_SYNC=1 spins
+// in cudaStreamSynchronize, BGPU_BLOCKING_SYNC=1 sleeps on an event created with cudaEventBlockingSync: for hosts that run
+// more waiting threads than they have cores (blasr's one pthread per core, several GPUs per box).
 static bool blocking_sync() { static const bool on = [] { const char *e = getenv("BGPU_BLOCKING_SYNC"); return e && *e && *e != '0'; }(); return on; }
 static bool spin_sync() { static const bool on = [] { const char *e = getenv("BGPU_SPIN_SYNC"); return e && *e && *e != '0'; }(); return on; }
 static cudaError_t wait_event(cudaEvent_t ev);
