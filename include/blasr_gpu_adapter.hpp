@@ -12,6 +12,8 @@
 // Replaces, per batch of candidates instead of per candidate:
 //   AffineGuidedAlign / GuidedAlign + ComputeAlignmentStats      alignment/Blasr.cpp:863-878   (RefineBatch)
 //   KBandAlign / AffineKBandAlign / SWAlign                      Blasr.cpp:717-730,820-824,1067-1076; SDPAlign.h:440,503,563   (DenseBatch)
+//   SDPAlign                                                     Blasr.cpp:1716-1722,1080-1090   (SdpBatch)
+//   MapReadToGenome (read and reverse complement)                Blasr.cpp:2282-2296             (AnchorBatch)
 #ifndef BLASR_GPU_ADAPTER_HPP_
 #define BLASR_GPU_ADAPTER_HPP_
 #include <algorithm>
@@ -34,8 +36,10 @@ namespace blasr_gpu {
 
 struct Error : std::runtime_error { int code; Error(int c, const std::string &m) : std::runtime_error(m), code(c) {} };
 
-// One GPU context; the blasr thread driver (MapReads, Blasr.cpp:3193) creates one per device and shares it between
-// its pthreads (calls are serialised inside the library).
+// One GPU context = one stream + one allocation cache.  Calls into a context are serialised inside the library, so the
+// throughput configuration is ONE CONTEXT PER HOST THREAD of the blasr thread driver (MapReads, Blasr.cpp:3193) on the shared
+// device -- the library's per-device phase gates keep the threads' tickets pipelined -- or a RefineService (below), which owns
+// a few contexts and merges the requests of all threads into tickets.  A context shared by several pthreads works, serialised.
 class Context {
  public:
   explicit Context(int device = 0) {
