@@ -21,12 +21,16 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BL = os.path.join(ROOT, "baseline")
 STOCK, GPU, SAW = (os.path.join(BL, "_ref", x) for x in ("blasrmc", "blasrmc_gpu", "sawritermc"))
+RUN_TIMEOUT_S = 240      # one program run (a few seconds on configs[0]): a hung child must not hang the bench line
 
 
 def run(exe, d, out, nproc, extra=(), reads="reads.fa", env=None):
     cmd = [exe, reads, "genome.fa", "-sa", "genome.sa", "-sam", "-nproc", str(nproc), "-out", out] + list(extra)
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, env=env)
+    try:
+        r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, env=env, timeout=RUN_TIMEOUT_S)
+    except subprocess.TimeoutExpired:              # the child is killed; bench.py reports the leg as unavailable and goes on
+        raise SystemExit(f"{' '.join(cmd)} did not finish within {RUN_TIMEOUT_S} s")
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise SystemExit(f"{' '.join(cmd)} failed: {r.stdout[-1000:]} {r.stderr[-1000:]}")
